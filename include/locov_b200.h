@@ -1,0 +1,168 @@
+/*
+ * locov_b200.h — C ABI of liblocov_b200.so: the B200 (sm_100a) implementation of LocOV's
+ * region-text matching hot path.
+ *
+ * The reference (lmb-freiburg/locov) is pure Python on top of Detectron2 and exposes no FFI; its
+ * "plugin API" for this path is the set of nn.Module classes registered in Detectron2's registries
+ * (SURVEY.md §8b).  Each entry point below therefore cites the reference *call site* whose library
+ * kernel(s) it replaces.  The Python host side (package locov_b200) binds these symbols with ctypes
+ * and re-exposes them behind the reference's module interfaces.
+ *
+ * Conventions
+ *   - every function returns int: 0 = LOCO_OK, <0 = LOCO_E_*, >0 = a cudaError_t value;
+ *     loco_last_error() returns a thread-local human-readable message for the last failure.
+ *   - all pointers are DEVICE pointers unless the parameter is called `host_*`; the caller owns all
+ *     memory; the library never allocates user-visible memory and never synchronises `stream`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - bf16 tensors are raw uint16 bit patterns; "ld" = leading dimension in ELEMENTS (row stride).
+ *     Every bf16 matrix handed to a tensor-core entry point must have a 16-byte aligned base and
+ *     ld % 8 == 0 (TMA global-stride rule), otherwise LOCO_E_ALIGN.
+ *   - "hi/lo" operand pairs implement the fp32-accurate mode: x ≈ hi + lo with hi = bf16(x),
+ *     lo = bf16(x - hi); a product is evaluated as hi*hi + hi*lo + lo*hi on the bf16 tensor pipe with
+ *     fp32 accumulation in TMEM (≈2^-16 relative per product).  Passing lo == NULL selects plain
+ *     bf16 mode.
+ *   - thread-safe and re-entrant (autograd calls backward entries from another host thread).
+ */
+#ifndef LOCOV_B200_H
+#define LOCOV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LOCO_OK 0
+#define LOCO_E_BADARG (-1)
+#define LOCO_E_UNSUPPORTED (-2)
+#define LOCO_E_ALIGN (-3)
+#define LOCO_E_DEVICE (-4)
+#define LOCO_E_DRIVER (-5)
+
+/* tensor element types */
+#define LOCO_F32 0
+#define LOCO_BF16 1
+/* feature-map layouts */
+#define LOCO_NCHW 0
+#define LOCO_NHWC 1
+/* LSM alignment modes — MODEL.MMSS_HEAD.GROUNDING.ALIGNMENT, reference grounding_head.py:162-175 */
+#define LOCO_ALIGN_SOFTMAX 0
+#define LOCO_ALIGN_HARDMAX 1
+
+/* ---- library / device ------------------------------------------------------------------------- */
+int loco_version(void);                 /* 10000*major + 100*minor + patch */
+const char *loco_last_error(void);      /* thread-local; never NULL */
+int loco_device_check(int device);      /* LOCO_OK iff `device` is compute capability 10.x */
+int loco_sm_count(int device);          /* number of SMs (148 on B200) or <0 */
+
+/* ---- RoIAlign ----------------------------------------------------------------------------------
+ * Replaces: roi_emb_heads.py:182-187,243-245  self.pooler(features, boxes)
+ *           -> Detectron2 ROIPooler/ROIAlign -> torchvision.ops.roi_align(aligned=True) CUDA kernel.
+ * feat  [N,C,H,W] (LOCO_NCHW) or [N,H,W,C] (LOCO_NHWC), fp32.
+ * rois  [R,5] fp32 rows (batch_idx, x1, y1, x2, y2) in image coordinates.
+ * out   [R,C,PH,PW] fp32 (NCHW).
+ * Sampling-grid coordinates and integer tap indices are bit-exact with the float32 reference
+ * arithmetic (loco_roi_align_grid_dump exposes them); pooled values are toleranced (1e-4 rel).
+ * workspace: loco_roi_align_workspace_bytes() bytes (0 for LOCO_NHWC; an NCHW map is transposed to
+ * channels-last into it once per call).
+ */
+int64_t loco_roi_align_workspace_bytes(int N, int C, int H, int W, int feat_layout);
+int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_layout,
+                       const float *rois, int R, int PH, int PW, float spatial_scale,
+                       int sampling_ratio, int aligned, float *out, void *workspace, void *stream);
+
+/* Backward of the above (torchvision roi_align_backward semantics).  dfeat [N,C,H,W] fp32 must be
+ * zero-filled by the caller; contributions are accumulated with atomic adds. */
+int loco_roi_align_bwd(const float *dout, int N, int C, int H, int W, const float *rois, int R,
+                       int PH, int PW, float spatial_scale, int sampling_ratio, int aligned,
+                       float *dfeat, void *stream);
+
+/* Debug/parity entry: for every roi r, bin (ph,pw) and sample (iy,ix) with iy,ix < max_grid writes
+ *   grid_hw [R,2] int32            (gh, gw) — the adaptive sample counts
+ *   yx      [R,PH,PW,max_grid,max_grid,2] fp32   unclamped sample coordinate (y, x)
+ *   idx     [R,PH,PW,max_grid,max_grid,4] int32  (y_low, x_low, y_high, x_high), -1 = skipped sample
+ * Entries with iy >= gh or ix >= gw are left untouched. */
+int loco_roi_align_grid_dump(const float *rois, int R, int H, int W, int PH, int PW,
+                             float spatial_scale, int sampling_ratio, int aligned, int max_grid,
+                             int32_t *grid_hw, float *yx, int32_t *idx, void *stream);
+
+/* ---- operand preparation ------------------------------------------------------------------------
+ * fp32 [rows, cols] (row stride src_ld) -> bf16 hi (and lo when lo != NULL), row stride dst_ld.
+ * Columns cols..dst_ld-1 of the destination are zero-filled so padded matrices are TMA-safe.
+ * transpose != 0 writes dst[c, r] instead (dst is [cols, rows_padded]; dst_ld >= rows).
+ * Replaces nothing in the reference (which is fp32-only); it is the fp32 -> tensor-core boundary. */
+int loco_split_bf16(const float *src, int64_t rows, int64_t cols, int64_t src_ld, uint16_t *hi,
+                    uint16_t *lo, int64_t dst_ld, int transpose, void *stream);
+
+/* ---- projection GEMM  out[M,N] = A[M,K] · W[N,K]^T + bias ------------------------------------------
+ * Replaces: box_emb_head.py:196,206 (bbox_pred(x), emb_pred(x)) and grounding_head.py:111
+ *           (v2l_projection(region_features)) — cuBLAS SGEMM + bias.
+ * A_hi/A_lo [M,K] bf16 (lda), W_hi/W_lo [N,K] bf16 (ldw), bias [N] fp32 or NULL.
+ * Outputs (each may be NULL): out_f32 [M,N] (ld_f32); out_hi/out_lo [M, n_bf16] bf16 (ld_bf16) holding
+ * the first n_bf16 output columns split as hi/lo for a following tensor-core GEMM.
+ * tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM), operands staged by TMA (128B swizzle). */
+int loco_linear_fwd(const uint16_t *A_hi, const uint16_t *A_lo, int64_t lda, const uint16_t *W_hi,
+                    const uint16_t *W_lo, int64_t ldw, const float *bias, int M, int N, int K,
+                    float *out_f32, int64_t ld_f32, uint16_t *out_hi, uint16_t *out_lo,
+                    int n_bf16, int64_t ld_bf16, void *stream);
+
+/* ---- RoI x class scoring with fused softmax epilogue -----------------------------------------------
+ * Replaces: box_emb_head.py:211 cls_score(e) (cuBLAS) + Detectron2 FastRCNNOutputLayers.predict_probs
+ *           F.softmax / .losses log_softmax (ATen) reached from roi_emb_heads.py:266,280,347,357.
+ * E_hi/E_lo [R,D] bf16 (lde), C_hi/C_lo [K1,D] bf16 class-embedding matrix (ldc; last row = background),
+ * cls_bias [K1] fp32 or NULL.
+ * Outputs: logits [R,K1] fp32 (ld_logits) required; probs [R,K1] fp32 or NULL (same ld);
+ *          lse [R] fp32 (log-sum-exp over the K1 columns) or NULL;
+ *          argmax_fg [R] int64 = argmax over the first K1-1 (foreground) columns, or NULL. */
+int loco_box_score_fwd(const uint16_t *E_hi, const uint16_t *E_lo, int64_t lde, const uint16_t *C_hi,
+                       const uint16_t *C_lo, int64_t ldc, const float *cls_bias, int R, int K1, int D,
+                       float *logits, float *probs, int64_t ld_logits, float *lse,
+                       int64_t *argmax_fg, void *stream);
+
+/* Cross-entropy over the scored logits (Detectron2 FastRCNNOutputLayers.losses: F.cross_entropy mean).
+ * labels [R] int64 in [0,K1).  loss_sum: 1 fp32, accumulated (caller zero-fills) with sum_r(lse_r -
+ * logit[r,label_r]) * scale.  dlogits (may be NULL): [R,K1] (softmax - onehot) * grad_scale written
+ * as fp32 (dlogits_f32, ld_logits) and/or bf16 hi (dlogits_bf16, ld_bf16; zero padded). */
+int loco_box_ce_fwd_bwd(const float *logits, int64_t ld_logits, const float *lse, const int64_t *labels,
+                        int R, int K1, float scale, float *loss_sum, float grad_scale,
+                        float *dlogits_f32, uint16_t *dlogits_bf16, int64_t ld_bf16, void *stream);
+
+/* ---- LSM pair scoring ------------------------------------------------------------------------------
+ * Replaces: grounding_head.py:116-256 — B^2 .repeat() replication, torch.bmm, torch.where mask fill,
+ *           two F.softmax passes, masked weighted sums (all ATen/cuBLAS launches over [B^2,T,Rg]).
+ * cap_hi/cap_lo [Bc*T, D] bf16 (ldcap): caption word embeddings; cap_mask [Bc,T] fp32 (0/1) =
+ *           attention_mask * (1 - special_tokens_mask);
+ * emb_hi/emb_lo [Bi*Rg, D] bf16 (ldemb): projected region embeddings; reg_mask [Bi,Rg] fp32 (0/1).
+ * Writes d_w2r, d_r2w [Bc, Bi] fp32 (row stride ld_out) — rows = captions, cols = images:
+ *   d_w2r[c,i] = sum_t m_c[t] sum_r softmax_r(S~)[t,r] * (-S[t,r]) / max(n_words_c, 1)
+ *   d_r2w[c,i] = sum_r m_i[r] sum_t softmax_t(S~)[t,r] * (-S[t,r]) / max(n_regions_i, 1)
+ * with S = <cap, emb> * inv_temperature and S~ = S where both masks are set, else a finite
+ * very-negative fill (an all-masked row/column therefore yields a uniform softmax, as the reference).
+ * Either output may be NULL (ALIGN_WORDS_TO_REGIONS / ALIGN_REGIONS_TO_WORDS off).
+ * The [B^2,T,Rg] similarity tensor never leaves the SM (TMEM -> registers -> two scalars per pair).
+ * Limits: T <= 128, Rg <= 256 (else LOCO_E_UNSUPPORTED).
+ * workspace: loco_lsm_pair_workspace_bytes(Bc,T,Bi,Rg) bytes of scratch, 16-byte aligned. */
+int64_t loco_lsm_pair_workspace_bytes(int Bc, int T, int Bi, int Rg);
+int loco_lsm_pair_fwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ldcap,
+                      const float *cap_mask, const uint16_t *emb_hi, const uint16_t *emb_lo,
+                      int64_t ldemb, const float *reg_mask, int Bc, int T, int Bi, int Rg, int D,
+                      float inv_temperature, int alignment, float *d_w2r, float *d_r2w,
+                      int64_t ld_out, void *workspace, void *stream);
+
+/* ---- pair-matrix losses ---------------------------------------------------------------------------
+ * Replaces: grounding_head.py:240-251 (empty-pair guard), :272-290 (4 CE losses), :354-379 (accuracies).
+ * pw [Bc, Bi] fp32 (ld) is modified IN PLACE by the empty-pair guard:
+ *   pw[c,i] = max(pw) + 100 where n_words[c] == 0 and n_regions[i] == 0.
+ * cap_mask [Bc,T], reg_mask [Bi,Rg] as above.  The matching caption of image column i is row
+ * i + diag_offset (diag_offset = first global image index of this shard when columns are sharded).
+ * out[4] fp32: { CE choose-caption (mean over the Bi columns of -log_softmax(-pw, dim=0)[i+off, i]),
+ *               CE choose-image   (mean over rows c in [diag_offset, diag_offset+Bi) of
+ *                                  -log_softmax(-pw, dim=1)[c, c-off]; only valid when Bi == Bc),
+ *               accuracy choose-caption, accuracy choose-image }. */
+int loco_pair_ce(float *pw, int64_t ld, int Bc, int Bi, int diag_offset, const float *cap_mask, int T,
+                 const float *reg_mask, int Rg, float *out4, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOCOV_B200_H */

@@ -1,0 +1,107 @@
+// api.cu — library-level pieces of the C ABI: version, thread-local error string, device checks and
+// the TMA tensor-map factory (driver entry point resolved at run time, so the .so links against
+// libcudart only and loads on a machine without a GPU for the symbol/ABI tests).
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace loco {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return (int)e;
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode_fn() {
+    static std::once_flag once;
+    static encode_tiled_fn fn = nullptr;
+    std::call_once(once, []() {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_tiled_fn>(p);
+    });
+    return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows) {
+    encode_tiled_fn fn = get_encode_fn();
+    LOCO_REQUIRE(fn != nullptr, LOCO_E_DRIVER, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    LOCO_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, LOCO_E_ALIGN, "bf16 operand base %p is not 16-byte aligned", base);
+    LOCO_REQUIRE(ld_elems % 8 == 0, LOCO_E_ALIGN, "bf16 operand leading dimension %llu is not a multiple of 8",
+                 (unsigned long long)ld_elems);
+    LOCO_REQUIRE(box_rows >= 1 && box_rows <= 256, LOCO_E_BADARG, "TMA box rows %u out of range", box_rows);
+    LOCO_REQUIRE(rows >= 1 && cols >= 1, LOCO_E_BADARG, "empty TMA tensor");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld_elems * 2};   // bytes, dimension 1
+    cuuint32_t box[2] = {64, box_rows};       // 64 bf16 = 128 B inner box = one swizzle span
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LOCO_REQUIRE(r == CUDA_SUCCESS, LOCO_E_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box_rows=%u)",
+                 (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows);
+    return LOCO_OK;
+}
+
+int current_device_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+}  // namespace loco
+
+extern "C" {
+
+int loco_version(void) { return 10000 * 0 + 100 * 1 + 0; }
+
+const char *loco_last_error(void) { return loco::g_err; }
+
+int loco_device_check(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        loco::set_error("no CUDA device visible (%s)", cudaGetErrorString(e));
+        return LOCO_E_DEVICE;
+    }
+    LOCO_REQUIRE(device >= 0 && device < n, LOCO_E_DEVICE, "device ordinal %d out of range (%d devices)", device, n);
+    int major = 0, minor = 0;
+    LOCO_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    LOCO_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    LOCO_REQUIRE(major == 10, LOCO_E_DEVICE, "device %d is compute capability %d.%d; liblocov_b200 is built for sm_100a only",
+                 device, major, minor);
+    return LOCO_OK;
+}
+
+int loco_sm_count(int device) {
+    int n = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return -loco::cuda_fail(e, "cudaDeviceGetAttribute(MultiProcessorCount)");
+    return n;
+}
+
+}  // extern "C"

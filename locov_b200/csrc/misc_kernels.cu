@@ -1,0 +1,265 @@
+// misc_kernels.cu — bandwidth-bound helpers around the tensor-core kernels:
+//   * loco_split_bf16   : fp32 -> bf16 hi (+lo) operand preparation (optionally transposed)
+//   * loco_box_ce_fwd_bwd: cross-entropy loss + dlogits from the fused-softmax statistics
+//   * loco_pair_ce      : empty-pair guard, 4 CE losses and 4 batch accuracies on the [Bc,Bi] pair matrix
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace loco {
+
+// ---- fp32 -> bf16 hi/lo -------------------------------------------------------------------------------
+// One thread per 4 destination columns; pad columns [cols, dst_ld) are written as zeros.
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float *__restrict__ src, int64_t rows, int64_t cols,
+                                                         int64_t src_ld, uint16_t *__restrict__ hi,
+                                                         uint16_t *__restrict__ lo, int64_t dst_ld) {
+    const int64_t quads_per_row = dst_ld / 4;      // dst_ld % 8 == 0
+    const int64_t total = rows * quads_per_row;
+    const bool vec_ok = (src_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / quads_per_row;
+        const int64_t c = (idx - r * quads_per_row) * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        const float *s = src + r * src_ld + c;
+        if (c + 3 < cols && vec_ok) {
+            const float4 f = __ldg(reinterpret_cast<const float4 *>(s));
+            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c + j < cols) v[j] = __ldg(s + j);
+        }
+        uint16_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_bf16(v[j], h[j], l[j]);
+        uint2 ph, pl;
+        ph.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16); ph.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
+        pl.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16); pl.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
+        *reinterpret_cast<uint2 *>(hi + r * dst_ld + c) = ph;
+        if (lo != nullptr) *reinterpret_cast<uint2 *>(lo + r * dst_ld + c) = pl;
+    }
+}
+
+// transposed variant: dst[c, r] = src[r, c]; dst is [cols, dst_ld] with pad [rows, dst_ld) zeroed.
+__global__ void __launch_bounds__(256) split_bf16_t_kernel(const float *__restrict__ src, int rows, int cols, int64_t src_ld,
+                                                           uint16_t *__restrict__ hi, uint16_t *__restrict__ lo,
+                                                           int64_t dst_ld) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = r0 + ty + 8 * k, c = c0 + tx;
+        tile[ty + 8 * k][tx] = (r < rows && c < cols) ? __ldg(src + (int64_t)r * src_ld + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k, r = r0 + tx;     // dst row = c, dst col = r
+        if (c < cols && r < dst_ld) {
+            uint16_t h, l;
+            split_bf16(tile[tx][ty + 8 * k], h, l);
+            hi[(int64_t)c * dst_ld + r] = h;
+            if (lo != nullptr) lo[(int64_t)c * dst_ld + r] = l;
+        }
+    }
+}
+
+// ---- cross entropy over scored logits -------------------------------------------------------------------
+// one warp per RoI row
+__global__ void __launch_bounds__(256) box_ce_kernel(const float *__restrict__ logits, int64_t ld, const float *__restrict__ lse,
+                                                     const int64_t *__restrict__ labels, int R, int K1, float scale,
+                                                     float *__restrict__ loss_sum, float grad_scale,
+                                                     float *__restrict__ dl_f32, uint16_t *__restrict__ dl_bf16,
+                                                     int64_t ld_bf16) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    float local = 0.f;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += gridDim.x * wpb) {
+        const int64_t y = labels[r];
+        const float l = lse[r];
+        const float *row = logits + (int64_t)r * ld;
+        if (lane == 0 && y >= 0 && y < K1) local += (l - row[y]);
+        if (dl_f32 != nullptr || dl_bf16 != nullptr) {
+            const int64_t lim = dl_bf16 ? ld_bf16 : K1;
+            for (int64_t c = lane; c < lim; c += 32) {
+                float g = 0.f;
+                if (c < K1) g = (expf(row[c] - l) - (c == y ? 1.f : 0.f)) * grad_scale;
+                if (dl_f32 != nullptr && c < K1) dl_f32[(int64_t)r * ld + c] = g;
+                if (dl_bf16 != nullptr) dl_bf16[(int64_t)r * ld_bf16 + c] = f32_to_bf16_rn(g);
+            }
+        }
+    }
+    // block reduction of lane-0 partials -> one atomic per block
+    __shared__ float red[32];
+    local = warp_sum(local);
+    if (lane == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < wpb ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0 && v != 0.f) atomicAdd(loss_sum, v * scale);
+    }
+}
+
+// ---- pair-matrix losses (single CTA; the matrix is at most a few hundred KB) ----------------------------------
+__device__ __forceinline__ float block_reduce_max(float v, float *red) {
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -FLT_MAX;
+    r = warp_max(r);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float *red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    r = warp_sum(r);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw, int64_t ld, int Bc, int Bi, int diag_off,
+                                                       const float *__restrict__ cap_mask, int T,
+                                                       const float *__restrict__ reg_mask, int Rg, float *__restrict__ out4) {
+    extern __shared__ float sm[];
+    float *red = sm;                 // [32]
+    float *cap_empty = sm + 32;      // [Bc] 1 if caption has no valid word
+    float *img_empty = cap_empty + Bc;   // [Bi]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int c = tid; c < Bc; c += nt) {
+        float s = 0.f;
+        for (int t = 0; t < T; ++t) s += cap_mask[(int64_t)c * T + t];
+        cap_empty[c] = s > 0.f ? 0.f : 1.f;
+    }
+    for (int i = tid; i < Bi; i += nt) {
+        float s = 0.f;
+        for (int r = 0; r < Rg; ++r) s += reg_mask[(int64_t)i * Rg + r];
+        img_empty[i] = s > 0.f ? 0.f : 1.f;
+    }
+    __syncthreads();
+    // empty-pair guard (grounding_head.py:240-251): max over the whole matrix, then overwrite
+    float mx = -FLT_MAX;
+    for (int idx = tid; idx < Bc * Bi; idx += nt) mx = fmaxf(mx, pw[(int64_t)(idx / Bi) * ld + idx % Bi]);
+    mx = block_reduce_max(mx, red);
+    for (int idx = tid; idx < Bc * Bi; idx += nt) {
+        const int c = idx / Bi, i = idx % Bi;
+        if (cap_empty[c] > 0.f && img_empty[i] > 0.f) pw[(int64_t)c * ld + i] = mx + 100.0f;
+    }
+    __syncthreads();
+    // choose caption: per image column i, log-softmax over rows of -pw; target row = i + diag_off
+    float ce_cap = 0.f, acc_cap = 0.f;
+    for (int i = tid; i < Bi; i += nt) {
+        float m = -FLT_MAX, best = FLT_MAX;
+        int arg = 0;
+        for (int c = 0; c < Bc; ++c) {
+            const float v = pw[(int64_t)c * ld + i];
+            m = fmaxf(m, -v);
+            if (v < best) { best = v; arg = c; }
+        }
+        float s = 0.f;
+        for (int c = 0; c < Bc; ++c) s += expf(-pw[(int64_t)c * ld + i] - m);
+        const int tgt = i + diag_off;
+        if (tgt < Bc) {
+            ce_cap += (m + logf(s)) + pw[(int64_t)tgt * ld + i];
+            acc_cap += (arg == tgt) ? 1.f : 0.f;
+        }
+    }
+    ce_cap = block_reduce_sum(ce_cap, red);
+    acc_cap = block_reduce_sum(acc_cap, red);
+    // choose image: per caption row c in [diag_off, diag_off + Bi), log-softmax over columns of -pw
+    float ce_img = 0.f, acc_img = 0.f;
+    for (int k = tid; k < Bi; k += nt) {
+        const int c = k + diag_off;
+        if (c >= Bc) continue;
+        float m = -FLT_MAX, best = FLT_MAX;
+        int arg = 0;
+        for (int i = 0; i < Bi; ++i) {
+            const float v = pw[(int64_t)c * ld + i];
+            m = fmaxf(m, -v);
+            if (v < best) { best = v; arg = i; }
+        }
+        float s = 0.f;
+        for (int i = 0; i < Bi; ++i) s += expf(-pw[(int64_t)c * ld + i] - m);
+        ce_img += (m + logf(s)) + pw[(int64_t)c * ld + k];
+        acc_img += (arg == k) ? 1.f : 0.f;
+    }
+    ce_img = block_reduce_sum(ce_img, red);
+    acc_img = block_reduce_sum(acc_img, red);
+    if (tid == 0) {
+        const float inv = 1.0f / (float)Bi;
+        out4[0] = ce_cap * inv;
+        out4[1] = ce_img * inv;
+        out4[2] = acc_cap * inv;
+        out4[3] = acc_img * inv;
+    }
+}
+
+}  // namespace loco
+
+using namespace loco;
+
+extern "C" {
+
+int loco_split_bf16(const float *src, int64_t rows, int64_t cols, int64_t src_ld, uint16_t *hi, uint16_t *lo,
+                    int64_t dst_ld, int transpose, void *stream) {
+    LOCO_REQUIRE(rows >= 0 && cols >= 0 && src_ld >= cols, LOCO_E_BADARG, "split_bf16: bad shape rows=%lld cols=%lld src_ld=%lld",
+                 (long long)rows, (long long)cols, (long long)src_ld);
+    if (rows == 0 || cols == 0) return LOCO_OK;
+    LOCO_REQUIRE(src && hi, LOCO_E_BADARG, "split_bf16: null pointer");
+    LOCO_REQUIRE(dst_ld % 8 == 0, LOCO_E_ALIGN, "split_bf16: dst_ld %lld is not a multiple of 8", (long long)dst_ld);
+    LOCO_REQUIRE((reinterpret_cast<uintptr_t>(hi) & 15) == 0 && (!lo || (reinterpret_cast<uintptr_t>(lo) & 15) == 0), LOCO_E_ALIGN,
+                 "split_bf16: destination must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!transpose) {
+        LOCO_REQUIRE(dst_ld >= cols, LOCO_E_BADARG, "split_bf16: dst_ld < cols");
+        const int64_t total = rows * (dst_ld / 4);
+        const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+        split_bf16_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, src_ld, hi, lo, dst_ld);
+    } else {
+        LOCO_REQUIRE(dst_ld >= rows, LOCO_E_BADARG, "split_bf16: transposed dst_ld < rows");
+        LOCO_REQUIRE(rows < (1ll << 31) && cols < (1ll << 31), LOCO_E_UNSUPPORTED, "split_bf16: matrix too large to transpose");
+        dim3 grid((unsigned)((dst_ld + 31) / 32), (unsigned)((cols + 31) / 32));
+        LOCO_REQUIRE(grid.y <= 65535, LOCO_E_UNSUPPORTED, "split_bf16: too many columns to transpose");
+        split_bf16_t_kernel<<<grid, 256, 0, st>>>(src, (int)rows, (int)cols, src_ld, hi, lo, dst_ld);
+    }
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+int loco_box_ce_fwd_bwd(const float *logits, int64_t ld_logits, const float *lse, const int64_t *labels, int R, int K1,
+                        float scale, float *loss_sum, float grad_scale, float *dlogits_f32, uint16_t *dlogits_bf16,
+                        int64_t ld_bf16, void *stream) {
+    LOCO_REQUIRE(R >= 0 && K1 >= 1 && ld_logits >= K1, LOCO_E_BADARG, "box_ce: bad shape R=%d K1=%d ld=%lld", R, K1, (long long)ld_logits);
+    if (R == 0) return LOCO_OK;
+    LOCO_REQUIRE(logits && lse && labels && loss_sum, LOCO_E_BADARG, "box_ce: null pointer");
+    if (dlogits_bf16) LOCO_REQUIRE(ld_bf16 >= K1 && ld_bf16 % 8 == 0, LOCO_E_ALIGN, "box_ce: ld_bf16 must be >= K1 and a multiple of 8");
+    const int wpb = 8;
+    int blocks = (R + wpb - 1) / wpb;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    box_ce_kernel<<<blocks, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld_logits, lse, labels, R, K1, scale, loss_sum,
+                                                                             grad_scale, dlogits_f32, dlogits_bf16, ld_bf16);
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+int loco_pair_ce(float *pw, int64_t ld, int Bc, int Bi, int diag_offset, const float *cap_mask, int T, const float *reg_mask,
+                 int Rg, float *out4, void *stream) {
+    LOCO_REQUIRE(Bc > 0 && Bi > 0 && ld >= Bi && T > 0 && Rg > 0 && diag_offset >= 0, LOCO_E_BADARG, "pair_ce: bad shape Bc=%d Bi=%d ld=%lld", Bc, Bi, (long long)ld);
+    LOCO_REQUIRE(pw && cap_mask && reg_mask && out4, LOCO_E_BADARG, "pair_ce: null pointer");
+    const size_t smem = (32 + (size_t)Bc + Bi) * sizeof(float);
+    LOCO_REQUIRE(smem <= 48 * 1024, LOCO_E_UNSUPPORTED, "pair_ce: batch too large (Bc=%d Bi=%d)", Bc, Bi);
+    int threads = 32;
+    while (threads < Bc && threads < 1024) threads <<= 1;
+    if (threads < 128) threads = 128;
+    pair_ce_kernel<<<1, threads, smem, static_cast<cudaStream_t>(stream)>>>(pw, ld, Bc, Bi, diag_offset, cap_mask, T, reg_mask, Rg, out4);
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,270 @@
+// tc_gemm.cuh — the tcgen05 / TMEM / TMA tensor-core core shared by every dense contraction of the
+// region-text path (projection, RoI x class scoring, LSM word<->region pair scoring).
+//
+// One CTA computes one or more 128 x BLOCK_N fp32 accumulator tiles ("chunks") in tensor memory:
+//   warp 0   : TMA producer  — cp.async.bulk.tensor 2-D tiles (128B swizzle) of A [128 x 64] and
+//              B [BLOCK_N x 64] bf16 into a `stages`-deep shared-memory ring, mbarrier complete_tx.
+//   warp 1   : MMA issuer    — one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N,
+//              K=16) x4 per stage, tcgen05.commit releases the stage / publishes the accumulator.
+//              Also owns the TMEM allocation.
+//   warps 2-5: epilogue      — tcgen05.ld 32x32b (lane = accumulator row) and an operation-specific
+//              fused reduction (bias / softmax / log-sum-exp / argmax / attention pooling) supplied as the
+//              `Epi` policy.  With two accumulator stages the epilogue of chunk i overlaps the MMAs
+//              of chunk i+1.
+// fp32-accurate mode = three bf16 passes (hi*hi, hi*lo, lo*hi) accumulated into the same TMEM tile.
+// BLOCK_N, the pipeline depth and the pass count are run-time values (the UMMA instruction descriptor
+// and the TMA boxes are built from them), so a single instantiation per epilogue serves all shapes.
+#pragma once
+#include "common.cuh"
+
+namespace loco {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;   // bf16 elements: 128 bytes = one swizzle span
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
+
+struct TcMaps {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+};
+
+struct TcCore {
+    int block_n;        // UMMA N: multiple of 16 in [16, 256]
+    int num_k_blocks;   // ceil(K / 64); the K tail is zero-filled by TMA
+    int passes;         // 1 = bf16, 3 = hi*hi + hi*lo + lo*hi
+    int stages;         // shared-memory ring depth
+    int chunks;         // accumulator tiles per CTA
+    int acc_stages;     // TMEM accumulator buffers (1 or 2)
+    int tmem_cols;      // allocation: power of two >= 32
+    int epi_smem;       // bytes of epilogue scratch
+};
+
+__host__ __device__ inline int tc_round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+inline int tc_tmem_cols(int block_n, int acc_stages) {
+    const int need = (acc_stages - 1) * block_n + tc_round_up(block_n, 32);
+    int c = 32;
+    while (c < need) c <<= 1;
+    return c;
+}
+
+// Fill stages / tmem / smem for a given block_n; returns dynamic shared memory bytes.
+inline size_t tc_finalize(TcCore &core, int K, int passes, int chunks, int epi_smem) {
+    core.num_k_blocks = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+    core.passes = passes;
+    core.chunks = chunks;
+    core.acc_stages = chunks > 1 ? 2 : 1;
+    if (core.acc_stages * core.block_n > 512) core.acc_stages = 1;
+    core.tmem_cols = tc_tmem_cols(core.block_n, core.acc_stages);
+    core.epi_smem = epi_smem;
+    const size_t stage_bytes = TC_A_BYTES + (size_t)core.block_n * 128;
+    const size_t fixed = 1024 /*alignment slack*/ + 512 /*barriers*/ + (size_t)epi_smem;
+    int stages = (int)((110 * 1024 - fixed) / stage_bytes);          // two CTAs per SM when possible
+    if (stages < 3) stages = (int)((225 * 1024 - fixed) / stage_bytes);
+    const int total_iters = core.num_k_blocks * passes * chunks;
+    if (stages > 6) stages = 6;
+    if (stages > total_iters) stages = total_iters;
+    if (stages < 1) stages = 1;
+    core.stages = stages;
+    return fixed + stages * stage_bytes;
+}
+
+#if defined(__CUDACC__)
+
+// ---- epilogue store helpers (per-warp shared scratch of 32 x 33 words) ----------------------------------
+constexpr int TC_WARP_SCRATCH_WORDS = 32 * 33;
+
+// v = this lane's row (tile row = 32*q + lane), columns [0,32) of a 32x32 block.  Writes rows < rows_valid
+// and columns < cols_valid to dst (row-major, ld) as fully coalesced 128-byte rows.
+__device__ __forceinline__ void warp_store_f32(float *scratch, const float (&v)[32], float *dst, int64_t ld,
+                                               int rows_valid, int cols_valid, int lane) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = v[j];
+    __syncwarp();
+    if (lane < cols_valid)
+        for (int rr = 0; rr < rows_valid; ++rr) dst[(int64_t)rr * ld + lane] = scratch[rr * 33 + lane];
+    __syncwarp();
+}
+
+// Same block written as bf16 hi (and optionally lo): two rows per instruction, 64 contiguous bytes each.
+__device__ __forceinline__ void warp_store_bf16(uint32_t *scratch, const float (&v)[32], uint16_t *dst_hi,
+                                                uint16_t *dst_lo, int64_t ld, int rows_valid, int cols_valid,
+                                                int lane) {
+    uint32_t lo_pack[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        uint16_t h0, l0, h1, l1;
+        split_bf16(v[2 * j], h0, l0);
+        split_bf16(v[2 * j + 1], h1, l1);
+        scratch[lane * 17 + j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+        lo_pack[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    }
+    __syncwarp();
+    const int sub = lane >> 4, cc = lane & 15;
+    for (int it = 0; it < 16; ++it) {
+        const int rr = 2 * it + sub;
+        if (rr < rows_valid && 2 * cc < cols_valid)
+            *reinterpret_cast<uint32_t *>(dst_hi + (int64_t)rr * ld + 2 * cc) = scratch[rr * 17 + cc];
+    }
+    __syncwarp();
+    if (dst_lo != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) scratch[lane * 17 + j] = lo_pack[j];
+        __syncwarp();
+        for (int it = 0; it < 16; ++it) {
+            const int rr = 2 * it + sub;
+            if (rr < rows_valid && 2 * cc < cols_valid)
+                *reinterpret_cast<uint32_t *>(dst_lo + (int64_t)rr * ld + 2 * cc) = scratch[rr * 17 + cc];
+        }
+        __syncwarp();
+    }
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------
+// Epi interface:
+//   struct Params;                                       (trivially copyable, passed by value)
+//   static __device__ void coords(const Params&, const TcCore&, int cta, int chunk, int &row_a, int &row_b);
+//   __device__ void begin(const Params&, const TcCore&, int cta, int row, int lane, int q, unsigned char *smem);
+//   __device__ void chunk(const Params&, const TcCore&, int cta, int chunk, uint32_t taddr, ...same...);
+//   __device__ void finish(const Params&, const TcCore&, int cta, ...same...);
+template <class Epi>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcCore core, const typename Epi::Params ep) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char *smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+
+    const uint32_t b_bytes = (uint32_t)core.block_n * 128u;
+    const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
+    unsigned char *bar_base = smem + (size_t)core.stages * stage_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(bar_base);
+    uint64_t *empty = full + TC_MAX_STAGES;
+    uint64_t *tfull = empty + TC_MAX_STAGES;
+    uint64_t *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    unsigned char *epi_smem = bar_base + 512;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < core.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&maps.a_hi);
+        prefetch_tmap(&maps.b_hi);
+        if (core.passes > 1) {
+            prefetch_tmap(&maps.a_lo);
+            prefetch_tmap(&maps.b_lo);
+        }
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)core.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int cta = blockIdx.x;
+    const int iters_per_chunk = core.num_k_blocks * core.passes;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int ch = 0; ch < core.chunks; ++ch) {
+                int row_a, row_b;
+                Epi::coords(ep, core, cta, ch, row_a, row_b);
+                for (int pass = 0; pass < core.passes; ++pass) {
+                    const CUtensorMap *ma = (pass == 2) ? &maps.a_lo : &maps.a_hi;
+                    const CUtensorMap *mb = (pass == 1) ? &maps.b_lo : &maps.b_hi;
+                    for (int kb = 0; kb < core.num_k_blocks; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1u);
+                        unsigned char *sa = smem + (size_t)stage * stage_bytes;
+                        mbar_arrive_expect_tx(&full[stage], stage_bytes);
+                        tma_load_2d(sa, ma, &full[stage], kb * TC_BLOCK_K, row_a);
+                        tma_load_2d(sa + TC_A_BYTES, mb, &full[stage], kb * TC_BLOCK_K, row_b);
+                        if (++stage == (uint32_t)core.stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(TC_BLOCK_M, (uint32_t)core.block_n);
+            uint32_t stage = 0, phase = 0;
+            for (int ch = 0; ch < core.chunks; ++ch) {
+                const int acc = ch % core.acc_stages;
+                const uint32_t acc_phase = (uint32_t)(ch / core.acc_stages) & 1u;
+                mbar_wait(&tempty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * core.block_n);
+                uint32_t accumulate = 0;
+                for (int it = 0; it < iters_per_chunk; ++it) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t da = umma_desc_k128(a_addr);
+                    const uint64_t db = umma_desc_k128(a_addr + TC_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+                        umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);   // +32 B per K=16 step
+                        accumulate = 1;
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == (uint32_t)core.stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;            // TMEM lane quarter accessible to this warp
+        const int row = q * 32 + lane;     // accumulator row owned by this thread
+        Epi epi;
+        epi.begin(ep, core, cta, row, lane, q, epi_smem);
+        for (int ch = 0; ch < core.chunks; ++ch) {
+            const int acc = ch % core.acc_stages;
+            const uint32_t acc_phase = (uint32_t)(ch / core.acc_stages) & 1u;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * core.block_n);
+            epi.chunk(ep, core, cta, ch, taddr, row, lane, q, epi_smem);
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+        }
+        epi.finish(ep, core, cta, row, lane, q, epi_smem);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)core.tmem_cols);
+    }
+}
+
+template <class Epi>
+int tc_launch(const TcMaps &maps, const TcCore &core, const typename Epi::Params &ep, int grid, size_t smem_bytes,
+              cudaStream_t st) {
+    LOCO_REQUIRE(smem_bytes <= 227 * 1024, LOCO_E_UNSUPPORTED, "tensor-core kernel needs %zu B of shared memory", smem_bytes);
+    LOCO_REQUIRE(core.block_n >= 16 && core.block_n <= 256 && core.block_n % 16 == 0, LOCO_E_BADARG, "bad block_n %d", core.block_n);
+    LOCO_REQUIRE(core.tmem_cols <= 512, LOCO_E_UNSUPPORTED, "tensor memory request %d columns", core.tmem_cols);
+    static thread_local size_t configured = 0;   // per (thread, Epi) high-water mark
+    if (smem_bytes > configured) {
+        LOCO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        configured = 227 * 1024;
+    }
+    tc_gemm_kernel<Epi><<<grid, TC_THREADS, smem_bytes, st>>>(maps, core, ep);
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace loco

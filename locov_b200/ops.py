@@ -1,0 +1,260 @@
+"""Thin torch-tensor front-ends of the C ABI (include/locov_b200.h).
+
+PyTorch is used for device memory and streams only; every computation below is a call into
+liblocov_b200.so.  All functions require CUDA tensors and raise ``LocoError`` on failure — there is
+no eager/CPU fallback.
+"""
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import LocoError
+
+ALIGN_SOFTMAX, ALIGN_HARDMAX = 0, 1
+NCHW, NHWC = 0, 1
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise LocoError("locov_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------------
+# RoIAlign
+# ------------------------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def _workspace(device, nbytes, tag):
+    key = (device.index, tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def roi_align(feat: torch.Tensor, rois: torch.Tensor, output_size, spatial_scale: float, sampling_ratio: int = 0,
+              aligned: bool = True) -> torch.Tensor:
+    """feat [N,C,H,W] fp32 (contiguous NCHW, or channels_last memory format), rois [R,5] -> [R,C,PH,PW]."""
+    _need_cuda(feat, rois)
+    if feat.dtype != torch.float32:
+        raise LocoError("roi_align: fp32 features only")
+    ph, pw = (output_size, output_size) if isinstance(output_size, int) else output_size
+    n, c, h, w = feat.shape
+    if feat.is_contiguous():
+        layout = NCHW
+    elif feat.is_contiguous(memory_format=torch.channels_last):
+        layout = NHWC
+    else:
+        feat, layout = feat.contiguous(), NCHW
+    rois = rois.to(torch.float32).contiguous()
+    r = rois.shape[0]
+    out = torch.empty((r, c, ph, pw), dtype=torch.float32, device=feat.device)
+    lib = _lib.load()
+    ws = _workspace(feat.device, lib.loco_roi_align_workspace_bytes(n, c, h, w, layout), "roi_align")
+    _lib.check(lib.loco_roi_align_fwd(_p(feat), n, c, h, w, layout, _p(rois), r, ph, pw, float(spatial_scale),
+                                      int(sampling_ratio), int(bool(aligned)), _p(out), _p(ws), _stream(feat)),
+               "loco_roi_align_fwd")
+    return out
+
+
+def roi_align_backward(dout: torch.Tensor, feat_shape, rois: torch.Tensor, spatial_scale: float,
+                       sampling_ratio: int = 0, aligned: bool = True) -> torch.Tensor:
+    _need_cuda(dout, rois)
+    n, c, h, w = feat_shape
+    dout = dout.to(torch.float32).contiguous()
+    rois = rois.to(torch.float32).contiguous()
+    r, _, ph, pw = dout.shape
+    dfeat = torch.zeros(feat_shape, dtype=torch.float32, device=dout.device)
+    lib = _lib.load()
+    _lib.check(lib.loco_roi_align_bwd(_p(dout), n, c, h, w, _p(rois), r, ph, pw, float(spatial_scale),
+                                      int(sampling_ratio), int(bool(aligned)), _p(dfeat), _stream(dout)),
+               "loco_roi_align_bwd")
+    return dfeat
+
+
+def roi_align_grid(rois: torch.Tensor, h: int, w: int, output_size, spatial_scale: float, sampling_ratio: int = 0,
+                   aligned: bool = True, max_grid: int = 4):
+    """Sampling grid as computed ON THE DEVICE: (grid_hw [R,2] i32, yx [R,PH,PW,G,G,2] f32, idx [...,4] i32)."""
+    _need_cuda(rois)
+    ph, pw = (output_size, output_size) if isinstance(output_size, int) else output_size
+    rois = rois.to(torch.float32).contiguous()
+    r = rois.shape[0]
+    ghw = torch.zeros((r, 2), dtype=torch.int32, device=rois.device)
+    yx = torch.full((r, ph, pw, max_grid, max_grid, 2), float("nan"), dtype=torch.float32, device=rois.device)
+    idx = torch.full((r, ph, pw, max_grid, max_grid, 4), -2, dtype=torch.int32, device=rois.device)
+    lib = _lib.load()
+    _lib.check(lib.loco_roi_align_grid_dump(_p(rois), r, h, w, ph, pw, float(spatial_scale), int(sampling_ratio),
+                                            int(bool(aligned)), max_grid, _p(ghw), _p(yx), _p(idx), _stream(rois)),
+               "loco_roi_align_grid_dump")
+    return ghw, yx, idx
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 operands
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Bf16Operand:
+    """A [rows, cols] matrix as bf16 ``hi`` (+ optional ``lo`` residual) with row stride ``ld`` elements."""
+    hi: torch.Tensor
+    lo: Optional[torch.Tensor]
+    rows: int
+    cols: int
+
+    @property
+    def ld(self):
+        return self.hi.shape[1]
+
+
+def split_bf16(x: torch.Tensor, accurate: bool, transpose: bool = False, out: Optional[Bf16Operand] = None) -> Bf16Operand:
+    """fp32 2-D tensor -> Bf16Operand (ld padded to a multiple of 8, pad zero-filled).
+
+    accurate=True also produces the ``lo`` residual (fp32-accurate three-pass mode)."""
+    _need_cuda(x)
+    if x.dim() != 2 or x.dtype != torch.float32:
+        raise LocoError("split_bf16: expects a 2-D fp32 tensor")
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    rows, cols = x.shape
+    drows, dcols = (cols, rows) if transpose else (rows, cols)
+    ld = _round_up(max(dcols, 1), 8)
+    if out is None:
+        hi = torch.empty((drows, ld), dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty((drows, ld), dtype=torch.bfloat16, device=x.device) if accurate else None
+        out = Bf16Operand(hi, lo, drows, dcols)
+    lib = _lib.load()
+    _lib.check(lib.loco_split_bf16(_p(x), rows, cols, x.stride(0), _p(out.hi), _p(out.lo) if accurate else None,
+                                   out.ld, int(transpose), _stream(x)), "loco_split_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core contractions
+# ------------------------------------------------------------------------------------------------
+def linear_fwd(a: Bf16Operand, w: Bf16Operand, bias: Optional[torch.Tensor], want_f32: bool = True,
+               n_bf16: int = 0, accurate_out: bool = False) -> Tuple[Optional[torch.Tensor], Optional[Bf16Operand]]:
+    """out[M,N] = A[M,K] · W[N,K]^T + bias.  Returns (out_f32 or None, bf16 operand of the first n_bf16 columns or None)."""
+    if a.cols != w.cols:
+        raise LocoError(f"linear_fwd: K mismatch {a.cols} vs {w.cols}")
+    if (a.lo is None) != (w.lo is None):
+        raise LocoError("linear_fwd: both operands must be in the same precision mode")
+    m, n, k = a.rows, w.rows, a.cols
+    dev = a.hi.device
+    out_f32 = torch.empty((m, n), dtype=torch.float32, device=dev) if want_f32 else None
+    ob = None
+    if n_bf16 > 0:
+        ld = _round_up(n_bf16, 8)
+        hi = torch.empty((m, ld), dtype=torch.bfloat16, device=dev)
+        if ld != n_bf16:
+            hi[:, n_bf16:].zero_()
+        lo = None
+        if accurate_out:
+            lo = torch.empty((m, ld), dtype=torch.bfloat16, device=dev)
+            if ld != n_bf16:
+                lo[:, n_bf16:].zero_()
+        ob = Bf16Operand(hi, lo, m, n_bf16)
+    if bias is not None:
+        bias = bias.to(torch.float32).contiguous()
+    lib = _lib.load()
+    _lib.check(lib.loco_linear_fwd(_p(a.hi), _p(a.lo), a.ld, _p(w.hi), _p(w.lo), w.ld, _p(bias), m, n, k,
+                                   _p(out_f32), n if want_f32 else 0, _p(ob.hi) if ob else None,
+                                   _p(ob.lo) if (ob and ob.lo is not None) else None, n_bf16, ob.ld if ob else 0,
+                                   _stream(a.hi)), "loco_linear_fwd")
+    return out_f32, ob
+
+
+def box_score(e: Bf16Operand, cls: Bf16Operand, cls_bias: Optional[torch.Tensor] = None, want_probs: bool = True):
+    """RoI x class logits with fused softmax: returns (logits [R,K1], probs or None, lse [R], argmax_fg [R] i64)."""
+    if e.cols != cls.cols:
+        raise LocoError(f"box_score: embedding dim mismatch {e.cols} vs {cls.cols}")
+    if (e.lo is None) != (cls.lo is None):
+        raise LocoError("box_score: both operands must be in the same precision mode")
+    r, k1, d = e.rows, cls.rows, e.cols
+    dev = e.hi.device
+    logits = torch.empty((r, k1), dtype=torch.float32, device=dev)
+    probs = torch.empty((r, k1), dtype=torch.float32, device=dev) if want_probs else None
+    lse = torch.empty((r,), dtype=torch.float32, device=dev)
+    arg = torch.empty((r,), dtype=torch.int64, device=dev)
+    if cls_bias is not None:
+        cls_bias = cls_bias.to(torch.float32).contiguous()
+    lib = _lib.load()
+    _lib.check(lib.loco_box_score_fwd(_p(e.hi), _p(e.lo), e.ld, _p(cls.hi), _p(cls.lo), cls.ld, _p(cls_bias), r, k1, d,
+                                      _p(logits), _p(probs), k1, _p(lse), _p(arg), _stream(e.hi)),
+               "loco_box_score_fwd")
+    return logits, probs, lse, arg
+
+
+def box_ce(logits: torch.Tensor, lse: torch.Tensor, labels: torch.Tensor, want_grad: bool = False,
+           grad_bf16: bool = False):
+    """Mean cross-entropy (Detectron2 FastRCNNOutputLayers.losses) from the fused softmax statistics.
+    Returns (loss scalar tensor, dlogits fp32 or None, dlogits bf16 [R, pad8(K1)] or None); gradients are of the MEAN loss."""
+    _need_cuda(logits, lse, labels)
+    r, k1 = logits.shape
+    dev = logits.device
+    loss = torch.zeros((), dtype=torch.float32, device=dev)
+    if r == 0:
+        return loss, None, None
+    labels = labels.to(torch.int64).contiguous()
+    dl = torch.empty_like(logits) if want_grad else None
+    dlb = torch.empty((r, _round_up(k1, 8)), dtype=torch.bfloat16, device=dev) if grad_bf16 else None
+    lib = _lib.load()
+    _lib.check(lib.loco_box_ce_fwd_bwd(_p(logits), logits.stride(0), _p(lse), _p(labels), r, k1, 1.0 / r, _p(loss),
+                                       1.0 / r, _p(dl), _p(dlb), dlb.shape[1] if dlb is not None else 0,
+                                       _stream(logits)), "loco_box_ce_fwd_bwd")
+    return loss, dl, dlb
+
+
+def lsm_pair(cap: Bf16Operand, cap_mask: torch.Tensor, emb: Bf16Operand, reg_mask: torch.Tensor, inv_temperature: float,
+             alignment: int = ALIGN_SOFTMAX, want_w2r: bool = True, want_r2w: bool = True,
+             out_w2r: Optional[torch.Tensor] = None, out_r2w: Optional[torch.Tensor] = None):
+    """Pair distances d_w2r, d_r2w [Bc, Bi] (rows captions, cols images) from caption word embeddings
+    cap [Bc*T, D] and projected region embeddings emb [Bi*Rg, D]."""
+    bc, t = cap_mask.shape
+    bi, rg = reg_mask.shape
+    if cap.rows != bc * t or emb.rows != bi * rg or cap.cols != emb.cols:
+        raise LocoError("lsm_pair: operand shapes do not match the masks")
+    if (cap.lo is None) != (emb.lo is None):
+        raise LocoError("lsm_pair: both operands must be in the same precision mode")
+    dev = cap.hi.device
+    cap_mask = cap_mask.to(torch.float32).contiguous()
+    reg_mask = reg_mask.to(torch.float32).contiguous()
+    w2r = (out_w2r if out_w2r is not None else torch.empty((bc, bi), dtype=torch.float32, device=dev)) if want_w2r else None
+    r2w = (out_r2w if out_r2w is not None else torch.empty((bc, bi), dtype=torch.float32, device=dev)) if want_r2w else None
+    ld = (w2r if w2r is not None else r2w).stride(0)
+    if w2r is not None and r2w is not None and w2r.stride(0) != r2w.stride(0):
+        raise LocoError("lsm_pair: outputs must share a row stride")
+    lib = _lib.load()
+    ws = _workspace(dev, lib.loco_lsm_pair_workspace_bytes(bc, t, bi, rg), "lsm")
+    _lib.check(lib.loco_lsm_pair_fwd(_p(cap.hi), _p(cap.lo), cap.ld, _p(cap_mask), _p(emb.hi), _p(emb.lo), emb.ld,
+                                     _p(reg_mask), bc, t, bi, rg, cap.cols, float(inv_temperature), int(alignment),
+                                     _p(w2r), _p(r2w), ld, _p(ws), _stream(cap.hi)), "loco_lsm_pair_fwd")
+    return w2r, r2w
+
+
+def pair_ce(pw: torch.Tensor, cap_mask: torch.Tensor, reg_mask: torch.Tensor, diag_offset: int = 0) -> torch.Tensor:
+    """Empty-pair guard (in place on pw) + [CE choose caption, CE choose image, acc caption, acc image]."""
+    _need_cuda(pw, cap_mask, reg_mask)
+    bc, bi = pw.shape
+    cap_mask = cap_mask.to(torch.float32).contiguous()
+    reg_mask = reg_mask.to(torch.float32).contiguous()
+    out = torch.empty((4,), dtype=torch.float32, device=pw.device)
+    lib = _lib.load()
+    _lib.check(lib.loco_pair_ce(_p(pw), pw.stride(0), bc, bi, int(diag_offset), _p(cap_mask), cap_mask.shape[1],
+                                _p(reg_mask), reg_mask.shape[1], _p(out), _stream(pw)), "loco_pair_ce")
+    return out
