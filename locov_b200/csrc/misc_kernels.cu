@@ -103,25 +103,34 @@ __global__ void __launch_bounds__(256) box_ce_kernel(const float *__restrict__ l
 }
 
 // ---- pair-matrix losses (single CTA; the matrix is at most a few hundred KB) ----------------------------------
+// Both reductions return the block-wide result to EVERY thread (broadcast through red[0]).
 __device__ __forceinline__ float block_reduce_max(float v, float *red) {
     v = warp_max(v);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    float r = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -FLT_MAX;
-    r = warp_max(r);
-    r = __shfl_sync(0xffffffffu, r, 0);
+    if (threadIdx.x < 32) {
+        float r = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -FLT_MAX;
+        r = warp_max(r);
+        if (threadIdx.x == 0) red[0] = r;
+    }
     __syncthreads();
-    return r;
+    const float out = red[0];
+    __syncthreads();
+    return out;
 }
 __device__ __forceinline__ float block_reduce_sum(float v, float *red) {
     v = warp_sum(v);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    float r = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
-    r = warp_sum(r);
-    r = __shfl_sync(0xffffffffu, r, 0);
+    if (threadIdx.x < 32) {
+        float r = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+        r = warp_sum(r);
+        if (threadIdx.x == 0) red[0] = r;
+    }
     __syncthreads();
-    return r;
+    const float out = red[0];
+    __syncthreads();
+    return out;
 }
 
 __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw, int64_t ld, int Bc, int Bi, int diag_off,
