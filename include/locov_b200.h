@@ -54,6 +54,7 @@ int loco_version(void);                 /* 10000*major + 100*minor + patch */
 const char *loco_last_error(void);      /* thread-local; never NULL */
 int loco_device_check(int device);      /* LOCO_OK iff `device` is compute capability 10.x */
 int loco_sm_count(int device);          /* number of SMs (148 on B200) or <0 */
+long long loco_launch_count(void);      /* kernels this library has launched so far (process-wide, monotonic) */
 
 /* ---- RoIAlign ----------------------------------------------------------------------------------
  * Replaces: roi_emb_heads.py:182-187,243-245  self.pooler(features, boxes)
@@ -158,9 +159,12 @@ int loco_lsm_pair_fwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ld
  * out[4] fp32: { CE choose-caption (mean over the Bi columns of -log_softmax(-pw, dim=0)[i+off, i]),
  *               CE choose-image   (mean over rows c in [diag_offset, diag_offset+Bi) of
  *                                  -log_softmax(-pw, dim=1)[c, c-off]; only valid when Bi == Bc),
- *               accuracy choose-caption, accuracy choose-image }. */
+ *               accuracy choose-caption, accuracy choose-image }.
+ * dpw_caption / dpw_image (each may be NULL): dense [Bc, Bi] fp32 gradients of out4[0] / out4[1] with
+ * respect to pw (zero at guard-filled entries, which are constants in the reference: .detach()). */
 int loco_pair_ce(float *pw, int64_t ld, int Bc, int Bi, int diag_offset, const float *cap_mask, int T,
-                 const float *reg_mask, int Rg, float *out4, void *stream);
+                 const float *reg_mask, int Rg, float *out4, float *dpw_caption, float *dpw_image,
+                 void *stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ SIGNATURES = {
     "loco_last_error": (_c.c_char_p, []),
     "loco_device_check": (_i, [_i]),
     "loco_sm_count": (_i, [_i]),
+    "loco_launch_count": (_c.c_longlong, []),
     "loco_roi_align_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
     "loco_roi_align_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp]),
     "loco_roi_align_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp]),
@@ -33,7 +34,7 @@ SIGNATURES = {
     "loco_box_ce_fwd_bwd": (_i, [_vp, _i64, _vp, _vp, _i, _i, _f, _vp, _f, _vp, _vp, _i64, _vp]),
     "loco_lsm_pair_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "loco_lsm_pair_fwd": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _i64, _vp, _vp]),
-    "loco_pair_ce": (_i, [_vp, _i64, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
+    "loco_pair_ce": (_i, [_vp, _i64, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
 }
 
 _lock = threading.Lock()

@@ -3,6 +3,7 @@
 // libcudart only and loads on a machine without a GPU for the symbol/ABI tests).
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -10,6 +11,9 @@
 namespace loco {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -76,6 +80,8 @@ int current_device_sm_count() {
 }  // namespace loco
 
 extern "C" {
+
+long long loco_launch_count(void) { return loco::g_launches.load(std::memory_order_relaxed); }
 
 int loco_version(void) { return 10000 * 0 + 100 * 1 + 0; }
 

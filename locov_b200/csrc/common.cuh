@@ -38,6 +38,7 @@ int make_tmap_bf16_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_
                       uint32_t box_rows);
 
 int current_device_sm_count();
+void count_launch(int n = 1);   // bumps the library-wide kernel-launch counter (loco_launch_count)
 
 // ------------------------------------------------------------------------------------------------
 // device side

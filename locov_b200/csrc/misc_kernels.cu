@@ -135,7 +135,8 @@ __device__ __forceinline__ float block_reduce_sum(float v, float *red) {
 
 __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw, int64_t ld, int Bc, int Bi, int diag_off,
                                                        const float *__restrict__ cap_mask, int T,
-                                                       const float *__restrict__ reg_mask, int Rg, float *__restrict__ out4) {
+                                                       const float *__restrict__ reg_mask, int Rg, float *__restrict__ out4,
+                                                       float *__restrict__ dcap, float *__restrict__ dimg) {
     extern __shared__ float sm[];
     float *red = sm;                 // [32]
     float *cap_empty = sm + 32;      // [Bc] 1 if caption has no valid word
@@ -178,10 +179,23 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw, i
             ce_cap += (m + logf(s)) + pw[(int64_t)tgt * ld + i];
             acc_cap += (arg == tgt) ? 1.f : 0.f;
         }
+        if (dcap != nullptr) {
+            // d/dpw[c,i] of mean_i( lse_c(-pw[:,i]) + pw[tgt,i] ); guard-filled entries are constants
+            const float inv = 1.0f / (float)Bi;
+            for (int c = 0; c < Bc; ++c) {
+                float g = 0.f;
+                if (tgt < Bc && !(cap_empty[c] > 0.f && img_empty[i] > 0.f))
+                    g = (((c == tgt) ? 1.f : 0.f) - expf(-pw[(int64_t)c * ld + i] - m) / s) * inv;
+                dcap[(int64_t)c * Bi + i] = g;
+            }
+        }
     }
     ce_cap = block_reduce_sum(ce_cap, red);
     acc_cap = block_reduce_sum(acc_cap, red);
     // choose image: per caption row c in [diag_off, diag_off + Bi), log-softmax over columns of -pw
+    if (dimg != nullptr)    // rows outside [diag_off, diag_off + Bi) carry no choose-image loss
+        for (int idx = tid; idx < Bc * Bi; idx += nt) dimg[idx] = 0.f;
+    __syncthreads();
     float ce_img = 0.f, acc_img = 0.f;
     for (int k = tid; k < Bi; k += nt) {
         const int c = k + diag_off;
@@ -197,6 +211,15 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw, i
         for (int i = 0; i < Bi; ++i) s += expf(-pw[(int64_t)c * ld + i] - m);
         ce_img += (m + logf(s)) + pw[(int64_t)c * ld + k];
         acc_img += (arg == k) ? 1.f : 0.f;
+        if (dimg != nullptr) {
+            const float inv = 1.0f / (float)Bi;
+            for (int i = 0; i < Bi; ++i) {
+                float g = 0.f;
+                if (!(cap_empty[c] > 0.f && img_empty[i] > 0.f))
+                    g = (((i == k) ? 1.f : 0.f) - expf(-pw[(int64_t)c * ld + i] - m) / s) * inv;
+                dimg[(int64_t)c * Bi + i] = g;
+            }
+        }
     }
     ce_img = block_reduce_sum(ce_img, red);
     acc_img = block_reduce_sum(acc_img, red);
@@ -230,12 +253,14 @@ int loco_split_bf16(const float *src, int64_t rows, int64_t cols, int64_t src_ld
         const int64_t total = rows * (dst_ld / 4);
         const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
         split_bf16_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, src_ld, hi, lo, dst_ld);
+    count_launch();
     } else {
         LOCO_REQUIRE(dst_ld >= rows, LOCO_E_BADARG, "split_bf16: transposed dst_ld < rows");
         LOCO_REQUIRE(rows < (1ll << 31) && cols < (1ll << 31), LOCO_E_UNSUPPORTED, "split_bf16: matrix too large to transpose");
         dim3 grid((unsigned)((dst_ld + 31) / 32), (unsigned)((cols + 31) / 32));
         LOCO_REQUIRE(grid.y <= 65535, LOCO_E_UNSUPPORTED, "split_bf16: too many columns to transpose");
         split_bf16_t_kernel<<<grid, 256, 0, st>>>(src, (int)rows, (int)cols, src_ld, hi, lo, dst_ld);
+    count_launch();
     }
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;
@@ -253,12 +278,13 @@ int loco_box_ce_fwd_bwd(const float *logits, int64_t ld_logits, const float *lse
     if (blocks > 148 * 8) blocks = 148 * 8;
     box_ce_kernel<<<blocks, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld_logits, lse, labels, R, K1, scale, loss_sum,
                                                                              grad_scale, dlogits_f32, dlogits_bf16, ld_bf16);
+    count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;
 }
 
 int loco_pair_ce(float *pw, int64_t ld, int Bc, int Bi, int diag_offset, const float *cap_mask, int T, const float *reg_mask,
-                 int Rg, float *out4, void *stream) {
+                 int Rg, float *out4, float *dpw_caption, float *dpw_image, void *stream) {
     LOCO_REQUIRE(Bc > 0 && Bi > 0 && ld >= Bi && T > 0 && Rg > 0 && diag_offset >= 0, LOCO_E_BADARG, "pair_ce: bad shape Bc=%d Bi=%d ld=%lld", Bc, Bi, (long long)ld);
     LOCO_REQUIRE(pw && cap_mask && reg_mask && out4, LOCO_E_BADARG, "pair_ce: null pointer");
     const size_t smem = (32 + (size_t)Bc + Bi) * sizeof(float);
@@ -266,7 +292,9 @@ int loco_pair_ce(float *pw, int64_t ld, int Bc, int Bi, int diag_offset, const f
     int threads = 32;
     while (threads < Bc && threads < 1024) threads <<= 1;
     if (threads < 128) threads = 128;
-    pair_ce_kernel<<<1, threads, smem, static_cast<cudaStream_t>(stream)>>>(pw, ld, Bc, Bi, diag_offset, cap_mask, T, reg_mask, Rg, out4);
+    pair_ce_kernel<<<1, threads, smem, static_cast<cudaStream_t>(stream)>>>(pw, ld, Bc, Bi, diag_offset, cap_mask, T, reg_mask, Rg, out4,
+                                                                            dpw_caption, dpw_image);
+    count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;
 }

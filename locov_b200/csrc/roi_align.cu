@@ -332,6 +332,7 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
         dim3 grid((HW + 31) / 32, (C + 31) / 32, N);
         LOCO_REQUIRE(grid.y <= 65535 && grid.z <= 65535, LOCO_E_UNSUPPORTED, "roi_align_fwd: feature map too large for the transpose grid");
         nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(feat, static_cast<float *>(workspace), C, HW);
+    count_launch();
         LOCO_CUDA(cudaGetLastError());
         nhwc = static_cast<const float *>(workspace);
     }
@@ -346,6 +347,7 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
     }
     roi_align_fwd_kernel<<<R * nchunks, RA_THREADS, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio,
                                                                 aligned, nchunks, out);
+    count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;
 }
@@ -359,6 +361,7 @@ int loco_roi_align_bwd(const float *dout, int N, int C, int H, int W, const floa
     const int blocks = (int)min((size_t)148 * 32, (total + 255) / 256);
     roi_align_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dout, rois, C, H, W, PH, PW, spatial_scale,
                                                                                sampling_ratio, aligned, total, dfeat);
+    count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;
 }
@@ -371,6 +374,7 @@ int loco_roi_align_grid_dump(const float *rois, int R, int H, int W, int PH, int
     LOCO_REQUIRE(rois && grid_hw && yx && idx, LOCO_E_BADARG, "roi_align_grid_dump: null pointer");
     roi_align_grid_kernel<<<R, 256, 0, static_cast<cudaStream_t>(stream)>>>(rois, R, H, W, PH, PW, spatial_scale,
                                                                            sampling_ratio, aligned, max_grid, grid_hw, yx, idx);
+    count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;
 }

@@ -261,6 +261,7 @@ int tc_launch(const TcMaps &maps, const TcCore &core, const typename Epi::Params
         configured = 227 * 1024;
     }
     tc_gemm_kernel<Epi><<<grid, TC_THREADS, smem_bytes, st>>>(maps, core, ep);
+    count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;
 }

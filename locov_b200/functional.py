@@ -1,0 +1,324 @@
+"""torch.autograd Functions over the C-ABI entry points (include/locov_b200.h).
+
+Every forward AND backward computation is a call into liblocov_b200.so; torch is used for memory,
+streams and the autograd graph only.  ``precision`` selects the tensor-core operand mode:
+  "fp32" : fp32-accurate — operands split into bf16 hi+lo, three tcgen05 passes (≈1e-5 relative)
+  "bf16" : single bf16 pass (≈4e-3 relative; the north-star tolerance for bf16 is 2e-2)
+"""
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ops
+from ._lib import LocoError
+
+PRECISIONS = ("fp32", "bf16")
+
+
+def _acc(precision: str) -> bool:
+    if precision not in PRECISIONS:
+        raise LocoError(f"precision must be one of {PRECISIONS}, got {precision!r}")
+    return precision == "fp32"
+
+
+# ------------------------------------------------------------------------------------------------
+# weight operand cache: bf16 (hi, lo) shadows of parameters, refreshed when the parameter changes.
+# Parameters are aliased between modules (v2l_projection <-> emb_pred weight tying), so the cache is
+# keyed on storage identity + version counter, never on the module.
+# ------------------------------------------------------------------------------------------------
+_wcache = {}
+
+
+def weight_operand(w: torch.Tensor, accurate: bool, transpose: bool = False, tag: str = "") -> ops.Bf16Operand:
+    key = (w.data_ptr(), tuple(w.shape), tuple(w.stride()), accurate, transpose, tag, w.device.index)
+    ent = _wcache.get(key)
+    ver = w._version
+    if ent is not None and ent[0] == ver:
+        return ent[1]
+    op = ops.split_bf16(w.detach(), accurate, transpose=transpose, out=ent[1] if ent is not None else None)
+    _wcache[key] = (ver, op)
+    if len(_wcache) > 256:      # parameters re-created by set_class_embeddings: drop the oldest shadows
+        for k in list(_wcache)[:128]:
+            del _wcache[k]
+    return op
+
+
+def clear_weight_cache():
+    _wcache.clear()
+
+
+# ------------------------------------------------------------------------------------------------
+# RoIAlign
+# ------------------------------------------------------------------------------------------------
+class _RoIAlign(Function):
+    @staticmethod
+    def forward(ctx, feat, rois, ph, pw, scale, sampling_ratio, aligned):
+        ctx.save_for_backward(rois)
+        ctx.cfg = (tuple(feat.shape), scale, sampling_ratio, aligned)
+        return ops.roi_align(feat, rois, (ph, pw), scale, sampling_ratio, aligned)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        (rois,) = ctx.saved_tensors
+        shape, scale, sampling_ratio, aligned = ctx.cfg
+        dfeat = ops.roi_align_backward(dout, shape, rois, scale, sampling_ratio, aligned)
+        return dfeat, None, None, None, None, None, None
+
+
+def roi_align(feat, rois, output_size, spatial_scale, sampling_ratio=0, aligned=True):
+    """Differentiable RoIAlign (torchvision.ops.roi_align semantics; reference roi_emb_heads.py:243-245)."""
+    ph, pw = (output_size, output_size) if isinstance(output_size, int) else output_size
+    return _RoIAlign.apply(feat, rois, int(ph), int(pw), float(spatial_scale), int(sampling_ratio), bool(aligned))
+
+
+# ------------------------------------------------------------------------------------------------
+# y = x W^T + b on the tcgen05 core
+# ------------------------------------------------------------------------------------------------
+class _Linear(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, precision):
+        acc = _acc(precision)
+        x2 = x.reshape(-1, x.shape[-1])
+        a_op = ops.split_bf16(x2, acc)
+        w_op = weight_operand(w, acc)
+        out, _ = ops.linear_fwd(a_op, w_op, b, want_f32=True)
+        ctx.save_for_backward(x2, w)
+        ctx.meta = (precision, b is not None, x.shape)
+        return out.reshape(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        precision, has_b, xshape = ctx.meta
+        acc = _acc(precision)
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            g_op = ops.split_bf16(dy2, acc)
+            wt_op = weight_operand(w, acc, transpose=True)
+            dx, _ = ops.linear_fwd(g_op, wt_op, None, want_f32=True)
+            dx = dx.reshape(xshape)
+        if ctx.needs_input_grad[1]:
+            gt_op = ops.split_bf16(dy2, acc, transpose=True)
+            xt_op = ops.split_bf16(x2, acc, transpose=True)
+            dw, _ = ops.linear_fwd(gt_op, xt_op, None, want_f32=True)
+        if has_b and ctx.needs_input_grad[2]:
+            db = dy2.sum(0)
+        return dx, dw, db, None
+
+
+def linear(x, w, b=None, precision="fp32"):
+    return _Linear.apply(x, w, b, precision)
+
+
+# ------------------------------------------------------------------------------------------------
+# box predictor: x -> (scores [R,K+1], deltas [R,4]) with fused softmax statistics
+# ------------------------------------------------------------------------------------------------
+class BoxScoreAux:
+    """Side outputs of the fused scoring epilogue (never differentiated)."""
+    __slots__ = ("lse", "probs", "argmax_fg")
+
+    def __init__(self, lse, probs, argmax_fg):
+        self.lse, self.probs, self.argmax_fg = lse, probs, argmax_fg
+
+
+class _BoxPredict(Function):
+    """emb|deltas = x·[W_emb; W_box]^T + [b_emb; b_box];  scores = emb·W_cls^T + b_cls.
+    reference box_emb_head.py:179-212 (bbox_pred, emb_pred, cls_score as three cuBLAS GEMMs)."""
+
+    @staticmethod
+    def forward(ctx, x, w_emb, b_emb, w_box, b_box, w_cls, b_cls, precision, want_probs, aux_box):
+        acc = _acc(precision)
+        d = w_emb.shape[0]
+        nbox = w_box.shape[0]
+        w_cat = _cat_weight(w_emb, w_box)
+        b_cat = torch.cat([b_emb.detach(), b_box.detach()]).to(torch.float32)
+        a_op = ops.split_bf16(x, acc)
+        wcat_op = weight_operand(w_cat, acc, tag="cat")
+        out, e_op = ops.linear_fwd(a_op, wcat_op, b_cat, want_f32=True, n_bf16=d, accurate_out=acc)
+        deltas = out[:, d:d + nbox]
+        cls_op = weight_operand(w_cls, acc)
+        logits, probs, lse, arg = ops.box_score(e_op, cls_op, b_cls, want_probs)
+        aux_box.append(BoxScoreAux(lse, probs, arg))
+        ctx.save_for_backward(x, w_emb, w_box, w_cls)
+        ctx.meta = (precision, d, nbox)
+        return logits, deltas.contiguous()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dscores, ddeltas):
+        x, w_emb, w_box, w_cls = ctx.saved_tensors
+        precision, d, nbox = ctx.meta
+        acc = _acc(precision)
+        r = x.shape[0]
+        dev = x.device
+        # dE = dscores · W_cls   [R, D]
+        g_cat = torch.zeros((r, d + nbox), dtype=torch.float32, device=dev)
+        if dscores is not None:
+            gs_op = ops.split_bf16(dscores.contiguous(), acc)
+            clst_op = weight_operand(w_cls, acc, transpose=True)
+            de, _ = ops.linear_fwd(gs_op, clst_op, None, want_f32=True)
+            g_cat[:, :d] = de
+        if ddeltas is not None:
+            g_cat[:, d:] = ddeltas
+        dx = dwe = dbe = dwb = dbb = None
+        w_cat = _cat_weight(w_emb, w_box)
+        if ctx.needs_input_grad[0]:
+            g_op = ops.split_bf16(g_cat, acc)
+            wt_op = weight_operand(w_cat, acc, transpose=True, tag="cat")
+            dx, _ = ops.linear_fwd(g_op, wt_op, None, want_f32=True)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[3]:
+            gt_op = ops.split_bf16(g_cat, acc, transpose=True)
+            xt_op = ops.split_bf16(x, acc, transpose=True)
+            dw_cat, _ = ops.linear_fwd(gt_op, xt_op, None, want_f32=True)
+            if ctx.needs_input_grad[1]:
+                dwe = dw_cat[:d]
+            if ctx.needs_input_grad[3]:
+                dwb = dw_cat[d:]
+        if ctx.needs_input_grad[2]:
+            dbe = g_cat[:, :d].sum(0)
+        if ctx.needs_input_grad[4]:
+            dbb = g_cat[:, d:].sum(0)
+        return dx, dwe, dbe, dwb, dbb, None, None, None, None, None
+
+
+_cat_cache = {}
+
+
+def _cat_weight(w_emb, w_box):
+    """[W_emb; W_box] as one [D+4, V] matrix, rebuilt only when either parameter changed."""
+    key = (w_emb.data_ptr(), w_box.data_ptr(), tuple(w_emb.shape), tuple(w_box.shape))
+    ver = (w_emb._version, w_box._version)
+    ent = _cat_cache.get(key)
+    if ent is not None and ent[0] == ver:
+        return ent[1]
+    if ent is not None:
+        cat = ent[1]
+        cat[:w_emb.shape[0]].copy_(w_emb.detach())      # in place: bumps cat._version -> bf16 shadow refreshes
+        cat[w_emb.shape[0]:].copy_(w_box.detach())
+    else:
+        cat = torch.cat([w_emb.detach(), w_box.detach()], 0).to(torch.float32).contiguous()
+    _cat_cache[key] = (ver, cat)
+    if len(_cat_cache) > 64:
+        for k in list(_cat_cache)[:32]:
+            del _cat_cache[k]
+    return cat
+
+
+def box_predict(x, w_emb, b_emb, w_box, b_box, w_cls, b_cls=None, precision="fp32", want_probs=True):
+    """Returns (scores, deltas, BoxScoreAux)."""
+    aux = []
+    scores, deltas = _BoxPredict.apply(x, w_emb, b_emb, w_box, b_box, w_cls, b_cls, precision, want_probs, aux)
+    return scores, deltas, aux[0]
+
+
+class _BoxCE(Function):
+    """mean cross-entropy from logits + the log-sum-exp the scoring epilogue already produced
+    (Detectron2 FastRCNNOutputLayers.losses -> F.cross_entropy, reached from roi_emb_heads.py:266,347)."""
+
+    @staticmethod
+    def forward(ctx, logits, lse, labels):
+        loss, dl, _ = ops.box_ce(logits, lse, labels, want_grad=True)
+        ctx.save_for_backward(dl)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return (dl * g if dl is not None else None), None, None
+
+
+def box_cross_entropy(logits, lse, labels):
+    return _BoxCE.apply(logits, lse, labels)
+
+
+# ------------------------------------------------------------------------------------------------
+# LSM grounding head: projection + pair distances in one autograd node
+# ------------------------------------------------------------------------------------------------
+class _LsmHead(Function):
+    """(region_features, W, b, cap) -> (d_w2r, d_r2w) [Bc, Bi]; reference grounding_head.py:111-256."""
+
+    @staticmethod
+    def forward(ctx, feats, w, b, cap, cap_mask, reg_mask, inv_temp, alignment, precision, want_w2r, want_r2w):
+        acc = _acc(precision)
+        bi, rg, v = feats.shape
+        bc, t, d = cap.shape
+        x_op = ops.split_bf16(feats.reshape(bi * rg, v), acc)
+        w_op = weight_operand(w, acc)
+        _, emb_op = ops.linear_fwd(x_op, w_op, b, want_f32=False, n_bf16=d, accurate_out=acc)
+        cap_op = ops.split_bf16(cap.reshape(bc * t, d), acc)
+        w2r, r2w = ops.lsm_pair(cap_op, cap_mask, emb_op, reg_mask, inv_temp, alignment, want_w2r, want_r2w)
+        ctx.ops_saved = (x_op, emb_op, cap_op)
+        ctx.save_for_backward(feats, w, cap_mask, reg_mask)
+        ctx.meta = (inv_temp, alignment, precision, b is not None, tuple(cap.shape))
+        outs = tuple(o if o is not None else feats.new_zeros(()) for o in (w2r, r2w))
+        ctx.mark_non_differentiable(*[o for o, want in zip(outs, (want_w2r, want_r2w)) if not want])
+        return outs
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_w2r, g_r2w):
+        feats, w, cap_mask, reg_mask = ctx.saved_tensors
+        x_op, emb_op, cap_op = ctx.ops_saved
+        inv_temp, alignment, precision, has_b, cap_shape = ctx.meta
+        acc = _acc(precision)
+        bi, rg, v = feats.shape
+        need_cap = ctx.needs_input_grad[3]
+        demb, dcap = ops.lsm_pair_bwd(cap_op, cap_mask, emb_op, reg_mask, inv_temp, alignment,
+                                      g_w2r if g_w2r is not None and g_w2r.dim() == 2 else None,
+                                      g_r2w if g_r2w is not None and g_r2w.dim() == 2 else None, need_cap)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            g_op = ops.split_bf16(demb, acc)
+            wt_op = weight_operand(w, acc, transpose=True)
+            dx, _ = ops.linear_fwd(g_op, wt_op, None, want_f32=True)
+            dx = dx.reshape(bi, rg, v)
+        if ctx.needs_input_grad[1]:
+            gt_op = ops.split_bf16(demb, acc, transpose=True)
+            xt_op = ops.split_bf16(feats.reshape(bi * rg, v), acc, transpose=True)
+            dw, _ = ops.linear_fwd(gt_op, xt_op, None, want_f32=True)
+        if has_b and ctx.needs_input_grad[2]:
+            db = demb.sum(0)
+        if need_cap:
+            dcap = dcap.reshape(cap_shape)
+        return dx, dw, db, (dcap if need_cap else None), None, None, None, None, None, None, None
+
+
+def lsm_head(feats, w, b, cap, cap_mask, reg_mask, temperature, alignment="softmax", precision="fp32",
+             want_w2r=True, want_r2w=True):
+    """Pair distance matrices (rows = captions, cols = images) before the empty-pair guard."""
+    amode = {"softmax": ops.ALIGN_SOFTMAX, "hardmax": ops.ALIGN_HARDMAX}.get(alignment)
+    if amode is None:
+        raise NotImplementedError(f"alignment {alignment!r} is not implemented on the B200 path")
+    w2r, r2w = _LsmHead.apply(feats, w, b, cap, cap_mask, reg_mask, 1.0 / float(temperature), amode, precision,
+                              bool(want_w2r), bool(want_r2w))
+    return (w2r if want_w2r else None), (r2w if want_r2w else None)
+
+
+class _PairCE(Function):
+    """Empty-pair guard + the two cross-entropy losses and two accuracies of one pair matrix
+    (grounding_head.py:240-251, 272-290, 354-379).  Returns (guarded pw, out4)."""
+
+    @staticmethod
+    def forward(ctx, pw, cap_mask, reg_mask, diag_offset):
+        pw = pw.clone()
+        out4, dcap, dimg = ops.pair_ce(pw, cap_mask, reg_mask, diag_offset, want_grad=True)
+        ctx.save_for_backward(dcap, dimg)
+        ctx.mark_non_differentiable(pw)
+        return pw, out4
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, _gpw, g4):
+        dcap, dimg = ctx.saved_tensors
+        return dcap * g4[0] + dimg * g4[1], None, None, None
+
+
+def pair_losses(pw, cap_mask, reg_mask, diag_offset=0):
+    """-> (guarded pw [detached constant guard entries], out4 = [CE caption, CE image, acc caption, acc image])."""
+    return _PairCE.apply(pw, cap_mask, reg_mask, int(diag_offset))

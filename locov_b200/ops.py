@@ -247,14 +247,21 @@ def lsm_pair(cap: Bf16Operand, cap_mask: torch.Tensor, emb: Bf16Operand, reg_mas
     return w2r, r2w
 
 
-def pair_ce(pw: torch.Tensor, cap_mask: torch.Tensor, reg_mask: torch.Tensor, diag_offset: int = 0) -> torch.Tensor:
-    """Empty-pair guard (in place on pw) + [CE choose caption, CE choose image, acc caption, acc image]."""
+def pair_ce(pw: torch.Tensor, cap_mask: torch.Tensor, reg_mask: torch.Tensor, diag_offset: int = 0,
+            want_grad: bool = False):
+    """Empty-pair guard (in place on pw) + out4 = [CE choose caption, CE choose image, acc caption, acc image].
+    want_grad=True returns (out4, d out4[0]/d pw, d out4[1]/d pw), else out4."""
     _need_cuda(pw, cap_mask, reg_mask)
     bc, bi = pw.shape
+    if pw.stride(1) != 1:
+        raise LocoError("pair_ce: pw must have unit column stride")
     cap_mask = cap_mask.to(torch.float32).contiguous()
     reg_mask = reg_mask.to(torch.float32).contiguous()
     out = torch.empty((4,), dtype=torch.float32, device=pw.device)
+    dcap = torch.empty((bc, bi), dtype=torch.float32, device=pw.device) if want_grad else None
+    dimg = torch.empty((bc, bi), dtype=torch.float32, device=pw.device) if want_grad else None
     lib = _lib.load()
     _lib.check(lib.loco_pair_ce(_p(pw), pw.stride(0), bc, bi, int(diag_offset), _p(cap_mask), cap_mask.shape[1],
-                                _p(reg_mask), reg_mask.shape[1], _p(out), _stream(pw)), "loco_pair_ce")
-    return out
+                                _p(reg_mask), reg_mask.shape[1], _p(out), _p(dcap), _p(dimg), _stream(pw)),
+               "loco_pair_ce")
+    return (out, dcap, dimg) if want_grad else out

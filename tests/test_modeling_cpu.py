@@ -1,0 +1,81 @@
+"""Host-side mirror of the reference interfaces: names, constructor/config keys, parameter layouts,
+registries, and that the product path refuses to run without the CUDA library (no CPU fallback)."""
+import pytest
+import torch
+
+import locov_b200.modeling as M
+from locov_b200 import LocoError
+from oracle import lsm_head
+
+
+def test_registries_expose_the_reference_names():
+    assert "GroundingHead" in M.MMSS_HEADS_REGISTRY
+    assert "EmbeddingRes5ROIHeads" in M.ROI_HEADS_REGISTRY and "EmbeddingProposalsRes5ROIHeads" in M.ROI_HEADS_REGISTRY
+    assert "EmbeddingFastRCNNOutputLayers" in M.BOX_PREDICTORS
+    with pytest.raises(KeyError):
+        M.MMSS_HEADS_REGISTRY.get("NoSuchHead")
+
+
+def test_box_predictor_state_dict_and_class_embeddings():
+    cfg = M.get_cfg("stt")
+    bp = M.build_box_predictor(cfg, 2048)
+    sd = bp.state_dict()
+    assert sd["emb_pred.weight"].shape == (768, 2048) and sd["emb_pred.bias"].shape == (768,)
+    assert sd["bbox_pred.weight"].shape == (4, 2048) and sd["bbox_pred.bias"].shape == (4,)
+    assert not bp.emb_pred.weight.requires_grad          # FREEZE_EMB_PRED (coco_stt.yaml:36)
+    assert bp.cls_score is None and bp.num_classes is None
+    embs = torch.cat([torch.randn(48, 768), torch.zeros(1, 768)])
+    bp.set_class_embeddings(embs.numpy())
+    assert bp.num_classes == 48 and bp.cls_score.weight.shape == (49, 768)
+    assert not bp.cls_score.weight.requires_grad and float(bp.cls_score.bias.abs().sum()) == 0.0
+    assert "cls_score.weight" in bp.state_dict()
+    bp.set_class_embeddings(torch.cat([torch.randn(65, 768), torch.zeros(1, 768)]))     # re-settable (trainer.py:191)
+    assert bp.num_classes == 65
+    lsm = M.build_box_predictor(M.get_cfg("lsm"), 2048)
+    assert lsm.detach_cls_predictor and lsm.loss_weight["loss_cls"] == 0.0 and lsm.emb_pred.weight.requires_grad
+
+
+def test_grounding_head_options_and_tying():
+    cfg = M.get_cfg("lsm")
+    heads = M.build_mmss_heads(cfg, 2048, 768)
+    gh = heads["GroundingHead"]
+    assert isinstance(gh.v2l_projection.weight, torch.nn.Parameter) and gh.v2l_projection.weight.shape == (768, 2048)
+    assert gh.temperature == 10.0 and gh.return_dist and isinstance(gh.log_info, dict)
+    bad = M.get_cfg("lsm")
+    bad.MODEL.MMSS_HEAD.GROUNDING.ALIGNMENT = "random_top3"
+    with pytest.raises(NotImplementedError):
+        M.GroundingHead(bad, 2048, 768)
+    bad = M.get_cfg("lsm")
+    bad.MODEL.MMSS_HEAD.GROUNDING.GLOBAL_METRIC = "reconstruction_mse"
+    with pytest.raises(NotImplementedError):
+        M.GroundingHead(bad, 2048, 768)
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are rejected loudly — the product path is the CUDA library or nothing."""
+    cfg = M.get_cfg("lsm")
+    gh = M.GroundingHead(cfg, 32, 16)
+    ii, ic, w, b = lsm_head.make_lsm_inputs(B=2, Rg=4, T=5, V=32, D=16)
+    with pytest.raises(LocoError):
+        gh(ii, ic)
+    pool = M.ROIPooler(7, (1 / 16,), 0, "ROIAlignV2")
+    with pytest.raises(LocoError):
+        pool([torch.randn(1, 4, 8, 8)], [M.Boxes(torch.tensor([[0., 0., 32., 32.]]))])
+    with pytest.raises(NotImplementedError):
+        M.ROIPooler(7, (1 / 16,), 0, "ROIPool")
+
+
+def test_logged_module_is_lazy():
+    m = M.LoggedModule()
+    t = torch.arange(6.0).reshape(2, 3)
+    m.log("x", t)
+    s = m.log_info["x"]
+    assert s["min"] == 0.0 and s["max"] == 5.0 and abs(s["mean"] - 2.5) < 1e-6 and tuple(s["shape"]) == (2, 3)
+    m.log_dict({"loss": torch.tensor(1.0)})
+    assert float(m.log_info["loss"]) == 1.0
+
+
+def test_pooler_box_format():
+    from locov_b200.modeling.poolers import convert_boxes_to_pooler_format
+    r = convert_boxes_to_pooler_format([M.Boxes(torch.ones(2, 4)), M.Boxes(torch.zeros(0, 4)), M.Boxes(2 * torch.ones(1, 4))])
+    assert r.tolist() == [[0, 1, 1, 1, 1], [0, 1, 1, 1, 1], [2, 2, 2, 2, 2]]
