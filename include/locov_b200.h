@@ -95,6 +95,11 @@ int loco_roi_align_grid_dump(const float *rois, int R, int H, int W, int PH, int
 int loco_split_bf16(const float *src, int64_t rows, int64_t cols, int64_t src_ld, uint16_t *hi,
                     uint16_t *lo, int64_t dst_ld, int transpose, void *stream);
 
+/* bf16 [rows, cols] (src_ld) -> bf16 [cols, rows] (dst_ld >= rows; pad columns zero-filled): operand
+ * re-layout for the backward GEMMs (dX = dY . W needs W^T K-major, dW = dY^T . X needs both transposed). */
+int loco_transpose_bf16(const uint16_t *src, int64_t rows, int64_t cols, int64_t src_ld, uint16_t *dst,
+                        int64_t dst_ld, void *stream);
+
 /* ---- projection GEMM  out[M,N] = A[M,K] · W[N,K]^T + bias ------------------------------------------
  * Replaces: box_emb_head.py:196,206 (bbox_pred(x), emb_pred(x)) and grounding_head.py:111
  *           (v2l_projection(region_features)) — cuBLAS SGEMM + bias.
@@ -128,6 +133,14 @@ int loco_box_ce_fwd_bwd(const float *logits, int64_t ld_logits, const float *lse
                         int R, int K1, float scale, float *loss_sum, float grad_scale,
                         float *dlogits_f32, uint16_t *dlogits_bf16, int64_t ld_bf16, void *stream);
 
+/* ---- LSM masks -------------------------------------------------------------------------------------
+ * Replaces: grounding_head.py:94-96,101,105-106 (attention_mask * (1 - special_tokens_mask), two .to(float32)).
+ * attention_mask / special_tokens_mask: n_cap int64 values; region_mask: n_reg values of kind
+ * 0 = uint8, 1 = fp32, 2 = int64.  Writes cap_mask / reg_mask as fp32 0/1. */
+int loco_lsm_masks(const int64_t *attention_mask, const int64_t *special_tokens_mask, int64_t n_cap,
+                   const void *region_mask, int region_kind, int64_t n_reg, float *cap_mask,
+                   float *reg_mask, void *stream);
+
 /* ---- LSM pair scoring ------------------------------------------------------------------------------
  * Replaces: grounding_head.py:116-256 — B^2 .repeat() replication, torch.bmm, torch.where mask fill,
  *           two F.softmax passes, masked weighted sums (all ATen/cuBLAS launches over [B^2,T,Rg]).
@@ -150,21 +163,41 @@ int loco_lsm_pair_fwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ld
                       float inv_temperature, int alignment, float *d_w2r, float *d_r2w,
                       int64_t ld_out, void *workspace, void *stream);
 
+/* Backward of loco_lsm_pair_fwd with respect to the raw similarities <cap, emb>.
+ * Replaces: the autograd graph PyTorch records for grounding_head.py:147-236 (bmm / where / softmax x2 /
+ *           mul / sum backward kernels over [B^2,T,Rg]).
+ * g_w2r / g_r2w [Bc,Bi] fp32 (ld_g; either may be NULL): upstream gradients of the two distance matrices.
+ * The kernel recomputes the similarity tile (same GEMM as forward), evaluates
+ *   dS[c,t,i,r] = g_w2r[c,i] * d(d_w2r)/dS + g_r2w[c,i] * d(d_r2w)/dS        (softmax Jacobians included; for
+ *   hardmax the one-hot attention is piece-wise constant and only the direct term remains, as in autograd)
+ * on-chip and writes it as bf16 hi (+lo when dst_lo != NULL) in the layouts the gradient GEMMs consume:
+ *   dst  = dS^T [Bi*Rg, Bc*T] (ld_dst >= Bc*T, % 8)  ->  dEmb [Bi*Rg, D] = dS^T . cap   (loco_linear_fwd)
+ *   ds   = dS   [Bc*T, Bi*Rg] (ld_ds, optional)      ->  dCap [Bc*T, D]  = dS . emb
+ * Every element of the logical matrices is written (no zero-fill needed). */
+int loco_lsm_pair_bwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ldcap,
+                      const float *cap_mask, const uint16_t *emb_hi, const uint16_t *emb_lo,
+                      int64_t ldemb, const float *reg_mask, int Bc, int T, int Bi, int Rg, int D,
+                      float inv_temperature, int alignment, const float *g_w2r, const float *g_r2w,
+                      int64_t ld_g, uint16_t *dst_hi, uint16_t *dst_lo, int64_t ld_dst,
+                      uint16_t *ds_hi, uint16_t *ds_lo, int64_t ld_ds, void *stream);
+
 /* ---- pair-matrix losses ---------------------------------------------------------------------------
  * Replaces: grounding_head.py:240-251 (empty-pair guard), :272-290 (4 CE losses), :354-379 (accuracies).
- * pw [Bc, Bi] fp32 (ld) is modified IN PLACE by the empty-pair guard:
+ * pw: nmat pair matrices [Bc, Bi] fp32 (row stride ld, matrix stride mat_stride elements; nmat = 2
+ * evaluates the w2r and r2w matrices in one launch), each modified IN PLACE by the empty-pair guard:
  *   pw[c,i] = max(pw) + 100 where n_words[c] == 0 and n_regions[i] == 0.
  * cap_mask [Bc,T], reg_mask [Bi,Rg] as above.  The matching caption of image column i is row
  * i + diag_offset (diag_offset = first global image index of this shard when columns are sharded).
- * out[4] fp32: { CE choose-caption (mean over the Bi columns of -log_softmax(-pw, dim=0)[i+off, i]),
+ * out4 [nmat,4] fp32 per matrix:
+ *             { CE choose-caption (mean over the Bi columns of -log_softmax(-pw, dim=0)[i+off, i]),
  *               CE choose-image   (mean over rows c in [diag_offset, diag_offset+Bi) of
- *                                  -log_softmax(-pw, dim=1)[c, c-off]; only valid when Bi == Bc),
+ *                                  -log_softmax(-pw, dim=1)[c, c-off]; only meaningful when Bi == Bc),
  *               accuracy choose-caption, accuracy choose-image }.
- * dpw_caption / dpw_image (each may be NULL): dense [Bc, Bi] fp32 gradients of out4[0] / out4[1] with
- * respect to pw (zero at guard-filled entries, which are constants in the reference: .detach()). */
-int loco_pair_ce(float *pw, int64_t ld, int Bc, int Bi, int diag_offset, const float *cap_mask, int T,
-                 const float *reg_mask, int Rg, float *out4, float *dpw_caption, float *dpw_image,
-                 void *stream);
+ * dpw_caption / dpw_image (each may be NULL): dense [nmat, Bc, Bi] fp32 gradients of out4[.,0] / out4[.,1]
+ * with respect to pw (zero at guard-filled entries, which are constants in the reference: .detach()). */
+int loco_pair_ce(float *pw, int nmat, int64_t mat_stride, int64_t ld, int Bc, int Bi, int diag_offset,
+                 const float *cap_mask, int T, const float *reg_mask, int Rg, float *out4,
+                 float *dpw_caption, float *dpw_image, void *stream);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,44 @@ __global__ void __launch_bounds__(256) split_bf16_t_kernel(const float *__restri
     }
 }
 
+// ---- LSM mask preparation: caption_mask = attention_mask * (1 - special_tokens_mask) as fp32 (grounding_head.py:94-101),
+// region_mask (uint8 / fp32 / int64) as fp32 (:105-106) — one launch instead of four ATen elementwise kernels.
+__global__ void __launch_bounds__(256) lsm_masks_kernel(const int64_t *__restrict__ att, const int64_t *__restrict__ spe, int64_t n_cap,
+                                                        const void *__restrict__ reg, int reg_kind, int64_t n_reg,
+                                                        float *__restrict__ cap_mask, float *__restrict__ reg_mask) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cap + n_reg; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < n_cap) {
+            cap_mask[i] = (float)(att[i] * (1 - spe[i]));
+        } else {
+            const int64_t j = i - n_cap;
+            float v;
+            if (reg_kind == 0) v = (float)static_cast<const uint8_t *>(reg)[j];
+            else if (reg_kind == 1) v = static_cast<const float *>(reg)[j];
+            else v = (float)static_cast<const int64_t *>(reg)[j];
+            reg_mask[j] = v;
+        }
+    }
+}
+
+// ---- 16-bit transpose: dst[c, r] = src[r, c] (bf16 operands for the backward GEMMs) ---------------------------
+__global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t *__restrict__ src, int rows, int cols, int64_t src_ld,
+                                                          uint16_t *__restrict__ dst, int64_t dst_ld) {
+    __shared__ uint16_t tile[32][34];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = r0 + ty + 8 * k, c = c0 + tx;
+        tile[ty + 8 * k][tx] = (r < rows && c < cols) ? src[(int64_t)r * src_ld + c] : (uint16_t)0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k, r = r0 + tx;     // dst row = c, dst col = r; pad columns [rows, dst_ld) get zeros
+        if (c < cols && r < dst_ld) dst[(int64_t)c * dst_ld + r] = tile[tx][ty + 8 * k];
+    }
+}
+
 // ---- cross entropy over scored logits -------------------------------------------------------------------
 // one warp per RoI row
 __global__ void __launch_bounds__(256) box_ce_kernel(const float *__restrict__ logits, int64_t ld, const float *__restrict__ lse,
@@ -133,56 +171,75 @@ __device__ __forceinline__ float block_reduce_sum(float v, float *red) {
     return out;
 }
 
-__global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw, int64_t ld, int Bc, int Bi, int diag_off,
-                                                       const float *__restrict__ cap_mask, int T,
-                                                       const float *__restrict__ reg_mask, int Rg, float *__restrict__ out4,
-                                                       float *__restrict__ dcap, float *__restrict__ dimg) {
+// One CTA per pair matrix (blockIdx.x), warp-parallel: a warp owns a column (choose caption) or a row
+// (choose image) at a time, lanes stride over the other index, all reductions by shuffles in a fixed order.
+__global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_all, int64_t mat_stride, int64_t ld, int Bc, int Bi,
+                                                       int diag_off, const float *__restrict__ cap_mask, int T,
+                                                       const float *__restrict__ reg_mask, int Rg, float *__restrict__ out4_all,
+                                                       float *__restrict__ dcap_all, float *__restrict__ dimg_all) {
     extern __shared__ float sm[];
     float *red = sm;                 // [32]
-    float *cap_empty = sm + 32;      // [Bc] 1 if caption has no valid word
+    float *cap_empty = sm + 32;      // [Bc] 1 if the caption has no valid word
     float *img_empty = cap_empty + Bc;   // [Bi]
+    float *acc = img_empty + Bi;     // [4][32] per-warp partial sums: ce_cap, acc_cap, ce_img, acc_img
+    float *pw = pw_all + (int64_t)blockIdx.x * mat_stride;
+    float *out4 = out4_all + 4 * blockIdx.x;
+    float *dcap = dcap_all ? dcap_all + (int64_t)blockIdx.x * Bc * Bi : nullptr;
+    float *dimg = dimg_all ? dimg_all + (int64_t)blockIdx.x * Bc * Bi : nullptr;
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int c = tid; c < Bc; c += nt) {
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+
+    for (int c = warp; c < Bc; c += nwarp) {
         float s = 0.f;
-        for (int t = 0; t < T; ++t) s += cap_mask[(int64_t)c * T + t];
-        cap_empty[c] = s > 0.f ? 0.f : 1.f;
+        for (int t = lane; t < T; t += 32) s += cap_mask[(int64_t)c * T + t];
+        s = warp_sum(s);
+        if (lane == 0) cap_empty[c] = s > 0.f ? 0.f : 1.f;
     }
-    for (int i = tid; i < Bi; i += nt) {
+    for (int i = warp; i < Bi; i += nwarp) {
         float s = 0.f;
-        for (int r = 0; r < Rg; ++r) s += reg_mask[(int64_t)i * Rg + r];
-        img_empty[i] = s > 0.f ? 0.f : 1.f;
+        for (int r = lane; r < Rg; r += 32) s += reg_mask[(int64_t)i * Rg + r];
+        s = warp_sum(s);
+        if (lane == 0) img_empty[i] = s > 0.f ? 0.f : 1.f;
     }
-    __syncthreads();
+    if (tid < 128) acc[tid] = 0.f;
     // empty-pair guard (grounding_head.py:240-251): max over the whole matrix, then overwrite
     float mx = -FLT_MAX;
     for (int idx = tid; idx < Bc * Bi; idx += nt) mx = fmaxf(mx, pw[(int64_t)(idx / Bi) * ld + idx % Bi]);
-    mx = block_reduce_max(mx, red);
+    mx = block_reduce_max(mx, red);            // (contains the __syncthreads that publish cap_empty / img_empty)
     for (int idx = tid; idx < Bc * Bi; idx += nt) {
         const int c = idx / Bi, i = idx % Bi;
         if (cap_empty[c] > 0.f && img_empty[i] > 0.f) pw[(int64_t)c * ld + i] = mx + 100.0f;
     }
     __syncthreads();
-    // choose caption: per image column i, log-softmax over rows of -pw; target row = i + diag_off
-    float ce_cap = 0.f, acc_cap = 0.f;
-    for (int i = tid; i < Bi; i += nt) {
+    const float inv = 1.0f / (float)Bi;
+
+    // choose caption: per image column i, log-softmax over the rows of -pw; target row = i + diag_off
+    for (int i = warp; i < Bi; i += nwarp) {
         float m = -FLT_MAX, best = FLT_MAX;
-        int arg = 0;
-        for (int c = 0; c < Bc; ++c) {
+        int arg = 0x7fffffff;
+        for (int c = lane; c < Bc; c += 32) {
             const float v = pw[(int64_t)c * ld + i];
             m = fmaxf(m, -v);
             if (v < best) { best = v; arg = c; }
         }
+        m = warp_max(m);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {     // argmin with first-index tie-break (torch.argmin)
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
         float s = 0.f;
-        for (int c = 0; c < Bc; ++c) s += expf(-pw[(int64_t)c * ld + i] - m);
+        for (int c = lane; c < Bc; c += 32) s += expf(-pw[(int64_t)c * ld + i] - m);
+        s = warp_sum(s);
         const int tgt = i + diag_off;
-        if (tgt < Bc) {
-            ce_cap += (m + logf(s)) + pw[(int64_t)tgt * ld + i];
-            acc_cap += (arg == tgt) ? 1.f : 0.f;
+        if (lane == 0 && tgt < Bc) {
+            acc[0 * 32 + warp] += (m + logf(s)) + pw[(int64_t)tgt * ld + i];
+            acc[1 * 32 + warp] += (arg == tgt) ? 1.f : 0.f;
         }
         if (dcap != nullptr) {
             // d/dpw[c,i] of mean_i( lse_c(-pw[:,i]) + pw[tgt,i] ); guard-filled entries are constants
-            const float inv = 1.0f / (float)Bi;
-            for (int c = 0; c < Bc; ++c) {
+            for (int c = lane; c < Bc; c += 32) {
                 float g = 0.f;
                 if (tgt < Bc && !(cap_empty[c] > 0.f && img_empty[i] > 0.f))
                     g = (((c == tgt) ? 1.f : 0.f) - expf(-pw[(int64_t)c * ld + i] - m) / s) * inv;
@@ -190,45 +247,47 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw, i
             }
         }
     }
-    ce_cap = block_reduce_sum(ce_cap, red);
-    acc_cap = block_reduce_sum(acc_cap, red);
-    // choose image: per caption row c in [diag_off, diag_off + Bi), log-softmax over columns of -pw
-    if (dimg != nullptr)    // rows outside [diag_off, diag_off + Bi) carry no choose-image loss
-        for (int idx = tid; idx < Bc * Bi; idx += nt) dimg[idx] = 0.f;
-    __syncthreads();
-    float ce_img = 0.f, acc_img = 0.f;
-    for (int k = tid; k < Bi; k += nt) {
-        const int c = k + diag_off;
-        if (c >= Bc) continue;
-        float m = -FLT_MAX, best = FLT_MAX;
-        int arg = 0;
-        for (int i = 0; i < Bi; ++i) {
-            const float v = pw[(int64_t)c * ld + i];
-            m = fmaxf(m, -v);
-            if (v < best) { best = v; arg = i; }
+    // choose image: per caption row c, log-softmax over the columns of -pw; rows outside
+    // [diag_off, diag_off + Bi) carry no choose-image loss
+    for (int c = warp; c < Bc; c += nwarp) {
+        const int k = c - diag_off;
+        const bool has = (k >= 0 && k < Bi);
+        float m = -FLT_MAX, best = FLT_MAX, s = 0.f;
+        int arg = 0x7fffffff;
+        if (has) {
+            for (int i = lane; i < Bi; i += 32) {
+                const float v = pw[(int64_t)c * ld + i];
+                m = fmaxf(m, -v);
+                if (v < best) { best = v; arg = i; }
+            }
+            m = warp_max(m);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+                if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+            }
+            for (int i = lane; i < Bi; i += 32) s += expf(-pw[(int64_t)c * ld + i] - m);
+            s = warp_sum(s);
+            if (lane == 0) {
+                acc[2 * 32 + warp] += (m + logf(s)) + pw[(int64_t)c * ld + k];
+                acc[3 * 32 + warp] += (arg == k) ? 1.f : 0.f;
+            }
         }
-        float s = 0.f;
-        for (int i = 0; i < Bi; ++i) s += expf(-pw[(int64_t)c * ld + i] - m);
-        ce_img += (m + logf(s)) + pw[(int64_t)c * ld + k];
-        acc_img += (arg == k) ? 1.f : 0.f;
         if (dimg != nullptr) {
-            const float inv = 1.0f / (float)Bi;
-            for (int i = 0; i < Bi; ++i) {
+            for (int i = lane; i < Bi; i += 32) {
                 float g = 0.f;
-                if (!(cap_empty[c] > 0.f && img_empty[i] > 0.f))
+                if (has && !(cap_empty[c] > 0.f && img_empty[i] > 0.f))
                     g = (((i == k) ? 1.f : 0.f) - expf(-pw[(int64_t)c * ld + i] - m) / s) * inv;
                 dimg[(int64_t)c * Bi + i] = g;
             }
         }
     }
-    ce_img = block_reduce_sum(ce_img, red);
-    acc_img = block_reduce_sum(acc_img, red);
-    if (tid == 0) {
-        const float inv = 1.0f / (float)Bi;
-        out4[0] = ce_cap * inv;
-        out4[1] = ce_img * inv;
-        out4[2] = acc_cap * inv;
-        out4[3] = acc_img * inv;
+    __syncthreads();
+    if (warp < 4) {                  // warp w sums partial w over the (fixed-order) per-warp slots
+        float v = (lane < nwarp) ? acc[warp * 32 + lane] : 0.f;
+        v = warp_sum(v);
+        if (lane == 0) out4[warp] = v * inv;
     }
 }
 
@@ -266,6 +325,36 @@ int loco_split_bf16(const float *src, int64_t rows, int64_t cols, int64_t src_ld
     return LOCO_OK;
 }
 
+int loco_lsm_masks(const int64_t *attention_mask, const int64_t *special_tokens_mask, int64_t n_cap, const void *region_mask,
+                   int region_kind, int64_t n_reg, float *cap_mask, float *reg_mask, void *stream) {
+    LOCO_REQUIRE(n_cap >= 0 && n_reg >= 0 && region_kind >= 0 && region_kind <= 2, LOCO_E_BADARG, "lsm_masks: bad arguments");
+    if (n_cap + n_reg == 0) return LOCO_OK;
+    LOCO_REQUIRE((n_cap == 0 || (attention_mask && special_tokens_mask && cap_mask)) && (n_reg == 0 || (region_mask && reg_mask)), LOCO_E_BADARG,
+                 "lsm_masks: null pointer");
+    const int64_t total = n_cap + n_reg;
+    const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    lsm_masks_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(attention_mask, special_tokens_mask, n_cap, region_mask,
+                                                                            region_kind, n_reg, cap_mask, reg_mask);
+    count_launch();
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+int loco_transpose_bf16(const uint16_t *src, int64_t rows, int64_t cols, int64_t src_ld, uint16_t *dst, int64_t dst_ld,
+                        void *stream) {
+    LOCO_REQUIRE(rows >= 0 && cols >= 0 && src_ld >= cols && dst_ld >= rows, LOCO_E_BADARG, "transpose_bf16: bad shape rows=%lld cols=%lld",
+                 (long long)rows, (long long)cols);
+    if (rows == 0 || cols == 0) return LOCO_OK;
+    LOCO_REQUIRE(src && dst, LOCO_E_BADARG, "transpose_bf16: null pointer");
+    LOCO_REQUIRE(rows < (1ll << 31) && cols < (1ll << 31), LOCO_E_UNSUPPORTED, "transpose_bf16: matrix too large");
+    dim3 grid((unsigned)((dst_ld + 31) / 32), (unsigned)((cols + 31) / 32));
+    LOCO_REQUIRE(grid.y <= 65535, LOCO_E_UNSUPPORTED, "transpose_bf16: too many columns");
+    transpose16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, (int)rows, (int)cols, src_ld, dst, dst_ld);
+    count_launch();
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
 int loco_box_ce_fwd_bwd(const float *logits, int64_t ld_logits, const float *lse, const int64_t *labels, int R, int K1,
                         float scale, float *loss_sum, float grad_scale, float *dlogits_f32, uint16_t *dlogits_bf16,
                         int64_t ld_bf16, void *stream) {
@@ -283,17 +372,18 @@ int loco_box_ce_fwd_bwd(const float *logits, int64_t ld_logits, const float *lse
     return LOCO_OK;
 }
 
-int loco_pair_ce(float *pw, int64_t ld, int Bc, int Bi, int diag_offset, const float *cap_mask, int T, const float *reg_mask,
-                 int Rg, float *out4, float *dpw_caption, float *dpw_image, void *stream) {
-    LOCO_REQUIRE(Bc > 0 && Bi > 0 && ld >= Bi && T > 0 && Rg > 0 && diag_offset >= 0, LOCO_E_BADARG, "pair_ce: bad shape Bc=%d Bi=%d ld=%lld", Bc, Bi, (long long)ld);
+int loco_pair_ce(float *pw, int nmat, int64_t mat_stride, int64_t ld, int Bc, int Bi, int diag_offset, const float *cap_mask,
+                 int T, const float *reg_mask, int Rg, float *out4, float *dpw_caption, float *dpw_image, void *stream) {
+    LOCO_REQUIRE(Bc > 0 && Bi > 0 && ld >= Bi && T > 0 && Rg > 0 && diag_offset >= 0 && nmat >= 1, LOCO_E_BADARG,
+                 "pair_ce: bad shape nmat=%d Bc=%d Bi=%d ld=%lld", nmat, Bc, Bi, (long long)ld);
     LOCO_REQUIRE(pw && cap_mask && reg_mask && out4, LOCO_E_BADARG, "pair_ce: null pointer");
-    const size_t smem = (32 + (size_t)Bc + Bi) * sizeof(float);
+    const size_t smem = (32 + (size_t)Bc + Bi + 128) * sizeof(float);
     LOCO_REQUIRE(smem <= 48 * 1024, LOCO_E_UNSUPPORTED, "pair_ce: batch too large (Bc=%d Bi=%d)", Bc, Bi);
-    int threads = 32;
-    while (threads < Bc && threads < 1024) threads <<= 1;
+    int threads = 32 * (Bc > Bi ? Bc : Bi);
+    if (threads > 1024) threads = 1024;
     if (threads < 128) threads = 128;
-    pair_ce_kernel<<<1, threads, smem, static_cast<cudaStream_t>(stream)>>>(pw, ld, Bc, Bi, diag_offset, cap_mask, T, reg_mask, Rg, out4,
-                                                                            dpw_caption, dpw_image);
+    pair_ce_kernel<<<nmat, threads, smem, static_cast<cudaStream_t>(stream)>>>(pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T,
+                                                                               reg_mask, Rg, out4, dpw_caption, dpw_image);
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;

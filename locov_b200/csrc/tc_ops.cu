@@ -2,8 +2,8 @@
 // with its reductions fused into the TMEM epilogue:
 //   EpiLinear : out = A·Wᵀ + bias                  (emb_pred / bbox_pred / v2l_projection)
 //   EpiScore  : logits = E·Cᵀ (+bias), online softmax statistics, argmax, probabilities
-//   EpiW2R    : word→region attention pooling of the caption×image similarity tile
-//   EpiR2W    : region→word attention pooling of the transposed tile
+//   EpiLsm    : caption×image similarity tile with BOTH attention poolings (word→region, region→word)
+//               from one GEMM; the backward variant emits dS for the dEmb / dCap GEMMs
 #include <cfloat>
 
 #include "tc_gemm.cuh"
@@ -146,225 +146,266 @@ struct EpiScore {
 };
 
 // ------------------------------------------------------------------------------------------------
-// LSM epilogues.  Tile rows are always owned one-per-thread; a "segment" is the span of columns that
-// belongs to one softmax (all regions of the image for W2R; the T words of one caption for R2W).
+// LSM pair epilogue (forward and backward share it).
+//
+// One CTA owns the similarity tile of `per_tile` captions x ONE image: rows = caption words
+// (row = cl*T + t), columns = the image's regions.  After the MMAs the tile is scaled by 1/temperature
+// and parked in shared memory (row stride odd => conflict-free row- and column-wise walks), so BOTH
+// softmax directions of grounding_head.py:162-166 are evaluated from a single GEMM:
+//   row phase    (thread = word row)          : softmax over regions  -> attention-pooled f_t   (w2r)
+//   column phase (thread = (caption, region)) : softmax over the caption's T words -> h_r       (r2w)
+// followed by fixed-order warp reductions (deterministic, no atomics) to the two scalars of each pair.
+// BWD additionally turns the tile into dS = d(loss)/d(raw similarity) in place and streams it out
+// transposed (dS^T [Bi*Rg, Bc*T], the A operand of dEmb = dS^T . cap) and optionally as dS (for dCap).
 // ------------------------------------------------------------------------------------------------
+constexpr int LSM_MAX_PER_TILE = 16;
+
 struct LsmParams {
     const float *cap_mask;   // [Bc, T]
     const float *reg_mask;   // [Bi, Rg]
-    float *out;              // [Bc, Bi] (ld)
-    int64_t ld;
+    float *out_w2r, *out_r2w;   // [Bc, Bi] (ld_out); forward outputs, each may be null
+    int64_t ld_out;
+    const float *g_w2r, *g_r2w; // [Bc, Bi] (ld_g); upstream gradients (BWD), each may be null
+    int64_t ld_g;
+    uint16_t *dst_hi, *dst_lo;  // dS^T [Bi*Rg, Bc*T] (ld_dst) bf16 hi / lo (lo may be null)
+    int64_t ld_dst;
+    uint16_t *ds_hi, *ds_lo;    // dS [Bc*T, Bi*Rg] (ld_ds), optional
+    int64_t ld_ds;
     int Bc, T, Bi, Rg;
-    int per_tile;            // W2R: captions per M tile; R2W: captions per N tile
-    int groups;              // W2R: caption groups; R2W: caption chunks
-    int row_blocks;          // R2W: 128-row blocks per image (1 or 2)
+    int per_tile;               // captions per 128-row tile
+    int lds;                    // shared-memory row stride of the tile (floats, odd)
     float inv_temp;
     int hardmax;
 };
 
-// W2R: rows = words of `per_tile` captions (row = cl*T + t), columns = regions of image i.
-struct EpiW2R {
+// shared-memory carve-up (floats) after the [128][lds] tile
+struct LsmSmem {
+    float *S, *rmask, *cmask, *rowval, *colval, *rowmx, *rowden, *rowf, *colmx, *colden, *colh, *capnw, *capw2r, *capr2w;
+    __device__ __forceinline__ LsmSmem(unsigned char *base, int lds, int block_n, int per_tile, int Rg, bool bwd) {
+        float *p = reinterpret_cast<float *>(base);
+        S = p; p += 128 * lds;
+        rmask = p; p += block_n;
+        cmask = p; p += 128;
+        rowval = p; p += 128;
+        colval = p; p += per_tile * Rg;
+        capnw = p; p += LSM_MAX_PER_TILE;
+        capw2r = p; p += LSM_MAX_PER_TILE;
+        capr2w = p; p += LSM_MAX_PER_TILE;
+        rowmx = rowden = rowf = colmx = colden = colh = nullptr;
+        if (bwd) {
+            rowmx = p; p += 128;
+            rowden = p; p += 128;
+            rowf = p; p += 128;
+            colmx = p; p += per_tile * Rg;
+            colden = p; p += per_tile * Rg;
+            colh = p; p += per_tile * Rg;
+        }
+    }
+};
+static size_t lsm_epi_smem_bytes(int lds, int block_n, int per_tile, int Rg, bool bwd) {
+    size_t f = (size_t)128 * lds + block_n + 128 + 128 + (size_t)per_tile * Rg + 3 * LSM_MAX_PER_TILE;
+    if (bwd) f += 3 * 128 + 3 * (size_t)per_tile * Rg;
+    return f * sizeof(float) + 16;
+}
+
+template <bool BWD>
+struct EpiLsm {
     typedef LsmParams Params;
     static __device__ __forceinline__ void coords(const Params &p, const TcCore &, int cta, int, int &row_a, int &row_b) {
         const int g = cta / p.Bi, i = cta - g * p.Bi;
-        row_a = g * p.per_tile * p.T;    // caption rows
-        row_b = i * p.Rg;                // region rows
+        row_a = g * p.per_tile * p.T;    // caption word rows (A operand)
+        row_b = i * p.Rg;                // region rows of image i (B operand)
     }
     __device__ __forceinline__ void begin(const Params &, const TcCore &, int, int, int, int, unsigned char *) {}
+    __device__ __forceinline__ void finish(const Params &, const TcCore &, int, int, int, int, unsigned char *) {}
+
     __device__ __forceinline__ void chunk(const Params &p, const TcCore &core, int cta, int, uint32_t taddr, int row, int lane,
                                           int q, unsigned char *smem) {
-        (void)lane; (void)q;
-        float *row_val = reinterpret_cast<float *>(smem);      // [128] masked pooled value per word row
-        float *row_msk = row_val + 128;                        // [128] caption mask per word row
-        float *rmask_s = row_msk + 128;                        // [block_n] region mask of image i
+        const LsmSmem sm(smem, p.lds, core.block_n, p.per_tile, p.Rg, BWD);
         const int g = cta / p.Bi, i = cta - g * p.Bi;
-        const int cl = row / p.T, t = row - cl * p.T;
-        const int c = g * p.per_tile + cl;
-        const bool row_ok = (cl < p.per_tile) && (c < p.Bc);
-        const float mc = row_ok ? __ldg(p.cap_mask + (int64_t)c * p.T + t) : 0.f;
-        // stage the region mask of this image (shared by all rows)
-        const int et = threadIdx.x - 64;                       // 0..127 among epilogue threads
-        for (int r = et; r < core.block_n; r += 128) rmask_s[r] = (r < p.Rg) ? __ldg(p.reg_mask + (int64_t)i * p.Rg + r) : 0.f;
+        const int et = threadIdx.x - 64;                            // 0..127 among the epilogue threads
+        const int c_first = g * p.per_tile;
+        const int ncap = max(0, min(p.per_tile, p.Bc - c_first));    // valid captions of this tile
+        const int nrows = ncap * p.T;                                // valid word rows
+        const int T = p.T, Rg = p.Rg, lds = p.lds;
+        const bool want_w = BWD ? (p.g_w2r != nullptr) : (p.out_w2r != nullptr);
+        const bool want_r = BWD ? (p.g_r2w != nullptr) : (p.out_r2w != nullptr);
+
+        // ---- phase 0: masks ---------------------------------------------------------------------------
+        for (int r = et; r < core.block_n; r += 128) sm.rmask[r] = (r < Rg) ? __ldg(p.reg_mask + (int64_t)i * Rg + r) : 0.f;
+        const float mc = (row < nrows) ? __ldg(p.cap_mask + (int64_t)c_first * T + row) : 0.f;
+        sm.cmask[row] = mc;
         named_bar_sync(1, 128);
 
-        const int nblk = (p.Rg + 31) / 32;
-        float pooled = 0.f;
-        if (!p.hardmax) {
-            // pass 1: row maximum of the masked logits
-            float mx = -FLT_MAX;
-            for (int b = 0; b < nblk; ++b) {
-                float v[32];
-                tmem_ld32(taddr + (uint32_t)(b * 32), v);
+        // ---- phase 1: TMEM -> scaled tile in smem; row softmax statistics ----------------------------------
+        const int nblk = (Rg + 31) / 32;
+        float *srow = sm.S + (size_t)row * lds;
+        float mx = -FLT_MAX, best_s = 0.f;
+        int best_r = 0;
+        for (int b = 0; b < nblk; ++b) {
+            float v[32];
+            tmem_ld32(taddr + (uint32_t)(b * 32), v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int r = b * 32 + j;
-                    if (r < p.Rg) {
-                        const float s = v[j] * p.inv_temp;
-                        const float sm = (mc > 0.f && rmask_s[r] > 0.f) ? s : LSM_FILL;
-                        mx = fmaxf(mx, sm);
-                    }
+            for (int j = 0; j < 32; ++j) {
+                const int r = b * 32 + j;
+                if (r < Rg) {
+                    const float s = v[j] * p.inv_temp;
+                    srow[r] = s;
+                    const float sv = (mc > 0.f && sm.rmask[r] > 0.f) ? s : LSM_FILL;
+                    if (sv > mx) { mx = sv; best_s = s; best_r = r; }   // strict >: first maximum (torch.argmax)
                 }
             }
-            // pass 2: softmax-weighted sum of the UNMASKED similarities (reference grounding_head.py:228-231)
-            float den = 0.f, num = 0.f;
-            for (int b = 0; b < nblk; ++b) {
-                float v[32];
-                tmem_ld32(taddr + (uint32_t)(b * 32), v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int r = b * 32 + j;
-                    if (r < p.Rg) {
-                        const float s = v[j] * p.inv_temp;
-                        const float sm = (mc > 0.f && rmask_s[r] > 0.f) ? s : LSM_FILL;
-                        const float e = expf(sm - mx);
-                        den += e;
+        }
+        float f_t = best_s, den = (float)best_r;                   // hardmax: `den` carries the argmax index
+        if (want_w && !p.hardmax) {
+            float num = 0.f;
+            den = 0.f;
+            for (int r = 0; r < Rg; ++r) {
+                const float s = srow[r];
+                const float sv = (mc > 0.f && sm.rmask[r] > 0.f) ? s : LSM_FILL;
+                const float e = __expf(sv - mx);
+                den += e;
+                num = fmaf(e, s, num);
+            }
+            f_t = num / den;
+        }
+        sm.rowval[row] = (mc > 0.f) ? f_t : 0.f;
+        if (BWD) {
+            sm.rowmx[row] = mx;
+            sm.rowden[row] = den;
+            sm.rowf[row] = f_t;
+        }
+        named_bar_sync(1, 128);
+
+        // ---- phase 2: column softmax over the T words of each caption ----------------------------------------
+        if (want_r) {
+            const int items = ncap * Rg;
+            for (int it = et; it < items; it += 128) {
+                const int cl = it / Rg, r = it - cl * Rg;
+                const float rm = sm.rmask[r];
+                const float *col = sm.S + (size_t)cl * T * lds + r;
+                const float *cm = sm.cmask + cl * T;
+                float cmx = -FLT_MAX, cbest = 0.f;
+                int best_t = 0;
+                for (int t = 0; t < T; ++t) {
+                    const float s = col[(size_t)t * lds];
+                    const float sv = (rm > 0.f && cm[t] > 0.f) ? s : LSM_FILL;
+                    if (sv > cmx) { cmx = sv; cbest = s; best_t = t; }
+                }
+                float h = cbest, cden = (float)best_t;              // hardmax: argmax index
+                if (!p.hardmax) {
+                    float num = 0.f;
+                    cden = 0.f;
+                    for (int t = 0; t < T; ++t) {
+                        const float s = col[(size_t)t * lds];
+                        const float sv = (rm > 0.f && cm[t] > 0.f) ? s : LSM_FILL;
+                        const float e = __expf(sv - cmx);
+                        cden += e;
                         num = fmaf(e, s, num);
                     }
+                    h = num / cden;
+                }
+                sm.colval[it] = (rm > 0.f) ? h : 0.f;
+                if (BWD) {
+                    sm.colmx[it] = cmx;
+                    sm.colden[it] = cden;
+                    sm.colh[it] = h;
                 }
             }
-            pooled = num / den;
-        } else {
-            float best = -FLT_MAX, best_s = 0.f;
-            for (int b = 0; b < nblk; ++b) {
-                float v[32];
-                tmem_ld32(taddr + (uint32_t)(b * 32), v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int r = b * 32 + j;
-                    if (r < p.Rg) {
-                        const float s = v[j] * p.inv_temp;
-                        const float sm = (mc > 0.f && rmask_s[r] > 0.f) ? s : LSM_FILL;
-                        if (sm > best) { best = sm; best_s = s; }
-                    }
-                }
-            }
-            pooled = best_s;
+            named_bar_sync(1, 128);
         }
-        row_val[row] = (mc > 0.f) ? pooled : 0.f;
-        row_msk[row] = mc;
-        named_bar_sync(1, 128);
-        // deterministic per-caption reduction: thread k sums the T rows of caption slot k
-        if (et < p.per_tile) {
-            const int cc = g * p.per_tile + et;
-            if (cc < p.Bc) {
-                float acc = 0.f, nw = 0.f;
-                for (int tt = 0; tt < p.T; ++tt) {
-                    acc += row_val[et * p.T + tt];
-                    nw += row_msk[et * p.T + tt];
-                }
-                p.out[(int64_t)cc * p.ld + i] = -acc / fmaxf(nw, 1.f);
-            }
-        }
-    }
-    __device__ __forceinline__ void finish(const Params &, const TcCore &, int, int, int, int, unsigned char *) {}
-};
 
-// R2W: rows = regions of image i (row block m), columns = words of `per_tile` captions (col = cl*T + t).
-struct EpiR2W {
-    typedef LsmParams Params;
-    static __device__ __forceinline__ void decode(const Params &p, int cta, int &i, int &m, int &cc) {
-        cc = cta % p.groups;
-        const int rest = cta / p.groups;
-        m = rest % p.row_blocks;
-        i = rest / p.row_blocks;
-    }
-    static __device__ __forceinline__ void coords(const Params &p, const TcCore &, int cta, int, int &row_a, int &row_b) {
-        int i, m, cc;
-        decode(p, cta, i, m, cc);
-        row_a = i * p.Rg + m * TC_BLOCK_M;       // region rows (A operand = region embeddings)
-        row_b = cc * p.per_tile * p.T;           // caption word rows (B operand)
-    }
-    __device__ __forceinline__ void begin(const Params &, const TcCore &, int, int, int, int, unsigned char *) {}
-    __device__ __forceinline__ void chunk(const Params &p, const TcCore &core, int cta, int, uint32_t taddr, int row, int lane,
-                                          int q, unsigned char *smem) {
-        float *cmask_s = reinterpret_cast<float *>(smem);      // [block_n] caption mask per column
-        float *part = cmask_s + 256;                            // [4][per_tile] per-warp partial sums
-        int i, m, cc;
-        decode(p, cta, i, m, cc);
-        const int r = m * TC_BLOCK_M + row;
-        const bool row_ok = r < p.Rg;
-        const float mr = row_ok ? __ldg(p.reg_mask + (int64_t)i * p.Rg + r) : 0.f;
-        const int et = threadIdx.x - 64;
-        const int c_first = cc * p.per_tile;
-        const int ncap = max(0, min(p.per_tile, p.Bc - c_first));
-        for (int col = et; col < core.block_n; col += 128) {
-            const int cl = col / p.T;
-            cmask_s[col] = (cl < ncap) ? __ldg(p.cap_mask + (int64_t)(c_first + cl) * p.T + (col - cl * p.T)) : 0.f;
-        }
-        // number of valid regions of the image (every warp computes it redundantly)
+        // ---- phase 3: per-caption reductions in a fixed order (warp q handles captions q, q+4, ...) ----------
         float nr = 0.f;
-        for (int rr = lane; rr < p.Rg; rr += 32) nr += __ldg(p.reg_mask + (int64_t)i * p.Rg + rr);
+        for (int r = lane; r < Rg; r += 32) nr += sm.rmask[r];
         nr = warp_sum(nr);
-        named_bar_sync(1, 128);
-
-        // Column blocks of 32 do not line up with the T-word segments, so the online state of the current
-        // segment is carried across blocks.  Two sweeps over TMEM: segment maxima, then pooled sums.
-        const int ncols = ncap * p.T;
-        const int nblk = (ncols + 31) / 32;
-        float pooled_seg = 0.f;                 // value for the segment being finalised
-        // sweep over segments; per segment: max pass then sum pass restricted to its column range
-        for (int cl = 0; cl < ncap; ++cl) {
-            const int cb = cl * p.T, ce = cb + p.T;
-            const int b0 = cb / 32, b1 = (ce - 1) / 32;
-            float mx = -FLT_MAX, best_s = 0.f;
-            for (int b = b0; b <= b1; ++b) {
-                float v[32];
-                tmem_ld32(taddr + (uint32_t)(b * 32), v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = b * 32 + j;
-                    if (col >= cb && col < ce) {
-                        const float s = v[j] * p.inv_temp;
-                        const float sm = (mr > 0.f && cmask_s[col] > 0.f) ? s : LSM_FILL;
-                        if (sm > mx) { mx = sm; best_s = s; }
-                    }
-                }
+        for (int cl = q; cl < ncap; cl += 4) {
+            float a = 0.f, nw = 0.f, bsum = 0.f;
+            for (int t = lane; t < T; t += 32) {
+                a += sm.rowval[cl * T + t];
+                nw += sm.cmask[cl * T + t];
             }
-            if (!p.hardmax) {
-                float den = 0.f, num = 0.f;
-                for (int b = b0; b <= b1; ++b) {
-                    float v[32];
-                    tmem_ld32(taddr + (uint32_t)(b * 32), v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = b * 32 + j;
-                        if (col >= cb && col < ce) {
-                            const float s = v[j] * p.inv_temp;
-                            const float sm = (mr > 0.f && cmask_s[col] > 0.f) ? s : LSM_FILL;
-                            const float e = expf(sm - mx);
-                            den += e;
-                            num = fmaf(e, s, num);
-                        }
-                    }
-                }
-                pooled_seg = num / den;
-            } else {
-                pooled_seg = best_s;
+            a = warp_sum(a);
+            nw = warp_sum(nw);
+            if (want_r) {
+                for (int r = lane; r < Rg; r += 32) bsum += sm.colval[cl * Rg + r];
+                bsum = warp_sum(bsum);
             }
-            // sum over the 32 region rows of this warp (rows with region mask 0 contribute exactly 0)
-            const float contrib = warp_sum((mr > 0.f) ? pooled_seg : 0.f);
-            if (lane == 0) part[q * 16 + (cl & 15)] = contrib;
-            if ((cl & 15) == 15 || cl == ncap - 1) {
-                named_bar_sync(1, 128);
-                const int base = cl & ~15;
-                if (et <= (cl & 15)) {
-                    // fixed summation order over the four warps (tile row quarters 0..3): deterministic
-                    float tot = 0.f;
-                    for (int w = 0; w < 4; ++w) {
-                        // warp index -> quarter: warps 2,3,4,5 own quarters 2,3,0,1; order by quarter
-                        tot += part[w * 16 + et];
-                    }
-                    const int c = c_first + base + et;
-                    const float val = -tot / fmaxf(nr, 1.f);
-                    float *dst = p.out + (int64_t)c * p.ld + i;
-                    if (p.row_blocks == 1) *dst = val; else atomicAdd(dst, val);
+            if (lane == 0) {
+                const int c = c_first + cl;
+                if (!BWD) {
+                    if (p.out_w2r) p.out_w2r[(int64_t)c * p.ld_out + i] = -a / fmaxf(nw, 1.f);
+                    if (p.out_r2w) p.out_r2w[(int64_t)c * p.ld_out + i] = -bsum / fmaxf(nr, 1.f);
+                } else {
+                    sm.capnw[cl] = nw;
                 }
-                named_bar_sync(1, 128);
             }
         }
-        (void)nblk;
+        if (!BWD) return;
+
+        // ---- phase 4 (BWD): dS in place -----------------------------------------------------------------------
+        named_bar_sync(1, 128);
+        if (row < nrows) {
+            const int cl = row / T, t = row - cl * T;
+            const int c = c_first + cl;
+            // d(d_w2r)/ds = -(m_c/nw) P (1 + valid (s - f_t));  d(d_r2w)/ds = -(m_r/nr) Q (1 + valid (s - h_r));
+            // raw similarity = s * temperature  =>  one more factor 1/temperature
+            const float gw = want_w ? -__ldg(p.g_w2r + (int64_t)c * p.ld_g + i) * mc / fmaxf(sm.capnw[cl], 1.f) * p.inv_temp : 0.f;
+            const float gr = want_r ? -__ldg(p.g_r2w + (int64_t)c * p.ld_g + i) / fmaxf(nr, 1.f) * p.inv_temp : 0.f;
+            const float rmx = sm.rowmx[row], rinv = 1.f / sm.rowden[row], rf = sm.rowf[row];
+            for (int r = 0; r < Rg; ++r) {
+                const float s = srow[r];
+                const float rm = sm.rmask[r];
+                const bool valid = (mc > 0.f && rm > 0.f);
+                const float sv = valid ? s : LSM_FILL;
+                float d = 0.f;
+                if (want_w) {
+                    if (!p.hardmax) {
+                        const float P = __expf(sv - rmx) * rinv;
+                        d += gw * P * (1.f + (valid ? s - rf : 0.f));
+                    } else {
+                        d += (r == (int)sm.rowden[row]) ? gw : 0.f;
+                    }
+                }
+                if (want_r) {
+                    const int it = cl * Rg + r;
+                    if (!p.hardmax) {
+                        const float Q = __expf(sv - sm.colmx[it]) / sm.colden[it];
+                        d += gr * rm * Q * (1.f + (valid ? s - sm.colh[it] : 0.f));
+                    } else {
+                        d += (t == (int)sm.colden[it]) ? gr * rm : 0.f;
+                    }
+                }
+                srow[r] = d;
+            }
+        }
+        named_bar_sync(1, 128);
+
+        // ---- phase 5 (BWD): coalesced write-out ------------------------------------------------------------------
+        const int64_t col0 = (int64_t)c_first * T;                  // first caption-word column of this tile in dS^T
+        for (int r = q; r < Rg; r += 4) {                           // warp per region row of dS^T
+            uint16_t *dh = p.dst_hi + ((int64_t)i * Rg + r) * p.ld_dst + col0;
+            uint16_t *dl = p.dst_lo ? p.dst_lo + ((int64_t)i * Rg + r) * p.ld_dst + col0 : nullptr;
+            for (int w = lane; w < nrows; w += 32) {
+                uint16_t h, l;
+                split_bf16(sm.S[(size_t)w * lds + r], h, l);
+                dh[w] = h;
+                if (dl) dl[w] = l;
+            }
+        }
+        if (p.ds_hi != nullptr) {
+            for (int w = q; w < nrows; w += 4) {                    // warp per caption-word row of dS
+                uint16_t *dh = p.ds_hi + (col0 + w) * p.ld_ds + (int64_t)i * Rg;
+                uint16_t *dl = p.ds_lo ? p.ds_lo + (col0 + w) * p.ld_ds + (int64_t)i * Rg : nullptr;
+                for (int r = lane; r < Rg; r += 32) {
+                    uint16_t h, l;
+                    split_bf16(sm.S[(size_t)w * lds + r], h, l);
+                    dh[r] = h;
+                    if (dl) dl[r] = l;
+                }
+            }
+        }
     }
-    __device__ __forceinline__ void finish(const Params &, const TcCore &, int, int, int, int, unsigned char *) {}
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -455,7 +496,29 @@ int loco_box_score_fwd(const uint16_t *E_hi, const uint16_t *E_lo, int64_t lde, 
 
 int64_t loco_lsm_pair_workspace_bytes(int Bc, int T, int Bi, int Rg) {
     (void)Bc; (void)T; (void)Bi; (void)Rg;
-    return 16;   // reserved (partial sums are reduced on-chip); kept so callers always pass a valid pointer
+    return 16;   // reserved (all reductions happen on-chip); kept so callers always pass a valid pointer
+}
+
+static int lsm_launch(bool bwd, const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ldcap, const uint16_t *emb_hi,
+                      const uint16_t *emb_lo, int64_t ldemb, int D, LsmParams &p, cudaStream_t st) {
+    LOCO_REQUIRE(p.Bc >= 0 && p.Bi >= 0 && p.T > 0 && p.Rg > 0 && D > 0, LOCO_E_BADARG, "lsm_pair: bad shape Bc=%d T=%d Bi=%d Rg=%d D=%d", p.Bc, p.T, p.Bi, p.Rg, D);
+    LOCO_REQUIRE(p.T <= 128 && p.Rg <= 256, LOCO_E_UNSUPPORTED, "lsm_pair: supports T <= 128 words and Rg <= 256 regions (got T=%d Rg=%d)", p.T, p.Rg);
+    LOCO_REQUIRE(cap_hi && emb_hi && p.cap_mask && p.reg_mask, LOCO_E_BADARG, "lsm_pair: null pointer");
+    LOCO_REQUIRE((cap_lo == nullptr) == (emb_lo == nullptr), LOCO_E_BADARG, "lsm_pair: cap_lo and emb_lo must both be given or both be NULL");
+    TcCore core;
+    core.block_n = tc_round_up(p.Rg, 16);
+    p.per_tile = TC_BLOCK_M / p.T;
+    if (p.per_tile > LSM_MAX_PER_TILE) p.per_tile = LSM_MAX_PER_TILE;
+    if (p.per_tile > p.Bc) p.per_tile = p.Bc;
+    p.lds = core.block_n | 1;
+    const int groups = (p.Bc + p.per_tile - 1) / p.per_tile;
+    const size_t epi = lsm_epi_smem_bytes(p.lds, core.block_n, p.per_tile, p.Rg, bwd);
+    const size_t smem = tc_finalize(core, D, cap_lo ? 3 : 1, 1, (int)epi);
+    TcMaps maps;
+    int rc = fill_maps(maps, cap_hi, cap_lo, (uint64_t)p.Bc * p.T, ldcap, emb_hi, emb_lo, (uint64_t)p.Bi * p.Rg, ldemb, D, core.block_n);
+    if (rc != LOCO_OK) return rc;
+    LOCO_REQUIRE((long long)groups * p.Bi < (1ll << 31), LOCO_E_UNSUPPORTED, "lsm_pair: too many tiles");
+    return bwd ? tc_launch<EpiLsm<true>>(maps, core, p, groups * p.Bi, smem, st) : tc_launch<EpiLsm<false>>(maps, core, p, groups * p.Bi, smem, st);
 }
 
 int loco_lsm_pair_fwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ldcap, const float *cap_mask,
@@ -463,52 +526,33 @@ int loco_lsm_pair_fwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ld
                       int Bi, int Rg, int D, float inv_temperature, int alignment, float *d_w2r, float *d_r2w,
                       int64_t ld_out, void *workspace, void *stream) {
     (void)workspace;
-    LOCO_REQUIRE(Bc >= 0 && Bi >= 0 && T > 0 && Rg > 0 && D > 0, LOCO_E_BADARG, "lsm_pair_fwd: bad shape Bc=%d T=%d Bi=%d Rg=%d D=%d", Bc, T, Bi, Rg, D);
     if (Bc == 0 || Bi == 0) return LOCO_OK;
     LOCO_REQUIRE(T <= 128 && Rg <= 256, LOCO_E_UNSUPPORTED, "lsm_pair_fwd: supports T <= 128 words and Rg <= 256 regions (got T=%d Rg=%d)", T, Rg);
     LOCO_REQUIRE(alignment == LOCO_ALIGN_SOFTMAX || alignment == LOCO_ALIGN_HARDMAX, LOCO_E_UNSUPPORTED, "lsm_pair_fwd: alignment %d not implemented", alignment);
-    LOCO_REQUIRE(cap_hi && emb_hi && cap_mask && reg_mask, LOCO_E_BADARG, "lsm_pair_fwd: null pointer");
-    LOCO_REQUIRE((cap_lo == nullptr) == (emb_lo == nullptr), LOCO_E_BADARG, "lsm_pair_fwd: cap_lo and emb_lo must both be given or both be NULL");
     LOCO_REQUIRE(d_w2r || d_r2w, LOCO_E_BADARG, "lsm_pair_fwd: no output requested");
     LOCO_REQUIRE(ld_out >= Bi, LOCO_E_BADARG, "lsm_pair_fwd: ld_out < Bi");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int passes = cap_lo ? 3 : 1;
-    LsmParams p;
-    p.cap_mask = cap_mask; p.reg_mask = reg_mask; p.ld = ld_out; p.Bc = Bc; p.T = T; p.Bi = Bi; p.Rg = Rg;
-    p.inv_temp = inv_temperature; p.hardmax = (alignment == LOCO_ALIGN_HARDMAX);
-    int rc;
-    if (d_w2r) {
-        TcCore core;
-        core.block_n = tc_round_up(Rg, 16);
-        p.per_tile = TC_BLOCK_M / T;
-        p.groups = (Bc + p.per_tile - 1) / p.per_tile;
-        p.row_blocks = 1;
-        p.out = d_w2r;
-        const size_t smem = tc_finalize(core, D, passes, 1, (128 + 128 + 256) * 4);
-        TcMaps maps;
-        rc = fill_maps(maps, cap_hi, cap_lo, (uint64_t)Bc * T, ldcap, emb_hi, emb_lo, (uint64_t)Bi * Rg, ldemb, D, core.block_n);
-        if (rc != LOCO_OK) return rc;
-        rc = tc_launch<EpiW2R>(maps, core, p, p.groups * Bi, smem, st);
-        if (rc != LOCO_OK) return rc;
-    }
-    if (d_r2w) {
-        TcCore core;
-        p.per_tile = 256 / T < Bc ? 256 / T : Bc;
-        core.block_n = tc_round_up(p.per_tile * T, 16);
-        p.groups = (Bc + p.per_tile - 1) / p.per_tile;
-        p.row_blocks = (Rg + TC_BLOCK_M - 1) / TC_BLOCK_M;
-        p.out = d_r2w;
-        if (p.row_blocks > 1)
-            for (int c = 0; c < Bc; ++c)   // rows are ld_out apart: zero each row's Bi entries
-                LOCO_CUDA(cudaMemsetAsync(d_r2w + (int64_t)c * ld_out, 0, sizeof(float) * Bi, st));
-        const size_t smem = tc_finalize(core, D, passes, 1, (256 + 64) * 4);
-        TcMaps maps;
-        rc = fill_maps(maps, emb_hi, emb_lo, (uint64_t)Bi * Rg, ldemb, cap_hi, cap_lo, (uint64_t)Bc * T, ldcap, D, core.block_n);
-        if (rc != LOCO_OK) return rc;
-        rc = tc_launch<EpiR2W>(maps, core, p, Bi * p.row_blocks * p.groups, smem, st);
-        if (rc != LOCO_OK) return rc;
-    }
-    return LOCO_OK;
+    LsmParams p = {};
+    p.cap_mask = cap_mask; p.reg_mask = reg_mask; p.out_w2r = d_w2r; p.out_r2w = d_r2w; p.ld_out = ld_out;
+    p.Bc = Bc; p.T = T; p.Bi = Bi; p.Rg = Rg; p.inv_temp = inv_temperature; p.hardmax = (alignment == LOCO_ALIGN_HARDMAX);
+    return lsm_launch(false, cap_hi, cap_lo, ldcap, emb_hi, emb_lo, ldemb, D, p, static_cast<cudaStream_t>(stream));
+}
+
+int loco_lsm_pair_bwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ldcap, const float *cap_mask,
+                      const uint16_t *emb_hi, const uint16_t *emb_lo, int64_t ldemb, const float *reg_mask, int Bc, int T,
+                      int Bi, int Rg, int D, float inv_temperature, int alignment, const float *g_w2r, const float *g_r2w,
+                      int64_t ld_g, uint16_t *dst_hi, uint16_t *dst_lo, int64_t ld_dst, uint16_t *ds_hi, uint16_t *ds_lo,
+                      int64_t ld_ds, void *stream) {
+    if (Bc == 0 || Bi == 0) return LOCO_OK;
+    LOCO_REQUIRE(alignment == LOCO_ALIGN_SOFTMAX || alignment == LOCO_ALIGN_HARDMAX, LOCO_E_UNSUPPORTED, "lsm_pair_bwd: alignment %d not implemented", alignment);
+    LOCO_REQUIRE(g_w2r || g_r2w, LOCO_E_BADARG, "lsm_pair_bwd: no upstream gradient given");
+    LOCO_REQUIRE(ld_g >= Bi, LOCO_E_BADARG, "lsm_pair_bwd: ld_g < Bi");
+    LOCO_REQUIRE(dst_hi != nullptr && ld_dst >= (int64_t)Bc * T, LOCO_E_BADARG, "lsm_pair_bwd: dS^T buffer missing or ld_dst < Bc*T");
+    LOCO_REQUIRE(ds_hi == nullptr || ld_ds >= (int64_t)Bi * Rg, LOCO_E_BADARG, "lsm_pair_bwd: ld_ds < Bi*Rg");
+    LsmParams p = {};
+    p.cap_mask = cap_mask; p.reg_mask = reg_mask; p.g_w2r = g_w2r; p.g_r2w = g_r2w; p.ld_g = ld_g;
+    p.dst_hi = dst_hi; p.dst_lo = dst_lo; p.ld_dst = ld_dst; p.ds_hi = ds_hi; p.ds_lo = ds_lo; p.ld_ds = ld_ds;
+    p.Bc = Bc; p.T = T; p.Bi = Bi; p.Rg = Rg; p.inv_temp = inv_temperature; p.hardmax = (alignment == LOCO_ALIGN_HARDMAX);
+    return lsm_launch(true, cap_hi, cap_lo, ldcap, emb_hi, emb_lo, ldemb, D, p, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

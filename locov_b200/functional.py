@@ -5,6 +5,7 @@ streams and the autograd graph only.  ``precision`` selects the tensor-core oper
   "fp32" : fp32-accurate — operands split into bf16 hi+lo, three tcgen05 passes (≈1e-5 relative)
   "bf16" : single bf16 pass (≈4e-3 relative; the north-star tolerance for bf16 is 2e-2)
 """
+import weakref
 from typing import Optional
 
 import torch
@@ -35,12 +36,15 @@ def weight_operand(w: torch.Tensor, accurate: bool, transpose: bool = False, tag
     key = (w.data_ptr(), tuple(w.shape), tuple(w.stride()), accurate, transpose, tag, w.device.index)
     ent = _wcache.get(key)
     ver = w._version
-    if ent is not None and ent[0] == ver:
+    # identity check through a weak reference: a freed parameter's address (and version count) can be
+    # re-used by a new tensor, which must never be served the old shadow.
+    if ent is not None and ent[0] == ver and ent[2]() is w:
         return ent[1]
-    op = ops.split_bf16(w.detach(), accurate, transpose=transpose, out=ent[1] if ent is not None else None)
-    _wcache[key] = (ver, op)
-    if len(_wcache) > 256:      # parameters re-created by set_class_embeddings: drop the oldest shadows
-        for k in list(_wcache)[:128]:
+    reuse = ent[1] if (ent is not None and ent[2]() is w) else None
+    op = ops.split_bf16(w.detach(), accurate, transpose=transpose, out=reuse)
+    _wcache[key] = (ver, op, weakref.ref(w))
+    if len(_wcache) > 256:      # parameters re-created by set_class_embeddings: drop dead / oldest shadows
+        for k in [k for k, v in _wcache.items() if v[2]() is None] or list(_wcache)[:128]:
             del _wcache[k]
     return op
 
@@ -194,17 +198,18 @@ def _cat_weight(w_emb, w_box):
     key = (w_emb.data_ptr(), w_box.data_ptr(), tuple(w_emb.shape), tuple(w_box.shape))
     ver = (w_emb._version, w_box._version)
     ent = _cat_cache.get(key)
-    if ent is not None and ent[0] == ver:
+    alive = ent is not None and ent[2]() is w_emb and ent[3]() is w_box
+    if alive and ent[0] == ver:
         return ent[1]
-    if ent is not None:
+    if alive:
         cat = ent[1]
         cat[:w_emb.shape[0]].copy_(w_emb.detach())      # in place: bumps cat._version -> bf16 shadow refreshes
         cat[w_emb.shape[0]:].copy_(w_box.detach())
     else:
         cat = torch.cat([w_emb.detach(), w_box.detach()], 0).to(torch.float32).contiguous()
-    _cat_cache[key] = (ver, cat)
+    _cat_cache[key] = (ver, cat, weakref.ref(w_emb), weakref.ref(w_box))
     if len(_cat_cache) > 64:
-        for k in list(_cat_cache)[:32]:
+        for k in [k for k, v in _cat_cache.items() if v[2]() is None] or list(_cat_cache)[:32]:
             del _cat_cache[k]
     return cat
 
@@ -240,8 +245,14 @@ def box_cross_entropy(logits, lse, labels):
 # ------------------------------------------------------------------------------------------------
 # LSM grounding head: projection + pair distances in one autograd node
 # ------------------------------------------------------------------------------------------------
+def new_pair_stack(bc, bi, device, both=True):
+    """[2, Bc, Bi] buffer for (w2r, r2w): one allocation so the pair-CE kernel handles both in one launch."""
+    return (torch.empty if both else torch.zeros)((2, bc, bi), dtype=torch.float32, device=device)
+
+
 class _LsmHead(Function):
-    """(region_features, W, b, cap) -> (d_w2r, d_r2w) [Bc, Bi]; reference grounding_head.py:111-256."""
+    """(region_features, W, b, cap) -> pw [2, Bc, Bi] = (d_w2r, d_r2w); reference grounding_head.py:111-256.
+    A slice whose alignment is switched off is zero and carries no gradient."""
 
     @staticmethod
     def forward(ctx, feats, w, b, cap, cap_mask, reg_mask, inv_temp, alignment, precision, want_w2r, want_r2w):
@@ -252,36 +263,35 @@ class _LsmHead(Function):
         w_op = weight_operand(w, acc)
         _, emb_op = ops.linear_fwd(x_op, w_op, b, want_f32=False, n_bf16=d, accurate_out=acc)
         cap_op = ops.split_bf16(cap.reshape(bc * t, d), acc)
-        w2r, r2w = ops.lsm_pair(cap_op, cap_mask, emb_op, reg_mask, inv_temp, alignment, want_w2r, want_r2w)
-        ctx.ops_saved = (x_op, emb_op, cap_op)
+        stack = new_pair_stack(bc, bi, feats.device, want_w2r and want_r2w)
+        ops.lsm_pair(cap_op, cap_mask, emb_op, reg_mask, inv_temp, alignment, want_w2r, want_r2w, stack[0], stack[1])
+        ctx.ops_saved = (emb_op, cap_op)
         ctx.save_for_backward(feats, w, cap_mask, reg_mask)
-        ctx.meta = (inv_temp, alignment, precision, b is not None, tuple(cap.shape))
-        outs = tuple(o if o is not None else feats.new_zeros(()) for o in (w2r, r2w))
-        ctx.mark_non_differentiable(*[o for o, want in zip(outs, (want_w2r, want_r2w)) if not want])
-        return outs
+        ctx.meta = (inv_temp, alignment, precision, b is not None, tuple(cap.shape), want_w2r, want_r2w)
+        return stack
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, g_w2r, g_r2w):
+    def backward(ctx, g):
         feats, w, cap_mask, reg_mask = ctx.saved_tensors
-        x_op, emb_op, cap_op = ctx.ops_saved
-        inv_temp, alignment, precision, has_b, cap_shape = ctx.meta
+        emb_op, cap_op = ctx.ops_saved
+        inv_temp, alignment, precision, has_b, cap_shape, want_w2r, want_r2w = ctx.meta
         acc = _acc(precision)
         bi, rg, v = feats.shape
         need_cap = ctx.needs_input_grad[3]
+        g = g.contiguous()
         demb, dcap = ops.lsm_pair_bwd(cap_op, cap_mask, emb_op, reg_mask, inv_temp, alignment,
-                                      g_w2r if g_w2r is not None and g_w2r.dim() == 2 else None,
-                                      g_r2w if g_r2w is not None and g_r2w.dim() == 2 else None, need_cap)
+                                      g[0] if want_w2r else None, g[1] if want_r2w else None, need_cap)
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             g_op = ops.split_bf16(demb, acc)
+        if ctx.needs_input_grad[0]:
             wt_op = weight_operand(w, acc, transpose=True)
             dx, _ = ops.linear_fwd(g_op, wt_op, None, want_f32=True)
             dx = dx.reshape(bi, rg, v)
         if ctx.needs_input_grad[1]:
-            gt_op = ops.split_bf16(demb, acc, transpose=True)
-            xt_op = ops.split_bf16(feats.reshape(bi * rg, v), acc, transpose=True)
-            dw, _ = ops.linear_fwd(gt_op, xt_op, None, want_f32=True)
+            x_op = ops.split_bf16(feats.reshape(bi * rg, v), acc)
+            dw, _ = ops.linear_fwd(ops.transpose_operand(g_op), ops.transpose_operand(x_op), None, want_f32=True)
         if has_b and ctx.needs_input_grad[2]:
             db = demb.sum(0)
         if need_cap:
@@ -291,34 +301,44 @@ class _LsmHead(Function):
 
 def lsm_head(feats, w, b, cap, cap_mask, reg_mask, temperature, alignment="softmax", precision="fp32",
              want_w2r=True, want_r2w=True):
-    """Pair distance matrices (rows = captions, cols = images) before the empty-pair guard."""
+    """Stacked pair distance matrices [2, Bc, Bi] = (w2r, r2w) (rows = captions, cols = images) before the
+    empty-pair guard; the slice of a switched-off alignment is zero."""
     amode = {"softmax": ops.ALIGN_SOFTMAX, "hardmax": ops.ALIGN_HARDMAX}.get(alignment)
     if amode is None:
         raise NotImplementedError(f"alignment {alignment!r} is not implemented on the B200 path")
-    w2r, r2w = _LsmHead.apply(feats, w, b, cap, cap_mask, reg_mask, 1.0 / float(temperature), amode, precision,
-                              bool(want_w2r), bool(want_r2w))
-    return (w2r if want_w2r else None), (r2w if want_r2w else None)
+    return _LsmHead.apply(feats, w, b, cap, cap_mask, reg_mask, 1.0 / float(temperature), amode, precision,
+                          bool(want_w2r), bool(want_r2w))
 
 
 class _PairCE(Function):
-    """Empty-pair guard + the two cross-entropy losses and two accuracies of one pair matrix
-    (grounding_head.py:240-251, 272-290, 354-379).  Returns (guarded pw, out4)."""
+    """Empty-pair guard + the two cross-entropy losses and two accuracies of each stacked pair matrix
+    (grounding_head.py:240-251, 272-290, 354-379), one launch.  Returns (guarded pw [n,Bc,Bi], out [n,4])."""
 
     @staticmethod
     def forward(ctx, pw, cap_mask, reg_mask, diag_offset):
-        pw = pw.clone()
-        out4, dcap, dimg = ops.pair_ce(pw, cap_mask, reg_mask, diag_offset, want_grad=True)
-        ctx.save_for_backward(dcap, dimg)
+        need = ctx.needs_input_grad[0]
+        if need:
+            pw = pw.clone()          # the guard writes in place; without a graph the fresh kernel output is reused
+
+        res = ops.pair_ce(pw, cap_mask, reg_mask, diag_offset, want_grad=need)
+        if need:
+            out, dcap, dimg = res
+            ctx.save_for_backward(dcap, dimg)
+        else:
+            out = res
         ctx.mark_non_differentiable(pw)
-        return pw, out4
+        return pw, out
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, _gpw, g4):
+    def backward(ctx, _gpw, g):
         dcap, dimg = ctx.saved_tensors
-        return dcap * g4[0] + dimg * g4[1], None, None, None
+        return dcap * g[:, 0, None, None] + dimg * g[:, 1, None, None], None, None, None
 
 
 def pair_losses(pw, cap_mask, reg_mask, diag_offset=0):
-    """-> (guarded pw [detached constant guard entries], out4 = [CE caption, CE image, acc caption, acc image])."""
+    """pw [n,Bc,Bi] -> (guarded pw, out [n,4] = [CE caption, CE image, acc caption, acc image] per matrix)."""
+    if not (torch.is_grad_enabled() and pw.requires_grad):
+        # no graph: `pw` is the fresh output of the pair kernel, so the guard may write it in place
+        return pw, ops.pair_ce(pw, cap_mask, reg_mask, int(diag_offset))
     return _PairCE.apply(pw, cap_mask, reg_mask, int(diag_offset))

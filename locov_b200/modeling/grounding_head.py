@@ -16,6 +16,7 @@ import torch
 from torch import nn
 
 from .. import functional as LF
+from .. import ops
 from .logged_module import LoggedModule
 from .registry import MMSS_HEADS_REGISTRY
 
@@ -64,14 +65,18 @@ class GroundingHead(LoggedModule):
     # ---------------------------------------------------------------------------------------------
     def forward(self, input_image, input_caption):
         caption_emb = input_caption[self.grounding_text_input]
-        caption_mask = input_caption["attention_mask"] * (1 - input_caption["special_tokens_mask"])
-        self.log("attention_mask", input_caption["attention_mask"])
-        self.log("special_tokens_mask", input_caption["special_tokens_mask"])
+        att, spe = input_caption["attention_mask"], input_caption["special_tokens_mask"]
+        region_features = input_image["region_features"]
+        region_mask = input_image["region_mask"]
+        if att.is_cuda and att.dtype == torch.int64 and spe.dtype == torch.int64 and region_mask.dtype in ops._REG_KIND:
+            caption_mask, region_mask = ops.lsm_masks(att, spe, region_mask)       # grounding_head.py:94-106, one launch
+        else:
+            caption_mask = (att * (1 - spe)).to(torch.float32)
+            region_mask = region_mask.to(torch.float32)
+        self.log("attention_mask", att)
+        self.log("special_tokens_mask", spe)
         self.log("caption_mask", caption_mask)
         self.log("caption_emb", caption_emb)
-        caption_mask = caption_mask.to(torch.float32)
-        region_features = input_image["region_features"]
-        region_mask = input_image["region_mask"].to(torch.float32)
         self.log("region_features", region_features)
         self.log("region_mask", region_mask)
         batch_size = region_features.shape[0]
@@ -80,35 +85,40 @@ class GroundingHead(LoggedModule):
             from .. import parallel
             return parallel.sharded_grounding_forward(self, region_features, region_mask, caption_emb, caption_mask)
 
-        w2r, r2w = LF.lsm_head(region_features.to(torch.float32).contiguous(), self.v2l_projection.weight,
-                               self.v2l_projection.bias, caption_emb.to(torch.float32).contiguous(), caption_mask,
-                               region_mask, self.temperature, self.alignment, self.precision,
-                               want_w2r=self.align_words, want_r2w=self.align_regions)
-        losses, other_info, dists = {}, {}, {}
-        for key, pw in (("w2r", w2r), ("r2w", r2w)):
-            if pw is None:
-                continue
-            assert pw.shape == (batch_size, batch_size)
-            pw_g, out4 = LF.pair_losses(pw, caption_mask, region_mask, 0)
-            # guarded matrix: value of pw_g, gradient path of pw (guard entries are constants)
-            pw_cost = pw + (pw_g - pw).detach() if pw.requires_grad else pw_g
-            self.log(f"global_dist_{key}", pw_cost)
-            dists[key] = pw_cost
-            name = _NAMES[key]
-            if self.loss_type == "cross_entropy":
-                losses[f"CE_loss (Align {name}, Choose Caption)"] = out4[0]
-                losses[f"CE_loss (Align {name}, Choose Image)"] = out4[1]
-            else:
-                cap_l, img_l = self._triplet(pw_cost)
-                losses[f"Triplet Loss (Align {name}, Choose Caption)"] = cap_l
-                losses[f"Triplet Loss (Align {name}, Choose Image)"] = img_l
-            other_info[f"Batch Accuracy (Align {name}, Choose Caption)"] = out4[2].detach()
-            other_info[f"Batch Accuracy (Align {name}, Choose Image)"] = out4[3].detach()
+        pw = LF.lsm_head(region_features.to(torch.float32).contiguous(), self.v2l_projection.weight,
+                         self.v2l_projection.bias, caption_emb.to(torch.float32).contiguous(), caption_mask,
+                         region_mask, self.temperature, self.alignment, self.precision,
+                         want_w2r=self.align_words, want_r2w=self.align_regions)
+        assert pw.shape == (2, batch_size, batch_size)
+        losses, other_info, dists = self._pair_outputs(pw, caption_mask, region_mask)
         self.log_dict(losses)
         self.log_dict(other_info)
         if self.return_dist:
             return other_info, losses, dists
         return other_info, losses
+
+    def _pair_outputs(self, pw, caption_mask, region_mask):
+        """Stacked [2,B,B] distances -> (losses, other_info, dists) with the reference's key strings."""
+        pw_g, out = LF.pair_losses(pw, caption_mask, region_mask, 0)
+        # guarded matrix: value of pw_g, gradient path of pw (guard entries are constants)
+        pw_cost = pw + (pw_g - pw).detach() if pw.requires_grad else pw_g
+        losses, other_info, dists = {}, {}, {}
+        for k, (key, on) in enumerate((("w2r", self.align_words), ("r2w", self.align_regions))):
+            if not on:
+                continue
+            self.log(f"global_dist_{key}", pw_cost[k])
+            dists[key] = pw_cost[k]
+            name = _NAMES[key]
+            if self.loss_type == "cross_entropy":
+                losses[f"CE_loss (Align {name}, Choose Caption)"] = out[k, 0]
+                losses[f"CE_loss (Align {name}, Choose Image)"] = out[k, 1]
+            else:
+                cap_l, img_l = self._triplet(pw_cost[k])
+                losses[f"Triplet Loss (Align {name}, Choose Caption)"] = cap_l
+                losses[f"Triplet Loss (Align {name}, Choose Image)"] = img_l
+            other_info[f"Batch Accuracy (Align {name}, Choose Caption)"] = out[k, 2].detach()
+            other_info[f"Batch Accuracy (Align {name}, Choose Image)"] = out[k, 3].detach()
+        return losses, other_info, dists
 
     def _triplet(self, pw):
         """grounding_head.py:292-350 on the [B,B] matrix (a few hundred floats: PyTorch glue, not hot path)."""

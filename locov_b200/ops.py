@@ -220,6 +220,23 @@ def box_ce(logits: torch.Tensor, lse: torch.Tensor, labels: torch.Tensor, want_g
     return loss, dl, dlb
 
 
+_REG_KIND = {torch.uint8: 0, torch.bool: 0, torch.float32: 1, torch.int64: 2}
+
+
+def lsm_masks(attention_mask: torch.Tensor, special_tokens_mask: torch.Tensor, region_mask: torch.Tensor):
+    """-> (caption_mask [B,T] fp32 = attention * (1 - special), region_mask [B,Rg] fp32), one launch."""
+    _need_cuda(attention_mask, special_tokens_mask, region_mask)
+    if attention_mask.dtype != torch.int64 or special_tokens_mask.dtype != torch.int64 or region_mask.dtype not in _REG_KIND:
+        raise LocoError("lsm_masks: expects int64 token masks and a uint8/bool/fp32/int64 region mask")
+    att, spe, reg = attention_mask.contiguous(), special_tokens_mask.contiguous(), region_mask.contiguous()
+    cap_mask = torch.empty(att.shape, dtype=torch.float32, device=att.device)
+    reg_mask = torch.empty(reg.shape, dtype=torch.float32, device=att.device)
+    lib = _lib.load()
+    _lib.check(lib.loco_lsm_masks(_p(att), _p(spe), att.numel(), _p(reg), _REG_KIND[reg.dtype], reg.numel(), _p(cap_mask),
+                                  _p(reg_mask), _stream(att)), "loco_lsm_masks")
+    return cap_mask, reg_mask
+
+
 def lsm_pair(cap: Bf16Operand, cap_mask: torch.Tensor, emb: Bf16Operand, reg_mask: torch.Tensor, inv_temperature: float,
              alignment: int = ALIGN_SOFTMAX, want_w2r: bool = True, want_r2w: bool = True,
              out_w2r: Optional[torch.Tensor] = None, out_r2w: Optional[torch.Tensor] = None):
@@ -234,8 +251,12 @@ def lsm_pair(cap: Bf16Operand, cap_mask: torch.Tensor, emb: Bf16Operand, reg_mas
     dev = cap.hi.device
     cap_mask = cap_mask.to(torch.float32).contiguous()
     reg_mask = reg_mask.to(torch.float32).contiguous()
-    w2r = (out_w2r if out_w2r is not None else torch.empty((bc, bi), dtype=torch.float32, device=dev)) if want_w2r else None
-    r2w = (out_r2w if out_r2w is not None else torch.empty((bc, bi), dtype=torch.float32, device=dev)) if want_r2w else None
+    if out_w2r is None and want_w2r:
+        out_w2r = torch.empty((bc, bi), dtype=torch.float32, device=dev)
+    if out_r2w is None and want_r2w:
+        out_r2w = torch.empty((bc, bi), dtype=torch.float32, device=dev)
+    w2r = out_w2r if want_w2r else None
+    r2w = out_r2w if want_r2w else None
     ld = (w2r if w2r is not None else r2w).stride(0)
     if w2r is not None and r2w is not None and w2r.stride(0) != r2w.stride(0):
         raise LocoError("lsm_pair: outputs must share a row stride")
@@ -247,21 +268,77 @@ def lsm_pair(cap: Bf16Operand, cap_mask: torch.Tensor, emb: Bf16Operand, reg_mas
     return w2r, r2w
 
 
+def transpose_operand(op: Bf16Operand) -> Bf16Operand:
+    """bf16 operand [rows, cols] -> [cols, rows] (hi and lo)."""
+    ld = _round_up(max(op.rows, 1), 8)
+    dev = op.hi.device
+    hi = torch.empty((op.cols, ld), dtype=torch.bfloat16, device=dev)
+    lo = torch.empty((op.cols, ld), dtype=torch.bfloat16, device=dev) if op.lo is not None else None
+    lib = _lib.load()
+    for s_, d_ in ((op.hi, hi), (op.lo, lo)):
+        if s_ is not None:
+            _lib.check(lib.loco_transpose_bf16(_p(s_), op.rows, op.cols, op.ld, _p(d_), ld, _stream(op.hi)), "loco_transpose_bf16")
+    return Bf16Operand(hi, lo, op.cols, op.rows)
+
+
+def lsm_pair_bwd(cap: Bf16Operand, cap_mask: torch.Tensor, emb: Bf16Operand, reg_mask: torch.Tensor, inv_temperature: float,
+                 alignment: int, g_w2r: Optional[torch.Tensor], g_r2w: Optional[torch.Tensor], need_cap: bool = False):
+    """Gradients of the pair distances: returns (dEmb [Bi*Rg, D] fp32, dCap [Bc*T, D] fp32 or None).
+    One recompute kernel (similarity GEMM + softmax Jacobians -> dS in bf16) and one tcgen05 GEMM per gradient."""
+    bc, t = cap_mask.shape
+    bi, rg = reg_mask.shape
+    acc = cap.lo is not None
+    dev = cap.hi.device
+    d = cap.cols
+    if g_w2r is None and g_r2w is None:
+        return torch.zeros((bi * rg, d), dtype=torch.float32, device=dev), (torch.zeros((bc * t, d), dtype=torch.float32, device=dev) if need_cap else None)
+    cap_mask = cap_mask.to(torch.float32).contiguous()
+    reg_mask = reg_mask.to(torch.float32).contiguous()
+    gs = [g.to(torch.float32).contiguous() if g is not None else None for g in (g_w2r, g_r2w)]
+    ld_g = bi
+    ld_t = _round_up(bc * t, 8)
+    dst_hi = torch.empty((bi * rg, ld_t), dtype=torch.bfloat16, device=dev)
+    dst_lo = torch.empty((bi * rg, ld_t), dtype=torch.bfloat16, device=dev) if acc else None
+    ds_hi = ds_lo = None
+    ld_s = _round_up(bi * rg, 8)
+    if need_cap:
+        ds_hi = torch.empty((bc * t, ld_s), dtype=torch.bfloat16, device=dev)
+        ds_lo = torch.empty((bc * t, ld_s), dtype=torch.bfloat16, device=dev) if acc else None
+    lib = _lib.load()
+    _lib.check(lib.loco_lsm_pair_bwd(_p(cap.hi), _p(cap.lo), cap.ld, _p(cap_mask), _p(emb.hi), _p(emb.lo), emb.ld, _p(reg_mask),
+                                     bc, t, bi, rg, d, float(inv_temperature), int(alignment), _p(gs[0]), _p(gs[1]), ld_g,
+                                     _p(dst_hi), _p(dst_lo), ld_t, _p(ds_hi), _p(ds_lo), ld_s, _stream(cap.hi)),
+               "loco_lsm_pair_bwd")
+    # dEmb = dS^T [Bi*Rg, Bc*T] . cap [Bc*T, D]  ->  W operand = cap^T [D, Bc*T]
+    demb, _ = linear_fwd(Bf16Operand(dst_hi, dst_lo, bi * rg, bc * t), transpose_operand(cap), None, want_f32=True)
+    dcap = None
+    if need_cap:
+        dcap, _ = linear_fwd(Bf16Operand(ds_hi, ds_lo, bc * t, bi * rg), transpose_operand(emb), None, want_f32=True)
+    return demb, dcap
+
+
 def pair_ce(pw: torch.Tensor, cap_mask: torch.Tensor, reg_mask: torch.Tensor, diag_offset: int = 0,
             want_grad: bool = False):
-    """Empty-pair guard (in place on pw) + out4 = [CE choose caption, CE choose image, acc caption, acc image].
-    want_grad=True returns (out4, d out4[0]/d pw, d out4[1]/d pw), else out4."""
+    """Empty-pair guard (in place on pw) + [CE choose caption, CE choose image, acc caption, acc image].
+    pw is one matrix [Bc,Bi] -> out [4], or a stack [nmat,Bc,Bi] -> out [nmat,4] (one launch).
+    want_grad=True returns (out, d out[...,0]/d pw, d out[...,1]/d pw), else out."""
     _need_cuda(pw, cap_mask, reg_mask)
-    bc, bi = pw.shape
-    if pw.stride(1) != 1:
+    single = pw.dim() == 2
+    pw3 = pw.unsqueeze(0) if single else pw
+    nmat, bc, bi = pw3.shape
+    if pw3.stride(2) != 1:
         raise LocoError("pair_ce: pw must have unit column stride")
     cap_mask = cap_mask.to(torch.float32).contiguous()
     reg_mask = reg_mask.to(torch.float32).contiguous()
-    out = torch.empty((4,), dtype=torch.float32, device=pw.device)
-    dcap = torch.empty((bc, bi), dtype=torch.float32, device=pw.device) if want_grad else None
-    dimg = torch.empty((bc, bi), dtype=torch.float32, device=pw.device) if want_grad else None
+    out = torch.empty((nmat, 4), dtype=torch.float32, device=pw.device)
+    dcap = torch.empty((nmat, bc, bi), dtype=torch.float32, device=pw.device) if want_grad else None
+    dimg = torch.empty((nmat, bc, bi), dtype=torch.float32, device=pw.device) if want_grad else None
     lib = _lib.load()
-    _lib.check(lib.loco_pair_ce(_p(pw), pw.stride(0), bc, bi, int(diag_offset), _p(cap_mask), cap_mask.shape[1],
-                                _p(reg_mask), reg_mask.shape[1], _p(out), _p(dcap), _p(dimg), _stream(pw)),
-               "loco_pair_ce")
+    _lib.check(lib.loco_pair_ce(_p(pw3), nmat, pw3.stride(0), pw3.stride(1), bc, bi, int(diag_offset), _p(cap_mask),
+                                cap_mask.shape[1], _p(reg_mask), reg_mask.shape[1], _p(out), _p(dcap), _p(dimg),
+                                _stream(pw)), "loco_pair_ce")
+    if single:
+        out = out[0]
+        dcap = dcap[0] if want_grad else None
+        dimg = dimg[0] if want_grad else None
     return (out, dcap, dimg) if want_grad else out

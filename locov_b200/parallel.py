@@ -55,51 +55,34 @@ def gather_rows(t: torch.Tensor, group) -> torch.Tensor:
 
 
 class _GatherBlocks(Function):
-    """[B, B_loc] column block per rank -> full [B, B] matrix on every rank.  Backward = this rank's
-    column slice of the (replicated) full gradient: no communication."""
+    """[n, B, B_loc] column blocks per rank -> full [n, B, B] matrices on every rank.  Backward = this
+    rank's column slice of the (replicated) full gradient: no communication."""
 
     @staticmethod
     def forward(ctx, block, group):
         w, r = dist.get_world_size(group), dist.get_rank(group)
-        b, bl = block.shape
-        parts = block.new_empty((w, b, bl))
+        n, b, bl = block.shape
+        parts = block.new_empty((w, n, b, bl))
         dist.all_gather_into_tensor(parts, block.contiguous(), group=group)
         ctx.cols = (r * bl, (r + 1) * bl)
-        return parts.permute(1, 0, 2).reshape(b, w * bl).contiguous()
+        return parts.permute(1, 2, 0, 3).reshape(n, b, w * bl).contiguous()
 
     @staticmethod
     def backward(ctx, g):
         c0, c1 = ctx.cols
-        return g[:, c0:c1].contiguous(), None
+        return g[:, :, c0:c1].contiguous(), None
 
 
 def assemble_blocks(block, group):
     return _GatherBlocks.apply(block, group)
 
 
-def global_pair_outputs(head, w2r_blk, r2w_blk, cap_mask_all, reg_mask_loc, group):
-    """Blocks -> (other_info, losses, dists) on the full matrix; shared by the CUDA path and the
-    gloo/CPU test of the exchange logic (``pair_fn`` decides who evaluates the losses)."""
+def global_pair_outputs(head, blocks, cap_mask_all, reg_mask_loc, group):
+    """[2, B, B_loc] blocks -> (losses, other_info, dists) on the full matrices; shared by the CUDA path
+    and the gloo/CPU test of the exchange logic (``head._pair_outputs`` evaluates the losses)."""
     reg_mask_all = gather_rows(reg_mask_loc, group)
-    losses, info, dists = {}, {}, {}
-    for key, blk in (("w2r", w2r_blk), ("r2w", r2w_blk)):
-        if blk is None:
-            continue
-        full = assemble_blocks(blk, group)
-        pw_g, out4 = head._pair_fn(full, cap_mask_all, reg_mask_all)
-        pw_cost = full + (pw_g - full).detach() if full.requires_grad else pw_g
-        dists[key] = pw_cost
-        name = _NAMES[key]
-        if head.loss_type == "cross_entropy":
-            losses[f"CE_loss (Align {name}, Choose Caption)"] = out4[0]
-            losses[f"CE_loss (Align {name}, Choose Image)"] = out4[1]
-        else:
-            cap_l, img_l = head._triplet(pw_cost)
-            losses[f"Triplet Loss (Align {name}, Choose Caption)"] = cap_l
-            losses[f"Triplet Loss (Align {name}, Choose Image)"] = img_l
-        info[f"Batch Accuracy (Align {name}, Choose Caption)"] = out4[2].detach()
-        info[f"Batch Accuracy (Align {name}, Choose Image)"] = out4[3].detach()
-    return info, losses, dists
+    full = assemble_blocks(blocks, group)
+    return head._pair_outputs(full, cap_mask_all, reg_mask_all)
 
 
 class _ShardedLsm(Function):
@@ -129,34 +112,35 @@ class _ShardedLsm(Function):
         _, emb_op = ops.linear_fwd(x_op, w_op, b, want_f32=False, n_bf16=d, accurate_out=acc)
         main.wait_stream(side)
         cap_all = ops.Bf16Operand(hi_all, lo_all, hi_all.shape[0], d)
-        w2r, r2w = ops.lsm_pair(cap_all, mask_all, emb_op, reg_mask, inv_temp, alignment, want_w2r, want_r2w)
-        ctx.ops_saved = (x_op, emb_op, cap_all)
+        stack = LF.new_pair_stack(hi_all.shape[0] // t, bi, dev, want_w2r and want_r2w)
+        ops.lsm_pair(cap_all, mask_all, emb_op, reg_mask, inv_temp, alignment, want_w2r, want_r2w, stack[0], stack[1])
+        ctx.ops_saved = (emb_op, cap_all)
         ctx.save_for_backward(feats, w, mask_all, reg_mask)
-        ctx.meta = (inv_temp, alignment, precision, b is not None)
-        outs = tuple(o if o is not None else feats.new_zeros(()) for o in (w2r, r2w))
-        ctx.mark_non_differentiable(mask_all, *[o for o, want in zip(outs, (want_w2r, want_r2w)) if not want])
-        return outs + (mask_all,)
+        ctx.meta = (inv_temp, alignment, precision, b is not None, want_w2r, want_r2w)
+        ctx.mark_non_differentiable(mask_all)
+        return stack, mask_all
 
     @staticmethod
-    def backward(ctx, g_w2r, g_r2w, _gm):
+    def backward(ctx, g, _gm):
         feats, w, mask_all, reg_mask = ctx.saved_tensors
-        x_op, emb_op, cap_all = ctx.ops_saved
-        inv_temp, alignment, precision, has_b = ctx.meta
+        emb_op, cap_all = ctx.ops_saved
+        inv_temp, alignment, precision, has_b, want_w2r, want_r2w = ctx.meta
         acc = LF._acc(precision)
         bi, rg, v = feats.shape
         if ctx.needs_input_grad[3]:
             raise NotImplementedError("sharded LSM: caption embeddings are frozen inputs (LANGUAGE_BACKBONE.FREEZE); "
                                       "a reduce-scatter of d(captions) is not implemented")
+        g = g.contiguous()
         demb, _ = ops.lsm_pair_bwd(cap_all, mask_all, emb_op, reg_mask, inv_temp, alignment,
-                                   g_w2r if g_w2r is not None and g_w2r.dim() == 2 else None,
-                                   g_r2w if g_r2w is not None and g_r2w.dim() == 2 else None, False)
+                                   g[0] if want_w2r else None, g[1] if want_r2w else None, False)
         dx = dw = db = None
+        g_op = ops.split_bf16(demb, acc)
         if ctx.needs_input_grad[0]:
-            dx, _ = ops.linear_fwd(ops.split_bf16(demb, acc), LF.weight_operand(w, acc, transpose=True), None, want_f32=True)
+            dx, _ = ops.linear_fwd(g_op, LF.weight_operand(w, acc, transpose=True), None, want_f32=True)
             dx = dx.reshape(bi, rg, v)
         if ctx.needs_input_grad[1]:
-            dw, _ = ops.linear_fwd(ops.split_bf16(demb, acc, transpose=True),
-                                   ops.split_bf16(feats.reshape(bi * rg, v), acc, transpose=True), None, want_f32=True)
+            x_op = ops.split_bf16(feats.reshape(bi * rg, v), acc)
+            dw, _ = ops.linear_fwd(ops.transpose_operand(g_op), ops.transpose_operand(x_op), None, want_f32=True)
         if has_b and ctx.needs_input_grad[2]:
             db = demb.sum(0)
         return dx, dw, db, None, None, None, None, None, None, None, None, None
@@ -165,15 +149,11 @@ class _ShardedLsm(Function):
 def sharded_grounding_forward(head, region_features, region_mask, caption_emb, caption_mask):
     group = head.process_group
     amode = {"softmax": ops.ALIGN_SOFTMAX, "hardmax": ops.ALIGN_HARDMAX}[head.alignment]
-    w2r, r2w, mask_all = _ShardedLsm.apply(
+    blocks, mask_all = _ShardedLsm.apply(
         region_features.to(torch.float32).contiguous(), head.v2l_projection.weight, head.v2l_projection.bias,
         caption_emb.to(torch.float32).contiguous(), caption_mask, region_mask, 1.0 / float(head.temperature), amode,
         head.precision, bool(head.align_words), bool(head.align_regions), group)
-    head._pair_fn = lambda full, cm, rm: LF.pair_losses(full, cm, rm, 0)
-    info, losses, dists = global_pair_outputs(head, w2r if head.align_words else None, r2w if head.align_regions else None,
-                                              mask_all, region_mask, group)
-    for key, pw in dists.items():
-        head.log(f"global_dist_{key}", pw)
+    losses, info, dists = global_pair_outputs(head, blocks, mask_all, region_mask, group)
     head.log_dict(losses)
     head.log_dict(info)
     if head.return_dist:

@@ -96,3 +96,50 @@ def test_large_batch_properties(cuda_device):
     _, _, ref = lsm_head.grounding_head_forward({k: v[c] for k, v in ii.items()}, {k: v[c] for k, v in ic.items()}, w, b, dtype=torch.float64)
     for k in ("w2r", "r2w"):
         assert relerr(full[k][c, c].cpu(), ref[k]) < 1e-4
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 3e-4), ("bf16", 4e-2)])
+@pytest.mark.parametrize("alignment", ["softmax", "hardmax"])
+@pytest.mark.parametrize("B,Rg,T,kw", [(6, 37, 11, dict(ragged_regions=True)), (5, 100, 20, dict(empty_caption=1, empty_image=3)),
+                                        (3, 100, 70, dict(ragged_regions=True))])
+def test_backward_matches_autograd_of_the_oracle(cuda_device, precision, tol, alignment, B, Rg, T, kw):
+    """d(sum of the 4 CE losses)/d(region_features, W, b, caption embeddings) vs torch autograd through the
+    fp64 oracle — the gradients PyTorch derives for the reference module."""
+    if alignment == "hardmax" and precision == "bf16":
+        pytest.skip("hardmax is an argmax: bf16 rounding may legitimately flip near-ties")
+    V, D = 192, 256
+    ii, ic, w, b = lsm_head.make_lsm_inputs(B=B, Rg=Rg, T=T, V=V, D=D, seed=B * 7 + T, gain=8.0, **kw)
+    head = _head(cuda_device, V, D, w, b, precision, alignment=alignment).train()
+    feats = ii["region_features"].to(cuda_device).requires_grad_(True)
+    cap = ic["input_embeddings"].to(cuda_device).requires_grad_(True)
+    iid = dict(_to(ii, cuda_device), region_features=feats)
+    icd = dict(_to(ic, cuda_device), input_embeddings=cap)
+    info, losses, dists = head(iid, icd)
+    weights = [1.0, 0.7, 1.3, 0.4]
+    total = sum(wt * l for wt, l in zip(weights, losses.values()))
+    total.backward()
+    # oracle
+    fr = ii["region_features"].double().requires_grad_(True)
+    cr = ic["input_embeddings"].double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    _, rl, _ = lsm_head.grounding_head_forward(dict(ii, region_features=fr), dict(ic, input_embeddings=cr), wr, br,
+                                               alignment=alignment, dtype=torch.float64)
+    assert list(rl) == list(losses)
+    rtotal = sum(wt * l for wt, l in zip(weights, rl.values()))
+    rtotal.backward()
+    assert relerr(total.detach().cpu(), rtotal.detach()) < tol
+    assert relerr(feats.grad.cpu(), fr.grad) < tol * 3
+    assert relerr(head.v2l_projection.weight.grad.cpu(), wr.grad) < tol * 3
+    assert relerr(head.v2l_projection.bias.grad.cpu(), br.grad) < tol * 3
+    assert relerr(cap.grad.cpu(), cr.grad) < tol * 3
+
+
+def test_masks_kernel(cuda_device):
+    from locov_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    att = torch.randint(0, 2, (9, 13), generator=g)
+    spe = torch.randint(0, 2, (9, 13), generator=g)
+    for reg in (torch.randint(0, 2, (9, 21), generator=g).to(torch.uint8), torch.randint(0, 2, (9, 21), generator=g).float(),
+                torch.randint(0, 2, (9, 21), generator=g)):
+        cm, rm = ops.lsm_masks(att.to(cuda_device), spe.to(cuda_device), reg.to(cuda_device))
+        assert torch.equal(cm.cpu(), lsm_head.caption_mask_of(att, spe)) and torch.equal(rm.cpu(), reg.float())

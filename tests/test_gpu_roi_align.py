@@ -57,7 +57,7 @@ def test_sampling_grid_bit_exact(cuda_device, ps, scale, hw):
         assert np.array_equal(a.view(np.uint32), yx2.view(np.uint32)), f"roi {r}: coordinates differ"
         assert np.array_equal(b, idx2), f"roi {r}: tap indices differ"
         checked += a.shape[0]
-    assert checked > 50000
+    assert checked > 15000
 
 
 @pytest.mark.parametrize("layout", ["nchw", "nhwc"])
