@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
     float *red = sm;                 // [32]
     float *cap_empty = sm + 32;      // [Bc] 1 if the caption has no valid word
     float *img_empty = cap_empty + Bc;   // [Bi]
-    float *acc = img_empty + Bi;     // [4][32] per-warp partial sums: ce_cap, acc_cap, ce_img, acc_img
+    float *acc = img_empty + Bi;     // [4][32] per-warp partial sums: ce_cap, ce_img, acc_cap, acc_img (= out4 order)
     float *pw = pw_all + (int64_t)blockIdx.x * mat_stride;
     float *out4 = out4_all + 4 * blockIdx.x;
     float *dcap = dcap_all ? dcap_all + (int64_t)blockIdx.x * Bc * Bi : nullptr;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
         const int tgt = i + diag_off;
         if (lane == 0 && tgt < Bc) {
             acc[0 * 32 + warp] += (m + logf(s)) + pw[(int64_t)tgt * ld + i];
-            acc[1 * 32 + warp] += (arg == tgt) ? 1.f : 0.f;
+            acc[2 * 32 + warp] += (arg == tgt) ? 1.f : 0.f;
         }
         if (dcap != nullptr) {
             // d/dpw[c,i] of mean_i( lse_c(-pw[:,i]) + pw[tgt,i] ); guard-filled entries are constants
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
             for (int i = lane; i < Bi; i += 32) s += expf(-pw[(int64_t)c * ld + i] - m);
             s = warp_sum(s);
             if (lane == 0) {
-                acc[2 * 32 + warp] += (m + logf(s)) + pw[(int64_t)c * ld + k];
+                acc[1 * 32 + warp] += (m + logf(s)) + pw[(int64_t)c * ld + k];
                 acc[3 * 32 + warp] += (arg == k) ? 1.f : 0.f;
             }
         }

@@ -38,6 +38,11 @@ struct TcCore {
     int acc_stages;     // TMEM accumulator buffers (1 or 2)
     int tmem_cols;      // allocation: power of two >= 32
     int epi_smem;       // bytes of epilogue scratch
+    // thread-block cluster with TMA multicast (cm x cn CTAs; 1 x 1 = no cluster): CTA (rm, rn) computes tile
+    // (tile_m0 + rm, tile_n0 + rn); the A tile of a row is shared by its cn CTAs (each loads 1/cn of it and
+    // multicasts), the B tile of a column by its cm CTAs — L2->SM operand traffic drops by the same factors.
+    int cm, cn;
+    int clusters_n;     // clusters along the virtual tile grid's n axis (virtual tiles_n = clusters_n * cn)
 };
 
 __host__ __device__ inline int tc_round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -58,10 +63,12 @@ inline size_t tc_finalize(TcCore &core, int K, int passes, int chunks, int epi_s
     if (core.acc_stages * core.block_n > 512) core.acc_stages = 1;
     core.tmem_cols = tc_tmem_cols(core.block_n, core.acc_stages);
     core.epi_smem = epi_smem;
+    if (core.cm < 1) core.cm = 1;
+    if (core.cn < 1) core.cn = 1;
     const size_t stage_bytes = TC_A_BYTES + (size_t)core.block_n * 128;
     const size_t fixed = 1024 /*alignment slack*/ + 512 /*barriers*/ + (size_t)epi_smem;
-    int stages = (int)((110 * 1024 - fixed) / stage_bytes);          // two CTAs per SM when possible
-    if (stages < 3) stages = (int)((225 * 1024 - fixed) / stage_bytes);
+    int stages = (int)(((long long)110 * 1024 - (long long)fixed) / (long long)stage_bytes);   // two CTAs per SM when possible
+    if (stages < 3) stages = (int)(((long long)225 * 1024 - (long long)fixed) / (long long)stage_bytes);
     const int total_iters = core.num_k_blocks * passes * chunks;
     if (stages > 6) stages = 6;
     if (stages > total_iters) stages = total_iters;
@@ -148,10 +155,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    // cluster geometry -> virtual CTA index handed to the epilogue policy
+    const int csize = core.cm * core.cn;
+    int rm = 0, rn = 0, cta = blockIdx.x;
+    uint16_t mask_a = 1, mask_b = 1;
+    if (csize > 1) {
+        const int rank = (int)cluster_ctarank();
+        rm = rank / core.cn;
+        rn = rank - rm * core.cn;
+        const int cluster_id = blockIdx.x / csize;
+        const int tile_m = (cluster_id / core.clusters_n) * core.cm + rm;
+        const int tile_n = (cluster_id % core.clusters_n) * core.cn + rn;
+        cta = tile_m * (core.clusters_n * core.cn) + tile_n;
+        mask_a = (uint16_t)(((1u << core.cn) - 1u) << (rm * core.cn));          // CTAs (rm, *)
+        uint32_t mb = 0;
+        for (int j = 0; j < core.cm; ++j) mb |= 1u << (j * core.cn + rn);        // CTAs (*, rn)
+        mask_b = (uint16_t)mb;
+    }
+
     if (threadIdx.x == 0) {
         for (int s = 0; s < core.stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], (uint32_t)(core.cm + core.cn - 1));   // one release per CTA that reads what this CTA loads
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
@@ -169,10 +194,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)core.tmem_cols);
     tc_fence_before();
-    __syncthreads();
+    if (csize > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers must be initialised before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int cta = blockIdx.x;
     const int iters_per_chunk = core.num_k_blocks * core.passes;
 
     if (warp == 0) {
@@ -188,8 +212,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         mbar_wait(&empty[stage], phase ^ 1u);
                         unsigned char *sa = smem + (size_t)stage * stage_bytes;
                         mbar_arrive_expect_tx(&full[stage], stage_bytes);
-                        tma_load_2d(sa, ma, &full[stage], kb * TC_BLOCK_K, row_a);
-                        tma_load_2d(sa + TC_A_BYTES, mb, &full[stage], kb * TC_BLOCK_K, row_b);
+                        if (csize == 1) {
+                            tma_load_2d(sa, ma, &full[stage], kb * TC_BLOCK_K, row_a);
+                            tma_load_2d(sa + TC_A_BYTES, mb, &full[stage], kb * TC_BLOCK_K, row_b);
+                        } else {
+                            // this CTA's slice of the shared tiles, delivered to every CTA of the row / column
+                            const int a_rows = TC_BLOCK_M / core.cn, b_rows = core.block_n / core.cm;
+                            tma_load_2d_mc(sa + (size_t)rn * a_rows * 128, ma, &full[stage], kb * TC_BLOCK_K, row_a + rn * a_rows, mask_a);
+                            tma_load_2d_mc(sa + TC_A_BYTES + (size_t)rm * b_rows * 128, mb, &full[stage], kb * TC_BLOCK_K,
+                                           row_b + rm * b_rows, mask_b);
+                        }
                         if (++stage == (uint32_t)core.stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -217,7 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);   // +32 B per K=16 step
                         accumulate = 1;
                     }
-                    umma_commit(&empty[stage]);
+                    if (csize == 1) umma_commit(&empty[stage]); else umma_commit_mc(&empty[stage], (uint16_t)(mask_a | mask_b));
                     if (++stage == (uint32_t)core.stages) { stage = 0; phase ^= 1u; }
                 }
                 umma_commit(&tfull[acc]);
@@ -241,7 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         epi.finish(ep, core, cta, row, lane, q, epi_smem);
     }
     tc_fence_before();
-    __syncthreads();
+    if (csize > 1) cluster_sync_all(); else __syncthreads();      // no CTA may exit while peers still signal its barriers
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
@@ -260,7 +292,26 @@ int tc_launch(const TcMaps &maps, const TcCore &core, const typename Epi::Params
         LOCO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         configured = 227 * 1024;
     }
-    tc_gemm_kernel<Epi><<<grid, TC_THREADS, smem_bytes, st>>>(maps, core, ep);
+    if (core.cm * core.cn == 1) {
+        tc_gemm_kernel<Epi><<<grid, TC_THREADS, smem_bytes, st>>>(maps, core, ep);
+    } else {
+        LOCO_REQUIRE(core.cm * core.cn <= 8 && grid % (core.cm * core.cn) == 0, LOCO_E_BADARG, "bad cluster %dx%d for grid %d", core.cm, core.cn, grid);
+        LOCO_REQUIRE(TC_BLOCK_M % core.cn == 0 && (TC_BLOCK_M / core.cn) % 8 == 0 && core.block_n % core.cm == 0 && (core.block_n / core.cm) % 8 == 0,
+                     LOCO_E_BADARG, "cluster %dx%d does not slice a 128x%d tile on 8-row boundaries", core.cm, core.cn, core.block_n);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)(core.cm * core.cn);
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        LOCO_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<Epi>, maps, core, ep));
+    }
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;

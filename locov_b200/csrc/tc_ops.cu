@@ -5,6 +5,7 @@
 //   EpiLsm    : caption×image similarity tile with BOTH attention poolings (word→region, region→word)
 //               from one GEMM; the backward variant emits dS for the dEmb / dCap GEMMs
 #include <cfloat>
+#include <cstdlib>
 
 #include "tc_gemm.cuh"
 
@@ -172,6 +173,7 @@ struct LsmParams {
     uint16_t *ds_hi, *ds_lo;    // dS [Bc*T, Bi*Rg] (ld_ds), optional
     int64_t ld_ds;
     int Bc, T, Bi, Rg;
+    int Bi_pad;                 // images padded to the cluster width: virtual CTA index = g * Bi_pad + i
     int per_tile;               // captions per 128-row tile
     int lds;                    // shared-memory row stride of the tile (floats, odd)
     float inv_temp;
@@ -212,7 +214,7 @@ template <bool BWD>
 struct EpiLsm {
     typedef LsmParams Params;
     static __device__ __forceinline__ void coords(const Params &p, const TcCore &, int cta, int, int &row_a, int &row_b) {
-        const int g = cta / p.Bi, i = cta - g * p.Bi;
+        const int g = cta / p.Bi_pad, i = cta - g * p.Bi_pad;
         row_a = g * p.per_tile * p.T;    // caption word rows (A operand)
         row_b = i * p.Rg;                // region rows of image i (B operand)
     }
@@ -222,7 +224,8 @@ struct EpiLsm {
     __device__ __forceinline__ void chunk(const Params &p, const TcCore &core, int cta, int, uint32_t taddr, int row, int lane,
                                           int q, unsigned char *smem) {
         const LsmSmem sm(smem, p.lds, core.block_n, p.per_tile, p.Rg, BWD);
-        const int g = cta / p.Bi, i = cta - g * p.Bi;
+        const int g = cta / p.Bi_pad, i = cta - g * p.Bi_pad;
+        if (i >= p.Bi || g * p.per_tile >= p.Bc) return;            // padding tile of the cluster grid (CTA-uniform)
         const int et = threadIdx.x - 64;                            // 0..127 among the epilogue threads
         const int c_first = g * p.per_tile;
         const int ncap = max(0, min(p.per_tile, p.Bc - c_first));    // valid captions of this tile
@@ -412,29 +415,56 @@ struct EpiLsm {
 // host-side helpers
 // ------------------------------------------------------------------------------------------------
 static int fill_maps(TcMaps &maps, const uint16_t *a_hi, const uint16_t *a_lo, uint64_t a_rows, uint64_t a_ld,
-                     const uint16_t *b_hi, const uint16_t *b_lo, uint64_t b_rows, uint64_t b_ld, uint64_t K, int block_n) {
+                     const uint16_t *b_hi, const uint16_t *b_lo, uint64_t b_rows, uint64_t b_ld, uint64_t K, const TcCore &core) {
+    // TMA boxes are the per-CTA SLICES of the tiles (the whole tile without a cluster)
+    const uint32_t a_box = (uint32_t)(TC_BLOCK_M / core.cn), b_box = (uint32_t)(core.block_n / core.cm);
     int rc;
-    if ((rc = make_tmap_bf16_2d(&maps.a_hi, a_hi, a_rows, K, a_ld, TC_BLOCK_M)) != LOCO_OK) return rc;
-    if ((rc = make_tmap_bf16_2d(&maps.a_lo, a_lo ? a_lo : a_hi, a_rows, K, a_ld, TC_BLOCK_M)) != LOCO_OK) return rc;
-    if ((rc = make_tmap_bf16_2d(&maps.b_hi, b_hi, b_rows, K, b_ld, (uint32_t)block_n)) != LOCO_OK) return rc;
-    if ((rc = make_tmap_bf16_2d(&maps.b_lo, b_lo ? b_lo : b_hi, b_rows, K, b_ld, (uint32_t)block_n)) != LOCO_OK) return rc;
+    if ((rc = make_tmap_bf16_2d(&maps.a_hi, a_hi, a_rows, K, a_ld, a_box)) != LOCO_OK) return rc;
+    if ((rc = make_tmap_bf16_2d(&maps.a_lo, a_lo ? a_lo : a_hi, a_rows, K, a_ld, a_box)) != LOCO_OK) return rc;
+    if ((rc = make_tmap_bf16_2d(&maps.b_hi, b_hi, b_rows, K, b_ld, b_box)) != LOCO_OK) return rc;
+    if ((rc = make_tmap_bf16_2d(&maps.b_lo, b_lo ? b_lo : b_hi, b_rows, K, b_ld, b_box)) != LOCO_OK) return rc;
     return LOCO_OK;
 }
 
-// BLOCK_N for a plain GEMM: minimise waves * per-tile MMA time.  Per K=16 step a 128xN tile costs
-// max(N/2, 32 + N/4) cycles (tensor pipe vs. shared-memory operand reads; B300_MICROARCH tcgen05 floor).
-static int pick_block_n(int M, int N, int sms) {
-    const int mt = (M + TC_BLOCK_M - 1) / TC_BLOCK_M;
-    int best = 256;
-    double best_cost = 1e30;
-    for (int bn = 256; bn >= 32; bn -= 32) {
-        const int tiles = mt * ((N + bn - 1) / bn);
-        const int waves = (tiles + sms - 1) / sms;
-        const double per = bn / 2.0 > 32 + bn / 4.0 ? bn / 2.0 : 32 + bn / 4.0;
-        const double cost = waves * (per + 6.0);   // +6: fixed per-step issue/barrier overhead
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+// LOCOV_B200_CLUSTER=0 disables thread-block clusters / TMA multicast (debug and A/B measurements).
+static bool clusters_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("LOCOV_B200_CLUSTER");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
-    return best;
+    return v != 0;
+}
+
+// Tile / cluster shape for a plain GEMM [M,K]x[N,K]^T: minimise  waves * k_blocks * max(MMA, L2)  per tile with
+//   MMA  = 4 * BLOCK_N/2 cycles per 64-wide k block (128 x BLOCK_N x 16 MACs at 4096 MAC/cycle/SM),
+//   L2   = operand bytes this CTA pulls per k block * concurrently running CTAs / ~3400 B/cycle  — the L2 -> SM
+//          fabric of a B200 moves about as much as HBM (profiles/README.md), so operand re-reads, not the tensor
+//          pipe, bound these GEMMs unless tiles are shared through TMA multicast.
+static void pick_gemm_shape(int M, int N, int sms, TcCore &core) {
+    const int mt = (M + TC_BLOCK_M - 1) / TC_BLOCK_M;
+    double best_cost = 1e300;
+    const int cms[2] = {1, 2}, cns[3] = {1, 2, 4};
+    for (int ci = 0; ci < 2; ++ci)
+        for (int cj = 0; cj < 3; ++cj) {
+            const int cm = cms[ci], cn = cns[cj];
+            if (cm * cn > 1 && !clusters_enabled()) continue;
+            for (int bn = 256; bn >= 32; bn -= 16) {
+                if ((bn / cm) % 8 != 0 || bn % cm != 0) continue;
+                const int tm = tc_round_up(mt, cm), tn = tc_round_up((N + bn - 1) / bn, cn);
+                if (cm > 1 && mt < cm) continue;
+                if (cn > 1 && (N + bn - 1) / bn < cn) continue;
+                const int ctas = tm * tn, csize = cm * cn;
+                const int slots = (sms / csize) * csize;
+                const int waves = (ctas + slots - 1) / slots;
+                const int active = ctas < slots ? ctas : slots;
+                const double mma = 4.0 * bn / 2.0;
+                const double l2 = (128.0 * 128.0 / cn + bn * 128.0 / cm) * active / 3400.0;
+                const double cost = waves * ((mma > l2 ? mma : l2) + 24.0) + 1e-3 * csize;
+                if (cost < best_cost) { best_cost = cost; core.block_n = bn; core.cm = cm; core.cn = cn; }
+            }
+        }
+    core.clusters_n = tc_round_up((N + core.block_n - 1) / core.block_n, core.cn) / core.cn;
 }
 
 }  // namespace loco
@@ -457,17 +487,17 @@ int loco_linear_fwd(const uint16_t *A_hi, const uint16_t *A_lo, int64_t lda, con
         LOCO_REQUIRE((reinterpret_cast<uintptr_t>(out_hi) & 15) == 0 && (!out_lo || (reinterpret_cast<uintptr_t>(out_lo) & 15) == 0), LOCO_E_ALIGN, "linear_fwd: bf16 outputs must be 16-byte aligned");
         LOCO_REQUIRE(n_bf16 % 2 == 0 || ld_bf16 > n_bf16, LOCO_E_ALIGN, "linear_fwd: odd n_bf16 needs a padded ld_bf16");
     }
-    TcCore core;
-    core.block_n = pick_block_n(M, N, current_device_sm_count());
+    TcCore core = {};
+    pick_gemm_shape(M, N, current_device_sm_count(), core);
     const size_t smem = tc_finalize(core, K, A_lo ? 3 : 1, 1, 4 * TC_WARP_SCRATCH_WORDS * 4);
     TcMaps maps;
-    int rc = fill_maps(maps, A_hi, A_lo, M, lda, W_hi, W_lo, N, ldw, K, core.block_n);
+    int rc = fill_maps(maps, A_hi, A_lo, M, lda, W_hi, W_lo, N, ldw, K, core);
     if (rc != LOCO_OK) return rc;
     EpiLinear::Params p;
     p.bias = bias; p.out_f32 = out_f32; p.ld_f32 = ld_f32; p.out_hi = out_hi; p.out_lo = out_lo;
     p.n_bf16 = out_hi ? n_bf16 : 0; p.ld_bf16 = ld_bf16; p.M = M; p.N = N;
-    p.tiles_n = (N + core.block_n - 1) / core.block_n;
-    const int grid = ((M + TC_BLOCK_M - 1) / TC_BLOCK_M) * p.tiles_n;
+    p.tiles_n = core.clusters_n * core.cn;                                      // virtual (padded) tile grid
+    const int grid = tc_round_up((M + TC_BLOCK_M - 1) / TC_BLOCK_M, core.cm) * p.tiles_n;
     return tc_launch<EpiLinear>(maps, core, p, grid, smem, static_cast<cudaStream_t>(stream));
 }
 
@@ -479,13 +509,13 @@ int loco_box_score_fwd(const uint16_t *E_hi, const uint16_t *E_lo, int64_t lde, 
     LOCO_REQUIRE(E_hi && C_hi && logits, LOCO_E_BADARG, "box_score_fwd: null pointer");
     LOCO_REQUIRE((E_lo == nullptr) == (C_lo == nullptr), LOCO_E_BADARG, "box_score_fwd: E_lo and C_lo must both be given or both be NULL");
     LOCO_REQUIRE(ld_logits >= K1, LOCO_E_BADARG, "box_score_fwd: ld_logits < K1");
-    TcCore core;
+    TcCore core = {};
     // one N tile when the class list fits (<= 256), otherwise 256-wide chunks with online softmax
     core.block_n = K1 <= 256 ? tc_round_up(K1, 32) : 256;
     const int chunks = (K1 + core.block_n - 1) / core.block_n;
     const size_t smem = tc_finalize(core, D, E_lo ? 3 : 1, chunks, 4 * TC_WARP_SCRATCH_WORDS * 4);
     TcMaps maps;
-    int rc = fill_maps(maps, E_hi, E_lo, R, lde, C_hi, C_lo, K1, ldc, D, core.block_n);
+    int rc = fill_maps(maps, E_hi, E_lo, R, lde, C_hi, C_lo, K1, ldc, D, core);
     if (rc != LOCO_OK) return rc;
     EpiScore::Params p;
     p.bias = cls_bias; p.logits = logits; p.probs = probs; p.ld = ld_logits; p.lse = lse; p.argmax_fg = argmax_fg;
@@ -505,20 +535,28 @@ static int lsm_launch(bool bwd, const uint16_t *cap_hi, const uint16_t *cap_lo, 
     LOCO_REQUIRE(p.T <= 128 && p.Rg <= 256, LOCO_E_UNSUPPORTED, "lsm_pair: supports T <= 128 words and Rg <= 256 regions (got T=%d Rg=%d)", p.T, p.Rg);
     LOCO_REQUIRE(cap_hi && emb_hi && p.cap_mask && p.reg_mask, LOCO_E_BADARG, "lsm_pair: null pointer");
     LOCO_REQUIRE((cap_lo == nullptr) == (emb_lo == nullptr), LOCO_E_BADARG, "lsm_pair: cap_lo and emb_lo must both be given or both be NULL");
-    TcCore core;
+    TcCore core = {};
     core.block_n = tc_round_up(p.Rg, 16);
     p.per_tile = TC_BLOCK_M / p.T;
     if (p.per_tile > LSM_MAX_PER_TILE) p.per_tile = LSM_MAX_PER_TILE;
     if (p.per_tile > p.Bc) p.per_tile = p.Bc;
     p.lds = core.block_n | 1;
-    const int groups = (p.Bc + p.per_tile - 1) / p.per_tile;
+    int groups = (p.Bc + p.per_tile - 1) / p.per_tile;
+    // cluster = cm caption groups x cn images: the caption tile is multicast to the cn image CTAs of its row, the
+    // region tile of an image to the cm caption-group CTAs of its column
+    core.cm = (clusters_enabled() && groups >= 2) ? 2 : 1;
+    core.cn = (clusters_enabled() && p.Bi >= 4) ? 4 : ((clusters_enabled() && p.Bi >= 2) ? 2 : 1);
+    groups = tc_round_up(groups, core.cm);
+    p.Bi_pad = tc_round_up(p.Bi, core.cn);
+    core.clusters_n = p.Bi_pad / core.cn;
     const size_t epi = lsm_epi_smem_bytes(p.lds, core.block_n, p.per_tile, p.Rg, bwd);
     const size_t smem = tc_finalize(core, D, cap_lo ? 3 : 1, 1, (int)epi);
     TcMaps maps;
-    int rc = fill_maps(maps, cap_hi, cap_lo, (uint64_t)p.Bc * p.T, ldcap, emb_hi, emb_lo, (uint64_t)p.Bi * p.Rg, ldemb, D, core.block_n);
+    int rc = fill_maps(maps, cap_hi, cap_lo, (uint64_t)p.Bc * p.T, ldcap, emb_hi, emb_lo, (uint64_t)p.Bi * p.Rg, ldemb, D, core);
     if (rc != LOCO_OK) return rc;
-    LOCO_REQUIRE((long long)groups * p.Bi < (1ll << 31), LOCO_E_UNSUPPORTED, "lsm_pair: too many tiles");
-    return bwd ? tc_launch<EpiLsm<true>>(maps, core, p, groups * p.Bi, smem, st) : tc_launch<EpiLsm<false>>(maps, core, p, groups * p.Bi, smem, st);
+    LOCO_REQUIRE((long long)groups * p.Bi_pad < (1ll << 31), LOCO_E_UNSUPPORTED, "lsm_pair: too many tiles");
+    const int grid = groups * p.Bi_pad;
+    return bwd ? tc_launch<EpiLsm<true>>(maps, core, p, grid, smem, st) : tc_launch<EpiLsm<false>>(maps, core, p, grid, smem, st);
 }
 
 int loco_lsm_pair_fwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ldcap, const float *cap_mask,

@@ -54,3 +54,11 @@ def golden_lsm(name):
             assert np.allclose(cs, z["checksum_" + key], rtol=1e-9), f"seeded input {key} drifted from the golden run"
     exp = {k: z[k] for k in z.files if k.startswith(("loss::", "info::", "dist::"))}
     return ii, ic, w, b, cfg_kw, exp
+
+
+def frob_relerr(a, b):
+    """||a-b||_F / ||b||_F — used for bf16 GRADIENTS, where a max-norm is dominated by the legitimate sign
+    flips of the L1 box loss at its kink (smooth_l1 beta = 0) and by argmax ties."""
+    a = torch.as_tensor(a).double()
+    b = torch.as_tensor(b).double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
