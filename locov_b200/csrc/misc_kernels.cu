@@ -173,6 +173,9 @@ __device__ __forceinline__ float block_reduce_sum(float v, float *red) {
 
 // One CTA per pair matrix (blockIdx.x), warp-parallel: a warp owns a column (choose caption) or a row
 // (choose image) at a time, lanes stride over the other index, all reductions by shuffles in a fixed order.
+// STAGED: the matrix is copied to shared memory once (one global round trip, overlapped with the mask loads)
+// and every later pass runs from there; matrices too large for shared memory are walked in global memory.
+template <bool STAGED>
 __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_all, int64_t mat_stride, int64_t ld, int Bc, int Bi,
                                                        int diag_off, const float *__restrict__ cap_mask, int T,
                                                        const float *__restrict__ reg_mask, int Rg, float *__restrict__ out4_all,
@@ -182,13 +185,23 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
     float *cap_empty = sm + 32;      // [Bc] 1 if the caption has no valid word
     float *img_empty = cap_empty + Bc;   // [Bi]
     float *acc = img_empty + Bi;     // [4][32] per-warp partial sums: ce_cap, ce_img, acc_cap, acc_img (= out4 order)
+    float *tile = acc + 128;         // [Bc][Bi + 1] when STAGED
     float *pw = pw_all + (int64_t)blockIdx.x * mat_stride;
     float *out4 = out4_all + 4 * blockIdx.x;
     float *dcap = dcap_all ? dcap_all + (int64_t)blockIdx.x * Bc * Bi : nullptr;
     float *dimg = dimg_all ? dimg_all + (int64_t)blockIdx.x * Bc * Bi : nullptr;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+    const int64_t mld = STAGED ? (Bi + 1) : ld;      // row stride of the matrix the passes read
+    float *mat = STAGED ? tile : pw;
 
+    float mx = -FLT_MAX;
+    for (int idx = tid; idx < Bc * Bi; idx += nt) {
+        const int c = idx / Bi, i = idx - c * Bi;
+        const float v = pw[(int64_t)c * ld + i];
+        if (STAGED) tile[c * (Bi + 1) + i] = v;
+        mx = fmaxf(mx, v);
+    }
     for (int c = warp; c < Bc; c += nwarp) {
         float s = 0.f;
         for (int t = lane; t < T; t += 32) s += cap_mask[(int64_t)c * T + t];
@@ -203,12 +216,13 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
     }
     if (tid < 128) acc[tid] = 0.f;
     // empty-pair guard (grounding_head.py:240-251): max over the whole matrix, then overwrite
-    float mx = -FLT_MAX;
-    for (int idx = tid; idx < Bc * Bi; idx += nt) mx = fmaxf(mx, pw[(int64_t)(idx / Bi) * ld + idx % Bi]);
-    mx = block_reduce_max(mx, red);            // (contains the __syncthreads that publish cap_empty / img_empty)
+    mx = block_reduce_max(mx, red);            // (contains the __syncthreads that publish tile / cap_empty / img_empty)
     for (int idx = tid; idx < Bc * Bi; idx += nt) {
-        const int c = idx / Bi, i = idx % Bi;
-        if (cap_empty[c] > 0.f && img_empty[i] > 0.f) pw[(int64_t)c * ld + i] = mx + 100.0f;
+        const int c = idx / Bi, i = idx - c * Bi;
+        if (cap_empty[c] > 0.f && img_empty[i] > 0.f) {
+            pw[(int64_t)c * ld + i] = mx + 100.0f;
+            if (STAGED) tile[c * (Bi + 1) + i] = mx + 100.0f;
+        }
     }
     __syncthreads();
     const float inv = 1.0f / (float)Bi;
@@ -218,7 +232,7 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
         float m = -FLT_MAX, best = FLT_MAX;
         int arg = 0x7fffffff;
         for (int c = lane; c < Bc; c += 32) {
-            const float v = pw[(int64_t)c * ld + i];
+            const float v = mat[(int64_t)c * mld + i];
             m = fmaxf(m, -v);
             if (v < best) { best = v; arg = c; }
         }
@@ -230,11 +244,11 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
             if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
         }
         float s = 0.f;
-        for (int c = lane; c < Bc; c += 32) s += expf(-pw[(int64_t)c * ld + i] - m);
+        for (int c = lane; c < Bc; c += 32) s += expf(-mat[(int64_t)c * mld + i] - m);
         s = warp_sum(s);
         const int tgt = i + diag_off;
         if (lane == 0 && tgt < Bc) {
-            acc[0 * 32 + warp] += (m + logf(s)) + pw[(int64_t)tgt * ld + i];
+            acc[0 * 32 + warp] += (m + logf(s)) + mat[(int64_t)tgt * mld + i];
             acc[2 * 32 + warp] += (arg == tgt) ? 1.f : 0.f;
         }
         if (dcap != nullptr) {
@@ -242,7 +256,7 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
             for (int c = lane; c < Bc; c += 32) {
                 float g = 0.f;
                 if (tgt < Bc && !(cap_empty[c] > 0.f && img_empty[i] > 0.f))
-                    g = (((c == tgt) ? 1.f : 0.f) - expf(-pw[(int64_t)c * ld + i] - m) / s) * inv;
+                    g = (((c == tgt) ? 1.f : 0.f) - expf(-mat[(int64_t)c * mld + i] - m) / s) * inv;
                 dcap[(int64_t)c * Bi + i] = g;
             }
         }
@@ -256,7 +270,7 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
         int arg = 0x7fffffff;
         if (has) {
             for (int i = lane; i < Bi; i += 32) {
-                const float v = pw[(int64_t)c * ld + i];
+                const float v = mat[(int64_t)c * mld + i];
                 m = fmaxf(m, -v);
                 if (v < best) { best = v; arg = i; }
             }
@@ -267,10 +281,10 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
                 const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
                 if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
             }
-            for (int i = lane; i < Bi; i += 32) s += expf(-pw[(int64_t)c * ld + i] - m);
+            for (int i = lane; i < Bi; i += 32) s += expf(-mat[(int64_t)c * mld + i] - m);
             s = warp_sum(s);
             if (lane == 0) {
-                acc[1 * 32 + warp] += (m + logf(s)) + pw[(int64_t)c * ld + k];
+                acc[1 * 32 + warp] += (m + logf(s)) + mat[(int64_t)c * mld + k];
                 acc[3 * 32 + warp] += (arg == k) ? 1.f : 0.f;
             }
         }
@@ -278,7 +292,7 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
             for (int i = lane; i < Bi; i += 32) {
                 float g = 0.f;
                 if (has && !(cap_empty[c] > 0.f && img_empty[i] > 0.f))
-                    g = (((i == k) ? 1.f : 0.f) - expf(-pw[(int64_t)c * ld + i] - m) / s) * inv;
+                    g = (((i == k) ? 1.f : 0.f) - expf(-mat[(int64_t)c * mld + i] - m) / s) * inv;
                 dimg[(int64_t)c * Bi + i] = g;
             }
         }
@@ -377,13 +391,25 @@ int loco_pair_ce(float *pw, int nmat, int64_t mat_stride, int64_t ld, int Bc, in
     LOCO_REQUIRE(Bc > 0 && Bi > 0 && ld >= Bi && T > 0 && Rg > 0 && diag_offset >= 0 && nmat >= 1, LOCO_E_BADARG,
                  "pair_ce: bad shape nmat=%d Bc=%d Bi=%d ld=%lld", nmat, Bc, Bi, (long long)ld);
     LOCO_REQUIRE(pw && cap_mask && reg_mask && out4, LOCO_E_BADARG, "pair_ce: null pointer");
-    const size_t smem = (32 + (size_t)Bc + Bi + 128) * sizeof(float);
-    LOCO_REQUIRE(smem <= 48 * 1024, LOCO_E_UNSUPPORTED, "pair_ce: batch too large (Bc=%d Bi=%d)", Bc, Bi);
+    const size_t base = (32 + (size_t)Bc + Bi + 128) * sizeof(float);
+    LOCO_REQUIRE(base <= 48 * 1024, LOCO_E_UNSUPPORTED, "pair_ce: batch too large (Bc=%d Bi=%d)", Bc, Bi);
+    const size_t staged = base + (size_t)Bc * (Bi + 1) * sizeof(float);
     int threads = 32 * (Bc > Bi ? Bc : Bi);
     if (threads > 1024) threads = 1024;
     if (threads < 128) threads = 128;
-    pair_ce_kernel<<<nmat, threads, smem, static_cast<cudaStream_t>(stream)>>>(pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T,
-                                                                               reg_mask, Rg, out4, dpw_caption, dpw_image);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (staged <= 200 * 1024) {
+        static thread_local size_t configured = 0;
+        if (staged > 48 * 1024 && staged > configured) {
+            LOCO_CUDA(cudaFuncSetAttribute(pair_ce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured = 200 * 1024;
+        }
+        pair_ce_kernel<true><<<nmat, threads, staged, st>>>(pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T, reg_mask, Rg, out4,
+                                                            dpw_caption, dpw_image);
+    } else {
+        pair_ce_kernel<false><<<nmat, threads, base, st>>>(pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T, reg_mask, Rg, out4,
+                                                           dpw_caption, dpw_image);
+    }
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;

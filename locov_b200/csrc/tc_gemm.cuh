@@ -15,6 +15,8 @@
 // BLOCK_N, the pipeline depth and the pass count are run-time values (the UMMA instruction descriptor
 // and the TMA boxes are built from them), so a single instantiation per epilogue serves all shapes.
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace loco {
@@ -71,6 +73,7 @@ inline size_t tc_finalize(TcCore &core, int K, int passes, int chunks, int epi_s
     if (stages < 3) stages = (int)(((long long)225 * 1024 - (long long)fixed) / (long long)stage_bytes);
     const int total_iters = core.num_k_blocks * passes * chunks;
     if (stages > 6) stages = 6;
+    if (const char *e = getenv("LOCOV_B200_STAGES")) { const int v = atoi(e); if (v >= 1 && v < stages) stages = v; }   // developer sweep knob
     if (stages > total_iters) stages = total_iters;
     if (stages < 1) stages = 1;
     core.stages = stages;

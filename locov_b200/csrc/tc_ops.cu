@@ -464,6 +464,10 @@ static void pick_gemm_shape(int M, int N, int sms, TcCore &core) {
                 if (cost < best_cost) { best_cost = cost; core.block_n = bn; core.cm = cm; core.cn = cn; }
             }
         }
+    // developer overrides for shape sweeps (scripts/gemm_sweep.py): LOCOV_B200_BN / _CM / _CN
+    if (const char *e = getenv("LOCOV_B200_BN")) { const int v = atoi(e); if (v >= 16 && v <= 256 && v % 16 == 0) core.block_n = v; }
+    if (const char *e = getenv("LOCOV_B200_CM")) { const int v = atoi(e); if (v == 1 || v == 2) core.cm = v; }
+    if (const char *e = getenv("LOCOV_B200_CN")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) core.cn = v; }
     core.clusters_n = tc_round_up((N + core.block_n - 1) / core.block_n, core.cn) / core.cn;
 }
 

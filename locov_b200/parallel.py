@@ -62,10 +62,10 @@ class _GatherBlocks(Function):
     def forward(ctx, block, group):
         w, r = dist.get_world_size(group), dist.get_rank(group)
         n, b, bl = block.shape
-        parts = block.new_empty((w, n, b, bl))
+        parts = block.new_empty((w * n, b, bl))           # dim-0 concatenation (the layout every backend accepts)
         dist.all_gather_into_tensor(parts, block.contiguous(), group=group)
         ctx.cols = (r * bl, (r + 1) * bl)
-        return parts.permute(1, 2, 0, 3).reshape(n, b, w * bl).contiguous()
+        return parts.view(w, n, b, bl).permute(1, 2, 0, 3).reshape(n, b, w * bl).contiguous()
 
     @staticmethod
     def backward(ctx, g):
