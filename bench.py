@@ -251,17 +251,27 @@ def run_b200(args):
     emb_ops = [ops.linear_fwd(x_ops[i], w_op, head.v2l_projection.bias.detach(), want_f32=False, n_bf16=D, accurate_out=acc)[1] for i in range(4)]
     pw = torch.randn(2, b_glob, b_glob, device=dev)
 
-    def time_kernel(fn, iters=100):
-        for i in range(5):
+    def time_kernel(fn, iters=24, reps=5):
+        """Average device time of ONE launch: `iters` launches (rotating operands) captured in a CUDA graph so that
+        host launch overhead (longer than these kernels) is not in the number; best of `reps` replays."""
+        for i in range(3):
             fn(i)
         torch.cuda.synchronize()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for i in range(iters):
-            fn(i)
-        b_.record()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(iters):
+                fn(i)
+        g.replay()
         torch.cuda.synchronize()
-        return a.elapsed_time(b_) / iters
+        best = 1e30
+        for _ in range(reps):
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            g.replay()
+            b_.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b_) / iters)
+        return best
 
     hi_buf = x_ops[0]
     k_ms = {

@@ -12,9 +12,11 @@
 //   * the per-roi sampling tables (y taps, x taps) are computed ONCE per CTA with explicitly rounded
 //     fp32 intrinsics (__fmul_rn/__fadd_rn/__fdiv_rn: no FMA contraction) so that coordinates and
 //     integer tap indices are bit-identical to the CPU reference arithmetic.
-//   * bilinear pooling is evaluated separably: a vertically pooled column value u(x) is computed once
-//     per distinct tap column and re-used by neighbouring samples/bins (taps are < 1 px apart by
-//     construction of the adaptive grid), cutting L1 requests per output from 4*gh*gw to ~1-3.
+//   * bilinear pooling is evaluated separably with MERGED tap lists: per bin and axis the weights of the
+//     samples are summed per distinct feature row / column first (samples are < 1 px apart by
+//     construction of the adaptive grid), so each pixel of a bin's footprint is loaded once — the
+//     L2 -> SM fabric of a B200 moves about as much as HBM, and 4 loads per sample made the kernel
+//     L2-bound at 12 % of the HBM roofline (profiles/README.md).
 //   * results are staged in a [32][PH*PW] shared-memory tile (odd stride: conflict-free column writes)
 //     and streamed out as fully coalesced 128-byte st.global.cs rows (evict-first keeps the feature
 //     map resident in the 126 MB L2).
@@ -110,21 +112,46 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float *__restri
 constexpr int RA_WARPS = 7;
 constexpr int RA_THREADS = RA_WARPS * 32;
 constexpr int RA_CC = 32;          // channels per CTA (lane = channel)
-constexpr int RA_TAB = 448;        // max samples per axis held in the shared tables
+constexpr int RA_TAB = 512;        // merged (index, weight) entries held per axis
+constexpr int RA_UCOLS = 48;       // feature columns whose vertically pooled values a warp keeps in shared memory
 
-struct alignas(16) TapEntry {
-    int lo, hi;
-    float wl, wh;
+// Merged tap list of one bin along one axis: the gh (gw) samples of a bin are < 1 px apart, so their 2*g bilinear
+// taps hit at most g + 1 distinct rows (columns); adding up the weights per distinct index first means every
+// feature pixel of the bin's footprint is loaded ONCE (L2 -> SM traffic ~ footprint, not 4 loads per sample).
+struct MergedEntry {
+    int idx;
+    float w;
 };
 
-__global__ void __launch_bounds__(RA_THREADS) roi_align_fwd_kernel(const float *__restrict__ feat,   // [N,H,W,C]
+// entries of bin `p` are written at tab[p * stride ...]; returns their number
+__device__ __forceinline__ int build_merged(MergedEntry *tab, float start, float bin, int p, int g, int size) {
+    int n = 0;
+    // taps are monotonic in the sample index, so an index can only repeat one of the last two entries
+    auto add = [&](int idx, float w) {
+        if (n > 0 && tab[n - 1].idx == idx) tab[n - 1].w += w;
+        else if (n > 1 && tab[n - 2].idx == idx) tab[n - 2].w += w;
+        else { tab[n].idx = idx; tab[n].w = w; ++n; }
+    };
+    for (int i = 0; i < g; ++i) {
+        const Tap t = make_tap(sample_coord(start, bin, p, i, g), size);
+        if (t.lo < 0) continue;                       // sample outside [-1, size]: contributes 0
+        add(t.lo, t.wl);
+        add(t.hi, t.wh);
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(RA_THREADS, 3) roi_align_fwd_kernel(const float *__restrict__ feat,   // [N,H,W,C]
                                                                    const float *__restrict__ rois, int C, int H, int W,
                                                                    int PH, int PW, float scale, int sampling_ratio,
                                                                    int aligned, int nchunks, float *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TapEntry *ytab = reinterpret_cast<TapEntry *>(smem_raw);
-    TapEntry *xtab = ytab + RA_TAB;
-    float *tile = reinterpret_cast<float *>(xtab + RA_TAB);
+    MergedEntry *ytab = reinterpret_cast<MergedEntry *>(smem_raw);
+    MergedEntry *xtab = ytab + RA_TAB;
+    int *ycnt = reinterpret_cast<int *>(xtab + RA_TAB);      // [PH]
+    int *xcnt = ycnt + PH;                                    // [PW]
+    float *tile = reinterpret_cast<float *>(xcnt + PW);
+    float *ubuf_all = tile + RA_CC * ((PH * PW) | 1);        // [RA_WARPS][RA_UCOLS][32]
 
     const int r = blockIdx.x / nchunks;
     const int chunk = blockIdx.x - r * nchunks;
@@ -134,23 +161,17 @@ __global__ void __launch_bounds__(RA_THREADS) roi_align_fwd_kernel(const float *
     const int tstride = PHW | 1;
 
     const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, aligned, PH, PW, sampling_ratio);
-    const int ny = PH * g.gh, nx = PW * g.gw;
-    const bool tables_fit = (g.gh <= 0 || ny <= RA_TAB) && (g.gw <= 0 || nx <= RA_TAB);
-    const float inv_cnt_den = (float)max(g.gh * g.gw, 1);
+    // max merged entries per bin: adaptive grids space the samples <= 1 px apart (g + 1 distinct indices, +1 slack);
+    // a fixed sampling_ratio may spread them further (2 per sample)
+    const int ystride = sampling_ratio > 0 ? 2 * g.gh : g.gh + 2, xstride = sampling_ratio > 0 ? 2 * g.gw : g.gw + 2;
+    const bool empty = (g.gh <= 0 || g.gw <= 0);
+    const bool tables_fit = !empty && (long long)PH * ystride <= RA_TAB && (long long)PW * xstride <= RA_TAB;
+    const float cnt = (float)max(g.gh * g.gw, 1);
 
-    if (tables_fit && g.gh > 0 && g.gw > 0) {
-        for (int s = threadIdx.x; s < ny + nx; s += RA_THREADS) {
-            if (s < ny) {
-                const int p = s / g.gh, i = s - p * g.gh;
-                const Tap t = make_tap(sample_coord(g.sh, g.bh, p, i, g.gh), H);
-                ytab[s] = TapEntry{t.lo, t.hi, t.wl, t.wh};
-            } else {
-                const int q = s - ny;
-                const int p = q / g.gw, i = q - p * g.gw;
-                const Tap t = make_tap(sample_coord(g.sw, g.bw, p, i, g.gw), W);
-                xtab[q] = TapEntry{t.lo, t.hi, t.wl, t.wh};
-            }
-        }
+    if (tables_fit) {
+        const int t = threadIdx.x;
+        if (t < PH) ycnt[t] = build_merged(ytab + t * ystride, g.sh, g.bh, t, g.gh, H);
+        else if (t >= 32 && t < 32 + PW) xcnt[t - 32] = build_merged(xtab + (t - 32) * xstride, g.sw, g.bw, t - 32, g.gw, W);
     }
     __syncthreads();
 
@@ -158,55 +179,105 @@ __global__ void __launch_bounds__(RA_THREADS) roi_align_fwd_kernel(const float *
     const bool active = c < C;
     const float *fb = feat + (size_t)g.batch * H * W * C + (active ? c : 0);
     float *trow = tile + lane * tstride;
+    const size_t rowpitch = (size_t)W * C;
 
-    if (g.gh <= 0 || g.gw <= 0) {
+    if (empty) {
         for (int ph = warp; ph < PH; ph += RA_WARPS)
             for (int pw = 0; pw < PW; ++pw) trow[ph * PW + pw] = 0.f;
     } else if (tables_fit) {
+        // column range touched by this roi (min / max over every merged entry: a fixed sampling_ratio on a box with
+        // x2 < x1 walks the columns backwards, so the first / last list entries are not the extremes)
+        int xmin = 0x7fffffff, xmax = -1;
+        for (int e = lane; e < PW * xstride; e += 32) {
+            const int pw = e / xstride, k = e - pw * xstride;
+            if (k < xcnt[pw]) {
+                xmin = min(xmin, xtab[e].idx);
+                xmax = max(xmax, xtab[e].idx);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+            xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        }
+        if (xmax < 0) xmin = 0;
+        const int ncols = xmax - xmin + 1;
+        float *ubuf = ubuf_all + (size_t)warp * RA_UCOLS * 32 + lane;
         for (int ph = warp; ph < PH; ph += RA_WARPS) {
-            const TapEntry *yt = ytab + ph * g.gh;
-            // vertically pooled value of feature column x for this bin row
-            auto column = [&](int x) -> float {
-                float u = 0.f;
-                const float *fx = fb + (size_t)x * C;
-                for (int iy = 0; iy < g.gh; ++iy) {
-                    const TapEntry e = yt[iy];
-                    if (e.lo < 0) continue;
-                    const float a = __ldg(fx + (size_t)e.lo * W * C);
-                    const float b = __ldg(fx + (size_t)e.hi * W * C);
-                    u = fmaf(e.wl, a, u);
-                    u = fmaf(e.wh, b, u);
-                }
-                return u;
-            };
-            int kx = -2;            // cached columns: ua = u(kx), ub = u(kx + 1) (or u(kx) at the right border)
-            float ua = 0.f, ub = 0.f;
-            for (int pw = 0; pw < PW; ++pw) {
-                float acc = 0.f;
-                const TapEntry *xt = xtab + pw * g.gw;
-                for (int ix = 0; ix < g.gw; ++ix) {
-                    const TapEntry e = xt[ix];
-                    if (e.lo < 0) continue;
-                    if (active) {
-                        if (e.lo != kx) {
-                            if (e.lo == kx + 1) {
-                                ua = ub;
-                                ub = column(e.hi);
-                            } else {
-                                ua = column(e.lo);
-                                ub = column(e.hi);
-                            }
-                            kx = e.lo;
+            const MergedEntry *yt = ytab + ph * ystride;
+            const int ny = ycnt[ph];
+            if (ncols <= RA_UCOLS) {
+                // pass 1: vertically pooled value u(x) of every column of the footprint, four columns per step so
+                // that 4 * ny independent coalesced loads are in flight per warp (the kernel is latency-bound otherwise)
+                if (active) {
+                    for (int x0 = xmin; x0 <= xmax; x0 += 4) {
+                        float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
+                        const float *f0 = fb + (size_t)x0 * C;
+                        const float *f1 = fb + (size_t)min(x0 + 1, xmax) * C;
+                        const float *f2 = fb + (size_t)min(x0 + 2, xmax) * C;
+                        const float *f3 = fb + (size_t)min(x0 + 3, xmax) * C;
+#pragma unroll 2
+                        for (int k = 0; k < ny; ++k) {
+                            const size_t ro = (size_t)yt[k].idx * rowpitch;
+                            const float wy = yt[k].w;
+                            const float a = __ldg(f0 + ro), b = __ldg(f1 + ro), c2 = __ldg(f2 + ro), d = __ldg(f3 + ro);
+                            u0 = fmaf(wy, a, u0);
+                            u1 = fmaf(wy, b, u1);
+                            u2 = fmaf(wy, c2, u2);
+                            u3 = fmaf(wy, d, u3);
                         }
-                        acc = fmaf(e.wl, ua, acc);
-                        acc = fmaf(e.wh, ub, acc);
+                        float *ub = ubuf + (size_t)(x0 - xmin) * 32;
+                        ub[0] = u0;
+                        if (x0 + 1 <= xmax) ub[32] = u1;
+                        if (x0 + 2 <= xmax) ub[64] = u2;
+                        if (x0 + 3 <= xmax) ub[96] = u3;
                     }
                 }
-                trow[ph * PW + pw] = __fdiv_rn(acc, inv_cnt_den);
+                __syncwarp();
+                // pass 2: horizontal pooling of each bin from the buffered column values
+                for (int pw = 0; pw < PW; ++pw) {
+                    float acc = 0.f;
+                    const MergedEntry *xt = xtab + pw * xstride;
+                    const int nx = xcnt[pw];
+                    if (active && ny > 0)
+                        for (int k = 0; k < nx; ++k) acc = fmaf(xt[k].w, ubuf[(size_t)(xt[k].idx - xmin) * 32], acc);
+                    trow[ph * PW + pw] = __fdiv_rn(acc, cnt);
+                }
+                __syncwarp();
+            } else {
+                // very wide roi: bin-driven sweep with the last column cached
+                auto column = [&](int x) -> float {
+                    const float *fx = fb + (size_t)x * C;
+                    float u0 = 0.f, u1 = 0.f;
+                    int k = 0;
+                    for (; k + 1 < ny; k += 2) {
+                        const float a = __ldg(fx + (size_t)yt[k].idx * rowpitch);
+                        const float b = __ldg(fx + (size_t)yt[k + 1].idx * rowpitch);
+                        u0 = fmaf(yt[k].w, a, u0);
+                        u1 = fmaf(yt[k + 1].w, b, u1);
+                    }
+                    if (k < ny) u0 = fmaf(yt[k].w, __ldg(fx + (size_t)yt[k].idx * rowpitch), u0);
+                    return u0 + u1;
+                };
+                int kx = -1;
+                float uk = 0.f;
+                for (int pw = 0; pw < PW; ++pw) {
+                    float acc = 0.f;
+                    const MergedEntry *xt = xtab + pw * xstride;
+                    const int nx = xcnt[pw];
+                    if (active && ny > 0) {
+                        for (int k = 0; k < nx; ++k) {
+                            const int x = xt[k].idx;
+                            if (x != kx) { uk = column(x); kx = x; }
+                            acc = fmaf(xt[k].w, uk, acc);
+                        }
+                    }
+                    trow[ph * PW + pw] = __fdiv_rn(acc, cnt);
+                }
             }
         }
     } else {
-        // generic path for rois whose sampling grid exceeds the shared tables (gh*PH > RA_TAB): direct taps
+        // generic path for rois whose sampling grid exceeds the shared tables: direct taps
         for (int ph = warp; ph < PH; ph += RA_WARPS)
             for (int pw = 0; pw < PW; ++pw) {
                 float acc = 0.f;
@@ -223,7 +294,7 @@ __global__ void __launch_bounds__(RA_THREADS) roi_align_fwd_kernel(const float *
                         acc += ty.wl * tx.wl * v1 + ty.wl * tx.wh * v2 + ty.wh * tx.wl * v3 + ty.wh * tx.wh * v4;
                     }
                 }
-                trow[ph * PW + pw] = __fdiv_rn(acc, inv_cnt_den);
+                trow[ph * PW + pw] = __fdiv_rn(acc, cnt);
             }
     }
     __syncthreads();
@@ -337,7 +408,9 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
         nhwc = static_cast<const float *>(workspace);
     }
     const int nchunks = (C + RA_CC - 1) / RA_CC;
-    const size_t smem = 2 * RA_TAB * sizeof(TapEntry) + (size_t)RA_CC * ((PH * PW) | 1) * sizeof(float);
+    LOCO_REQUIRE(PH <= 32 && PW <= 32, LOCO_E_UNSUPPORTED, "roi_align_fwd: output size %dx%d (at most 32x32)", PH, PW);
+    const size_t smem = 2 * RA_TAB * sizeof(MergedEntry) + (size_t)(PH + PW) * sizeof(int) + (size_t)RA_CC * ((PH * PW) | 1) * sizeof(float) +
+                        (size_t)RA_WARPS * RA_UCOLS * 32 * sizeof(float);
     LOCO_REQUIRE(smem <= 200 * 1024, LOCO_E_UNSUPPORTED, "roi_align_fwd: output size %dx%d needs %zu B of shared memory", PH, PW, smem);
     LOCO_REQUIRE((long long)R * nchunks < (1ll << 31), LOCO_E_UNSUPPORTED, "roi_align_fwd: too many (roi, channel-slab) tiles");
     static thread_local size_t smem_set = 0;

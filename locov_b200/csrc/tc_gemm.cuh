@@ -45,6 +45,12 @@ struct TcCore {
     // multicasts), the B tile of a column by its cm CTAs — L2->SM operand traffic drops by the same factors.
     int cm, cn;
     int clusters_n;     // clusters along the virtual tile grid's n axis (virtual tiles_n = clusters_n * cn)
+    int total_tiles;    // > 0: persistent mode — CTA b processes tiles b, b + grid, ... (chunks = its share); 0: `chunks` each
+    int debug_mode;     // developer experiments only (LOCOV_B200_DEBUG): 1 = skip the MMAs (pure TMA ingest rate),
+                        // 2 = skip the TMA loads (pure tensor-pipe + operand-read rate); results are garbage
+    int ring_bytes;     // bytes reserved for the operand ring (>= stages * stage_bytes; barriers follow it)
+    int epi_overlay;    // 1: the epilogue scratch overlays the operand ring (legal only with chunks == 1: the ring is
+                        // dead once the accumulator barrier fired — every load of this tile has landed and been consumed)
 };
 
 __host__ __device__ inline int tc_round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -68,16 +74,23 @@ inline size_t tc_finalize(TcCore &core, int K, int passes, int chunks, int epi_s
     if (core.cm < 1) core.cm = 1;
     if (core.cn < 1) core.cn = 1;
     const size_t stage_bytes = TC_A_BYTES + (size_t)core.block_n * 128;
-    const size_t fixed = 1024 /*alignment slack*/ + 512 /*barriers*/ + (size_t)epi_smem;
-    int stages = (int)(((long long)110 * 1024 - (long long)fixed) / (long long)stage_bytes);   // two CTAs per SM when possible
-    if (stages < 3) stages = (int)(((long long)225 * 1024 - (long long)fixed) / (long long)stage_bytes);
+    if (chunks != 1) core.epi_overlay = 0;
+    const long long fixed = 1024 /*alignment slack*/ + 512 /*barriers*/ + (core.epi_overlay ? 0 : (long long)epi_smem);
+    int stages = (int)(((long long)110 * 1024 - fixed) / (long long)stage_bytes);   // two CTAs per SM when possible
+    if (core.epi_overlay && (long long)epi_smem + fixed > 110 * 1024) stages = 0;    // the overlay itself needs a whole SM
+    if (stages < 3) stages = (int)(((long long)225 * 1024 - fixed) / (long long)stage_bytes);
     const int total_iters = core.num_k_blocks * passes * chunks;
     if (stages > 6) stages = 6;
     if (const char *e = getenv("LOCOV_B200_STAGES")) { const int v = atoi(e); if (v >= 1 && v < stages) stages = v; }   // developer sweep knob
     if (stages > total_iters) stages = total_iters;
     if (stages < 1) stages = 1;
     core.stages = stages;
-    return fixed + stages * stage_bytes;
+    core.debug_mode = 0;
+    if (const char *e = getenv("LOCOV_B200_DEBUG")) core.debug_mode = atoi(e);
+    size_t ring = (size_t)stages * stage_bytes;
+    if (core.epi_overlay && ring < (size_t)epi_smem) ring = ((size_t)epi_smem + 1023) / 1024 * 1024;
+    core.ring_bytes = (int)ring;
+    return (size_t)fixed + ring;
 }
 
 #if defined(__CUDACC__)
@@ -147,13 +160,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
     const uint32_t b_bytes = (uint32_t)core.block_n * 128u;
     const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
-    unsigned char *bar_base = smem + (size_t)core.stages * stage_bytes;
+    unsigned char *bar_base = smem + (size_t)core.ring_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(bar_base);
     uint64_t *empty = full + TC_MAX_STAGES;
     uint64_t *tfull = empty + TC_MAX_STAGES;
     uint64_t *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
-    unsigned char *epi_smem = bar_base + 512;
+    unsigned char *epi_smem = core.epi_overlay ? smem : bar_base + 512;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -201,11 +214,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int iters_per_chunk = core.num_k_blocks * core.passes;
+    const int nchunks = core.total_tiles > 0 ? max(0, (core.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) : core.chunks;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int ch = 0; ch < core.chunks; ++ch) {
+            for (int ch = 0; ch < nchunks; ++ch) {
                 int row_a, row_b;
                 Epi::coords(ep, core, cta, ch, row_a, row_b);
                 for (int pass = 0; pass < core.passes; ++pass) {
@@ -214,6 +228,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     for (int kb = 0; kb < core.num_k_blocks; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1u);
                         unsigned char *sa = smem + (size_t)stage * stage_bytes;
+                        if (core.debug_mode == 2) {
+                            mbar_arrive(&full[stage]);
+                        } else {
                         mbar_arrive_expect_tx(&full[stage], stage_bytes);
                         if (csize == 1) {
                             tma_load_2d(sa, ma, &full[stage], kb * TC_BLOCK_K, row_a);
@@ -225,6 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                             tma_load_2d_mc(sa + TC_A_BYTES + (size_t)rm * b_rows * 128, mb, &full[stage], kb * TC_BLOCK_K,
                                            row_b + rm * b_rows, mask_b);
                         }
+                        }
                         if (++stage == (uint32_t)core.stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -234,7 +252,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(TC_BLOCK_M, (uint32_t)core.block_n);
             uint32_t stage = 0, phase = 0;
-            for (int ch = 0; ch < core.chunks; ++ch) {
+            for (int ch = 0; ch < nchunks; ++ch) {
                 const int acc = ch % core.acc_stages;
                 const uint32_t acc_phase = (uint32_t)(ch / core.acc_stages) & 1u;
                 mbar_wait(&tempty[acc], acc_phase ^ 1u);
@@ -249,6 +267,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     const uint64_t db = umma_desc_k128(a_addr + TC_A_BYTES);
 #pragma unroll
                     for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+                        if (core.debug_mode == 1) break;
                         umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);   // +32 B per K=16 step
                         accumulate = 1;
                     }
@@ -263,7 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int row = q * 32 + lane;     // accumulator row owned by this thread
         Epi epi;
         epi.begin(ep, core, cta, row, lane, q, epi_smem);
-        for (int ch = 0; ch < core.chunks; ++ch) {
+        for (int ch = 0; ch < nchunks; ++ch) {
             const int acc = ch % core.acc_stages;
             const uint32_t acc_phase = (uint32_t)(ch / core.acc_stages) & 1u;
             mbar_wait(&tfull[acc], acc_phase);

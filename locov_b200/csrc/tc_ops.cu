@@ -25,19 +25,25 @@ struct EpiLinear {
         int n_bf16;
         int64_t ld_bf16;
         int M, N, tiles_n;
+        int grid;        // CTAs launched: persistent tile striding (tile = cta + chunk * grid)
+        int vec_f32;     // out_f32 rows are 16-byte aligned: 128-bit stores
     };
-    static __device__ __forceinline__ void coords(const Params &p, const TcCore &core, int cta, int, int &row_a, int &row_b) {
-        row_a = (cta / p.tiles_n) * TC_BLOCK_M;
-        row_b = (cta % p.tiles_n) * core.block_n;
+    static __device__ __forceinline__ void coords(const Params &p, const TcCore &core, int cta, int ch, int &row_a, int &row_b) {
+        const int tile = cta + ch * p.grid;
+        row_a = (tile / p.tiles_n) * TC_BLOCK_M;
+        row_b = (tile % p.tiles_n) * core.block_n;
     }
     __device__ __forceinline__ void begin(const Params &, const TcCore &, int, int, int, int, unsigned char *) {}
-    __device__ __forceinline__ void chunk(const Params &p, const TcCore &core, int cta, int, uint32_t taddr, int row, int lane,
-                                          int q, unsigned char *smem) {
-        float *scratch = reinterpret_cast<float *>(smem) + (size_t)q * TC_WARP_SCRATCH_WORDS;
-        const int m0 = (cta / p.tiles_n) * TC_BLOCK_M + q * 32;      // first global row of this warp
-        const int n0 = (cta % p.tiles_n) * core.block_n;
-        const int rows_valid = max(0, min(32, p.M - m0));
-        (void)row;
+    // Each thread owns one accumulator row: 32 consecutive columns per tcgen05.ld = 128 contiguous bytes of fp32 (or
+    // 64 of bf16) in the row-major output, written with 128-bit stores straight from registers — whole 32-byte
+    // sectors per thread, no shared-memory transpose, ~12 instructions per 32 outputs.
+    __device__ __forceinline__ void chunk(const Params &p, const TcCore &core, int cta, int ch, uint32_t taddr, int row, int lane,
+                                          int q, unsigned char *) {
+        (void)q;
+        const int tile = cta + ch * p.grid;
+        const int grow = (tile / p.tiles_n) * TC_BLOCK_M + row;
+        const int n0 = (tile % p.tiles_n) * core.block_n;
+        const bool row_ok = grow < p.M;
         for (int c0 = 0; c0 < core.block_n; c0 += 32) {
             float v[32];
             tmem_ld32(taddr + (uint32_t)c0, v);
@@ -45,19 +51,50 @@ struct EpiLinear {
             const int cols_valid = max(0, min(min(32, core.block_n - c0), p.N - gc0));
             if (cols_valid <= 0) continue;     // warp-uniform
             if (p.bias != nullptr) {
+                const float bl = (lane < cols_valid) ? __ldg(p.bias + gc0 + lane) : 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < cols_valid) v[j] += __ldg(p.bias + gc0 + j);
+                for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
             }
-            if (p.out_f32 != nullptr)
-                warp_store_f32(scratch, v, p.out_f32 + (int64_t)m0 * p.ld_f32 + gc0, p.ld_f32, rows_valid, cols_valid, lane);
+            if (!row_ok) continue;             // (after the warp-collective loads / shuffles)
+            if (p.out_f32 != nullptr) {
+                float *dst = p.out_f32 + (int64_t)grow * p.ld_f32 + gc0;
+                if (p.vec_f32 && cols_valid == 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < cols_valid) dst[j] = v[j];
+                }
+            }
             if (p.out_hi != nullptr && gc0 < p.n_bf16) {
                 const int cb = min(cols_valid, p.n_bf16 - gc0);
-                // odd column counts only occur at the very end of the matrix; pad lanes write zeros from
-                // the zero-filled accumulator columns (TMA out-of-bounds rows of W are zero).
-                warp_store_bf16(reinterpret_cast<uint32_t *>(scratch), v, p.out_hi + (int64_t)m0 * p.ld_bf16 + gc0,
-                                p.out_lo ? p.out_lo + (int64_t)m0 * p.ld_bf16 + gc0 : nullptr, p.ld_bf16, rows_valid,
-                                (cb + 1) & ~1, lane);
+                uint32_t hp[16], lp[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    uint16_t h0, l0, h1, l1;
+                    split_bf16(v[2 * j], h0, l0);
+                    split_bf16(v[2 * j + 1], h1, l1);
+                    hp[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                    lp[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                }
+                uint16_t *dh = p.out_hi + (int64_t)grow * p.ld_bf16 + gc0;     // 64-byte aligned: base 16 B, ld % 8, gc0 % 32
+                uint16_t *dl = p.out_lo ? p.out_lo + (int64_t)grow * p.ld_bf16 + gc0 : nullptr;
+                if (cb == 32) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        *reinterpret_cast<uint4 *>(dh + 2 * j) = make_uint4(hp[j], hp[j + 1], hp[j + 2], hp[j + 3]);
+                        if (dl) *reinterpret_cast<uint4 *>(dl + 2 * j) = make_uint4(lp[j], lp[j + 1], lp[j + 2], lp[j + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < cb) {
+                            dh[j] = (uint16_t)((j & 1) ? (hp[j >> 1] >> 16) : (hp[j >> 1] & 0xFFFFu));
+                            if (dl) dl[j] = (uint16_t)((j & 1) ? (lp[j >> 1] >> 16) : (lp[j >> 1] & 0xFFFFu));
+                        }
+                }
             }
         }
     }
@@ -75,6 +112,7 @@ struct EpiScore {
         float *lse;
         int64_t *argmax_fg;
         int R, K1;
+        int vec;        // logits rows are 16-byte aligned (base and ld): 128-bit stores straight from registers
     };
     float run_max, run_sum, best_val;
     int best_idx;
@@ -95,7 +133,6 @@ struct EpiScore {
         const int m0 = cta * TC_BLOCK_M + q * 32;
         const int rows_valid = max(0, min(32, p.R - m0));
         const int n0 = ch * core.block_n;
-        (void)row;
         for (int c0 = 0; c0 < core.block_n; c0 += 32) {
             float v[32];
             tmem_ld32(taddr + (uint32_t)c0, v);
@@ -121,7 +158,15 @@ struct EpiScore {
                 if (j < cols_valid) s += expf(v[j] - new_max);
             run_max = new_max;
             run_sum = s;
-            warp_store_f32(scratch, v, p.logits + (int64_t)m0 * p.ld + gc0, p.ld, rows_valid, cols_valid, lane);
+            if (p.vec && cols_valid == 32) {
+                if (row < rows_valid + q * 32) {
+                    float *dst = p.logits + (int64_t)(cta * TC_BLOCK_M + row) * p.ld + gc0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            } else {
+                warp_store_f32(scratch, v, p.logits + (int64_t)m0 * p.ld + gc0, p.ld, rows_valid, cols_valid, lane);
+            }
         }
     }
     __device__ __forceinline__ void finish(const Params &p, const TcCore &, int cta, int row, int lane, int q, unsigned char *) {
@@ -261,16 +306,31 @@ struct EpiLsm {
         }
         float f_t = best_s, den = (float)best_r;                   // hardmax: `den` carries the argmax index
         if (want_w && !p.hardmax) {
-            float num = 0.f;
-            den = 0.f;
-            for (int r = 0; r < Rg; ++r) {
-                const float s = srow[r];
-                const float sv = (mc > 0.f && sm.rmask[r] > 0.f) ? s : LSM_FILL;
-                const float e = __expf(sv - mx);
-                den += e;
-                num = fmaf(e, s, num);
+            // second sweep straight from TMEM (registers): 32 independent exponentials per block, four
+            // accumulator chains — the epilogue runs one warp per scheduler, so ILP is the only latency hiding
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+            for (int b = 0; b < nblk; ++b) {
+                float v[32];
+                tmem_ld32(taddr + (uint32_t)(b * 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int r = b * 32 + j;
+                    float e[4], sc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        sc[u] = v[j + u] * p.inv_temp;
+                        const bool ok = (r + u < Rg);
+                        const float sv = (mc > 0.f && ok && sm.rmask[ok ? r + u : 0] > 0.f) ? sc[u] : LSM_FILL;
+                        e[u] = ok ? __expf(sv - mx) : 0.f;
+                    }
+                    d0 += e[0]; n0 = fmaf(e[0], sc[0], n0);
+                    d1 += e[1]; n1 = fmaf(e[1], sc[1], n1);
+                    d2 += e[2]; n2 = fmaf(e[2], sc[2], n2);
+                    d3 += e[3]; n3 = fmaf(e[3], sc[3], n3);
+                }
             }
-            f_t = num / den;
+            den = (d0 + d1) + (d2 + d3);
+            f_t = ((n0 + n1) + (n2 + n3)) / den;
         }
         sm.rowval[row] = (mc > 0.f) ? f_t : 0.f;
         if (BWD) {
@@ -290,6 +350,7 @@ struct EpiLsm {
                 const float *cm = sm.cmask + cl * T;
                 float cmx = -FLT_MAX, cbest = 0.f;
                 int best_t = 0;
+#pragma unroll 4
                 for (int t = 0; t < T; ++t) {
                     const float s = col[(size_t)t * lds];
                     const float sv = (rm > 0.f && cm[t] > 0.f) ? s : LSM_FILL;
@@ -297,16 +358,23 @@ struct EpiLsm {
                 }
                 float h = cbest, cden = (float)best_t;              // hardmax: argmax index
                 if (!p.hardmax) {
-                    float num = 0.f;
-                    cden = 0.f;
-                    for (int t = 0; t < T; ++t) {
-                        const float s = col[(size_t)t * lds];
-                        const float sv = (rm > 0.f && cm[t] > 0.f) ? s : LSM_FILL;
-                        const float e = __expf(sv - cmx);
-                        cden += e;
-                        num = fmaf(e, s, num);
+                    float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f;
+                    int t = 0;
+#pragma unroll 2
+                    for (; t + 1 < T; t += 2) {
+                        const float s0 = col[(size_t)t * lds], s1 = col[(size_t)(t + 1) * lds];
+                        const float e0 = __expf(((rm > 0.f && cm[t] > 0.f) ? s0 : LSM_FILL) - cmx);
+                        const float e1 = __expf(((rm > 0.f && cm[t + 1] > 0.f) ? s1 : LSM_FILL) - cmx);
+                        d0 += e0; n0 = fmaf(e0, s0, n0);
+                        d1 += e1; n1 = fmaf(e1, s1, n1);
                     }
-                    h = num / cden;
+                    if (t < T) {
+                        const float s0 = col[(size_t)t * lds];
+                        const float e0 = __expf(((rm > 0.f && cm[t] > 0.f) ? s0 : LSM_FILL) - cmx);
+                        d0 += e0; n0 = fmaf(e0, s0, n0);
+                    }
+                    cden = d0 + d1;
+                    h = (n0 + n1) / cden;
                 }
                 sm.colval[it] = (rm > 0.f) ? h : 0.f;
                 if (BWD) {
@@ -356,6 +424,7 @@ struct EpiLsm {
             const float gw = want_w ? -__ldg(p.g_w2r + (int64_t)c * p.ld_g + i) * mc / fmaxf(sm.capnw[cl], 1.f) * p.inv_temp : 0.f;
             const float gr = want_r ? -__ldg(p.g_r2w + (int64_t)c * p.ld_g + i) / fmaxf(nr, 1.f) * p.inv_temp : 0.f;
             const float rmx = sm.rowmx[row], rinv = 1.f / sm.rowden[row], rf = sm.rowf[row];
+#pragma unroll 4
             for (int r = 0; r < Rg; ++r) {
                 const float s = srow[r];
                 const float rm = sm.rmask[r];
@@ -426,12 +495,14 @@ static int fill_maps(TcMaps &maps, const uint16_t *a_hi, const uint16_t *a_lo, u
     return LOCO_OK;
 }
 
-// LOCOV_B200_CLUSTER=0 disables thread-block clusters / TMA multicast (debug and A/B measurements).
+// Thread-block clusters with TMA multicast are implemented (tc_gemm.cuh) but OFF by default: on B200 they measured
+// no gain for these shapes (profiles/README.md — the kernels are bound by per-tile fixed cost and the tensor pipe, not by
+// L2 -> SM operand traffic).  LOCOV_B200_CLUSTER=1 enables them for A/B measurements.
 static bool clusters_enabled() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("LOCOV_B200_CLUSTER");
-        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
     }
     return v != 0;
 }
@@ -445,6 +516,7 @@ static void pick_gemm_shape(int M, int N, int sms, TcCore &core) {
     const int mt = (M + TC_BLOCK_M - 1) / TC_BLOCK_M;
     double best_cost = 1e300;
     const int cms[2] = {1, 2}, cns[3] = {1, 2, 4};
+    core.block_n = 128; core.cm = 1; core.cn = 1;
     for (int ci = 0; ci < 2; ++ci)
         for (int cj = 0; cj < 3; ++cj) {
             const int cm = cms[ci], cn = cns[cj];
@@ -457,10 +529,11 @@ static void pick_gemm_shape(int M, int N, int sms, TcCore &core) {
                 const int ctas = tm * tn, csize = cm * cn;
                 const int slots = (sms / csize) * csize;
                 const int waves = (ctas + slots - 1) / slots;
-                const int active = ctas < slots ? ctas : slots;
+                // per 64-wide k block: tensor pipe 4 * bn/2 cycles vs. shared-memory port (TMA fill + SS operand reads)
                 const double mma = 4.0 * bn / 2.0;
-                const double l2 = (128.0 * 128.0 / cn + bn * 128.0 / cm) * active / 3400.0;
-                const double cost = waves * ((mma > l2 ? mma : l2) + 24.0) + 1e-3 * csize;
+                const double port = ((128.0 + bn) * 128.0 * 2.0) / 128.0;
+                const double per_k = (mma > port ? mma : port);
+                const double cost = waves * (per_k + 60.0 + bn * 0.5) + 1e-3 * csize;   // + amortised per-tile fixed cost / epilogue
                 if (cost < best_cost) { best_cost = cost; core.block_n = bn; core.cm = cm; core.cn = cn; }
             }
         }
@@ -492,16 +565,27 @@ int loco_linear_fwd(const uint16_t *A_hi, const uint16_t *A_lo, int64_t lda, con
         LOCO_REQUIRE(n_bf16 % 2 == 0 || ld_bf16 > n_bf16, LOCO_E_ALIGN, "linear_fwd: odd n_bf16 needs a padded ld_bf16");
     }
     TcCore core = {};
-    pick_gemm_shape(M, N, current_device_sm_count(), core);
-    const size_t smem = tc_finalize(core, K, A_lo ? 3 : 1, 1, 4 * TC_WARP_SCRATCH_WORDS * 4);
-    TcMaps maps;
-    int rc = fill_maps(maps, A_hi, A_lo, M, lda, W_hi, W_lo, N, ldw, K, core);
-    if (rc != LOCO_OK) return rc;
+    const int sms = current_device_sm_count();
+    pick_gemm_shape(M, N, sms, core);
     EpiLinear::Params p;
     p.bias = bias; p.out_f32 = out_f32; p.ld_f32 = ld_f32; p.out_hi = out_hi; p.out_lo = out_lo;
     p.n_bf16 = out_hi ? n_bf16 : 0; p.ld_bf16 = ld_bf16; p.M = M; p.N = N;
+    p.vec_f32 = (out_f32 != nullptr && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0 && ld_f32 % 4 == 0) ? 1 : 0;
     p.tiles_n = core.clusters_n * core.cn;                                      // virtual (padded) tile grid
-    const int grid = tc_round_up((M + TC_BLOCK_M - 1) / TC_BLOCK_M, core.cm) * p.tiles_n;
+    const int tiles = tc_round_up((M + TC_BLOCK_M - 1) / TC_BLOCK_M, core.cm) * p.tiles_n;
+    int grid = tiles, chunks = 1;
+    if (core.cm * core.cn == 1 && tiles > sms) {
+        // persistent: one CTA per SM strides over the tiles; two TMEM accumulator stages let the epilogue of tile i
+        // overlap the MMAs of tile i + 1
+        grid = sms;
+        chunks = (tiles + grid - 1) / grid;
+        core.total_tiles = tiles;
+    }
+    p.grid = grid;
+    const size_t smem = tc_finalize(core, K, A_lo ? 3 : 1, chunks, 0);
+    TcMaps maps;
+    int rc = fill_maps(maps, A_hi, A_lo, M, lda, W_hi, W_lo, N, ldw, K, core);
+    if (rc != LOCO_OK) return rc;
     return tc_launch<EpiLinear>(maps, core, p, grid, smem, static_cast<cudaStream_t>(stream));
 }
 
@@ -524,6 +608,7 @@ int loco_box_score_fwd(const uint16_t *E_hi, const uint16_t *E_lo, int64_t lde, 
     EpiScore::Params p;
     p.bias = cls_bias; p.logits = logits; p.probs = probs; p.ld = ld_logits; p.lse = lse; p.argmax_fg = argmax_fg;
     p.R = R; p.K1 = K1;
+    p.vec = ((reinterpret_cast<uintptr_t>(logits) & 15) == 0 && ld_logits % 4 == 0) ? 1 : 0;
     const int grid = (R + TC_BLOCK_M - 1) / TC_BLOCK_M;
     return tc_launch<EpiScore>(maps, core, p, grid, smem, static_cast<cudaStream_t>(stream));
 }
@@ -554,6 +639,7 @@ static int lsm_launch(bool bwd, const uint16_t *cap_hi, const uint16_t *cap_lo, 
     p.Bi_pad = tc_round_up(p.Bi, core.cn);
     core.clusters_n = p.Bi_pad / core.cn;
     const size_t epi = lsm_epi_smem_bytes(p.lds, core.block_n, p.per_tile, p.Rg, bwd);
+    core.epi_overlay = 1;      // the parked tile re-uses the operand ring once the MMAs are done: two CTAs fit an SM
     const size_t smem = tc_finalize(core, D, cap_lo ? 3 : 1, 1, (int)epi);
     TcMaps maps;
     int rc = fill_maps(maps, cap_hi, cap_lo, (uint64_t)p.Bc * p.T, ldcap, emb_hi, emb_lo, (uint64_t)p.Bi * p.Rg, ldemb, D, core);
