@@ -112,6 +112,14 @@ int loco_linear_fwd(const uint16_t *A_hi, const uint16_t *A_lo, int64_t lda, con
                     float *out_f32, int64_t ld_f32, uint16_t *out_hi, uint16_t *out_lo,
                     int n_bf16, int64_t ld_bf16, void *stream);
 
+/* Same contraction with the fp32 operands read IN PLACE and multiplied as TF32 (tcgen05 kind::tf32, 10-bit mantissa,
+ * fp32 accumulate): no operand-split pass, half the tensor rate.  Used by the reduced-precision ("bf16") mode for
+ * the projections whose inputs arrive as fp32 activations.  A [M,K] (lda), W [N,K] (ldw): 16-byte aligned bases,
+ * lda % 4 == 0, ldw % 4 == 0. */
+int loco_linear_tf32_fwd(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, int M,
+                         int N, int K, float *out_f32, int64_t ld_f32, uint16_t *out_hi, uint16_t *out_lo,
+                         int n_bf16, int64_t ld_bf16, void *stream);
+
 /* ---- RoI x class scoring with fused softmax epilogue -----------------------------------------------
  * Replaces: box_emb_head.py:211 cls_score(e) (cuBLAS) + Detectron2 FastRCNNOutputLayers.predict_probs
  *           F.softmax / .losses log_softmax (ATen) reached from roi_emb_heads.py:266,280,347,357.

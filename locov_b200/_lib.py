@@ -31,6 +31,7 @@ SIGNATURES = {
     "loco_split_bf16": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i, _vp]),
     "loco_transpose_bf16": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "loco_linear_fwd": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _i, _i64, _vp]),
+    "loco_linear_tf32_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _i, _i64, _vp]),
     "loco_box_score_fwd": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
     "loco_box_ce_fwd_bwd": (_i, [_vp, _i64, _vp, _vp, _i, _i, _f, _vp, _f, _vp, _vp, _i64, _vp]),
     "loco_lsm_masks": (_i, [_vp, _vp, _i64, _vp, _i, _i64, _vp, _vp, _vp]),

@@ -44,25 +44,34 @@ static encode_tiled_fn get_encode_fn() {
     return fn;
 }
 
-int make_tmap_bf16_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                      uint32_t box_rows) {
+static int make_tmap_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                        CUtensorMapDataType dtype, uint32_t elem_bytes) {
     encode_tiled_fn fn = get_encode_fn();
     LOCO_REQUIRE(fn != nullptr, LOCO_E_DRIVER, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-    LOCO_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, LOCO_E_ALIGN, "bf16 operand base %p is not 16-byte aligned", base);
-    LOCO_REQUIRE(ld_elems % 8 == 0, LOCO_E_ALIGN, "bf16 operand leading dimension %llu is not a multiple of 8",
-                 (unsigned long long)ld_elems);
+    LOCO_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, LOCO_E_ALIGN, "tensor-core operand base %p is not 16-byte aligned", base);
+    LOCO_REQUIRE((ld_elems * elem_bytes) % 16 == 0, LOCO_E_ALIGN, "tensor-core operand row stride (%llu elements of %u bytes) is not a multiple of 16 bytes",
+                 (unsigned long long)ld_elems, elem_bytes);
     LOCO_REQUIRE(box_rows >= 1 && box_rows <= 256, LOCO_E_BADARG, "TMA box rows %u out of range", box_rows);
     LOCO_REQUIRE(rows >= 1 && cols >= 1, LOCO_E_BADARG, "empty TMA tensor");
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {ld_elems * 2};   // bytes, dimension 1
-    cuuint32_t box[2] = {64, box_rows};       // 64 bf16 = 128 B inner box = one swizzle span
+    cuuint64_t strides[1] = {ld_elems * elem_bytes};   // bytes, dimension 1
+    cuuint32_t box[2] = {128u / elem_bytes, box_rows};  // inner box = 128 B = one swizzle span
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(map, dtype, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LOCO_REQUIRE(r == CUDA_SUCCESS, LOCO_E_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box_rows=%u)",
                  (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows);
     return LOCO_OK;
+}
+
+int make_tmap_bf16_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows) {
+    return make_tmap_2d(map, base, rows, cols, ld_elems, box_rows, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+}
+
+int make_tmap_f32_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                     uint32_t box_rows) {
+    return make_tmap_2d(map, base, rows, cols, ld_elems, box_rows, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4);
 }
 
 int current_device_sm_count() {

@@ -37,6 +37,10 @@ int cuda_fail(cudaError_t e, const char *what);   // records message, returns (i
 int make_tmap_bf16_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows);
 
+// Same for an fp32 (TF32 operand) matrix: box {32 elements = 128 B, box_rows}.
+int make_tmap_f32_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                     uint32_t box_rows);
+
 int current_device_sm_count();
 void count_launch(int n = 1);   // bumps the library-wide kernel-launch counter (loco_launch_count)
 
@@ -166,6 +170,25 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
     d |= (N >> 3) << 17;       // [17,23) N >> 3
     d |= (M >> 4) << 24;       // [24,29) M >> 4
     return d;                  // a_major = b_major = 0 (K-major), no negate, dense
+}
+// Instruction descriptor, kind::tf32: D fp32, A/B tf32 (fp32 bit patterns in shared memory), both K-major.
+__device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
+    uint32_t d = 0;
+    d |= 1u << 4;              // D format = F32
+    d |= 2u << 7;              // A format = TF32
+    d |= 2u << 10;             // B format = TF32
+    d |= (N >> 3) << 17;
+    d |= (M >> 4) << 24;
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {      // M x N x 8 per instruction
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread on behalf of the CTA.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,

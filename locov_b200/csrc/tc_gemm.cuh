@@ -45,6 +45,7 @@ struct TcCore {
     // multicasts), the B tile of a column by its cm CTAs — L2->SM operand traffic drops by the same factors.
     int cm, cn;
     int clusters_n;     // clusters along the virtual tile grid's n axis (virtual tiles_n = clusters_n * cn)
+    int tf32;           // 1: operands are fp32 in memory and multiplied as TF32 (kind::tf32, 32 elements per 128-byte k block)
     int total_tiles;    // > 0: persistent mode — CTA b processes tiles b, b + grid, ... (chunks = its share); 0: `chunks` each
     int debug_mode;     // developer experiments only (LOCOV_B200_DEBUG): 1 = skip the MMAs (pure TMA ingest rate),
                         // 2 = skip the TMA loads (pure tensor-pipe + operand-read rate); results are garbage
@@ -64,7 +65,8 @@ inline int tc_tmem_cols(int block_n, int acc_stages) {
 
 // Fill stages / tmem / smem for a given block_n; returns dynamic shared memory bytes.
 inline size_t tc_finalize(TcCore &core, int K, int passes, int chunks, int epi_smem) {
-    core.num_k_blocks = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+    const int k_elems = core.tf32 ? TC_BLOCK_K / 2 : TC_BLOCK_K;      // one 128-byte swizzle span per k block
+    core.num_k_blocks = (K + k_elems - 1) / k_elems;
     core.passes = passes;
     core.chunks = chunks;
     core.acc_stages = chunks > 1 ? 2 : 1;
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int k_elems = core.tf32 ? TC_BLOCK_K / 2 : TC_BLOCK_K;
 
     // cluster geometry -> virtual CTA index handed to the epilogue policy
     const int csize = core.cm * core.cn;
@@ -233,13 +236,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         } else {
                         mbar_arrive_expect_tx(&full[stage], stage_bytes);
                         if (csize == 1) {
-                            tma_load_2d(sa, ma, &full[stage], kb * TC_BLOCK_K, row_a);
-                            tma_load_2d(sa + TC_A_BYTES, mb, &full[stage], kb * TC_BLOCK_K, row_b);
+                            tma_load_2d(sa, ma, &full[stage], kb * k_elems, row_a);
+                            tma_load_2d(sa + TC_A_BYTES, mb, &full[stage], kb * k_elems, row_b);
                         } else {
                             // this CTA's slice of the shared tiles, delivered to every CTA of the row / column
                             const int a_rows = TC_BLOCK_M / core.cn, b_rows = core.block_n / core.cm;
-                            tma_load_2d_mc(sa + (size_t)rn * a_rows * 128, ma, &full[stage], kb * TC_BLOCK_K, row_a + rn * a_rows, mask_a);
-                            tma_load_2d_mc(sa + TC_A_BYTES + (size_t)rm * b_rows * 128, mb, &full[stage], kb * TC_BLOCK_K,
+                            tma_load_2d_mc(sa + (size_t)rn * a_rows * 128, ma, &full[stage], kb * k_elems, row_a + rn * a_rows, mask_a);
+                            tma_load_2d_mc(sa + TC_A_BYTES + (size_t)rm * b_rows * 128, mb, &full[stage], kb * k_elems,
                                            row_b + rm * b_rows, mask_b);
                         }
                         }
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(TC_BLOCK_M, (uint32_t)core.block_n);
+            const uint32_t idesc = core.tf32 ? umma_idesc_tf32(TC_BLOCK_M, (uint32_t)core.block_n) : umma_idesc_bf16(TC_BLOCK_M, (uint32_t)core.block_n);
             uint32_t stage = 0, phase = 0;
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int acc = ch % core.acc_stages;
@@ -268,7 +271,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
                     for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
                         if (core.debug_mode == 1) break;
-                        umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);   // +32 B per K=16 step
+                        if (core.tf32) umma_tf32(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);   // +32 B per K=8 step
+                        else umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);            // +32 B per K=16 step
                         accumulate = 1;
                     }
                     if (csize == 1) umma_commit(&empty[stage]); else umma_commit_mc(&empty[stage], (uint16_t)(mask_a | mask_b));

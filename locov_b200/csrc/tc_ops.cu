@@ -488,6 +488,13 @@ static int fill_maps(TcMaps &maps, const uint16_t *a_hi, const uint16_t *a_lo, u
     // TMA boxes are the per-CTA SLICES of the tiles (the whole tile without a cluster)
     const uint32_t a_box = (uint32_t)(TC_BLOCK_M / core.cn), b_box = (uint32_t)(core.block_n / core.cm);
     int rc;
+    if (core.tf32) {       // operands are fp32 matrices read in place (no hi/lo split)
+        if ((rc = make_tmap_f32_2d(&maps.a_hi, a_hi, a_rows, K, a_ld, a_box)) != LOCO_OK) return rc;
+        if ((rc = make_tmap_f32_2d(&maps.b_hi, b_hi, b_rows, K, b_ld, b_box)) != LOCO_OK) return rc;
+        maps.a_lo = maps.a_hi;
+        maps.b_lo = maps.b_hi;
+        return LOCO_OK;
+    }
     if ((rc = make_tmap_bf16_2d(&maps.a_hi, a_hi, a_rows, K, a_ld, a_box)) != LOCO_OK) return rc;
     if ((rc = make_tmap_bf16_2d(&maps.a_lo, a_lo ? a_lo : a_hi, a_rows, K, a_ld, a_box)) != LOCO_OK) return rc;
     if ((rc = make_tmap_bf16_2d(&maps.b_hi, b_hi, b_rows, K, b_ld, b_box)) != LOCO_OK) return rc;
@@ -550,9 +557,9 @@ using namespace loco;
 
 extern "C" {
 
-int loco_linear_fwd(const uint16_t *A_hi, const uint16_t *A_lo, int64_t lda, const uint16_t *W_hi, const uint16_t *W_lo,
-                    int64_t ldw, const float *bias, int M, int N, int K, float *out_f32, int64_t ld_f32,
-                    uint16_t *out_hi, uint16_t *out_lo, int n_bf16, int64_t ld_bf16, void *stream) {
+static int linear_launch(const void *A_hi, const void *A_lo, int64_t lda, const void *W_hi, const void *W_lo, int64_t ldw, bool tf32,
+                         const float *bias, int M, int N, int K, float *out_f32, int64_t ld_f32, uint16_t *out_hi, uint16_t *out_lo,
+                         int n_bf16, int64_t ld_bf16, void *stream) {
     LOCO_REQUIRE(M >= 0 && N > 0 && K > 0, LOCO_E_BADARG, "linear_fwd: bad shape M=%d N=%d K=%d", M, N, K);
     if (M == 0) return LOCO_OK;
     LOCO_REQUIRE(A_hi && W_hi, LOCO_E_BADARG, "linear_fwd: null operand");
@@ -565,6 +572,7 @@ int loco_linear_fwd(const uint16_t *A_hi, const uint16_t *A_lo, int64_t lda, con
         LOCO_REQUIRE(n_bf16 % 2 == 0 || ld_bf16 > n_bf16, LOCO_E_ALIGN, "linear_fwd: odd n_bf16 needs a padded ld_bf16");
     }
     TcCore core = {};
+    core.tf32 = tf32 ? 1 : 0;
     const int sms = current_device_sm_count();
     pick_gemm_shape(M, N, sms, core);
     EpiLinear::Params p;
@@ -584,9 +592,22 @@ int loco_linear_fwd(const uint16_t *A_hi, const uint16_t *A_lo, int64_t lda, con
     p.grid = grid;
     const size_t smem = tc_finalize(core, K, A_lo ? 3 : 1, chunks, 0);
     TcMaps maps;
-    int rc = fill_maps(maps, A_hi, A_lo, M, lda, W_hi, W_lo, N, ldw, K, core);
+    int rc = fill_maps(maps, static_cast<const uint16_t *>(A_hi), static_cast<const uint16_t *>(A_lo), M, lda, static_cast<const uint16_t *>(W_hi),
+                       static_cast<const uint16_t *>(W_lo), N, ldw, K, core);
     if (rc != LOCO_OK) return rc;
     return tc_launch<EpiLinear>(maps, core, p, grid, smem, static_cast<cudaStream_t>(stream));
+}
+
+int loco_linear_fwd(const uint16_t *A_hi, const uint16_t *A_lo, int64_t lda, const uint16_t *W_hi, const uint16_t *W_lo,
+                    int64_t ldw, const float *bias, int M, int N, int K, float *out_f32, int64_t ld_f32,
+                    uint16_t *out_hi, uint16_t *out_lo, int n_bf16, int64_t ld_bf16, void *stream) {
+    return linear_launch(A_hi, A_lo, lda, W_hi, W_lo, ldw, false, bias, M, N, K, out_f32, ld_f32, out_hi, out_lo, n_bf16, ld_bf16, stream);
+}
+
+int loco_linear_tf32_fwd(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias, int M, int N, int K,
+                         float *out_f32, int64_t ld_f32, uint16_t *out_hi, uint16_t *out_lo, int n_bf16, int64_t ld_bf16,
+                         void *stream) {
+    return linear_launch(A, nullptr, lda, W, nullptr, ldw, true, bias, M, N, K, out_f32, ld_f32, out_hi, out_lo, n_bf16, ld_bf16, stream);
 }
 
 int loco_box_score_fwd(const uint16_t *E_hi, const uint16_t *E_lo, int64_t lde, const uint16_t *C_hi, const uint16_t *C_lo,

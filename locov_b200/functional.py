@@ -86,9 +86,10 @@ class _Linear(Function):
     def forward(ctx, x, w, b, precision):
         acc = _acc(precision)
         x2 = x.reshape(-1, x.shape[-1])
-        a_op = ops.split_bf16(x2, acc)
-        w_op = weight_operand(w, acc)
-        out, _ = ops.linear_fwd(a_op, w_op, b, want_f32=True)
+        if acc or x2.shape[1] % 4:
+            out, _ = ops.linear_fwd(ops.split_bf16(x2, acc), weight_operand(w, acc), b, want_f32=True)
+        else:       # reduced-precision mode: fp32 operands in place as TF32, no split pass
+            out, _ = ops.linear_tf32_fwd(x2, w.detach(), b, want_f32=True)
         ctx.save_for_backward(x2, w)
         ctx.meta = (precision, b is not None, x.shape)
         return out.reshape(*x.shape[:-1], w.shape[0])
@@ -141,9 +142,12 @@ class _BoxPredict(Function):
         nbox = w_box.shape[0]
         w_cat = _cat_weight(w_emb, w_box)
         b_cat = torch.cat([b_emb.detach(), b_box.detach()]).to(torch.float32)
-        a_op = ops.split_bf16(x, acc)
-        wcat_op = weight_operand(w_cat, acc, tag="cat")
-        out, e_op = ops.linear_fwd(a_op, wcat_op, b_cat, want_f32=True, n_bf16=d, accurate_out=acc)
+        if acc or x.shape[1] % 4:
+            a_op = ops.split_bf16(x, acc)
+            wcat_op = weight_operand(w_cat, acc, tag="cat")
+            out, e_op = ops.linear_fwd(a_op, wcat_op, b_cat, want_f32=True, n_bf16=d, accurate_out=acc)
+        else:       # reduced-precision mode: TF32 projection straight from the fp32 activations (no split pass)
+            out, e_op = ops.linear_tf32_fwd(x, w_cat, b_cat, want_f32=True, n_bf16=d)
         deltas = out[:, d:d + nbox]
         cls_op = weight_operand(w_cls, acc)
         logits, probs, lse, arg = ops.box_score(e_op, cls_op, b_cls, want_probs)
@@ -245,6 +249,16 @@ def box_cross_entropy(logits, lse, labels):
 # ------------------------------------------------------------------------------------------------
 # LSM grounding head: projection + pair distances in one autograd node
 # ------------------------------------------------------------------------------------------------
+def project_regions(x2d, w, b, d, acc):
+    """v2l_projection (grounding_head.py:111) -> bf16 tensor-core operand of the region embeddings.
+    fp32 mode: hi/lo split + three bf16 passes; reduced-precision mode: TF32 straight from the fp32 features."""
+    if acc or x2d.shape[1] % 4:
+        _, emb_op = ops.linear_fwd(ops.split_bf16(x2d, acc), weight_operand(w, acc), b, want_f32=False, n_bf16=d, accurate_out=acc)
+    else:
+        _, emb_op = ops.linear_tf32_fwd(x2d, w.detach(), b, want_f32=False, n_bf16=d)
+    return emb_op
+
+
 def new_pair_stack(bc, bi, device, both=True):
     """[2, Bc, Bi] buffer for (w2r, r2w): one allocation so the pair-CE kernel handles both in one launch."""
     return (torch.empty if both else torch.zeros)((2, bc, bi), dtype=torch.float32, device=device)
@@ -259,9 +273,7 @@ class _LsmHead(Function):
         acc = _acc(precision)
         bi, rg, v = feats.shape
         bc, t, d = cap.shape
-        x_op = ops.split_bf16(feats.reshape(bi * rg, v), acc)
-        w_op = weight_operand(w, acc)
-        _, emb_op = ops.linear_fwd(x_op, w_op, b, want_f32=False, n_bf16=d, accurate_out=acc)
+        emb_op = project_regions(feats.reshape(bi * rg, v), w, b, d, acc)
         cap_op = ops.split_bf16(cap.reshape(bc * t, d), acc)
         stack = new_pair_stack(bc, bi, feats.device, want_w2r and want_r2w)
         ops.lsm_pair(cap_op, cap_mask, emb_op, reg_mask, inv_temp, alignment, want_w2r, want_r2w, stack[0], stack[1])

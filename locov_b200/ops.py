@@ -179,6 +179,38 @@ def linear_fwd(a: Bf16Operand, w: Bf16Operand, bias: Optional[torch.Tensor], wan
     return out_f32, ob
 
 
+def linear_tf32_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], want_f32: bool = True, n_bf16: int = 0):
+    """out[M,N] = x[M,K] · w[N,K]^T + bias with the fp32 operands read in place as TF32 (no split pass).
+    Returns (out_f32 or None, bf16 operand of the first n_bf16 columns or None)."""
+    _need_cuda(x, w)
+    if x.dtype != torch.float32 or w.dtype != torch.float32 or x.dim() != 2 or w.dim() != 2 or x.shape[1] != w.shape[1]:
+        raise LocoError("linear_tf32_fwd: expects fp32 [M,K] and [N,K]")
+    if x.stride(1) != 1 or x.stride(0) % 4 or x.data_ptr() % 16:
+        x = x.contiguous()
+    if w.stride(1) != 1 or w.stride(0) % 4 or w.data_ptr() % 16:
+        w = w.contiguous()
+    m, k = x.shape
+    n = w.shape[0]
+    if k % 4:
+        raise LocoError("linear_tf32_fwd: K must be a multiple of 4 (16-byte TMA rows)")
+    dev = x.device
+    out_f32 = torch.empty((m, n), dtype=torch.float32, device=dev) if want_f32 else None
+    ob = None
+    if n_bf16 > 0:
+        ld = _round_up(n_bf16, 8)
+        hi = torch.empty((m, ld), dtype=torch.bfloat16, device=dev)
+        if ld != n_bf16:
+            hi[:, n_bf16:].zero_()
+        ob = Bf16Operand(hi, None, m, n_bf16)
+    if bias is not None:
+        bias = bias.to(torch.float32).contiguous()
+    lib = _lib.load()
+    _lib.check(lib.loco_linear_tf32_fwd(_p(x), x.stride(0), _p(w), w.stride(0), _p(bias), m, n, k, _p(out_f32),
+                                        n if want_f32 else 0, _p(ob.hi) if ob else None, None, n_bf16, ob.ld if ob else 0,
+                                        _stream(x)), "loco_linear_tf32_fwd")
+    return out_f32, ob
+
+
 def box_score(e: Bf16Operand, cls: Bf16Operand, cls_bias: Optional[torch.Tensor] = None, want_probs: bool = True):
     """RoI x class logits with fused softmax: returns (logits [R,K1], probs or None, lse [R], argmax_fg [R] i64)."""
     if e.cols != cls.cols:

@@ -107,9 +107,7 @@ class _ShardedLsm(Function):
                 if x is not None:
                     x.record_stream(side)
         # 2. projection of the local regions overlaps the gather
-        x_op = ops.split_bf16(feats.reshape(bi * rg, v), acc)
-        w_op = LF.weight_operand(w, acc)
-        _, emb_op = ops.linear_fwd(x_op, w_op, b, want_f32=False, n_bf16=d, accurate_out=acc)
+        emb_op = LF.project_regions(feats.reshape(bi * rg, v), w, b, d, acc)
         main.wait_stream(side)
         cap_all = ops.Bf16Operand(hi_all, lo_all, hi_all.shape[0], d)
         stack = LF.new_pair_stack(hi_all.shape[0] // t, bi, dev, want_w2r and want_r2w)
