@@ -23,7 +23,7 @@ namespace loco {
 
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;   // bf16 elements: 128 bytes = one swizzle span
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 192;          // 2 control warps + 4 epilogue warps (policies may ask for 8: Epi::kEpiWarps)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
 
@@ -154,7 +154,7 @@ __device__ __forceinline__ void warp_store_bf16(uint32_t *scratch, const float (
 //   __device__ void chunk(const Params&, const TcCore&, int cta, int chunk, uint32_t taddr, ...same...);
 //   __device__ void finish(const Params&, const TcCore&, int cta, ...same...);
 template <class Epi>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
     tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcCore core, const typename Epi::Params ep) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 128);
+            mbar_init(&tempty[a], 32u * Epi::kEpiWarps);
         }
         fence_mbar_init();
     }
@@ -319,14 +319,14 @@ int tc_launch(const TcMaps &maps, const TcCore &core, const typename Epi::Params
         configured = 227 * 1024;
     }
     if (core.cm * core.cn == 1) {
-        tc_gemm_kernel<Epi><<<grid, TC_THREADS, smem_bytes, st>>>(maps, core, ep);
+        tc_gemm_kernel<Epi><<<grid, 64 + 32 * Epi::kEpiWarps, smem_bytes, st>>>(maps, core, ep);
     } else {
         LOCO_REQUIRE(core.cm * core.cn <= 8 && grid % (core.cm * core.cn) == 0, LOCO_E_BADARG, "bad cluster %dx%d for grid %d", core.cm, core.cn, grid);
         LOCO_REQUIRE(TC_BLOCK_M % core.cn == 0 && (TC_BLOCK_M / core.cn) % 8 == 0 && core.block_n % core.cm == 0 && (core.block_n / core.cm) % 8 == 0,
                      LOCO_E_BADARG, "cluster %dx%d does not slice a 128x%d tile on 8-row boundaries", core.cm, core.cn, core.block_n);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3(TC_THREADS);
+        cfg.blockDim = dim3(64 + 32 * Epi::kEpiWarps);
         cfg.dynamicSmemBytes = smem_bytes;
         cfg.stream = st;
         cudaLaunchAttribute at[1];

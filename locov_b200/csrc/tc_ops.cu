@@ -11,12 +11,15 @@
 
 namespace loco {
 
-constexpr float LSM_FILL = -1.0e30f;   // finite "masked" logit: an all-masked row stays uniform, never NaN
+constexpr float LSM_FILL = -1.0e30f;
+constexpr float LSM_PAD = -3.0e38f;    // padding columns of a tile: exp2(LSM_PAD - anything finite) == 0   // finite "masked" logit: an all-masked row stays uniform, never NaN
 
 // ------------------------------------------------------------------------------------------------
 // EpiLinear
 // ------------------------------------------------------------------------------------------------
 struct EpiLinear {
+    static constexpr int kEpiWarps = 4;
+    static constexpr int kMinBlocks = 1;
     struct Params {
         const float *bias;
         float *out_f32;
@@ -105,6 +108,8 @@ struct EpiLinear {
 // EpiScore — RoI x class logits with online softmax statistics across N-chunks
 // ------------------------------------------------------------------------------------------------
 struct EpiScore {
+    static constexpr int kEpiWarps = 4;
+    static constexpr int kMinBlocks = 1;
     struct Params {
         const float *bias;
         float *logits, *probs;
@@ -227,17 +232,18 @@ struct LsmParams {
 
 // shared-memory carve-up (floats) after the [128][lds] tile
 struct LsmSmem {
-    float *S, *rmask, *cmask, *rowval, *colval, *rowmx, *rowden, *rowf, *colmx, *colden, *colh, *capnw, *capw2r, *capr2w;
+    float *S, *rbias, *cbias, *rowval, *colval, *pmax, *pden, *pnum, *rowmx, *rowden, *rowf, *colmx, *colden, *colh, *capnw;
     __device__ __forceinline__ LsmSmem(unsigned char *base, int lds, int block_n, int per_tile, int Rg, bool bwd) {
         float *p = reinterpret_cast<float *>(base);
         S = p; p += 128 * lds;
-        rmask = p; p += block_n;
-        cmask = p; p += 128;
+        rbias = p; p += block_n;          // 0 for a valid region, LSM_FILL for a masked one (additive mask)
+        cbias = p; p += 128;              // same per caption-word row
         rowval = p; p += 128;
         colval = p; p += per_tile * Rg;
+        pmax = p; p += 256;               // [2][128] partial row statistics of the two column halves
+        pden = p; p += 256;
+        pnum = p; p += 256;
         capnw = p; p += LSM_MAX_PER_TILE;
-        capw2r = p; p += LSM_MAX_PER_TILE;
-        capr2w = p; p += LSM_MAX_PER_TILE;
         rowmx = rowden = rowf = colmx = colden = colh = nullptr;
         if (bwd) {
             rowmx = p; p += 128;
@@ -250,13 +256,22 @@ struct LsmSmem {
     }
 };
 static size_t lsm_epi_smem_bytes(int lds, int block_n, int per_tile, int Rg, bool bwd) {
-    size_t f = (size_t)128 * lds + block_n + 128 + 128 + (size_t)per_tile * Rg + 3 * LSM_MAX_PER_TILE;
+    size_t f = (size_t)128 * lds + block_n + 128 + 128 + (size_t)per_tile * Rg + 3 * 256 + LSM_MAX_PER_TILE;
     if (bwd) f += 3 * 128 + 3 * (size_t)per_tile * Rg;
     return f * sizeof(float) + 16;
 }
 
+constexpr float LSM_LOG2E = 1.4426950408889634f;
+constexpr float LSM_LN2 = 0.6931471805599453f;
+
+// Eight epilogue warps: warps w and w + 4 own the same 32 accumulator rows (TMEM lane quarter w % 4) and split the
+// columns in interleaved 32-column blocks; the column / reduction phases run from shared memory on all 256 threads.
+// The tile is parked in log2 units (raw * inv_temp * log2 e) so that every exponential is one FADD + one MUFU.EX2.
 template <bool BWD>
 struct EpiLsm {
+    static constexpr int kEpiWarps = 8;
+    static constexpr int kMinBlocks = 2;      // two CTAs per SM: one tile's epilogue overlaps the other's loads / MMAs
+    static constexpr int kThreads = 32 * kEpiWarps;
     typedef LsmParams Params;
     static __device__ __forceinline__ void coords(const Params &p, const TcCore &, int cta, int, int &row_a, int &row_b) {
         const int g = cta / p.Bi_pad, i = cta - g * p.Bi_pad;
@@ -271,130 +286,180 @@ struct EpiLsm {
         const LsmSmem sm(smem, p.lds, core.block_n, p.per_tile, p.Rg, BWD);
         const int g = cta / p.Bi_pad, i = cta - g * p.Bi_pad;
         if (i >= p.Bi || g * p.per_tile >= p.Bc) return;            // padding tile of the cluster grid (CTA-uniform)
-        const int et = threadIdx.x - 64;                            // 0..127 among the epilogue threads
+        if (core.debug_mode == 3) return;                           // developer timing experiments (LOCOV_B200_DEBUG)
+        const int et = threadIdx.x - 64;                            // 0..255 among the epilogue threads
+        const int ew = et >> 5;                                     // epilogue warp 0..7
+        const int half = ew >> 2;                                   // which interleaved half of the column blocks
+        (void)q;
         const int c_first = g * p.per_tile;
         const int ncap = max(0, min(p.per_tile, p.Bc - c_first));    // valid captions of this tile
         const int nrows = ncap * p.T;                                // valid word rows
         const int T = p.T, Rg = p.Rg, lds = p.lds;
         const bool want_w = BWD ? (p.g_w2r != nullptr) : (p.out_w2r != nullptr);
         const bool want_r = BWD ? (p.g_r2w != nullptr) : (p.out_r2w != nullptr);
+        const float scale2 = p.inv_temp * LSM_LOG2E;
 
-        // ---- phase 0: masks ---------------------------------------------------------------------------
-        for (int r = et; r < core.block_n; r += 128) sm.rmask[r] = (r < Rg) ? __ldg(p.reg_mask + (int64_t)i * Rg + r) : 0.f;
+        // ---- phase 0: additive masks -----------------------------------------------------------------------
+        // (columns >= Rg are padding of the 32-column blocks: a fill far below LSM_FILL keeps them out of an all-masked
+        //  row's uniform softmax; the accumulator holds finite values there — block_n is a multiple of 32)
+        for (int r = et; r < core.block_n; r += kThreads)
+            sm.rbias[r] = (r < Rg) ? ((__ldg(p.reg_mask + (int64_t)i * Rg + r) > 0.f) ? 0.f : LSM_FILL) : LSM_PAD;
         const float mc = (row < nrows) ? __ldg(p.cap_mask + (int64_t)c_first * T + row) : 0.f;
-        sm.cmask[row] = mc;
-        named_bar_sync(1, 128);
+        if (half == 0) sm.cbias[row] = (mc > 0.f) ? 0.f : LSM_FILL;
+        named_bar_sync(1, kThreads);
 
-        // ---- phase 1: TMEM -> scaled tile in smem; row softmax statistics ----------------------------------
+        // ---- phase 1: TMEM -> tile (log2 units) in smem; row softmax statistics, columns split between the halves ----
         const int nblk = (Rg + 31) / 32;
         float *srow = sm.S + (size_t)row * lds;
+        const bool row_on = mc > 0.f;
         float mx = -FLT_MAX, best_s = 0.f;
         int best_r = 0;
-        for (int b = 0; b < nblk; ++b) {
-            float v[32];
-            tmem_ld32(taddr + (uint32_t)(b * 32), v);
+        float f_t = 0.f, den = 1.f;
+        if (!p.hardmax) {
+            // fast path (softmax): no per-element predicates.  Rows without a valid word (mc == 0) and padding columns
+            // need no special case: the additive region bias masks columns, and a masked row's result is discarded below.
+            for (int b = half; b < nblk; b += 2) {
+                float v[32];
+                tmem_ld32(taddr + (uint32_t)(b * 32), v);
+                const float4 *rb4 = reinterpret_cast<const float4 *>(sm.rbias + b * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int r = b * 32 + j;
-                if (r < Rg) {
-                    const float s = v[j] * p.inv_temp;
-                    srow[r] = s;
-                    const float sv = (mc > 0.f && sm.rmask[r] > 0.f) ? s : LSM_FILL;
-                    if (sv > mx) { mx = sv; best_s = s; best_r = r; }   // strict >: first maximum (torch.argmax)
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 rb = rb4[j >> 2];
+                    const float s0 = v[j] * scale2, s1 = v[j + 1] * scale2, s2 = v[j + 2] * scale2, s3 = v[j + 3] * scale2;
+                    srow[b * 32 + j] = s0; srow[b * 32 + j + 1] = s1; srow[b * 32 + j + 2] = s2; srow[b * 32 + j + 3] = s3;
+                    mx = fmaxf(mx, fmaxf(fmaxf(s0 + rb.x, s1 + rb.y), fmaxf(s2 + rb.z, s3 + rb.w)));
                 }
             }
-        }
-        float f_t = best_s, den = (float)best_r;                   // hardmax: `den` carries the argmax index
-        if (want_w && !p.hardmax) {
-            // second sweep straight from TMEM (registers): 32 independent exponentials per block, four
-            // accumulator chains — the epilogue runs one warp per scheduler, so ILP is the only latency hiding
-            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
-            for (int b = 0; b < nblk; ++b) {
+            sm.pmax[half * 128 + row] = mx;
+            named_bar_sync(1, kThreads);
+            mx = fmaxf(sm.pmax[row], sm.pmax[128 + row]);
+            if (want_w) {
+                // second sweep straight from TMEM: FFMA, FADD, MUFU.EX2, FADD, FFMA per element, four accumulator chains
+                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+                const float nmx = -mx;
+                for (int b = half; b < nblk; b += 2) {
+                    float v[32];
+                    tmem_ld32(taddr + (uint32_t)(b * 32), v);
+                    const float4 *rb4 = reinterpret_cast<const float4 *>(sm.rbias + b * 32);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 rb = rb4[j >> 2];
+                        const float e0 = ex2_ftz(fmaf(v[j], scale2, nmx) + rb.x);
+                        const float e1 = ex2_ftz(fmaf(v[j + 1], scale2, nmx) + rb.y);
+                        const float e2 = ex2_ftz(fmaf(v[j + 2], scale2, nmx) + rb.z);
+                        const float e3 = ex2_ftz(fmaf(v[j + 3], scale2, nmx) + rb.w);
+                        d0 += e0; n0 = fmaf(e0, v[j], n0);
+                        d1 += e1; n1 = fmaf(e1, v[j + 1], n1);
+                        d2 += e2; n2 = fmaf(e2, v[j + 2], n2);
+                        d3 += e3; n3 = fmaf(e3, v[j + 3], n3);
+                    }
+                }
+                sm.pden[half * 128 + row] = (d0 + d1) + (d2 + d3);
+                sm.pnum[half * 128 + row] = ((n0 + n1) + (n2 + n3)) * p.inv_temp;      // sum e * s in natural units
+            }
+            named_bar_sync(1, kThreads);
+            if (want_w) {
+                den = sm.pden[row] + sm.pden[128 + row];
+                f_t = (sm.pnum[row] + sm.pnum[128 + row]) / den;
+            }
+        } else {
+            for (int b = half; b < nblk; b += 2) {
                 float v[32];
                 tmem_ld32(taddr + (uint32_t)(b * 32), v);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
+                for (int j = 0; j < 32; ++j) {
                     const int r = b * 32 + j;
-                    float e[4], sc[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        sc[u] = v[j + u] * p.inv_temp;
-                        const bool ok = (r + u < Rg);
-                        const float sv = (mc > 0.f && ok && sm.rmask[ok ? r + u : 0] > 0.f) ? sc[u] : LSM_FILL;
-                        e[u] = ok ? __expf(sv - mx) : 0.f;
-                    }
-                    d0 += e[0]; n0 = fmaf(e[0], sc[0], n0);
-                    d1 += e[1]; n1 = fmaf(e[1], sc[1], n1);
-                    d2 += e[2]; n2 = fmaf(e[2], sc[2], n2);
-                    d3 += e[3]; n3 = fmaf(e[3], sc[3], n3);
+                    const float s2 = v[j] * scale2;
+                    srow[r] = s2;
+                    const float sv = (r < Rg) ? (row_on ? s2 + sm.rbias[r] : LSM_FILL) : LSM_PAD;
+                    if (sv > mx) { mx = sv; best_s = s2; best_r = r; }     // strict >: first maximum (torch.argmax)
                 }
             }
-            den = (d0 + d1) + (d2 + d3);
-            f_t = ((n0 + n1) + (n2 + n3)) / den;
+            sm.pmax[half * 128 + row] = mx;
+            sm.pden[half * 128 + row] = (float)best_r;
+            sm.pnum[half * 128 + row] = best_s;
+            named_bar_sync(1, kThreads);
+            // first maximum over the whole row: prefer the lower column index on ties (blocks are interleaved)
+            const float m0 = sm.pmax[row], m1 = sm.pmax[128 + row];
+            const float r0 = sm.pden[row], r1 = sm.pden[128 + row];
+            const bool take1 = (m1 > m0) || (m1 == m0 && r1 < r0);
+            mx = fmaxf(m0, m1);
+            den = take1 ? r1 : r0;                                  // hardmax: `den` carries the argmax index
+            f_t = (take1 ? sm.pnum[128 + row] : sm.pnum[row]) * LSM_LN2;
+            named_bar_sync(1, kThreads);
         }
-        sm.rowval[row] = (mc > 0.f) ? f_t : 0.f;
-        if (BWD) {
-            sm.rowmx[row] = mx;
-            sm.rowden[row] = den;
-            sm.rowf[row] = f_t;
+        if (half == 0) {
+            sm.rowval[row] = row_on ? f_t : 0.f;
+            if (BWD) {
+                sm.rowmx[row] = mx;
+                sm.rowden[row] = den;
+                sm.rowf[row] = f_t;
+            }
         }
-        named_bar_sync(1, 128);
 
-        // ---- phase 2: column softmax over the T words of each caption ----------------------------------------
+        // ---- phase 2: column softmax over the T words of each caption (tile complete after the barrier above) ----
+        if (core.debug_mode == 4) return;
         if (want_r) {
             const int items = ncap * Rg;
-            for (int it = et; it < items; it += 128) {
+            for (int it = et; it < items; it += kThreads) {
                 const int cl = it / Rg, r = it - cl * Rg;
-                const float rm = sm.rmask[r];
+                const bool rm_on = sm.rbias[r] == 0.f;
                 const float *col = sm.S + (size_t)cl * T * lds + r;
-                const float *cm = sm.cmask + cl * T;
-                float cmx = -FLT_MAX, cbest = 0.f;
-                int best_t = 0;
-#pragma unroll 4
-                for (int t = 0; t < T; ++t) {
-                    const float s = col[(size_t)t * lds];
-                    const float sv = (rm > 0.f && cm[t] > 0.f) ? s : LSM_FILL;
-                    if (sv > cmx) { cmx = sv; cbest = s; best_t = t; }
-                }
-                float h = cbest, cden = (float)best_t;              // hardmax: argmax index
+                const float *cb = sm.cbias + cl * T;
+                float cmx = -FLT_MAX, h, cden;
                 if (!p.hardmax) {
+                    // a masked region's column needs no special case (its result is discarded below)
+#pragma unroll 4
+                    for (int t = 0; t < T; ++t) cmx = fmaxf(cmx, col[(size_t)t * lds] + cb[t]);
                     float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f;
+                    const float ncmx = -cmx;
                     int t = 0;
 #pragma unroll 2
                     for (; t + 1 < T; t += 2) {
                         const float s0 = col[(size_t)t * lds], s1 = col[(size_t)(t + 1) * lds];
-                        const float e0 = __expf(((rm > 0.f && cm[t] > 0.f) ? s0 : LSM_FILL) - cmx);
-                        const float e1 = __expf(((rm > 0.f && cm[t + 1] > 0.f) ? s1 : LSM_FILL) - cmx);
+                        const float e0 = ex2_ftz((s0 + ncmx) + cb[t]);
+                        const float e1 = ex2_ftz((s1 + ncmx) + cb[t + 1]);
                         d0 += e0; n0 = fmaf(e0, s0, n0);
                         d1 += e1; n1 = fmaf(e1, s1, n1);
                     }
                     if (t < T) {
                         const float s0 = col[(size_t)t * lds];
-                        const float e0 = __expf(((rm > 0.f && cm[t] > 0.f) ? s0 : LSM_FILL) - cmx);
+                        const float e0 = ex2_ftz((s0 + ncmx) + cb[t]);
                         d0 += e0; n0 = fmaf(e0, s0, n0);
                     }
                     cden = d0 + d1;
-                    h = (n0 + n1) / cden;
+                    h = (n0 + n1) / cden * LSM_LN2;
+                } else {
+                    float cbest = 0.f;
+                    int best_t = 0;
+                    for (int t = 0; t < T; ++t) {
+                        const float s2 = col[(size_t)t * lds];
+                        const float sv = rm_on ? s2 + cb[t] : LSM_FILL;
+                        if (sv > cmx) { cmx = sv; cbest = s2; best_t = t; }
+                    }
+                    cden = (float)best_t;                              // hardmax: argmax index
+                    h = cbest * LSM_LN2;
                 }
-                sm.colval[it] = (rm > 0.f) ? h : 0.f;
+                sm.colval[it] = rm_on ? h : 0.f;
                 if (BWD) {
                     sm.colmx[it] = cmx;
                     sm.colden[it] = cden;
                     sm.colh[it] = h;
                 }
             }
-            named_bar_sync(1, 128);
         }
+        named_bar_sync(1, kThreads);
 
-        // ---- phase 3: per-caption reductions in a fixed order (warp q handles captions q, q+4, ...) ----------
+        // ---- phase 3: per-caption reductions in a fixed order (epilogue warp w handles captions w, w+8, ...) ----------
+        if (core.debug_mode == 5) return;
         float nr = 0.f;
-        for (int r = lane; r < Rg; r += 32) nr += sm.rmask[r];
+        for (int r = lane; r < Rg; r += 32) nr += (sm.rbias[r] == 0.f) ? 1.f : 0.f;
         nr = warp_sum(nr);
-        for (int cl = q; cl < ncap; cl += 4) {
+        for (int cl = ew; cl < ncap; cl += kEpiWarps) {
             float a = 0.f, nw = 0.f, bsum = 0.f;
             for (int t = lane; t < T; t += 32) {
                 a += sm.rowval[cl * T + t];
-                nw += sm.cmask[cl * T + t];
+                nw += (sm.cbias[cl * T + t] == 0.f) ? 1.f : 0.f;
             }
             a = warp_sum(a);
             nw = warp_sum(nw);
@@ -414,8 +479,8 @@ struct EpiLsm {
         }
         if (!BWD) return;
 
-        // ---- phase 4 (BWD): dS in place -----------------------------------------------------------------------
-        named_bar_sync(1, 128);
+        // ---- phase 4 (BWD): dS in place (row-owning threads, columns split between the halves) --------------------
+        named_bar_sync(1, kThreads);
         if (row < nrows) {
             const int cl = row / T, t = row - cl * T;
             const int c = c_first + cl;
@@ -424,38 +489,34 @@ struct EpiLsm {
             const float gw = want_w ? -__ldg(p.g_w2r + (int64_t)c * p.ld_g + i) * mc / fmaxf(sm.capnw[cl], 1.f) * p.inv_temp : 0.f;
             const float gr = want_r ? -__ldg(p.g_r2w + (int64_t)c * p.ld_g + i) / fmaxf(nr, 1.f) * p.inv_temp : 0.f;
             const float rmx = sm.rowmx[row], rinv = 1.f / sm.rowden[row], rf = sm.rowf[row];
+            for (int b = half; b < nblk; b += 2) {
+                const int r_end = min(Rg, b * 32 + 32);
 #pragma unroll 4
-            for (int r = 0; r < Rg; ++r) {
-                const float s = srow[r];
-                const float rm = sm.rmask[r];
-                const bool valid = (mc > 0.f && rm > 0.f);
-                const float sv = valid ? s : LSM_FILL;
-                float d = 0.f;
-                if (want_w) {
-                    if (!p.hardmax) {
-                        const float P = __expf(sv - rmx) * rinv;
-                        d += gw * P * (1.f + (valid ? s - rf : 0.f));
-                    } else {
-                        d += (r == (int)sm.rowden[row]) ? gw : 0.f;
+                for (int r = b * 32; r < r_end; ++r) {
+                    const float s2 = srow[r];
+                    const float s = s2 * LSM_LN2;
+                    const bool rm_on = sm.rbias[r] == 0.f;
+                    const bool valid = row_on && rm_on;
+                    const float sv = valid ? s2 : LSM_FILL;
+                    float d = 0.f;
+                    if (want_w) {
+                        if (!p.hardmax) d += gw * ex2_ftz(sv - rmx) * rinv * (1.f + (valid ? s - rf : 0.f));
+                        else d += (r == (int)sm.rowden[row]) ? gw : 0.f;
                     }
-                }
-                if (want_r) {
-                    const int it = cl * Rg + r;
-                    if (!p.hardmax) {
-                        const float Q = __expf(sv - sm.colmx[it]) / sm.colden[it];
-                        d += gr * rm * Q * (1.f + (valid ? s - sm.colh[it] : 0.f));
-                    } else {
-                        d += (t == (int)sm.colden[it]) ? gr * rm : 0.f;
+                    if (want_r) {
+                        const int it = cl * Rg + r;
+                        if (!p.hardmax) d += rm_on ? gr * ex2_ftz(sv - sm.colmx[it]) / sm.colden[it] * (1.f + (valid ? s - sm.colh[it] : 0.f)) : 0.f;
+                        else d += (rm_on && t == (int)sm.colden[it]) ? gr : 0.f;
                     }
+                    srow[r] = d;
                 }
-                srow[r] = d;
             }
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kThreads);
 
         // ---- phase 5 (BWD): coalesced write-out ------------------------------------------------------------------
         const int64_t col0 = (int64_t)c_first * T;                  // first caption-word column of this tile in dS^T
-        for (int r = q; r < Rg; r += 4) {                           // warp per region row of dS^T
+        for (int r = ew; r < Rg; r += kEpiWarps) {                  // warp per region row of dS^T
             uint16_t *dh = p.dst_hi + ((int64_t)i * Rg + r) * p.ld_dst + col0;
             uint16_t *dl = p.dst_lo ? p.dst_lo + ((int64_t)i * Rg + r) * p.ld_dst + col0 : nullptr;
             for (int w = lane; w < nrows; w += 32) {
@@ -466,7 +527,7 @@ struct EpiLsm {
             }
         }
         if (p.ds_hi != nullptr) {
-            for (int w = q; w < nrows; w += 4) {                    // warp per caption-word row of dS
+            for (int w = ew; w < nrows; w += kEpiWarps) {           // warp per caption-word row of dS
                 uint16_t *dh = p.ds_hi + (col0 + w) * p.ld_ds + (int64_t)i * Rg;
                 uint16_t *dl = p.ds_lo ? p.ds_lo + (col0 + w) * p.ld_ds + (int64_t)i * Rg : nullptr;
                 for (int r = lane; r < Rg; r += 32) {
@@ -646,7 +707,7 @@ static int lsm_launch(bool bwd, const uint16_t *cap_hi, const uint16_t *cap_lo, 
     LOCO_REQUIRE(cap_hi && emb_hi && p.cap_mask && p.reg_mask, LOCO_E_BADARG, "lsm_pair: null pointer");
     LOCO_REQUIRE((cap_lo == nullptr) == (emb_lo == nullptr), LOCO_E_BADARG, "lsm_pair: cap_lo and emb_lo must both be given or both be NULL");
     TcCore core = {};
-    core.block_n = tc_round_up(p.Rg, 16);
+    core.block_n = tc_round_up(p.Rg, 32);      // whole 32-column epilogue blocks: every accumulator column read is written by the MMA
     p.per_tile = TC_BLOCK_M / p.T;
     if (p.per_tile > LSM_MAX_PER_TILE) p.per_tile = LSM_MAX_PER_TILE;
     if (p.per_tile > p.Bc) p.per_tile = p.Bc;

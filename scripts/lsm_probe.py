@@ -8,6 +8,7 @@ B, T, RG, D = 32, 20, 100, 768
 if len(sys.argv) > 1:
     B = int(sys.argv[1])
 bi = int(sys.argv[2]) if len(sys.argv) > 2 else B
+D = int(sys.argv[3]) if len(sys.argv) > 3 else D
 cap = ops.split_bf16(torch.randn(B * T, D, device=dev) * 0.05, False)
 emb = ops.split_bf16(torch.randn(bi * RG, D, device=dev) * 0.5, False)
 mc = torch.ones(B, T, device=dev); mr = torch.ones(bi, RG, device=dev)
