@@ -378,7 +378,12 @@ def run_b200(args):
         }
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL collectives live inside the captured CUDA graphs: tear down without destroy_process_group (which can
+        # block on them) once every rank is past the timed regions
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

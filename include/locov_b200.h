@@ -202,10 +202,13 @@ int loco_lsm_pair_bwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ld
  *                                  -log_softmax(-pw, dim=1)[c, c-off]; only meaningful when Bi == Bc),
  *               accuracy choose-caption, accuracy choose-image }.
  * dpw_caption / dpw_image (each may be NULL): dense [nmat, Bc, Bi] fp32 gradients of out4[.,0] / out4[.,1]
- * with respect to pw (zero at guard-filled entries, which are constants in the reference: .detach()). */
+ * with respect to pw (zero at guard-filled entries, which are constants in the reference: .detach()).
+ * workspace: loco_pair_ce_workspace_bytes() bytes, needed when max(Bc, Bi) > 32 (several CTAs per matrix, partial sums
+ * combined in CTA order by the last one).  It must be zero-initialised ONCE; every launch leaves it zeroed again. */
+int64_t loco_pair_ce_workspace_bytes(int nmat, int Bc, int Bi);
 int loco_pair_ce(float *pw, int nmat, int64_t mat_stride, int64_t ld, int Bc, int Bi, int diag_offset,
                  const float *cap_mask, int T, const float *reg_mask, int Rg, float *out4,
-                 float *dpw_caption, float *dpw_image, void *stream);
+                 float *dpw_caption, float *dpw_image, void *workspace, void *stream);
 
 #ifdef __cplusplus
 }

@@ -171,29 +171,33 @@ __device__ __forceinline__ float block_reduce_sum(float v, float *red) {
     return out;
 }
 
-// One CTA per pair matrix (blockIdx.x), warp-parallel: a warp owns a column (choose caption) or a row
-// (choose image) at a time, lanes stride over the other index, all reductions by shuffles in a fixed order.
-// STAGED: the matrix is copied to shared memory once (one global round trip, overlapped with the mask loads)
-// and every later pass runs from there; matrices too large for shared memory are walked in global memory.
+// Pair-matrix losses.  grid = (nmat, nblk): CTA (m, j) owns 32 image columns (choose caption: a warp per column) and
+// 32 caption rows (choose image: a warp per row) of matrix m; lanes stride over the other index and every reduction is a
+// fixed-order shuffle tree.  nblk == 1 (B <= 32): the matrix is staged in shared memory once.  nblk > 1: each CTA scans the
+// whole (L2-resident) matrix for the guard's global maximum, applies the guard on the fly, and the last CTA to finish
+// (ticket counter in `scratch`) adds the per-CTA partial sums in CTA order — deterministic, no float atomics.
 template <bool STAGED>
 __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_all, int64_t mat_stride, int64_t ld, int Bc, int Bi,
                                                        int diag_off, const float *__restrict__ cap_mask, int T,
                                                        const float *__restrict__ reg_mask, int Rg, float *__restrict__ out4_all,
-                                                       float *__restrict__ dcap_all, float *__restrict__ dimg_all) {
+                                                       float *__restrict__ dcap_all, float *__restrict__ dimg_all,
+                                                       float *__restrict__ scratch) {
     extern __shared__ float sm[];
     float *red = sm;                 // [32]
     float *cap_empty = sm + 32;      // [Bc] 1 if the caption has no valid word
     float *img_empty = cap_empty + Bc;   // [Bi]
     float *acc = img_empty + Bi;     // [4][32] per-warp partial sums: ce_cap, ce_img, acc_cap, acc_img (= out4 order)
     float *tile = acc + 128;         // [Bc][Bi + 1] when STAGED
-    float *pw = pw_all + (int64_t)blockIdx.x * mat_stride;
-    float *out4 = out4_all + 4 * blockIdx.x;
-    float *dcap = dcap_all ? dcap_all + (int64_t)blockIdx.x * Bc * Bi : nullptr;
-    float *dimg = dimg_all ? dimg_all + (int64_t)blockIdx.x * Bc * Bi : nullptr;
+    __shared__ int s_last;
+    const int mat_id = blockIdx.x, blk = blockIdx.y, nblk = gridDim.y;
+    float *pw = pw_all + (int64_t)mat_id * mat_stride;
+    float *out4 = out4_all + 4 * mat_id;
+    float *dcap = dcap_all ? dcap_all + (int64_t)mat_id * Bc * Bi : nullptr;
+    float *dimg = dimg_all ? dimg_all + (int64_t)mat_id * Bc * Bi : nullptr;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     const int64_t mld = STAGED ? (Bi + 1) : ld;      // row stride of the matrix the passes read
-    float *mat = STAGED ? tile : pw;
+    const float *mat = STAGED ? tile : pw;
 
     float mx = -FLT_MAX;
     for (int idx = tid; idx < Bc * Bi; idx += nt) {
@@ -215,24 +219,40 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
         if (lane == 0) img_empty[i] = s > 0.f ? 0.f : 1.f;
     }
     if (tid < 128) acc[tid] = 0.f;
-    // empty-pair guard (grounding_head.py:240-251): max over the whole matrix, then overwrite
+    // empty-pair guard (grounding_head.py:240-251): max over the whole ORIGINAL matrix; with several CTAs the entries
+    // are rewritten by the last CTA only, after every CTA has finished scanning
     mx = block_reduce_max(mx, red);            // (contains the __syncthreads that publish tile / cap_empty / img_empty)
-    for (int idx = tid; idx < Bc * Bi; idx += nt) {
-        const int c = idx / Bi, i = idx - c * Bi;
-        if (cap_empty[c] > 0.f && img_empty[i] > 0.f) {
-            pw[(int64_t)c * ld + i] = mx + 100.0f;
-            if (STAGED) tile[c * (Bi + 1) + i] = mx + 100.0f;
+    const float guard = mx + 100.0f;
+    // value of entry (c, i) with the guard applied on the fly
+    auto val = [&](int c, int i) -> float {
+        const float v = mat[(int64_t)c * mld + i];
+        if (STAGED) return v;
+        return (cap_empty[c] > 0.f && img_empty[i] > 0.f) ? guard : v;
+    };
+    if (STAGED) {
+        for (int idx = tid; idx < Bc * Bi; idx += nt) {
+            const int c = idx / Bi, i = idx - c * Bi;
+            if (cap_empty[c] > 0.f && img_empty[i] > 0.f) {
+                pw[(int64_t)c * ld + i] = guard;
+                tile[c * (Bi + 1) + i] = guard;
+            }
         }
+        __syncthreads();
     }
-    __syncthreads();
     const float inv = 1.0f / (float)Bi;
+    const int i_beg = blk * 32, i_end = min(Bi, i_beg + 32);
+    const int c_beg = blk * 32, c_end = min(Bc, c_beg + 32);
+    // with several CTAs the last block also takes the rows beyond nblk * 32 (Bc > Bi never happens for square
+    // matrices; kept general)
+    const int c_end2 = (blk == nblk - 1) ? Bc : c_end;
+    const int i_end2 = (blk == nblk - 1) ? Bi : i_end;
 
     // choose caption: per image column i, log-softmax over the rows of -pw; target row = i + diag_off
-    for (int i = warp; i < Bi; i += nwarp) {
+    for (int i = i_beg + warp; i < i_end2; i += nwarp) {
         float m = -FLT_MAX, best = FLT_MAX;
         int arg = 0x7fffffff;
         for (int c = lane; c < Bc; c += 32) {
-            const float v = mat[(int64_t)c * mld + i];
+            const float v = val(c, i);
             m = fmaxf(m, -v);
             if (v < best) { best = v; arg = c; }
         }
@@ -244,11 +264,11 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
             if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
         }
         float s = 0.f;
-        for (int c = lane; c < Bc; c += 32) s += expf(-mat[(int64_t)c * mld + i] - m);
+        for (int c = lane; c < Bc; c += 32) s += expf(-val(c, i) - m);
         s = warp_sum(s);
         const int tgt = i + diag_off;
         if (lane == 0 && tgt < Bc) {
-            acc[0 * 32 + warp] += (m + logf(s)) + mat[(int64_t)tgt * mld + i];
+            acc[0 * 32 + warp] += (m + logf(s)) + val(tgt, i);
             acc[2 * 32 + warp] += (arg == tgt) ? 1.f : 0.f;
         }
         if (dcap != nullptr) {
@@ -256,21 +276,21 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
             for (int c = lane; c < Bc; c += 32) {
                 float g = 0.f;
                 if (tgt < Bc && !(cap_empty[c] > 0.f && img_empty[i] > 0.f))
-                    g = (((c == tgt) ? 1.f : 0.f) - expf(-mat[(int64_t)c * mld + i] - m) / s) * inv;
+                    g = (((c == tgt) ? 1.f : 0.f) - expf(-val(c, i) - m) / s) * inv;
                 dcap[(int64_t)c * Bi + i] = g;
             }
         }
     }
     // choose image: per caption row c, log-softmax over the columns of -pw; rows outside
     // [diag_off, diag_off + Bi) carry no choose-image loss
-    for (int c = warp; c < Bc; c += nwarp) {
+    for (int c = c_beg + warp; c < c_end2; c += nwarp) {
         const int k = c - diag_off;
         const bool has = (k >= 0 && k < Bi);
         float m = -FLT_MAX, best = FLT_MAX, s = 0.f;
         int arg = 0x7fffffff;
         if (has) {
             for (int i = lane; i < Bi; i += 32) {
-                const float v = mat[(int64_t)c * mld + i];
+                const float v = val(c, i);
                 m = fmaxf(m, -v);
                 if (v < best) { best = v; arg = i; }
             }
@@ -281,10 +301,10 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
                 const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
                 if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
             }
-            for (int i = lane; i < Bi; i += 32) s += expf(-mat[(int64_t)c * mld + i] - m);
+            for (int i = lane; i < Bi; i += 32) s += expf(-val(c, i) - m);
             s = warp_sum(s);
             if (lane == 0) {
-                acc[1 * 32 + warp] += (m + logf(s)) + mat[(int64_t)c * mld + k];
+                acc[1 * 32 + warp] += (m + logf(s)) + val(c, k);
                 acc[3 * 32 + warp] += (arg == k) ? 1.f : 0.f;
             }
         }
@@ -292,16 +312,41 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
             for (int i = lane; i < Bi; i += 32) {
                 float g = 0.f;
                 if (has && !(cap_empty[c] > 0.f && img_empty[i] > 0.f))
-                    g = (((i == k) ? 1.f : 0.f) - expf(-mat[(int64_t)c * mld + i] - m) / s) * inv;
+                    g = (((i == k) ? 1.f : 0.f) - expf(-val(c, i) - m) / s) * inv;
                 dimg[(int64_t)c * Bi + i] = g;
             }
         }
     }
     __syncthreads();
+    float part = 0.f;
     if (warp < 4) {                  // warp w sums partial w over the (fixed-order) per-warp slots
         float v = (lane < nwarp) ? acc[warp * 32 + lane] : 0.f;
-        v = warp_sum(v);
-        if (lane == 0) out4[warp] = v * inv;
+        part = warp_sum(v);
+    }
+    if (nblk == 1) {
+        if (warp < 4 && lane == 0) out4[warp] = part * inv;
+        return;
+    }
+    // several CTAs: publish the partials, the last CTA adds them in CTA order
+    float *parts = scratch + 16 + ((int64_t)mat_id * nblk) * 4;
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(scratch) + mat_id;
+    if (warp < 4 && lane == 0) parts[blk * 4 + warp] = part;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned)(nblk - 1)) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (tid < 4) {
+            float v = 0.f;
+            for (int j = 0; j < nblk; ++j) v += __ldcg(parts + j * 4 + tid);
+            out4[tid] = v * inv;
+        }
+        if (tid == 0) *ticket = 0;   // ready for the next launch
+        for (int idx = tid; idx < Bc * Bi; idx += nt) {
+            const int c = idx / Bi, i = idx - c * Bi;
+            if (cap_empty[c] > 0.f && img_empty[i] > 0.f) pw[(int64_t)c * ld + i] = guard;
+        }
     }
 }
 
@@ -386,29 +431,30 @@ int loco_box_ce_fwd_bwd(const float *logits, int64_t ld_logits, const float *lse
     return LOCO_OK;
 }
 
+int64_t loco_pair_ce_workspace_bytes(int nmat, int Bc, int Bi) {
+    const int nblk = ((Bc > Bi ? Bc : Bi) + 31) / 32;
+    return (int64_t)(16 + (int64_t)nmat * nblk * 4) * (int64_t)sizeof(float);
+}
+
 int loco_pair_ce(float *pw, int nmat, int64_t mat_stride, int64_t ld, int Bc, int Bi, int diag_offset, const float *cap_mask,
-                 int T, const float *reg_mask, int Rg, float *out4, float *dpw_caption, float *dpw_image, void *stream) {
-    LOCO_REQUIRE(Bc > 0 && Bi > 0 && ld >= Bi && T > 0 && Rg > 0 && diag_offset >= 0 && nmat >= 1, LOCO_E_BADARG,
+                 int T, const float *reg_mask, int Rg, float *out4, float *dpw_caption, float *dpw_image, void *workspace,
+                 void *stream) {
+    LOCO_REQUIRE(Bc > 0 && Bi > 0 && ld >= Bi && T > 0 && Rg > 0 && diag_offset >= 0 && nmat >= 1 && nmat <= 16, LOCO_E_BADARG,
                  "pair_ce: bad shape nmat=%d Bc=%d Bi=%d ld=%lld", nmat, Bc, Bi, (long long)ld);
     LOCO_REQUIRE(pw && cap_mask && reg_mask && out4, LOCO_E_BADARG, "pair_ce: null pointer");
     const size_t base = (32 + (size_t)Bc + Bi + 128) * sizeof(float);
     LOCO_REQUIRE(base <= 48 * 1024, LOCO_E_UNSUPPORTED, "pair_ce: batch too large (Bc=%d Bi=%d)", Bc, Bi);
-    const size_t staged = base + (size_t)Bc * (Bi + 1) * sizeof(float);
-    int threads = 32 * (Bc > Bi ? Bc : Bi);
-    if (threads > 1024) threads = 1024;
-    if (threads < 128) threads = 128;
+    const int nblk = ((Bc > Bi ? Bc : Bi) + 31) / 32;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (staged <= 200 * 1024) {
-        static thread_local size_t configured = 0;
-        if (staged > 48 * 1024 && staged > configured) {
-            LOCO_CUDA(cudaFuncSetAttribute(pair_ce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            configured = 200 * 1024;
-        }
-        pair_ce_kernel<true><<<nmat, threads, staged, st>>>(pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T, reg_mask, Rg, out4,
-                                                            dpw_caption, dpw_image);
+    if (nblk == 1) {
+        const size_t staged = base + (size_t)Bc * (Bi + 1) * sizeof(float);
+        pair_ce_kernel<true><<<dim3(nmat, 1), 1024, staged, st>>>(pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T, reg_mask, Rg, out4,
+                                                                  dpw_caption, dpw_image, nullptr);
     } else {
-        pair_ce_kernel<false><<<nmat, threads, base, st>>>(pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T, reg_mask, Rg, out4,
-                                                           dpw_caption, dpw_image);
+        LOCO_REQUIRE(workspace != nullptr, LOCO_E_BADARG, "pair_ce: B > 32 needs loco_pair_ce_workspace_bytes() of ZERO-INITIALISED workspace "
+                     "(the kernel leaves it zeroed again)");
+        pair_ce_kernel<false><<<dim3(nmat, nblk), 1024, base, st>>>(pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T, reg_mask, Rg, out4,
+                                                                    dpw_caption, dpw_image, static_cast<float *>(workspace));
     }
     count_launch();
     LOCO_CUDA(cudaGetLastError());

@@ -49,6 +49,16 @@ def _workspace(device, nbytes, tag):
     return buf
 
 
+def _zero_workspace(device, nbytes, tag):
+    """Scratch that is zero-initialised once and that the kernels leave zeroed (ticket counters)."""
+    key = (device.index, tag, "zero")
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
 def roi_align(feat: torch.Tensor, rois: torch.Tensor, output_size, spatial_scale: float, sampling_ratio: int = 0,
               aligned: bool = True) -> torch.Tensor:
     """feat [N,C,H,W] fp32 (contiguous NCHW, or channels_last memory format), rois [R,5] -> [R,C,PH,PW]."""
@@ -366,8 +376,9 @@ def pair_ce(pw: torch.Tensor, cap_mask: torch.Tensor, reg_mask: torch.Tensor, di
     dcap = torch.empty((nmat, bc, bi), dtype=torch.float32, device=pw.device) if want_grad else None
     dimg = torch.empty((nmat, bc, bi), dtype=torch.float32, device=pw.device) if want_grad else None
     lib = _lib.load()
+    ws = _zero_workspace(pw.device, lib.loco_pair_ce_workspace_bytes(nmat, bc, bi), "pair_ce") if max(bc, bi) > 32 else None
     _lib.check(lib.loco_pair_ce(_p(pw3), nmat, pw3.stride(0), pw3.stride(1), bc, bi, int(diag_offset), _p(cap_mask),
-                                cap_mask.shape[1], _p(reg_mask), reg_mask.shape[1], _p(out), _p(dcap), _p(dimg),
+                                cap_mask.shape[1], _p(reg_mask), reg_mask.shape[1], _p(out), _p(dcap), _p(dimg), _p(ws),
                                 _stream(pw)), "loco_pair_ce")
     if single:
         out = out[0]

@@ -55,34 +55,59 @@ def gather_rows(t: torch.Tensor, group) -> torch.Tensor:
 
 
 class _GatherBlocks(Function):
-    """[n, B, B_loc] column blocks per rank -> full [n, B, B] matrices on every rank.  Backward = this
+    """[n, B, B_loc] column blocks per rank (+ the rank's per-image valid-region counts, packed into the same
+    message) -> full [n, B, B] matrices and the [B] region counts on every rank: ONE collective.  Backward = this
     rank's column slice of the (replicated) full gradient: no communication."""
 
     @staticmethod
-    def forward(ctx, block, group):
+    def forward(ctx, block, nreg_loc, group):
         w, r = dist.get_world_size(group), dist.get_rank(group)
         n, b, bl = block.shape
-        parts = block.new_empty((w * n, b, bl))           # dim-0 concatenation (the layout every backend accepts)
-        dist.all_gather_into_tensor(parts, block.contiguous(), group=group)
+        msg = torch.cat([block.reshape(-1), nreg_loc.reshape(-1).to(block.dtype)])
+        parts = msg.new_empty((w * msg.numel(),))          # dim-0 concatenation (the layout every backend accepts)
+        dist.all_gather_into_tensor(parts, msg, group=group)
+        parts = parts.view(w, msg.numel())
         ctx.cols = (r * bl, (r + 1) * bl)
-        return parts.view(w, n, b, bl).permute(1, 2, 0, 3).reshape(n, b, w * bl).contiguous()
+        full = parts[:, :n * b * bl].reshape(w, n, b, bl).permute(1, 2, 0, 3).reshape(n, b, w * bl).contiguous()
+        nreg_all = parts[:, n * b * bl:].reshape(w * bl).contiguous()
+        ctx.mark_non_differentiable(nreg_all)
+        return full, nreg_all
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _gn):
         c0, c1 = ctx.cols
-        return g[:, :, c0:c1].contiguous(), None
+        return g[:, :, c0:c1].contiguous(), None, None
 
 
-def assemble_blocks(block, group):
-    return _GatherBlocks.apply(block, group)
+def assemble_blocks(block, nreg_loc, group):
+    return _GatherBlocks.apply(block, nreg_loc, group)
 
 
 def global_pair_outputs(head, blocks, cap_mask_all, reg_mask_loc, group):
     """[2, B, B_loc] blocks -> (losses, other_info, dists) on the full matrices; shared by the CUDA path
-    and the gloo/CPU test of the exchange logic (``head._pair_outputs`` evaluates the losses)."""
-    reg_mask_all = gather_rows(reg_mask_loc, group)
-    full = assemble_blocks(blocks, group)
-    return head._pair_outputs(full, cap_mask_all, reg_mask_all)
+    and the gloo/CPU test of the exchange logic (``head._pair_outputs`` evaluates the losses).  The empty-pair
+    guard only needs to know WHICH images have no valid region, so the per-image counts travel with the blocks
+    and stand in for the region mask ([B, 1])."""
+    full, nreg_all = assemble_blocks(blocks, reg_mask_loc.to(torch.float32).sum(1), group)
+    return head._pair_outputs(full, cap_mask_all, (nreg_all > 0).to(torch.float32).reshape(-1, 1))
+
+
+def gather_packed(tensors, group):
+    """all-gather several equally-shaped-per-rank tensors with ONE collective (byte-packed message);
+    returns the dim-0 concatenations."""
+    w = dist.get_world_size(group)
+    flat = [t.contiguous().view(torch.uint8).reshape(-1) for t in tensors]
+    sizes = [f.numel() for f in flat]
+    msg = torch.cat(flat) if len(flat) > 1 else flat[0]
+    parts = msg.new_empty((w * msg.numel(),))
+    dist.all_gather_into_tensor(parts, msg, group=group)
+    parts = parts.view(w, msg.numel())
+    outs, off = [], 0
+    for t, n in zip(tensors, sizes):
+        chunk = parts[:, off:off + n].contiguous().view(t.dtype)
+        outs.append(chunk.reshape((w * t.shape[0],) + tuple(t.shape[1:])))
+        off += n
+    return outs
 
 
 class _ShardedLsm(Function):
@@ -100,12 +125,12 @@ class _ShardedLsm(Function):
         cap_op = ops.split_bf16(cap_loc.reshape(bl * t, d), acc)
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            hi_all = gather_rows(cap_op.hi, group)
-            lo_all = gather_rows(cap_op.lo, group) if acc else None
-            mask_all = gather_rows(cap_mask_loc, group)
-            for x in (cap_op.hi, cap_op.lo, cap_mask_loc, hi_all, lo_all, mask_all):
-                if x is not None:
-                    x.record_stream(side)
+            parts = [cap_op.hi, cap_mask_loc] + ([cap_op.lo] if acc else [])
+            got = gather_packed(parts, group)                 # one NCCL all-gather for operands + masks
+            hi_all, mask_all = got[0], got[1]
+            lo_all = got[2] if acc else None
+            for x in parts + got:
+                x.record_stream(side)
         # 2. projection of the local regions overlaps the gather
         emb_op = LF.project_regions(feats.reshape(bi * rg, v), w, b, d, acc)
         main.wait_stream(side)

@@ -144,3 +144,31 @@ def test_masks_kernel(cuda_device):
                 torch.randint(0, 2, (9, 21), generator=g)):
         cm, rm = ops.lsm_masks(att.to(cuda_device), spe.to(cuda_device), reg.to(cuda_device))
         assert torch.equal(cm.cpu(), lsm_head.caption_mask_of(att, spe)) and torch.equal(rm.cpu(), reg.float())
+
+
+@pytest.mark.parametrize("B", [5, 32, 33, 100, 256])
+def test_pair_ce_kernel_all_batch_sizes(cuda_device, B):
+    """Single-CTA staged path (B <= 32) and the multi-CTA ticketed path (B > 32): losses, accuracies, guard and the
+    gradients of both cross-entropies vs torch autograd on the oracle."""
+    from locov_b200 import ops
+    g = torch.Generator().manual_seed(B)
+    pw = torch.randn(2, B, B, generator=g) * 3
+    mc = torch.ones(B, 7)
+    mr = torch.ones(B, 9)
+    mc[B // 2] = 0
+    mr[B // 2] = 0
+    mr[0] = 0
+    pwd = pw.clone().to(cuda_device)
+    for rep in range(2):                      # twice: the ticket counters must be left zeroed
+        pwd = pw.clone().to(cuda_device)
+        out, dcap, dimg = ops.pair_ce(pwd, mc.to(cuda_device), mr.to(cuda_device), 0, want_grad=True)
+    ok = (mc.sum(1)[:, None] > 0) | (mr.sum(1)[None, :] > 0)
+    for k in range(2):
+        ref_in = pw[k].double().clone().requires_grad_(True)
+        guarded = torch.where(ok, ref_in, (ref_in.max() + 100.0).detach())
+        ce_cap, ce_img, acc_cap, acc_img = lsm_head.pair_losses(guarded)
+        assert torch.allclose(pwd[k].cpu().double(), guarded.detach(), rtol=0, atol=1e-6)
+        assert relerr(out[k].cpu(), torch.stack([ce_cap, ce_img, acc_cap.double(), acc_img.double()]).detach()) < 1e-5
+        (gc,) = torch.autograd.grad(ce_cap, ref_in, retain_graph=True)
+        (gi,) = torch.autograd.grad(ce_img, ref_in)
+        assert relerr(dcap[k].cpu(), gc) < 1e-4 and relerr(dimg[k].cpu(), gi) < 1e-4

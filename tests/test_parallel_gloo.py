@@ -30,8 +30,8 @@ def _worker(rank, world, port, q):
         sl = slice(rank * bl, (rank + 1) * bl)
         cap_mask = lsm_head.caption_mask_of(ic["attention_mask"], ic["special_tokens_mask"])
         # --- what the CUDA path does, with the oracle standing in for the kernels -------------------
-        cap_all = parallel.gather_rows(ic["input_embeddings"][sl].contiguous(), dist.group.WORLD)
-        mask_all = parallel.gather_rows(cap_mask[sl].contiguous(), dist.group.WORLD)
+        cap_all, mask_all = parallel.gather_packed([ic["input_embeddings"][sl].contiguous(), cap_mask[sl].contiguous()],
+                                                   dist.group.WORLD)
         assert torch.equal(cap_all, ic["input_embeddings"]) and torch.equal(mask_all, cap_mask)
         emb_loc = lsm_head.project_regions(ii["region_features"][sl], w, b)
         # raw (unguarded) blocks of this rank's images against ALL captions
