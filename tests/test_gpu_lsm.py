@@ -167,7 +167,7 @@ def test_pair_ce_kernel_all_batch_sizes(cuda_device, B):
         ref_in = pw[k].double().clone().requires_grad_(True)
         guarded = torch.where(ok, ref_in, (ref_in.max() + 100.0).detach())
         ce_cap, ce_img, acc_cap, acc_img = lsm_head.pair_losses(guarded)
-        assert torch.allclose(pwd[k].cpu().double(), guarded.detach(), rtol=0, atol=1e-6)
+        assert torch.allclose(pwd[k].cpu().double(), guarded.detach(), rtol=0, atol=1e-5)   # fp32 ulp at max+100 is 7.6e-6
         assert relerr(out[k].cpu(), torch.stack([ce_cap, ce_img, acc_cap.double(), acc_img.double()]).detach()) < 1e-5
         (gc,) = torch.autograd.grad(ce_cap, ref_in, retain_graph=True)
         (gi,) = torch.autograd.grad(ce_img, ref_in)
