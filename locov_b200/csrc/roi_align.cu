@@ -124,7 +124,7 @@ struct MergedEntry {
 };
 
 // entries of bin `p` are written at tab[p * stride ...]; returns their number
-__device__ __forceinline__ int build_merged(MergedEntry *tab, float start, float bin, int p, int g, int size) {
+__device__ __forceinline__ int build_merged(MergedEntry *tab, float start, float bin, int p, int g, int size, int mul = 1) {
     int n = 0;
     // taps are monotonic in the sample index, so an index can only repeat one of the last two entries
     auto add = [&](int idx, float w) {
@@ -138,10 +138,12 @@ __device__ __forceinline__ int build_merged(MergedEntry *tab, float start, float
         add(t.lo, t.wl);
         add(t.hi, t.wh);
     }
+    if (mul != 1)
+        for (int i = 0; i < n; ++i) tab[i].idx *= mul;   // index -> byte offset (v4 kernel)
     return n;
 }
 
-__global__ void __launch_bounds__(RA_THREADS, 3) roi_align_fwd_kernel(const float *__restrict__ feat,   // [N,H,W,C]
+__global__ void __launch_bounds__(RA_THREADS, 3) roi_align_fwd_generic_kernel(const float *__restrict__ feat,   // [N,H,W,C]
                                                                    const float *__restrict__ rois, int C, int H, int W,
                                                                    int PH, int PW, float scale, int sampling_ratio,
                                                                    int aligned, int nchunks, float *__restrict__ out) {
@@ -311,6 +313,176 @@ __global__ void __launch_bounds__(RA_THREADS, 3) roi_align_fwd_kernel(const floa
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// forward, vectorised: one CTA = (roi, 128-channel slab), lane = 4 consecutive channels (one LDG.128 per tap
+// serves 4 channels, so the per-tap table lookups / address arithmetic are amortised 4x and a warp request is a
+// full 512-byte run of the NHWC pixel), warp = one bin row.
+//   * merged tap tables hold BYTE offsets (row offset = y * W * C * 4, column offset = x * C * 4), built once
+//     per CTA with the exactly rounded coordinate arithmetic above.
+//   * a bin row walks its bins left to right; the merged column lists of neighbouring bins are monotonic and
+//     share at most their boundary column, so caching the last vertically pooled column in registers makes every
+//     column of the row's footprint get loaded exactly once per bin row (no shared-memory column buffer).
+//     The rows shared by neighbouring bin rows are re-read through L1 (ld.global.nc), not L2.
+//   * up to four row taps per column are issued as independent predicated 128-bit loads (adaptive grids with
+//     gh <= 3 have at most 4 merged rows); longer lists continue in a loop.
+//   * results go to a [128][S] shared tile with channel 4*l + j stored at row j*32 + l.  For even PW two
+//     neighbouring bins are stored as one 8-byte word and S = 2 (mod 4): both the column-wise STS.64 and the
+//     row-wise LDS.64 of the write-out are bank-conflict free; odd PW uses scalar accesses with odd S.
+//   * write-out: the slab is contiguous in the NCHW output; fully coalesced st.global.cs (evict-first).
+// ------------------------------------------------------------------------------------------------
+constexpr int RV_WARPS = 14;
+constexpr int RV_THREADS = RV_WARPS * 32;
+constexpr int RV_CC = 128;
+
+__device__ __forceinline__ float4 ldg128(const char *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void fma4(float4 &a, float w, const float4 &v) {
+    a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+}
+
+template <bool PAIR>
+__global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const float *__restrict__ feat,   // [N,H,W,C]
+                                                                        const float *__restrict__ rois, int C, int H, int W,
+                                                                        int PH, int PW, float scale, int sampling_ratio,
+                                                                        int aligned, int nchunks, int tstride,
+                                                                        float *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MergedEntry *ytab = reinterpret_cast<MergedEntry *>(smem_raw);
+    MergedEntry *xtab = ytab + RA_TAB;
+    int *ycnt = reinterpret_cast<int *>(xtab + RA_TAB);      // [32]
+    int *xcnt = ycnt + 32;                                    // [32]
+    float *tile = reinterpret_cast<float *>(xcnt + 32);       // [RV_CC][tstride]
+
+    const int r = blockIdx.x / nchunks;
+    const int chunk = blockIdx.x - r * nchunks;
+    const int c0 = chunk * RV_CC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int PHW = PH * PW;
+
+    const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, aligned, PH, PW, sampling_ratio);
+    const int ystride = sampling_ratio > 0 ? 2 * g.gh : g.gh + 2, xstride = sampling_ratio > 0 ? 2 * g.gw : g.gw + 2;
+    const bool empty = (g.gh <= 0 || g.gw <= 0);
+    const bool tables_fit = !empty && (long long)PH * ystride <= RA_TAB && (long long)PW * xstride <= RA_TAB;
+    const float inv_cnt = __fdiv_rn(1.0f, (float)max(g.gh * g.gw, 1));
+
+    if (tables_fit) {
+        const int t = threadIdx.x;
+        if (t < PH) ycnt[t] = build_merged(ytab + t * ystride, g.sh, g.bh, t, g.gh, H, W * C * 4);
+        else if (t >= 32 && t < 32 + PW) xcnt[t - 32] = build_merged(xtab + (t - 32) * xstride, g.sw, g.bw, t - 32, g.gw, W, C * 4);
+    }
+    __syncthreads();
+
+    const int cl = 4 * lane;
+    const bool active = (c0 + cl) < C;                         // C % 4 == 0: a lane's 4 channels are all in or all out
+    const char *fb = reinterpret_cast<const char *>(feat + (size_t)g.batch * H * W * C + (active ? c0 + cl : 0));
+    float *t0 = tile + (size_t)lane * tstride;                 // rows lane, 32 + lane, 64 + lane, 96 + lane
+    const int rstep = 32 * tstride;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    auto store_bin = [&](int o, const float4 &a) {            // scalar stores (odd PW / generic paths)
+        t0[o] = a.x; t0[o + rstep] = a.y; t0[o + 2 * rstep] = a.z; t0[o + 3 * rstep] = a.w;
+    };
+
+    if (empty) {
+        for (int ph = warp; ph < PH; ph += RV_WARPS)
+            for (int pw = 0; pw < PW; ++pw) store_bin(ph * PW + pw, zero4);
+    } else if (tables_fit) {
+        for (int ph = warp; ph < PH; ph += RV_WARPS) {
+            const MergedEntry *yt = ytab + ph * ystride;
+            const int ny = ycnt[ph];
+            const int yo0 = ny > 0 ? yt[0].idx : 0, yo1 = ny > 1 ? yt[1].idx : 0, yo2 = ny > 2 ? yt[2].idx : 0, yo3 = ny > 3 ? yt[3].idx : 0;
+            const float yw0 = ny > 0 ? yt[0].w : 0.f, yw1 = ny > 1 ? yt[1].w : 0.f, yw2 = ny > 2 ? yt[2].w : 0.f, yw3 = ny > 3 ? yt[3].w : 0.f;
+            int lastoff = -1;
+            float4 u = zero4, prev = zero4;
+            for (int pw = 0; pw < PW; ++pw) {
+                float4 acc = zero4;
+                const MergedEntry *xt = xtab + pw * xstride;
+                const int nx = xcnt[pw];
+                for (int j = 0; j < nx; ++j) {
+                    const MergedEntry e = xt[j];
+                    if (e.idx != lastoff) {                    // warp-uniform
+                        lastoff = e.idx;
+                        u = zero4;
+                        if (active) {
+                            const char *p = fb + e.idx;
+                            float4 v0 = zero4, v1 = zero4, v2 = zero4, v3 = zero4;
+                            if (ny > 0) v0 = ldg128(p + yo0);
+                            if (ny > 1) v1 = ldg128(p + yo1);
+                            if (ny > 2) v2 = ldg128(p + yo2);
+                            if (ny > 3) v3 = ldg128(p + yo3);
+                            fma4(u, yw0, v0); fma4(u, yw1, v1); fma4(u, yw2, v2); fma4(u, yw3, v3);
+                            for (int k = 4; k < ny; ++k) fma4(u, yt[k].w, ldg128(p + yt[k].idx));
+                        }
+                    }
+                    fma4(acc, e.w, u);
+                }
+                acc.x *= inv_cnt; acc.y *= inv_cnt; acc.z *= inv_cnt; acc.w *= inv_cnt;
+                const int o = ph * PW + pw;
+                if (PAIR) {
+                    if (pw & 1) {
+                        *reinterpret_cast<float2 *>(t0 + o - 1) = make_float2(prev.x, acc.x);
+                        *reinterpret_cast<float2 *>(t0 + o - 1 + rstep) = make_float2(prev.y, acc.y);
+                        *reinterpret_cast<float2 *>(t0 + o - 1 + 2 * rstep) = make_float2(prev.z, acc.z);
+                        *reinterpret_cast<float2 *>(t0 + o - 1 + 3 * rstep) = make_float2(prev.w, acc.w);
+                    } else {
+                        prev = acc;
+                    }
+                } else {
+                    store_bin(o, acc);
+                }
+            }
+        }
+    } else {
+        // rois whose sampling grid exceeds the shared tables: direct taps (rare: > 36 samples per bin and axis)
+        for (int ph = warp; ph < PH; ph += RV_WARPS)
+            for (int pw = 0; pw < PW; ++pw) {
+                float4 acc = zero4;
+                for (int iy = 0; iy < g.gh; ++iy) {
+                    const Tap ty = make_tap(sample_coord(g.sh, g.bh, ph, iy, g.gh), H);
+                    if (ty.lo < 0) continue;
+                    for (int ix = 0; ix < g.gw; ++ix) {
+                        const Tap tx = make_tap(sample_coord(g.sw, g.bw, pw, ix, g.gw), W);
+                        if (tx.lo < 0 || !active) continue;
+                        const size_t pc = (size_t)C * 4;
+                        fma4(acc, ty.wl * tx.wl, ldg128(fb + ((size_t)ty.lo * W + tx.lo) * pc));
+                        fma4(acc, ty.wl * tx.wh, ldg128(fb + ((size_t)ty.lo * W + tx.hi) * pc));
+                        fma4(acc, ty.wh * tx.wl, ldg128(fb + ((size_t)ty.hi * W + tx.lo) * pc));
+                        fma4(acc, ty.wh * tx.wh, ldg128(fb + ((size_t)ty.hi * W + tx.hi) * pc));
+                    }
+                }
+                acc.x *= inv_cnt; acc.y *= inv_cnt; acc.z *= inv_cnt; acc.w *= inv_cnt;
+                store_bin(ph * PW + pw, acc);
+            }
+    }
+    __syncthreads();
+
+    // coalesced streaming write-out of the [cc, PH*PW] slab (contiguous in the NCHW output).  Threads are laid out as
+    // (channel-in-group, position) so that no division is needed inside the loop.
+    const int cc = min(RV_CC, C - c0);
+    float *ob = out + ((size_t)r * C + c0) * PHW;
+    if (PAIR) {
+        const int half = PHW >> 1;                       // 8-byte words per channel
+        const int cpi = RV_THREADS / half;               // channels per iteration
+        const int chs = threadIdx.x / half, w2 = threadIdx.x - chs * half;
+        if (chs < cpi) {
+            for (int ch = chs; ch < cc; ch += cpi) {
+                const int row = ((ch & 3) << 5) + (ch >> 2);
+                const float2 v = *reinterpret_cast<const float2 *>(tile + (size_t)row * tstride + 2 * w2);
+                __stcs(reinterpret_cast<float2 *>(ob + (size_t)ch * PHW) + w2, v);
+            }
+        }
+    } else {
+        const int cpi = RV_THREADS / PHW;
+        const int chs = threadIdx.x / PHW, w1 = threadIdx.x - chs * PHW;
+        if (chs < cpi) {
+            for (int ch = chs; ch < cc; ch += cpi) {
+                const int row = ((ch & 3) << 5) + (ch >> 2);
+                __stcs(ob + (size_t)ch * PHW + w1, tile[(size_t)row * tstride + w1]);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward (atomic scatter; one thread per (r, c, ph, pw))
 // ------------------------------------------------------------------------------------------------
@@ -407,18 +579,48 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
         LOCO_CUDA(cudaGetLastError());
         nhwc = static_cast<const float *>(workspace);
     }
-    const int nchunks = (C + RA_CC - 1) / RA_CC;
     LOCO_REQUIRE(PH <= 32 && PW <= 32, LOCO_E_UNSUPPORTED, "roi_align_fwd: output size %dx%d (at most 32x32)", PH, PW);
+    const int PHW = PH * PW;
+    // vectorised kernel: 4 channels per lane (128-bit taps), byte offsets inside one image kept in 32 bits
+    const bool v4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(nhwc) & 15) == 0) && ((long long)H * W * C * 4 < (1ll << 31)) &&
+                    PHW <= RV_THREADS;
+    if (v4) {
+        const bool pair = (PW % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+        int tstride;
+        if (pair) { tstride = PHW; while (tstride % 4 != 2) ++tstride; }     // S = 2 (mod 4): conflict-free STS.64 columns
+        else tstride = PHW | 1;
+        const int nchunks = (C + RV_CC - 1) / RV_CC;
+        const size_t smem = 2 * RA_TAB * sizeof(MergedEntry) + 64 * sizeof(int) + (size_t)RV_CC * tstride * sizeof(float);
+        LOCO_REQUIRE(smem <= 200 * 1024, LOCO_E_UNSUPPORTED, "roi_align_fwd: output size %dx%d needs %zu B of shared memory", PH, PW, smem);
+        LOCO_REQUIRE((long long)R * nchunks < (1ll << 31), LOCO_E_UNSUPPORTED, "roi_align_fwd: too many (roi, channel-slab) tiles");
+        static thread_local size_t smem_set[2] = {0, 0};
+        if (smem > 48 * 1024 && smem > smem_set[pair]) {
+            if (pair) LOCO_CUDA(cudaFuncSetAttribute(roi_align_fwd_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else LOCO_CUDA(cudaFuncSetAttribute(roi_align_fwd_v4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set[pair] = smem;
+        }
+        if (pair)
+            roi_align_fwd_v4_kernel<true><<<R * nchunks, RV_THREADS, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio,
+                                                                                 aligned, nchunks, tstride, out);
+        else
+            roi_align_fwd_v4_kernel<false><<<R * nchunks, RV_THREADS, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio,
+                                                                                  aligned, nchunks, tstride, out);
+        count_launch();
+        LOCO_CUDA(cudaGetLastError());
+        return LOCO_OK;
+    }
+    // generic kernel: any channel count / alignment, one channel per lane
+    const int nchunks = (C + RA_CC - 1) / RA_CC;
     const size_t smem = 2 * RA_TAB * sizeof(MergedEntry) + (size_t)(PH + PW) * sizeof(int) + (size_t)RA_CC * ((PH * PW) | 1) * sizeof(float) +
                         (size_t)RA_WARPS * RA_UCOLS * 32 * sizeof(float);
     LOCO_REQUIRE(smem <= 200 * 1024, LOCO_E_UNSUPPORTED, "roi_align_fwd: output size %dx%d needs %zu B of shared memory", PH, PW, smem);
     LOCO_REQUIRE((long long)R * nchunks < (1ll << 31), LOCO_E_UNSUPPORTED, "roi_align_fwd: too many (roi, channel-slab) tiles");
     static thread_local size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
-        LOCO_CUDA(cudaFuncSetAttribute(roi_align_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LOCO_CUDA(cudaFuncSetAttribute(roi_align_fwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    roi_align_fwd_kernel<<<R * nchunks, RA_THREADS, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio,
+    roi_align_fwd_generic_kernel<<<R * nchunks, RA_THREADS, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio,
                                                                 aligned, nchunks, out);
     count_launch();
     LOCO_CUDA(cudaGetLastError());

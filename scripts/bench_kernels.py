@@ -121,6 +121,8 @@ if __name__ == "__main__":
     quick = "--quick" in sys.argv
     roi_case("cfg1 faithful [2,1024,50,76]->[1024,1024,14,14]", 2, 1024, 50, 76, 512, 14, 1 / 16)
     roi_case("cfg1 literal [2,2048,25,38]->[1024,2048,7,7]", 2, 2048, 25, 38, 512, 7, 1 / 32)
+    if "--roi-only" in sys.argv:
+        sys.exit(0)
     if not quick:
         roi_case("cfg3 [16,1024,50,76]->[8192,1024,14,14]", 16, 1024, 50, 76, 512, 14, 1 / 16)
     box_case("cfg1 2x512 RoIs vs 65+1", 1024, 65, "fp32")
