@@ -124,7 +124,8 @@ struct MergedEntry {
 };
 
 // entries of bin `p` are written at tab[p * stride ...]; returns their number
-__device__ __forceinline__ int build_merged(MergedEntry *tab, float start, float bin, int p, int g, int size, int mul = 1) {
+__device__ __forceinline__ int build_merged(MergedEntry *tab, float start, float bin, int p, int g, int size, int mul = 1,
+                                            bool tag_parity = false) {
     int n = 0;
     // taps are monotonic in the sample index, so an index can only repeat one of the last two entries
     auto add = [&](int idx, float w) {
@@ -139,7 +140,8 @@ __device__ __forceinline__ int build_merged(MergedEntry *tab, float start, float
         add(t.hi, t.wh);
     }
     if (mul != 1)
-        for (int i = 0; i < n; ++i) tab[i].idx *= mul;   // index -> byte offset (v4 kernel)
+        for (int i = 0; i < n; ++i)                      // index -> byte offset (v4 kernel; mul is a multiple of 16)
+            tab[i].idx = tab[i].idx * mul | (tag_parity ? (tab[i].idx & 1) : 0);
     return n;
 }
 
@@ -340,11 +342,111 @@ __device__ __forceinline__ void fma4(float4 &a, float w, const float4 &v) {
     a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
 }
 
+// Four channels of one lane as two packed fp32 pairs: the arithmetic below uses Blackwell's packed FFMA2 / FMUL2
+// (two fp32 FMAs per issue slot) — the kernel is issue-bound, not FLOP-bound.
+struct Quad {
+    float2 lo, hi;
+};
+__device__ __forceinline__ Quad ldg_quad(const char *p) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    Quad q;
+    q.lo = make_float2(v.x, v.y);
+    q.hi = make_float2(v.z, v.w);
+    return q;
+}
+__device__ __forceinline__ void quad_fma(Quad &a, float w, const Quad &v) {
+    const float2 ww = make_float2(w, w);
+    a.lo = __ffma2_rn(ww, v.lo, a.lo);
+    a.hi = __ffma2_rn(ww, v.hi, a.hi);
+}
+__device__ __forceinline__ Quad quad_mul(float w, const Quad &v) {
+    const float2 ww = make_float2(w, w);
+    Quad r;
+    r.lo = __fmul2_rn(ww, v.lo);
+    r.hi = __fmul2_rn(ww, v.hi);
+    return r;
+}
+
+// Vertically pooled value of one footprint column for 4 channels: NY independent 128-bit loads, then the FMAs.
+template <int NY>
+__device__ __forceinline__ Quad pooled_column(const char *p, const int (&yo)[4], const float (&yw)[4]) {
+    Quad v[NY];
+#pragma unroll
+    for (int k = 0; k < NY; ++k) v[k] = ldg_quad(p + yo[k]);
+    Quad u = quad_mul(yw[0], v[0]);
+#pragma unroll
+    for (int k = 1; k < NY; ++k) quad_fma(u, yw[k], v[k]);
+    return u;
+}
+
+// One bin row (PW bins) of one roi for the 4 channels of this lane.  NY = number of merged row taps (1..4 static,
+// 0 = run-time count with the taps read from shared memory).  Two pooled columns are cached in registers, slot =
+// parity of the column index (bit 0 of the table offset): the merged column lists of neighbouring bins are monotonic
+// and overlap in at most two (consecutive) columns, so every column of the row's footprint is loaded exactly once.
+// The slot tags are compared at run time, so a non-monotonic list (fixed sampling ratio on a flipped box) only costs
+// extra loads.  All branches are warp-uniform.
+template <int NY, bool PAIR>
+__device__ __noinline__ void pool_bin_row(const char *fb, const MergedEntry *yt, int ny, const MergedEntry *xtab,
+                                             const int *xcnt, int xstride, int PW, float inv_cnt, float *trow, int rstep) {
+    int yo[4] = {0, 0, 0, 0};
+    float yw[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < (NY > 0 ? NY : 1); ++k) {
+        if (NY > 0) { yo[k] = yt[k].idx; yw[k] = yt[k].w; }
+    }
+    Quad zero;
+    zero.lo = make_float2(0.f, 0.f);
+    zero.hi = zero.lo;
+    int off0 = -1, off1 = -1;
+    Quad u0 = zero, u1 = zero;
+    auto column = [&](int off) -> Quad {
+        const char *p = fb + off;
+        if (NY > 0) return pooled_column<(NY > 0 ? NY : 1)>(p, yo, yw);
+        Quad t = zero;
+        for (int k = 0; k < ny; ++k) quad_fma(t, yt[k].w, ldg_quad(p + yt[k].idx));
+        return t;
+    };
+    auto bin = [&](const MergedEntry *xt, int nx) -> Quad {
+        Quad acc = zero;
+#pragma unroll 1
+        for (int j = 0; j < nx; ++j) {
+            const MergedEntry e = xt[j];
+            if (e.idx & 1) {
+                if (e.idx != off1) { u1 = column(e.idx - 1); off1 = e.idx; }
+                quad_fma(acc, e.w, u1);
+            } else {
+                if (e.idx != off0) { u0 = column(e.idx); off0 = e.idx; }
+                quad_fma(acc, e.w, u0);
+            }
+        }
+        return quad_mul(inv_cnt, acc);
+    };
+    if (PAIR) {
+#pragma unroll 1
+        for (int pw = 0; pw < PW; pw += 2) {
+            const Quad a = bin(xtab, xcnt[pw]);
+            const Quad b = bin(xtab + xstride, xcnt[pw + 1]);
+            xtab += 2 * xstride;
+            *reinterpret_cast<float2 *>(trow + pw) = make_float2(a.lo.x, b.lo.x);
+            *reinterpret_cast<float2 *>(trow + pw + rstep) = make_float2(a.lo.y, b.lo.y);
+            *reinterpret_cast<float2 *>(trow + pw + 2 * rstep) = make_float2(a.hi.x, b.hi.x);
+            *reinterpret_cast<float2 *>(trow + pw + 3 * rstep) = make_float2(a.hi.y, b.hi.y);
+        }
+    } else {
+#pragma unroll 1
+        for (int pw = 0; pw < PW; ++pw) {
+            const Quad a = bin(xtab, xcnt[pw]);
+            xtab += xstride;
+            trow[pw] = a.lo.x; trow[pw + rstep] = a.lo.y; trow[pw + 2 * rstep] = a.hi.x; trow[pw + 3 * rstep] = a.hi.y;
+        }
+    }
+}
+
 template <bool PAIR>
 __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const float *__restrict__ feat,   // [N,H,W,C]
                                                                         const float *__restrict__ rois, int C, int H, int W,
                                                                         int PH, int PW, float scale, int sampling_ratio,
-                                                                        int aligned, int nchunks, int tstride,
+                                                                        int aligned, int nchunks, int slabs, int tstride,
                                                                         float *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MergedEntry *ytab = reinterpret_cast<MergedEntry *>(smem_raw);
@@ -354,8 +456,7 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
     float *tile = reinterpret_cast<float *>(xcnt + 32);       // [RV_CC][tstride]
 
     const int r = blockIdx.x / nchunks;
-    const int chunk = blockIdx.x - r * nchunks;
-    const int c0 = chunk * RV_CC;
+    const int chunk = blockIdx.x - r * nchunks;               // this CTA pools `slabs` consecutive 128-channel slabs
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int PHW = PH * PW;
 
@@ -368,116 +469,94 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
     if (tables_fit) {
         const int t = threadIdx.x;
         if (t < PH) ycnt[t] = build_merged(ytab + t * ystride, g.sh, g.bh, t, g.gh, H, W * C * 4);
-        else if (t >= 32 && t < 32 + PW) xcnt[t - 32] = build_merged(xtab + (t - 32) * xstride, g.sw, g.bw, t - 32, g.gw, W, C * 4);
+        else if (t >= 32 && t < 32 + PW) xcnt[t - 32] = build_merged(xtab + (t - 32) * xstride, g.sw, g.bw, t - 32, g.gw, W, C * 4, true);
     }
     __syncthreads();
 
     const int cl = 4 * lane;
-    const bool active = (c0 + cl) < C;                         // C % 4 == 0: a lane's 4 channels are all in or all out
-    const char *fb = reinterpret_cast<const char *>(feat + (size_t)g.batch * H * W * C + (active ? c0 + cl : 0));
     float *t0 = tile + (size_t)lane * tstride;                 // rows lane, 32 + lane, 64 + lane, 96 + lane
     const int rstep = 32 * tstride;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    auto store_bin = [&](int o, const float4 &a) {            // scalar stores (odd PW / generic paths)
+    auto store_bin = [&](int o, const float4 &a) {
         t0[o] = a.x; t0[o + rstep] = a.y; t0[o + 2 * rstep] = a.z; t0[o + 3 * rstep] = a.w;
     };
 
-    if (empty) {
-        for (int ph = warp; ph < PH; ph += RV_WARPS)
-            for (int pw = 0; pw < PW; ++pw) store_bin(ph * PW + pw, zero4);
-    } else if (tables_fit) {
-        for (int ph = warp; ph < PH; ph += RV_WARPS) {
-            const MergedEntry *yt = ytab + ph * ystride;
-            const int ny = ycnt[ph];
-            const int yo0 = ny > 0 ? yt[0].idx : 0, yo1 = ny > 1 ? yt[1].idx : 0, yo2 = ny > 2 ? yt[2].idx : 0, yo3 = ny > 3 ? yt[3].idx : 0;
-            const float yw0 = ny > 0 ? yt[0].w : 0.f, yw1 = ny > 1 ? yt[1].w : 0.f, yw2 = ny > 2 ? yt[2].w : 0.f, yw3 = ny > 3 ? yt[3].w : 0.f;
-            int lastoff = -1;
-            float4 u = zero4, prev = zero4;
-            for (int pw = 0; pw < PW; ++pw) {
-                float4 acc = zero4;
-                const MergedEntry *xt = xtab + pw * xstride;
-                const int nx = xcnt[pw];
-                for (int j = 0; j < nx; ++j) {
-                    const MergedEntry e = xt[j];
-                    if (e.idx != lastoff) {                    // warp-uniform
-                        lastoff = e.idx;
-                        u = zero4;
-                        if (active) {
-                            const char *p = fb + e.idx;
-                            float4 v0 = zero4, v1 = zero4, v2 = zero4, v3 = zero4;
-                            if (ny > 0) v0 = ldg128(p + yo0);
-                            if (ny > 1) v1 = ldg128(p + yo1);
-                            if (ny > 2) v2 = ldg128(p + yo2);
-                            if (ny > 3) v3 = ldg128(p + yo3);
-                            fma4(u, yw0, v0); fma4(u, yw1, v1); fma4(u, yw2, v2); fma4(u, yw3, v3);
-                            for (int k = 4; k < ny; ++k) fma4(u, yt[k].w, ldg128(p + yt[k].idx));
+    for (int sl = 0; sl < slabs; ++sl) {
+        const int c0 = (chunk * slabs + sl) * RV_CC;
+        if (c0 >= C) break;
+        const bool active = (c0 + cl) < C;                     // C % 4 == 0: a lane's 4 channels are all in or all out
+        const char *fb = reinterpret_cast<const char *>(feat + (size_t)g.batch * H * W * C + (active ? c0 + cl : 0));
+        if (sl > 0) __syncthreads();                           // the previous slab's write-out has drained the tile
+
+        if (empty) {
+            for (int ph = warp; ph < PH; ph += RV_WARPS)
+                for (int pw = 0; pw < PW; ++pw) store_bin(ph * PW + pw, zero4);
+        } else if (tables_fit) {
+            for (int ph = warp; ph < PH; ph += RV_WARPS) {
+                const MergedEntry *yt = ytab + ph * ystride;
+                const int ny = ycnt[ph];
+                float *trow = t0 + ph * PW;
+                switch (ny) {                                  // warp-uniform
+                    case 1: pool_bin_row<1, PAIR>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
+                    case 2: pool_bin_row<2, PAIR>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
+                    case 3: pool_bin_row<3, PAIR>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
+                    case 4: pool_bin_row<4, PAIR>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
+                    default: pool_bin_row<0, PAIR>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
+                }
+            }
+        } else {
+            // rois whose sampling grid exceeds the shared tables: direct taps (rare: > 36 samples per bin and axis)
+            for (int ph = warp; ph < PH; ph += RV_WARPS)
+                for (int pw = 0; pw < PW; ++pw) {
+                    float4 acc = zero4;
+                    for (int iy = 0; iy < g.gh; ++iy) {
+                        const Tap ty = make_tap(sample_coord(g.sh, g.bh, ph, iy, g.gh), H);
+                        if (ty.lo < 0) continue;
+                        for (int ix = 0; ix < g.gw; ++ix) {
+                            const Tap tx = make_tap(sample_coord(g.sw, g.bw, pw, ix, g.gw), W);
+                            if (tx.lo < 0 || !active) continue;
+                            const size_t pc = (size_t)C * 4;
+                            fma4(acc, ty.wl * tx.wl, ldg128(fb + ((size_t)ty.lo * W + tx.lo) * pc));
+                            fma4(acc, ty.wl * tx.wh, ldg128(fb + ((size_t)ty.lo * W + tx.hi) * pc));
+                            fma4(acc, ty.wh * tx.wl, ldg128(fb + ((size_t)ty.hi * W + tx.lo) * pc));
+                            fma4(acc, ty.wh * tx.wh, ldg128(fb + ((size_t)ty.hi * W + tx.hi) * pc));
                         }
                     }
-                    fma4(acc, e.w, u);
+                    acc.x *= inv_cnt; acc.y *= inv_cnt; acc.z *= inv_cnt; acc.w *= inv_cnt;
+                    store_bin(ph * PW + pw, acc);
                 }
-                acc.x *= inv_cnt; acc.y *= inv_cnt; acc.z *= inv_cnt; acc.w *= inv_cnt;
-                const int o = ph * PW + pw;
-                if (PAIR) {
-                    if (pw & 1) {
-                        *reinterpret_cast<float2 *>(t0 + o - 1) = make_float2(prev.x, acc.x);
-                        *reinterpret_cast<float2 *>(t0 + o - 1 + rstep) = make_float2(prev.y, acc.y);
-                        *reinterpret_cast<float2 *>(t0 + o - 1 + 2 * rstep) = make_float2(prev.z, acc.z);
-                        *reinterpret_cast<float2 *>(t0 + o - 1 + 3 * rstep) = make_float2(prev.w, acc.w);
-                    } else {
-                        prev = acc;
-                    }
-                } else {
-                    store_bin(o, acc);
-                }
-            }
         }
-    } else {
-        // rois whose sampling grid exceeds the shared tables: direct taps (rare: > 36 samples per bin and axis)
-        for (int ph = warp; ph < PH; ph += RV_WARPS)
-            for (int pw = 0; pw < PW; ++pw) {
-                float4 acc = zero4;
-                for (int iy = 0; iy < g.gh; ++iy) {
-                    const Tap ty = make_tap(sample_coord(g.sh, g.bh, ph, iy, g.gh), H);
-                    if (ty.lo < 0) continue;
-                    for (int ix = 0; ix < g.gw; ++ix) {
-                        const Tap tx = make_tap(sample_coord(g.sw, g.bw, pw, ix, g.gw), W);
-                        if (tx.lo < 0 || !active) continue;
-                        const size_t pc = (size_t)C * 4;
-                        fma4(acc, ty.wl * tx.wl, ldg128(fb + ((size_t)ty.lo * W + tx.lo) * pc));
-                        fma4(acc, ty.wl * tx.wh, ldg128(fb + ((size_t)ty.lo * W + tx.hi) * pc));
-                        fma4(acc, ty.wh * tx.wl, ldg128(fb + ((size_t)ty.hi * W + tx.lo) * pc));
-                        fma4(acc, ty.wh * tx.wh, ldg128(fb + ((size_t)ty.hi * W + tx.hi) * pc));
-                    }
-                }
-                acc.x *= inv_cnt; acc.y *= inv_cnt; acc.z *= inv_cnt; acc.w *= inv_cnt;
-                store_bin(ph * PW + pw, acc);
-            }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // coalesced streaming write-out of the [cc, PH*PW] slab (contiguous in the NCHW output).  Threads are laid out as
-    // (channel-in-group, position) so that no division is needed inside the loop.
-    const int cc = min(RV_CC, C - c0);
-    float *ob = out + ((size_t)r * C + c0) * PHW;
-    if (PAIR) {
-        const int half = PHW >> 1;                       // 8-byte words per channel
-        const int cpi = RV_THREADS / half;               // channels per iteration
-        const int chs = threadIdx.x / half, w2 = threadIdx.x - chs * half;
+        // coalesced streaming write-out of the [cc, PH*PW] slab (contiguous in the NCHW output).  Thread = (channel
+        // within a group of `cpi`, position); cpi is a multiple of 4 whenever possible so that stepping to the next
+        // channel group is a constant stride in the (row-permuted) tile as well as in global memory.
+        const int cc = min(RV_CC, C - c0);
+        float *ob = out + ((size_t)r * C + c0) * PHW;
+        const int words = PAIR ? (PHW >> 1) : PHW;           // 8-byte (PAIR) or 4-byte words per channel
+        int cpi = RV_THREADS / words;
+        if (cpi >= 4) cpi &= ~3;
+        const int chs = threadIdx.x / words, wi = threadIdx.x - chs * words;
         if (chs < cpi) {
-            for (int ch = chs; ch < cc; ch += cpi) {
-                const int row = ((ch & 3) << 5) + (ch >> 2);
-                const float2 v = *reinterpret_cast<const float2 *>(tile + (size_t)row * tstride + 2 * w2);
-                __stcs(reinterpret_cast<float2 *>(ob + (size_t)ch * PHW) + w2, v);
-            }
-        }
-    } else {
-        const int cpi = RV_THREADS / PHW;
-        const int chs = threadIdx.x / PHW, w1 = threadIdx.x - chs * PHW;
-        if (chs < cpi) {
-            for (int ch = chs; ch < cc; ch += cpi) {
-                const int row = ((ch & 3) << 5) + (ch >> 2);
-                __stcs(ob + (size_t)ch * PHW + w1, tile[(size_t)row * tstride + w1]);
+            if ((cpi & 3) == 0) {
+                const int rinc = (cpi >> 2) * tstride;
+                const float *sp = tile + (size_t)(((chs & 3) << 5) + (chs >> 2)) * tstride + (PAIR ? 2 * wi : wi);
+                float *gp = ob + (size_t)chs * PHW + (PAIR ? 2 * wi : wi);
+                const size_t ginc = (size_t)cpi * PHW;
+#pragma unroll 4
+                for (int ch = chs; ch < cc; ch += cpi) {
+                    if (PAIR) __stcs(reinterpret_cast<float2 *>(gp), *reinterpret_cast<const float2 *>(sp));
+                    else __stcs(gp, *sp);
+                    sp += rinc;
+                    gp += ginc;
+                }
+            } else {
+                for (int ch = chs; ch < cc; ch += cpi) {
+                    const int row = ((ch & 3) << 5) + (ch >> 2);
+                    if (PAIR) __stcs(reinterpret_cast<float2 *>(ob + (size_t)ch * PHW) + wi,
+                                     *reinterpret_cast<const float2 *>(tile + (size_t)row * tstride + 2 * wi));
+                    else __stcs(ob + (size_t)ch * PHW + wi, tile[(size_t)row * tstride + wi]);
+                }
             }
         }
     }
@@ -589,7 +668,11 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
         int tstride;
         if (pair) { tstride = PHW; while (tstride % 4 != 2) ++tstride; }     // S = 2 (mod 4): conflict-free STS.64 columns
         else tstride = PHW | 1;
-        const int nchunks = (C + RV_CC - 1) / RV_CC;
+        const int nslab = (C + RV_CC - 1) / RV_CC;
+        // each CTA pools `slabs` consecutive slabs with one set of tap tables, as long as the grid keeps >= 8 waves
+        int slabs = 1;
+        while (slabs < 4 && nslab % (slabs * 2) == 0 && (long long)R * (nslab / (slabs * 2)) >= 8ll * 2 * 148) slabs *= 2;
+        const int nchunks = nslab / slabs;
         const size_t smem = 2 * RA_TAB * sizeof(MergedEntry) + 64 * sizeof(int) + (size_t)RV_CC * tstride * sizeof(float);
         LOCO_REQUIRE(smem <= 200 * 1024, LOCO_E_UNSUPPORTED, "roi_align_fwd: output size %dx%d needs %zu B of shared memory", PH, PW, smem);
         LOCO_REQUIRE((long long)R * nchunks < (1ll << 31), LOCO_E_UNSUPPORTED, "roi_align_fwd: too many (roi, channel-slab) tiles");
@@ -601,10 +684,10 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
         }
         if (pair)
             roi_align_fwd_v4_kernel<true><<<R * nchunks, RV_THREADS, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio,
-                                                                                 aligned, nchunks, tstride, out);
+                                                                                 aligned, nchunks, slabs, tstride, out);
         else
             roi_align_fwd_v4_kernel<false><<<R * nchunks, RV_THREADS, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio,
-                                                                                  aligned, nchunks, tstride, out);
+                                                                                  aligned, nchunks, slabs, tstride, out);
         count_launch();
         LOCO_CUDA(cudaGetLastError());
         return LOCO_OK;
