@@ -127,11 +127,16 @@ int loco_linear_tf32_fwd(const float *A, int64_t lda, const float *W, int64_t ld
  * cls_bias [K1] fp32 or NULL.
  * Outputs: logits [R,K1] fp32 (ld_logits) required; probs [R,K1] fp32 or NULL (same ld);
  *          lse [R] fp32 (log-sum-exp over the K1 columns) or NULL;
- *          argmax_fg [R] int64 = argmax over the first K1-1 (foreground) columns, or NULL. */
+ *          argmax_fg [R] int64 = argmax over the first K1-1 (foreground) columns, or NULL.
+ * Class lists wider than 256 are scored in 256-column chunks dealt to several CTAs per 128-row tile (so that a few
+ * thousand RoIs still fill every SM); their partial softmax statistics go through `workspace`
+ * (loco_box_score_workspace_bytes(R, K1) bytes, 16-byte aligned; may be NULL when K1 <= 256) and are combined by a second,
+ * bandwidth-bound kernel that also writes the probabilities (probs requires lse). */
+int64_t loco_box_score_workspace_bytes(int R, int K1);
 int loco_box_score_fwd(const uint16_t *E_hi, const uint16_t *E_lo, int64_t lde, const uint16_t *C_hi,
                        const uint16_t *C_lo, int64_t ldc, const float *cls_bias, int R, int K1, int D,
                        float *logits, float *probs, int64_t ld_logits, float *lse,
-                       int64_t *argmax_fg, void *stream);
+                       int64_t *argmax_fg, void *workspace, void *stream);
 
 /* Cross-entropy over the scored logits (Detectron2 FastRCNNOutputLayers.losses: F.cross_entropy mean).
  * labels [R] int64 in [0,K1).  loss_sum: 1 fp32, accumulated (caller zero-fills) with sum_r(lse_r -

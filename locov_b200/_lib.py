@@ -32,7 +32,8 @@ SIGNATURES = {
     "loco_transpose_bf16": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "loco_linear_fwd": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _i, _i64, _vp]),
     "loco_linear_tf32_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _i, _i64, _vp]),
-    "loco_box_score_fwd": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "loco_box_score_workspace_bytes": (_i64, [_i, _i]),
+    "loco_box_score_fwd": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "loco_box_ce_fwd_bwd": (_i, [_vp, _i64, _vp, _vp, _i, _i, _f, _vp, _f, _vp, _vp, _i64, _vp]),
     "loco_lsm_masks": (_i, [_vp, _vp, _i64, _vp, _i, _i64, _vp, _vp, _vp]),
     "loco_lsm_pair_workspace_bytes": (_i64, [_i, _i, _i, _i]),

@@ -112,19 +112,21 @@ struct EpiScore {
     static constexpr int kMinBlocks = 1;
     struct Params {
         const float *bias;
-        float *logits, *probs;
+        float *logits;
         int64_t ld;
         float *lse;
         int64_t *argmax_fg;
+        float *part;    // groups > 1: per (row, group) partial statistics {max, sum, best value, best index} for box_score_finalize_kernel
         int R, K1;
+        int groups;     // CTAs per 128-row tile: CTA (tile, g) scores the column chunks g, g + groups, ...
         int vec;        // logits rows are 16-byte aligned (base and ld): 128-bit stores straight from registers
     };
     float run_max, run_sum, best_val;
     int best_idx;
 
-    static __device__ __forceinline__ void coords(const Params &, const TcCore &core, int cta, int chunk, int &row_a, int &row_b) {
-        row_a = cta * TC_BLOCK_M;
-        row_b = chunk * core.block_n;
+    static __device__ __forceinline__ void coords(const Params &p, const TcCore &core, int cta, int chunk, int &row_a, int &row_b) {
+        row_a = (cta / p.groups) * TC_BLOCK_M;
+        row_b = (cta % p.groups + chunk * p.groups) * core.block_n;      // past K1: TMA zero fill, skipped by the epilogue
     }
     __device__ __forceinline__ void begin(const Params &, const TcCore &, int, int, int, int, unsigned char *) {
         run_max = -FLT_MAX;
@@ -135,15 +137,17 @@ struct EpiScore {
     __device__ __forceinline__ void chunk(const Params &p, const TcCore &core, int cta, int ch, uint32_t taddr, int row, int lane,
                                           int q, unsigned char *smem) {
         float *scratch = reinterpret_cast<float *>(smem) + (size_t)q * TC_WARP_SCRATCH_WORDS;
-        const int m0 = cta * TC_BLOCK_M + q * 32;
+        const int tile = cta / p.groups;
+        const int m0 = tile * TC_BLOCK_M + q * 32;
         const int rows_valid = max(0, min(32, p.R - m0));
-        const int n0 = ch * core.block_n;
+        const int n0 = (cta % p.groups + ch * p.groups) * core.block_n;
+        if (n0 >= p.K1) return;
         for (int c0 = 0; c0 < core.block_n; c0 += 32) {
-            float v[32];
-            tmem_ld32(taddr + (uint32_t)c0, v);
             const int gc0 = n0 + c0;
             const int cols_valid = max(0, min(min(32, core.block_n - c0), p.K1 - gc0));
-            if (cols_valid <= 0) continue;
+            if (cols_valid <= 0) break;
+            float v[32];
+            tmem_ld32(taddr + (uint32_t)c0, v);
             float blk_max = -FLT_MAX;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -157,15 +161,15 @@ struct EpiScore {
                 }
             }
             const float new_max = fmaxf(run_max, blk_max);
-            float s = run_sum * expf(run_max - new_max);
+            float s = run_sum * __expf(run_max - new_max);
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                if (j < cols_valid) s += expf(v[j] - new_max);
+                if (j < cols_valid) s += __expf(v[j] - new_max);
             run_max = new_max;
             run_sum = s;
             if (p.vec && cols_valid == 32) {
                 if (row < rows_valid + q * 32) {
-                    float *dst = p.logits + (int64_t)(cta * TC_BLOCK_M + row) * p.ld + gc0;
+                    float *dst = p.logits + (int64_t)(tile * TC_BLOCK_M + row) * p.ld + gc0;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
@@ -174,27 +178,70 @@ struct EpiScore {
             }
         }
     }
-    __device__ __forceinline__ void finish(const Params &p, const TcCore &, int cta, int row, int lane, int q, unsigned char *) {
-        const int m0 = cta * TC_BLOCK_M + q * 32;
-        const int grow = cta * TC_BLOCK_M + row;
-        const float lse = run_max + logf(run_sum);
-        if (grow < p.R) {
-            if (p.lse != nullptr) p.lse[grow] = lse;
+    __device__ __forceinline__ void finish(const Params &p, const TcCore &, int cta, int row, int, int, unsigned char *) {
+        const int grow = (cta / p.groups) * TC_BLOCK_M + row;
+        if (grow >= p.R) return;
+        if (p.groups == 1) {
+            if (p.lse != nullptr) p.lse[grow] = run_max + logf(run_sum);
             if (p.argmax_fg != nullptr) p.argmax_fg[grow] = (int64_t)best_idx;
-        }
-        if (p.probs != nullptr) {
-            // Every lane re-reads exactly the logits it wrote itself in warp_store_f32 (same row / column
-            // mapping), so program order makes them visible without a fence.
-            const int rows_valid = max(0, min(32, p.R - m0));
-            for (int rr = 0; rr < rows_valid; ++rr) {
-                const float l = __shfl_sync(0xffffffffu, lse, rr);
-                const float *src = p.logits + (int64_t)(m0 + rr) * p.ld;
-                float *dst = p.probs + (int64_t)(m0 + rr) * p.ld;
-                for (int c = lane; c < p.K1; c += 32) dst[c] = expf(src[c] - l);
-            }
+        } else {
+            float4 *dst = reinterpret_cast<float4 *>(p.part) + (int64_t)grow * p.groups + (cta % p.groups);
+            *dst = make_float4(run_max, run_sum, best_val, __int_as_float(best_idx));
         }
     }
 };
+
+// Second (bandwidth) pass of the scoring: one warp per RoI row combines the per-group statistics (groups > 1) into the
+// log-sum-exp and the foreground argmax, and streams out the softmax probabilities exp(logit - lse) when requested —
+// coalesced 128-bit rows, every SM busy (the GEMM epilogue that did this row by row per thread was latency bound).
+__global__ void __launch_bounds__(256) box_score_finalize_kernel(const float *__restrict__ logits, float *__restrict__ probs, int64_t ld,
+                                                                 int R, int K1, const float4 *__restrict__ part, int groups,
+                                                                 float *__restrict__ lse, int64_t *__restrict__ argmax_fg) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < R; row += gridDim.x * wpb) {
+        float l;
+        if (part != nullptr) {
+            float4 st = make_float4(-FLT_MAX, 0.f, -FLT_MAX, 0.f);
+            if (lane < groups) st = part[(int64_t)row * groups + lane];
+            float mx = st.x;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float sm = st.y * __expf(st.x - mx);
+            float bv = st.z;
+            int bi = __float_as_int(st.w);
+            if (lane >= groups) bi = 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }    // first maximum (smallest column) wins
+            }
+            l = mx + logf(sm);
+            if (lane == 0) {
+                if (lse != nullptr) lse[row] = l;
+                if (argmax_fg != nullptr) argmax_fg[row] = (int64_t)(bv == -FLT_MAX ? 0 : bi);
+            }
+        } else {
+            l = lse[row];
+        }
+        if (probs != nullptr) {
+            const float *src = logits + (int64_t)row * ld;
+            float *dst = probs + (int64_t)row * ld;
+            if ((ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(probs)) & 15) == 0) {
+                const int k4 = K1 >> 2;
+                for (int c = lane; c < k4; c += 32) {
+                    const float4 v = *reinterpret_cast<const float4 *>(src + 4 * c);
+                    *reinterpret_cast<float4 *>(dst + 4 * c) = make_float4(__expf(v.x - l), __expf(v.y - l), __expf(v.z - l), __expf(v.w - l));
+                }
+                for (int c = 4 * k4 + lane; c < K1; c += 32) dst[c] = __expf(src[c] - l);
+            } else {
+                for (int c = lane; c < K1; c += 32) dst[c] = __expf(src[c] - l);
+            }
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // LSM pair epilogue (forward and backward share it).
@@ -671,28 +718,63 @@ int loco_linear_tf32_fwd(const float *A, int64_t lda, const float *W, int64_t ld
     return linear_launch(A, nullptr, lda, W, nullptr, ldw, true, bias, M, N, K, out_f32, ld_f32, out_hi, out_lo, n_bf16, ld_bf16, stream);
 }
 
+// column-chunk groups per 128-row tile: spread a wide class list over the SMs that the row tiles alone leave idle
+static int box_score_groups(int R, int K1) {
+    if (K1 <= 256) return 1;
+    const int chunks = (K1 + 255) / 256;
+    const int tiles = (R + TC_BLOCK_M - 1) / TC_BLOCK_M;
+    int g = current_device_sm_count() / (tiles > 0 ? tiles : 1);
+    if (g < 1) g = 1;
+    if (g > chunks) g = chunks;
+    if (g > 32) g = 32;
+    return g;
+}
+
+int64_t loco_box_score_workspace_bytes(int R, int K1) {
+    const int g = box_score_groups(R, K1);
+    return g > 1 ? (int64_t)R * g * 16 : 16;
+}
+
 int loco_box_score_fwd(const uint16_t *E_hi, const uint16_t *E_lo, int64_t lde, const uint16_t *C_hi, const uint16_t *C_lo,
                        int64_t ldc, const float *cls_bias, int R, int K1, int D, float *logits, float *probs,
-                       int64_t ld_logits, float *lse, int64_t *argmax_fg, void *stream) {
+                       int64_t ld_logits, float *lse, int64_t *argmax_fg, void *workspace, void *stream) {
     LOCO_REQUIRE(R >= 0 && K1 >= 1 && D > 0, LOCO_E_BADARG, "box_score_fwd: bad shape R=%d K1=%d D=%d", R, K1, D);
     if (R == 0) return LOCO_OK;
     LOCO_REQUIRE(E_hi && C_hi && logits, LOCO_E_BADARG, "box_score_fwd: null pointer");
     LOCO_REQUIRE((E_lo == nullptr) == (C_lo == nullptr), LOCO_E_BADARG, "box_score_fwd: E_lo and C_lo must both be given or both be NULL");
     LOCO_REQUIRE(ld_logits >= K1, LOCO_E_BADARG, "box_score_fwd: ld_logits < K1");
+    LOCO_REQUIRE(probs == nullptr || lse != nullptr, LOCO_E_BADARG, "box_score_fwd: probs need the lse output");
     TcCore core = {};
-    // one N tile when the class list fits (<= 256), otherwise 256-wide chunks with online softmax
+    // one N tile when the class list fits (<= 256), otherwise 256-wide chunks with online softmax, dealt round-robin
+    // to `groups` CTAs per row tile (partial statistics combined by box_score_finalize_kernel)
     core.block_n = K1 <= 256 ? tc_round_up(K1, 32) : 256;
-    const int chunks = (K1 + core.block_n - 1) / core.block_n;
+    const int total_chunks = (K1 + core.block_n - 1) / core.block_n;
+    const int groups = box_score_groups(R, K1);
+    LOCO_REQUIRE(groups == 1 || workspace != nullptr, LOCO_E_BADARG, "box_score_fwd: K1 > 256 needs loco_box_score_workspace_bytes() of workspace");
+    const int chunks = (total_chunks + groups - 1) / groups;
     const size_t smem = tc_finalize(core, D, E_lo ? 3 : 1, chunks, 4 * TC_WARP_SCRATCH_WORDS * 4);
     TcMaps maps;
     int rc = fill_maps(maps, E_hi, E_lo, R, lde, C_hi, C_lo, K1, ldc, D, core);
     if (rc != LOCO_OK) return rc;
     EpiScore::Params p;
-    p.bias = cls_bias; p.logits = logits; p.probs = probs; p.ld = ld_logits; p.lse = lse; p.argmax_fg = argmax_fg;
-    p.R = R; p.K1 = K1;
+    p.bias = cls_bias; p.logits = logits; p.ld = ld_logits; p.lse = lse; p.argmax_fg = argmax_fg;
+    p.part = groups > 1 ? static_cast<float *>(workspace) : nullptr;
+    p.R = R; p.K1 = K1; p.groups = groups;
     p.vec = ((reinterpret_cast<uintptr_t>(logits) & 15) == 0 && ld_logits % 4 == 0) ? 1 : 0;
-    const int grid = (R + TC_BLOCK_M - 1) / TC_BLOCK_M;
-    return tc_launch<EpiScore>(maps, core, p, grid, smem, static_cast<cudaStream_t>(stream));
+    const int grid = ((R + TC_BLOCK_M - 1) / TC_BLOCK_M) * groups;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = tc_launch<EpiScore>(maps, core, p, grid, smem, st);
+    if (rc != LOCO_OK) return rc;
+    if (groups > 1 || probs != nullptr) {
+        int blocks = (R + 7) / 8;
+        const int cap = current_device_sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        box_score_finalize_kernel<<<blocks, 256, 0, st>>>(logits, probs, ld_logits, R, K1,
+                                                          groups > 1 ? static_cast<const float4 *>(workspace) : nullptr, groups, lse, argmax_fg);
+        count_launch();
+        LOCO_CUDA(cudaGetLastError());
+    }
+    return LOCO_OK;
 }
 
 int64_t loco_lsm_pair_workspace_bytes(int Bc, int T, int Bi, int Rg) {

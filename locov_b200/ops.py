@@ -236,8 +236,9 @@ def box_score(e: Bf16Operand, cls: Bf16Operand, cls_bias: Optional[torch.Tensor]
     if cls_bias is not None:
         cls_bias = cls_bias.to(torch.float32).contiguous()
     lib = _lib.load()
+    ws = _workspace(dev, lib.loco_box_score_workspace_bytes(r, k1), "box_score")
     _lib.check(lib.loco_box_score_fwd(_p(e.hi), _p(e.lo), e.ld, _p(cls.hi), _p(cls.lo), cls.ld, _p(cls_bias), r, k1, d,
-                                      _p(logits), _p(probs), k1, _p(lse), _p(arg), _stream(e.hi)),
+                                      _p(logits), _p(probs), k1, _p(lse), _p(arg), _p(ws), _stream(e.hi)),
                "loco_box_score_fwd")
     return logits, probs, lse, arg
 

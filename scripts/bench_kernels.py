@@ -40,7 +40,7 @@ def rois_for(n_img, per_img, h_img=800, w_img=1216, seed=1992):
     g = torch.Generator().manual_seed(seed)
     r = n_img * per_img
     cx, cy = torch.rand(r, generator=g) * w_img, torch.rand(r, generator=g) * h_img
-    s = 16 * (600 / 16) ** torch.rand(r, generator=g)
+    s = 16 * (float(os.environ.get('RA_SMAX', '600')) / 16) ** torch.rand(r, generator=g)
     a = 0.5 * 4 ** torch.rand(r, generator=g)
     bw, bh = s * a.sqrt(), s / a.sqrt()
     b = torch.stack([(cx - bw / 2).clamp(0, w_img), (cy - bh / 2).clamp(0, h_img), (cx + bw / 2).clamp(0, w_img), (cy + bh / 2).clamp(0, h_img)], 1)
@@ -119,14 +119,20 @@ def box_case(name, r, k, precision, bwd=False):
 
 if __name__ == "__main__":
     quick = "--quick" in sys.argv
-    roi_case("cfg1 faithful [2,1024,50,76]->[1024,1024,14,14]", 2, 1024, 50, 76, 512, 14, 1 / 16)
-    roi_case("cfg1 literal [2,2048,25,38]->[1024,2048,7,7]", 2, 2048, 25, 38, 512, 7, 1 / 32)
+    if "--box-only" not in sys.argv:
+      roi_case("cfg1 faithful [2,1024,50,76]->[1024,1024,14,14]", 2, 1024, 50, 76, 512, 14, 1 / 16)
+      roi_case("cfg1 literal [2,2048,25,38]->[1024,2048,7,7]", 2, 2048, 25, 38, 512, 7, 1 / 32)
     if "--roi-only" in sys.argv:
         sys.exit(0)
-    if not quick:
+    if "--box-only" not in sys.argv:
+        pass
+    if not quick and "--box-only" not in sys.argv:
         roi_case("cfg3 [16,1024,50,76]->[8192,1024,14,14]", 16, 1024, 50, 76, 512, 14, 1 / 16)
-    box_case("cfg1 2x512 RoIs vs 65+1", 1024, 65, "fp32")
-    box_case("cfg1 2x512 RoIs vs 65+1", 1024, 65, "bf16")
-    box_case("cfg3 16x512 RoIs vs 48+1", 8192, 48, "bf16", bwd=True)
-    box_case("cfg5 8x1000 RoIs vs 1203+1", 8000, 1203, "bf16")
-    box_case("cfg5 8x1000 RoIs vs 1203+1", 8000, 1203, "fp32")
+    only = os.environ.get("BK_ONLY", "")
+    cases = [("cfg1 2x512 RoIs vs 65+1", 1024, 65, "fp32", False), ("cfg1 2x512 RoIs vs 65+1", 1024, 65, "bf16", False),
+             ("cfg3 16x512 RoIs vs 48+1", 8192, 48, "bf16", True), ("cfg5 8x1000 RoIs vs 1203+1", 8000, 1203, "bf16", False),
+             ("cfg5 8x1000 RoIs vs 1203+1", 8000, 1203, "fp32", False)]
+    for name, r, k, prec, bwd in cases:
+        if only and only not in f"{name.split()[0]}-{prec}":
+            continue
+        box_case(name, r, k, prec, bwd=bwd)
