@@ -128,15 +128,24 @@ struct EpiScore {
         row_a = (cta / p.groups) * TC_BLOCK_M;
         row_b = (cta % p.groups + chunk * p.groups) * core.block_n;      // past K1: TMA zero fill, skipped by the epilogue
     }
-    __device__ __forceinline__ void begin(const Params &, const TcCore &, int, int, int, int, unsigned char *) {
+    static constexpr int kBiasCap = 4096;   // class-bias values staged in shared memory (wider lists read it from global)
+    __device__ __forceinline__ void begin(const Params &p, const TcCore &, int, int row, int, int, unsigned char *smem) {
         run_max = -FLT_MAX;
         run_sum = 0.f;
         best_val = -FLT_MAX;
         best_idx = 0;
+        if (p.bias != nullptr) {
+            // the class bias is staged once per CTA: a global load per 32-column block in front of the dependent
+            // shuffles (L2 latency x 8 blocks x chunks) dominated this epilogue
+            float *sb = reinterpret_cast<float *>(smem) + 4 * TC_WARP_SCRATCH_WORDS;
+            for (int c = row; c < min(p.K1, kBiasCap); c += 128) sb[c] = __ldg(p.bias + c);
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+        }
     }
     __device__ __forceinline__ void chunk(const Params &p, const TcCore &core, int cta, int ch, uint32_t taddr, int row, int lane,
                                           int q, unsigned char *smem) {
         float *scratch = reinterpret_cast<float *>(smem) + (size_t)q * TC_WARP_SCRATCH_WORDS;
+        const float *sb = reinterpret_cast<const float *>(smem) + 4 * TC_WARP_SCRATCH_WORDS;
         const int tile = cta / p.groups;
         const int m0 = tile * TC_BLOCK_M + q * 32;
         const int rows_valid = max(0, min(32, p.R - m0));
@@ -148,11 +157,17 @@ struct EpiScore {
             if (cols_valid <= 0) break;
             float v[32];
             tmem_ld32(taddr + (uint32_t)c0, v);
+            if (p.bias != nullptr) {           // one coalesced load per block, broadcast by shuffles (32 dependent global loads per
+                                               // block made this epilogue latency bound)
+                const int bc = gc0 + lane;
+                const float bl = (lane < cols_valid) ? (bc < kBiasCap ? sb[bc] : __ldg(p.bias + bc)) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
+            }
             float blk_max = -FLT_MAX;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 if (j < cols_valid) {
-                    if (p.bias != nullptr) v[j] += __ldg(p.bias + gc0 + j);
                     blk_max = fmaxf(blk_max, v[j]);
                     if (gc0 + j < p.K1 - 1 && v[j] > best_val) {   // strict >: first maximum wins (torch.argmax)
                         best_val = v[j];
@@ -752,7 +767,8 @@ int loco_box_score_fwd(const uint16_t *E_hi, const uint16_t *E_lo, int64_t lde, 
     const int groups = box_score_groups(R, K1);
     LOCO_REQUIRE(groups == 1 || workspace != nullptr, LOCO_E_BADARG, "box_score_fwd: K1 > 256 needs loco_box_score_workspace_bytes() of workspace");
     const int chunks = (total_chunks + groups - 1) / groups;
-    const size_t smem = tc_finalize(core, D, E_lo ? 3 : 1, chunks, 4 * TC_WARP_SCRATCH_WORDS * 4);
+    const size_t smem = tc_finalize(core, D, E_lo ? 3 : 1, chunks,
+                                    4 * TC_WARP_SCRATCH_WORDS * 4 + (cls_bias ? (K1 < EpiScore::kBiasCap ? K1 : EpiScore::kBiasCap) * 4 : 0));
     TcMaps maps;
     int rc = fill_maps(maps, E_hi, E_lo, R, lde, C_hi, C_lo, K1, ldc, D, core);
     if (rc != LOCO_OK) return rc;

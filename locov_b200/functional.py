@@ -5,6 +5,7 @@ streams and the autograd graph only.  ``precision`` selects the tensor-core oper
   "fp32" : fp32-accurate — operands split into bf16 hi+lo, three tcgen05 passes (≈1e-5 relative)
   "bf16" : single bf16 pass (≈4e-3 relative; the north-star tolerance for bf16 is 2e-2)
 """
+import os
 import weakref
 from typing import Optional
 
@@ -16,6 +17,17 @@ from . import ops
 from ._lib import LocoError
 
 PRECISIONS = ("fp32", "bf16")
+
+# How the reduced-precision ("bf16") mode multiplies fp32 activations by fp32 weights:
+#   "tf32": kind::tf32 straight from the fp32 operands (no conversion pass; L2 -> SM operand traffic bound) — default
+#   "bf16": one conversion pass (fp32 -> bf16, HBM bound) + a bf16 tcgen05 GEMM (half the operand bytes through L2 -> SM,
+#           twice the tensor rate).  Measured on B200 (profiles/README.md): the GEMM gets faster but the extra launch and
+#           pass cancel it at the BASELINE shapes (LSM step 71.8 vs 68.2 us, config-5 box chain 216 vs 225 us)
+PROJECTION = os.environ.get("LOCOV_B200_PROJECTION", "tf32")
+
+
+def _use_tf32(acc: bool, k: int) -> bool:
+    return (not acc) and PROJECTION == "tf32" and k % 4 == 0
 
 
 def _acc(precision: str) -> bool:
@@ -86,7 +98,7 @@ class _Linear(Function):
     def forward(ctx, x, w, b, precision):
         acc = _acc(precision)
         x2 = x.reshape(-1, x.shape[-1])
-        if acc or x2.shape[1] % 4:
+        if not _use_tf32(acc, x2.shape[1]):
             out, _ = ops.linear_fwd(ops.split_bf16(x2, acc), weight_operand(w, acc), b, want_f32=True)
         else:       # reduced-precision mode: fp32 operands in place as TF32, no split pass
             out, _ = ops.linear_tf32_fwd(x2, w.detach(), b, want_f32=True)
@@ -142,7 +154,7 @@ class _BoxPredict(Function):
         nbox = w_box.shape[0]
         w_cat = _cat_weight(w_emb, w_box)
         b_cat = torch.cat([b_emb.detach(), b_box.detach()]).to(torch.float32)
-        if acc or x.shape[1] % 4:
+        if not _use_tf32(acc, x.shape[1]):
             a_op = ops.split_bf16(x, acc)
             wcat_op = weight_operand(w_cat, acc, tag="cat")
             out, e_op = ops.linear_fwd(a_op, wcat_op, b_cat, want_f32=True, n_bf16=d, accurate_out=acc)
@@ -252,7 +264,7 @@ def box_cross_entropy(logits, lse, labels):
 def project_regions(x2d, w, b, d, acc):
     """v2l_projection (grounding_head.py:111) -> bf16 tensor-core operand of the region embeddings.
     fp32 mode: hi/lo split + three bf16 passes; reduced-precision mode: TF32 straight from the fp32 features."""
-    if acc or x2d.shape[1] % 4:
+    if not _use_tf32(acc, x2d.shape[1]):
         _, emb_op = ops.linear_fwd(ops.split_bf16(x2d, acc), weight_operand(w, acc), b, want_f32=False, n_bf16=d, accurate_out=acc)
     else:
         _, emb_op = ops.linear_tf32_fwd(x2d, w.detach(), b, want_f32=False, n_bf16=d)
