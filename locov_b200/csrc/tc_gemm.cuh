@@ -50,6 +50,8 @@ struct TcCore {
     int debug_mode;     // developer experiments only (LOCOV_B200_DEBUG): 1 = skip the MMAs (pure TMA ingest rate),
                         // 2 = skip the TMA loads (pure tensor-pipe + operand-read rate); results are garbage
     int ring_bytes;     // bytes reserved for the operand ring (>= stages * stage_bytes; barriers follow it)
+    int two_cta;        // 1: CTA pair along M (cm = 2, cn = 1): cta_group::2 MMAs of M = 256, each CTA stages its own 128 rows of
+                        // A and HALF of the B tile (no multicast); the leader CTA (rank 0) issues the MMAs
     int epi_overlay;    // 1: the epilogue scratch overlays the operand ring (legal only with chunks == 1: the ring is
                         // dead once the accumulator barrier fired — every load of this tile has landed and been consumed)
 };
@@ -75,7 +77,7 @@ inline size_t tc_finalize(TcCore &core, int K, int passes, int chunks, int epi_s
     core.epi_smem = epi_smem;
     if (core.cm < 1) core.cm = 1;
     if (core.cn < 1) core.cn = 1;
-    const size_t stage_bytes = TC_A_BYTES + (size_t)core.block_n * 128;
+    const size_t stage_bytes = TC_A_BYTES + (size_t)(core.two_cta ? core.block_n / 2 : core.block_n) * 128;
     if (chunks != 1) core.epi_overlay = 0;
     const long long fixed = 1024 /*alignment slack*/ + 512 /*barriers*/ + (core.epi_overlay ? 0 : (long long)epi_smem);
     int stages = (int)(((long long)110 * 1024 - fixed) / (long long)stage_bytes);   // two CTAs per SM when possible
@@ -153,14 +155,17 @@ __device__ __forceinline__ void warp_store_bf16(uint32_t *scratch, const float (
 //   __device__ void begin(const Params&, const TcCore&, int cta, int row, int lane, int q, unsigned char *smem);
 //   __device__ void chunk(const Params&, const TcCore&, int cta, int chunk, uint32_t taddr, ...same...);
 //   __device__ void finish(const Params&, const TcCore&, int cta, ...same...);
-template <class Epi>
+// PAIR = true is the CTA-pair (cta_group::2) instantiation: a kernel containing cta_group::2 instructions can only be
+// launched as a cluster of two, so it is a separate instantiation from the single-CTA / multicast-cluster one.
+template <class Epi, bool PAIR = false>
 __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
     tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcCore core, const typename Epi::Params ep) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char *smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
 
-    const uint32_t b_bytes = (uint32_t)core.block_n * 128u;
+    constexpr bool pair = PAIR;                               // CTA pair: this CTA stages half of the B tile
+    const uint32_t b_bytes = (uint32_t)(pair ? core.block_n / 2 : core.block_n) * 128u;
     const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
     unsigned char *bar_base = smem + (size_t)core.ring_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(bar_base);
@@ -195,11 +200,11 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
     if (threadIdx.x == 0) {
         for (int s = 0; s < core.stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], (uint32_t)(core.cm + core.cn - 1));   // one release per CTA that reads what this CTA loads
+            mbar_init(&empty[s], pair ? 1u : (uint32_t)(core.cm + core.cn - 1));   // one release per CTA that reads what this CTA loads
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 32u * Epi::kEpiWarps);
+            mbar_init(&tempty[a], (pair ? 64u : 32u) * Epi::kEpiWarps);          // pair: the epilogue threads of both CTAs
         }
         fence_mbar_init();
     }
@@ -211,7 +216,10 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
             prefetch_tmap(&maps.b_lo);
         }
     }
-    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)core.tmem_cols);
+    if (warp == 1) {
+        if constexpr (pair) tmem_alloc2(tmem_slot, (uint32_t)core.tmem_cols);
+        else tmem_alloc(tmem_slot, (uint32_t)core.tmem_cols);
+    }
     tc_fence_before();
     if (csize > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers must be initialised before any remote signal
     tc_fence_after();
@@ -234,6 +242,13 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
                         if (core.debug_mode == 2) {
                             mbar_arrive(&full[stage]);
                         } else {
+                        if constexpr (pair) {
+                            // both CTAs signal the LEADER's full barrier; the leader announces the bytes of both
+                            if (rm == 0) mbar_arrive_expect_tx(&full[stage], 2u * stage_bytes);
+                            const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+                            tma_load_2d_2sm(sa, ma, lead_full, kb * k_elems, row_a);
+                            tma_load_2d_2sm(sa + TC_A_BYTES, mb, lead_full, kb * k_elems, row_b + rm * (core.block_n / 2));
+                        } else {
                         mbar_arrive_expect_tx(&full[stage], stage_bytes);
                         if (csize == 1) {
                             tma_load_2d(sa, ma, &full[stage], kb * k_elems, row_a);
@@ -246,14 +261,16 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
                                            row_b + rm * b_rows, mask_b);
                         }
                         }
+                        }
                         if (++stage == (uint32_t)core.stages) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = core.tf32 ? umma_idesc_tf32(TC_BLOCK_M, (uint32_t)core.block_n) : umma_idesc_bf16(TC_BLOCK_M, (uint32_t)core.block_n);
+        if (lane == 0 && !(pair && rm != 0)) {                // CTA pair: only the leader issues
+            const uint32_t mma_m = pair ? 2u * TC_BLOCK_M : (uint32_t)TC_BLOCK_M;
+            const uint32_t idesc = core.tf32 ? umma_idesc_tf32(mma_m, (uint32_t)core.block_n) : umma_idesc_bf16(mma_m, (uint32_t)core.block_n);
             uint32_t stage = 0, phase = 0;
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int acc = ch % core.acc_stages;
@@ -271,14 +288,23 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
 #pragma unroll
                     for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
                         if (core.debug_mode == 1) break;
-                        if (core.tf32) umma_tf32(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);   // +32 B per K=8 step
-                        else umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);            // +32 B per K=16 step
+                        if constexpr (pair) {
+                            if (core.tf32) umma_tf32_2cta(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);
+                            else umma_bf16_2cta(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);
+                        } else {
+                            if (core.tf32) umma_tf32(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);   // +32 B per K=8 step
+                            else umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);            // +32 B per K=16 step
+                        }
                         accumulate = 1;
                     }
-                    if (csize == 1) umma_commit(&empty[stage]); else umma_commit_mc(&empty[stage], (uint16_t)(mask_a | mask_b));
+                    if constexpr (pair) {
+                        umma_commit_2cta(&empty[stage]);
+                    } else {
+                        if (csize == 1) umma_commit(&empty[stage]); else umma_commit_mc(&empty[stage], (uint16_t)(mask_a | mask_b));
+                    }
                     if (++stage == (uint32_t)core.stages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&tfull[acc]);
+                if constexpr (pair) umma_commit_2cta(&tfull[acc]); else umma_commit(&tfull[acc]);
             }
         }
     } else {
@@ -294,7 +320,8 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * core.block_n);
             epi.chunk(ep, core, cta, ch, taddr, row, lane, q, epi_smem);
             tc_fence_before();
-            mbar_arrive(&tempty[acc]);
+            if constexpr (pair) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));   // the leader's MMA thread waits for both CTAs
+            else mbar_arrive(&tempty[acc]);
         }
         epi.finish(ep, core, cta, row, lane, q, epi_smem);
     }
@@ -303,23 +330,24 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, (uint32_t)core.tmem_cols);
+        if constexpr (pair) tmem_dealloc2(tmem_base, (uint32_t)core.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)core.tmem_cols);
     }
 }
 
-template <class Epi>
+template <class Epi, bool PAIR = false>
 int tc_launch(const TcMaps &maps, const TcCore &core, const typename Epi::Params &ep, int grid, size_t smem_bytes,
               cudaStream_t st) {
     LOCO_REQUIRE(smem_bytes <= 227 * 1024, LOCO_E_UNSUPPORTED, "tensor-core kernel needs %zu B of shared memory", smem_bytes);
     LOCO_REQUIRE(core.block_n >= 16 && core.block_n <= 256 && core.block_n % 16 == 0, LOCO_E_BADARG, "bad block_n %d", core.block_n);
     LOCO_REQUIRE(core.tmem_cols <= 512, LOCO_E_UNSUPPORTED, "tensor memory request %d columns", core.tmem_cols);
-    static thread_local size_t configured = 0;   // per (thread, Epi) high-water mark
+    LOCO_REQUIRE(PAIR == (core.two_cta != 0) && (!PAIR || (core.cm == 2 && core.cn == 1)), LOCO_E_BADARG, "CTA-pair launch mismatch");
+    static thread_local size_t configured = 0;   // per (thread, Epi, PAIR) high-water mark
     if (smem_bytes > configured) {
-        LOCO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        LOCO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<Epi, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         configured = 227 * 1024;
     }
     if (core.cm * core.cn == 1) {
-        tc_gemm_kernel<Epi><<<grid, 64 + 32 * Epi::kEpiWarps, smem_bytes, st>>>(maps, core, ep);
+        tc_gemm_kernel<Epi, PAIR><<<grid, 64 + 32 * Epi::kEpiWarps, smem_bytes, st>>>(maps, core, ep);
     } else {
         LOCO_REQUIRE(core.cm * core.cn <= 8 && grid % (core.cm * core.cn) == 0, LOCO_E_BADARG, "bad cluster %dx%d for grid %d", core.cm, core.cn, grid);
         LOCO_REQUIRE(TC_BLOCK_M % core.cn == 0 && (TC_BLOCK_M / core.cn) % 8 == 0 && core.block_n % core.cm == 0 && (core.block_n / core.cm) % 8 == 0,
@@ -336,7 +364,7 @@ int tc_launch(const TcMaps &maps, const TcCore &core, const typename Epi::Params
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        LOCO_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<Epi>, maps, core, ep));
+        LOCO_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<Epi, PAIR>, maps, core, ep));
     }
     count_launch();
     LOCO_CUDA(cudaGetLastError());

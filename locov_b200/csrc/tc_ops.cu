@@ -674,6 +674,39 @@ static void pick_gemm_shape(int M, int N, int sms, TcCore &core) {
     core.clusters_n = tc_round_up((N + core.block_n - 1) / core.block_n, core.cn) / core.cn;
 }
 
+// CTA pairs (tcgen05 cta_group::2, tc_gemm.cuh) for the plain GEMMs: on by default, LOCOV_B200_2CTA=0 falls back to
+// single-CTA tiles (A/B measurements).
+static bool pair_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("LOCOV_B200_2CTA");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+// Tile width for a CTA-pair GEMM: a pair owns a 256 x bn tile, per CTA and 128-byte k block the tensor pipe needs 2 * bn
+// cycles and the shared-memory fill (128 rows of A + bn/2 rows of B at ~52 B/cycle/SM, measured) (16384 + 64 * bn) / 52;
+// minimise waves * max(pipe, fill) + per-tile fixed cost.  Returns false when a single row tile makes pairs pointless.
+static bool pick_pair_shape(int M, int N, int sms, TcCore &core) {
+    const int mt = (M + TC_BLOCK_M - 1) / TC_BLOCK_M;
+    if (!pair_enabled() || mt < 2 || sms < 2) return false;
+    double best = 1e300;
+    int best_bn = 0;
+    for (int bn = 256; bn >= 32; bn -= 16) {
+        const int pairs = ((mt + 1) / 2) * ((N + bn - 1) / bn);
+        const int waves = (pairs + sms / 2 - 1) / (sms / 2);
+        const double pipe = 2.0 * bn, fill = (16384.0 + 64.0 * bn) / 52.0;
+        const double cost = waves * ((pipe > fill ? pipe : fill) + 60.0 + bn * 0.5);
+        if (cost < best) { best = cost; best_bn = bn; }
+    }
+    if (const char *e = getenv("LOCOV_B200_BN")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 16 == 0) best_bn = v; }
+    core.block_n = best_bn;
+    core.cm = 2; core.cn = 1; core.two_cta = 1;
+    core.clusters_n = (N + best_bn - 1) / best_bn;
+    return true;
+}
+
 }  // namespace loco
 
 using namespace loco;
@@ -697,7 +730,7 @@ static int linear_launch(const void *A_hi, const void *A_lo, int64_t lda, const 
     TcCore core = {};
     core.tf32 = tf32 ? 1 : 0;
     const int sms = current_device_sm_count();
-    pick_gemm_shape(M, N, sms, core);
+    if (!pick_pair_shape(M, N, sms, core)) pick_gemm_shape(M, N, sms, core);
     EpiLinear::Params p;
     p.bias = bias; p.out_f32 = out_f32; p.ld_f32 = ld_f32; p.out_hi = out_hi; p.out_lo = out_lo;
     p.n_bf16 = out_hi ? n_bf16 : 0; p.ld_bf16 = ld_bf16; p.M = M; p.N = N;
@@ -718,6 +751,7 @@ static int linear_launch(const void *A_hi, const void *A_lo, int64_t lda, const 
     int rc = fill_maps(maps, static_cast<const uint16_t *>(A_hi), static_cast<const uint16_t *>(A_lo), M, lda, static_cast<const uint16_t *>(W_hi),
                        static_cast<const uint16_t *>(W_lo), N, ldw, K, core);
     if (rc != LOCO_OK) return rc;
+    if (core.two_cta) return tc_launch<EpiLinear, true>(maps, core, p, grid, smem, static_cast<cudaStream_t>(stream));
     return tc_launch<EpiLinear>(maps, core, p, grid, smem, static_cast<cudaStream_t>(stream));
 }
 
