@@ -3,6 +3,7 @@
 // libcudart only and loads on a machine without a GPU for the symbol/ABI tests).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <atomic>
 #include <mutex>
 
@@ -74,6 +75,24 @@ int make_tmap_f32_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t
     return make_tmap_2d(map, base, rows, cols, ld_elems, box_rows, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4);
 }
 
+// Developer probe: with LOCOV_B200_TIMELINE=1 every tensor-core kernel writes 8 globaltimer stamps per CTA (entry, setup
+// done, first stage landed, last MMA issued, last accumulator complete, epilogue done, exit) into this buffer; the most
+// recent launch overwrites it.  Read back with loco_debug_timeline_read().
+static unsigned long long *g_timeline = nullptr;
+static int g_timeline_ctas = 0;
+constexpr int kTimelineMaxCtas = 8192;
+unsigned long long *debug_timeline_buffer(int ctas) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char *e = getenv("LOCOV_B200_TIMELINE");
+        enabled = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    if (!enabled || ctas > kTimelineMaxCtas) return nullptr;
+    if (g_timeline == nullptr && cudaMalloc(&g_timeline, (size_t)kTimelineMaxCtas * 8 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+    g_timeline_ctas = ctas;
+    return g_timeline;
+}
+
 int current_device_sm_count() {
     static int cached[64] = {0};
     int dev = 0;
@@ -110,6 +129,13 @@ int loco_device_check(int device) {
     LOCO_REQUIRE(major == 10, LOCO_E_DEVICE, "device %d is compute capability %d.%d; liblocov_b200 is built for sm_100a only",
                  device, major, minor);
     return LOCO_OK;
+}
+
+int loco_debug_timeline_read(unsigned long long *host, int max_ctas) {
+    if (loco::g_timeline == nullptr || host == nullptr) return 0;
+    const int n = loco::g_timeline_ctas < max_ctas ? loco::g_timeline_ctas : max_ctas;
+    if (cudaMemcpy(host, loco::g_timeline, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return n;
 }
 
 int loco_sm_count(int device) {

@@ -117,6 +117,13 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// L2 prefetch of a 2-D tile (no shared-memory destination, no completion signal).
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *m, int32_t c_inner, int32_t c_outer) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c_inner),
+                 "r"(c_outer)
+                 : "memory");
+}
+
 // 2-D tile load multicast to every CTA of the cluster whose bit is set in `cta_mask`: the tile lands at the same
 // shared-memory offset in each destination CTA and signals complete_tx on the mbarrier at the same offset there.
 __device__ __forceinline__ void tma_load_2d_mc(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int32_t c_inner,
@@ -125,6 +132,17 @@ __device__ __forceinline__ void tma_load_2d_mc(void *smem_dst, const CUtensorMap
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer), "h"(cta_mask)
         : "memory");
+}
+// One lane of the (converged) warp, chosen by the hardware: code under this predicate is known to the compiler to run in a
+// single thread, so tcgen05 / TMA instructions (which take warp-uniform operands) need no per-lane serialisation loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -259,6 +277,18 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                  "h"((uint16_t)3)
                  : "memory");
+}
+
+// One K step (32 bytes of K per operand row) of the tile MMA, kind and CTA-group fixed at compile time.
+template <bool TF32, bool PAIR>
+__device__ __forceinline__ void umma_step(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (PAIR) {
+        if constexpr (TF32) umma_tf32_2cta(tmem_d, desc_a, desc_b, idesc, accumulate);
+        else umma_bf16_2cta(tmem_d, desc_a, desc_b, idesc, accumulate);
+    } else {
+        if constexpr (TF32) umma_tf32(tmem_d, desc_a, desc_b, idesc, accumulate);
+        else umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+    }
 }
 
 // TMEM -> registers: lane i of the warp reads TMEM lane (lane_base + i), 32 consecutive fp32 columns.

@@ -54,6 +54,12 @@ struct TcCore {
                         // A and HALF of the B tile (no multicast); the leader CTA (rank 0) issues the MMAs
     int epi_overlay;    // 1: the epilogue scratch overlays the operand ring (legal only with chunks == 1: the ring is
                         // dead once the accumulator barrier fired — every load of this tile has landed and been consumed)
+    unsigned long long *timeline;   // developer probe (LOCOV_B200_TIMELINE=1): per CTA 8 globaltimer stamps, NULL otherwise
+    int prefetch;       // > 0: the producer prefetches the A panel into L2 in bursts of `prefetch` consecutive k blocks, one burst
+                        // ahead of the loads: a 128-byte-wide k block touches every row's DRAM page for 128 bytes only; a burst
+                        // turns that into `prefetch` x 128 contiguous bytes per row while the page is open
+    int single_wave;    // 1: the grid is at most one CTA per SM, so a second resident CTA would never exist — give the whole
+                        // shared memory to the operand ring (bytes in flight per SM bound the TMA ingest rate: Little's law)
 };
 
 __host__ __device__ inline int tc_round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -80,17 +86,20 @@ inline size_t tc_finalize(TcCore &core, int K, int passes, int chunks, int epi_s
     const size_t stage_bytes = TC_A_BYTES + (size_t)(core.two_cta ? core.block_n / 2 : core.block_n) * 128;
     if (chunks != 1) core.epi_overlay = 0;
     const long long fixed = 1024 /*alignment slack*/ + 512 /*barriers*/ + (core.epi_overlay ? 0 : (long long)epi_smem);
-    int stages = (int)(((long long)110 * 1024 - fixed) / (long long)stage_bytes);   // two CTAs per SM when possible
+    long long budget = core.single_wave ? 225 : 110;                                // two CTAs per SM unless the grid is one wave
+    if (const char *e = getenv("LOCOV_B200_SMEMKB")) { const int v = atoi(e); if (v >= 32 && v <= 225) budget = v; }   // developer sweep knob
+    int stages = (int)((budget * 1024 - fixed) / (long long)stage_bytes);
     if (core.epi_overlay && (long long)epi_smem + fixed > 110 * 1024) stages = 0;    // the overlay itself needs a whole SM
     if (stages < 3) stages = (int)(((long long)225 * 1024 - fixed) / (long long)stage_bytes);
     const int total_iters = core.num_k_blocks * passes * chunks;
-    if (stages > 6) stages = 6;
+    if (stages > (core.single_wave ? TC_MAX_STAGES : 6)) stages = core.single_wave ? TC_MAX_STAGES : 6;
     if (const char *e = getenv("LOCOV_B200_STAGES")) { const int v = atoi(e); if (v >= 1 && v < stages) stages = v; }   // developer sweep knob
     if (stages > total_iters) stages = total_iters;
     if (stages < 1) stages = 1;
     core.stages = stages;
     core.debug_mode = 0;
     if (const char *e = getenv("LOCOV_B200_DEBUG")) core.debug_mode = atoi(e);
+    if (const char *e = getenv("LOCOV_B200_PF")) { const int v = atoi(e); if (v >= 0 && v <= 64) core.prefetch = v; }   // developer sweep knob
     size_t ring = (size_t)stages * stage_bytes;
     if (core.epi_overlay && ring < (size_t)epi_smem) ring = ((size_t)epi_smem + 1023) / 1024 * 1024;
     core.ring_bytes = (int)ring;
@@ -148,6 +157,62 @@ __device__ __forceinline__ void warp_store_bf16(uint32_t *scratch, const float (
     }
 }
 
+// ---- MMA issue loop (one elected thread) ---------------------------------------------------------------
+// The issuing thread is a single warp with no instruction-level parallelism: every instruction between two tcgen05.mma is
+// latency the tensor pipe may have to wait for (measured: ~170-200 cycles per MMA with run-time kind / pair / debug branches
+// and per-lane serialisation loops around each MMA, against an 80-128 cycle MMA).  Kind and CTA-group are therefore
+// template parameters, the four K steps of a stage are straight-line code and the descriptors advance by immediates.
+template <bool TF32, bool PAIR>
+__device__ __forceinline__ void mma_issue_loop(const TcCore &core, unsigned char *smem, uint32_t stage_bytes, uint64_t *full,
+                                               uint64_t *empty, uint64_t *tfull, uint64_t *tempty, uint32_t tmem_base, int nchunks,
+                                               int iters_per_chunk, unsigned long long *tl) {
+    const uint32_t mma_m = PAIR ? 2u * TC_BLOCK_M : (uint32_t)TC_BLOCK_M;
+    const uint32_t idesc = TF32 ? umma_idesc_tf32(mma_m, (uint32_t)core.block_n) : umma_idesc_bf16(mma_m, (uint32_t)core.block_n);
+    const bool skip_mma = core.debug_mode == 1;
+    const bool multicast_commit = !PAIR && core.cm * core.cn > 1;
+    uint16_t commit_mask = 1;
+    if (multicast_commit) {
+        const int rank = (int)cluster_ctarank();
+        const int rm = rank / core.cn, rn = rank - rm * core.cn;
+        uint32_t mb = ((1u << core.cn) - 1u) << (rm * core.cn);
+        for (int j = 0; j < core.cm; ++j) mb |= 1u << (j * core.cn + rn);
+        commit_mask = (uint16_t)mb;
+    }
+    const uint32_t smem_base = smem_u32(smem);
+    uint32_t stage = 0, phase = 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int acc = ch % core.acc_stages;
+        const uint32_t acc_phase = (uint32_t)(ch / core.acc_stages) & 1u;
+        mbar_wait(&tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * core.block_n);
+        uint32_t accumulate = 0;
+        for (int it = 0; it < iters_per_chunk; ++it) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            if (tl != nullptr && it == 0 && ch == 0) tl[2] = global_timer_ns();     // first operand stage landed
+            const uint32_t a_addr = smem_base + stage * stage_bytes;
+            const uint64_t da = umma_desc_k128(a_addr);
+            const uint64_t db = umma_desc_k128(a_addr + TC_A_BYTES);
+            if (!skip_mma) {
+                umma_step<TF32, PAIR>(tmem_d, da, db, idesc, accumulate);            // +32 B of K per step (descriptor units of 16 B)
+                umma_step<TF32, PAIR>(tmem_d, da + 2u, db + 2u, idesc, 1u);
+                umma_step<TF32, PAIR>(tmem_d, da + 4u, db + 4u, idesc, 1u);
+                umma_step<TF32, PAIR>(tmem_d, da + 6u, db + 6u, idesc, 1u);
+            }
+            accumulate = 1;
+            if constexpr (PAIR) {
+                umma_commit_2cta(&empty[stage]);
+            } else {
+                if (multicast_commit) umma_commit_mc(&empty[stage], commit_mask); else umma_commit(&empty[stage]);
+            }
+            if (++stage == (uint32_t)core.stages) { stage = 0; phase ^= 1u; }
+        }
+        if constexpr (PAIR) umma_commit_2cta(&tfull[acc]); else umma_commit(&tfull[acc]);
+        if (tl != nullptr && ch == nchunks - 1) tl[3] = global_timer_ns();           // last MMA issued
+    }
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------
 // Epi interface:
 //   struct Params;                                       (trivially copyable, passed by value)
@@ -178,6 +243,8 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int k_elems = core.tf32 ? TC_BLOCK_K / 2 : TC_BLOCK_K;
+    unsigned long long *tl = core.timeline ? core.timeline + (size_t)blockIdx.x * 8 : nullptr;
+    if (tl && threadIdx.x == 0) tl[0] = global_timer_ns();                       // CTA entry
 
     // cluster geometry -> virtual CTA index handed to the epilogue policy
     const int csize = core.cm * core.cn;
@@ -223,12 +290,13 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
     tc_fence_before();
     if (csize > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers must be initialised before any remote signal
     tc_fence_after();
+    if (tl && threadIdx.x == 0) tl[1] = global_timer_ns();                       // setup done (barriers, TMEM, cluster sync)
     const uint32_t tmem_base = *tmem_slot;
     const int iters_per_chunk = core.num_k_blocks * core.passes;
     const int nchunks = core.total_tiles > 0 ? max(0, (core.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) : core.chunks;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t stage = 0, phase = 0;
             for (int ch = 0; ch < nchunks; ++ch) {
                 int row_a, row_b;
@@ -237,6 +305,12 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
                     const CUtensorMap *ma = (pass == 2) ? &maps.a_lo : &maps.a_hi;
                     const CUtensorMap *mb = (pass == 1) ? &maps.b_lo : &maps.b_hi;
                     for (int kb = 0; kb < core.num_k_blocks; ++kb) {
+                        if (core.prefetch > 0 && kb % core.prefetch == 0 && core.debug_mode != 2) {
+                            const int a_rows_pf = pair ? TC_BLOCK_M : TC_BLOCK_M / core.cn;      // rows this CTA itself loads
+                            const int row_pf = pair ? row_a : row_a + rn * a_rows_pf;
+                            const int kb0 = kb + core.prefetch;
+                            for (int j = kb0; j < kb0 + core.prefetch && j < core.num_k_blocks; ++j) tma_prefetch_2d(ma, j * k_elems, row_pf);
+                        }
                         mbar_wait(&empty[stage], phase ^ 1u);
                         unsigned char *sa = smem + (size_t)stage * stage_bytes;
                         if (core.debug_mode == 2) {
@@ -268,44 +342,9 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && !(pair && rm != 0)) {                // CTA pair: only the leader issues
-            const uint32_t mma_m = pair ? 2u * TC_BLOCK_M : (uint32_t)TC_BLOCK_M;
-            const uint32_t idesc = core.tf32 ? umma_idesc_tf32(mma_m, (uint32_t)core.block_n) : umma_idesc_bf16(mma_m, (uint32_t)core.block_n);
-            uint32_t stage = 0, phase = 0;
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const int acc = ch % core.acc_stages;
-                const uint32_t acc_phase = (uint32_t)(ch / core.acc_stages) & 1u;
-                mbar_wait(&tempty[acc], acc_phase ^ 1u);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * core.block_n);
-                uint32_t accumulate = 0;
-                for (int it = 0; it < iters_per_chunk; ++it) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t da = umma_desc_k128(a_addr);
-                    const uint64_t db = umma_desc_k128(a_addr + TC_A_BYTES);
-#pragma unroll
-                    for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
-                        if (core.debug_mode == 1) break;
-                        if constexpr (pair) {
-                            if (core.tf32) umma_tf32_2cta(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);
-                            else umma_bf16_2cta(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);
-                        } else {
-                            if (core.tf32) umma_tf32(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);   // +32 B per K=8 step
-                            else umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);            // +32 B per K=16 step
-                        }
-                        accumulate = 1;
-                    }
-                    if constexpr (pair) {
-                        umma_commit_2cta(&empty[stage]);
-                    } else {
-                        if (csize == 1) umma_commit(&empty[stage]); else umma_commit_mc(&empty[stage], (uint16_t)(mask_a | mask_b));
-                    }
-                    if (++stage == (uint32_t)core.stages) { stage = 0; phase ^= 1u; }
-                }
-                if constexpr (pair) umma_commit_2cta(&tfull[acc]); else umma_commit(&tfull[acc]);
-            }
+        if (!(pair && rm != 0) && elect_one()) {              // CTA pair: only the leader issues
+            if (core.tf32) mma_issue_loop<true, pair>(core, smem, stage_bytes, full, empty, tfull, tempty, tmem_base, nchunks, iters_per_chunk, tl);
+            else mma_issue_loop<false, pair>(core, smem, stage_bytes, full, empty, tfull, tempty, tmem_base, nchunks, iters_per_chunk, tl);
         }
     } else {
         const int q = warp & 3;            // TMEM lane quarter accessible to this warp
@@ -317,6 +356,7 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
             const uint32_t acc_phase = (uint32_t)(ch / core.acc_stages) & 1u;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
+            if (tl && ch == nchunks - 1 && threadIdx.x == 64) tl[4] = global_timer_ns();   // last accumulator complete
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * core.block_n);
             epi.chunk(ep, core, cta, ch, taddr, row, lane, q, epi_smem);
             tc_fence_before();
@@ -324,6 +364,7 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
             else mbar_arrive(&tempty[acc]);
         }
         epi.finish(ep, core, cta, row, lane, q, epi_smem);
+        if (tl && threadIdx.x == 64) tl[5] = global_timer_ns();                  // epilogue done
     }
     tc_fence_before();
     if (csize > 1) cluster_sync_all(); else __syncthreads();      // no CTA may exit while peers still signal its barriers
@@ -332,11 +373,16 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
         tc_fence_after();
         if constexpr (pair) tmem_dealloc2(tmem_base, (uint32_t)core.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)core.tmem_cols);
     }
+    if (tl && threadIdx.x == 0) tl[6] = global_timer_ns();                       // CTA exit
 }
 
+unsigned long long *debug_timeline_buffer(int ctas);   // api.cu; NULL unless LOCOV_B200_TIMELINE=1
+
 template <class Epi, bool PAIR = false>
-int tc_launch(const TcMaps &maps, const TcCore &core, const typename Epi::Params &ep, int grid, size_t smem_bytes,
+int tc_launch(const TcMaps &maps, const TcCore &core_in, const typename Epi::Params &ep, int grid, size_t smem_bytes,
               cudaStream_t st) {
+    TcCore core = core_in;
+    core.timeline = debug_timeline_buffer(grid);
     LOCO_REQUIRE(smem_bytes <= 227 * 1024, LOCO_E_UNSUPPORTED, "tensor-core kernel needs %zu B of shared memory", smem_bytes);
     LOCO_REQUIRE(core.block_n >= 16 && core.block_n <= 256 && core.block_n % 16 == 0, LOCO_E_BADARG, "bad block_n %d", core.block_n);
     LOCO_REQUIRE(core.tmem_cols <= 512, LOCO_E_UNSUPPORTED, "tensor memory request %d columns", core.tmem_cols);

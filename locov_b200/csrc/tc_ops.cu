@@ -746,6 +746,7 @@ static int linear_launch(const void *A_hi, const void *A_lo, int64_t lda, const 
         core.total_tiles = tiles;
     }
     p.grid = grid;
+    core.single_wave = grid <= sms ? 1 : 0;
     const size_t smem = tc_finalize(core, K, A_lo ? 3 : 1, chunks, 0);
     TcMaps maps;
     int rc = fill_maps(maps, static_cast<const uint16_t *>(A_hi), static_cast<const uint16_t *>(A_lo), M, lda, static_cast<const uint16_t *>(W_hi),

@@ -48,12 +48,9 @@ def main():
     shapes = [(3200, 768, 2048), (8192, 768, 2048), (32768, 768, 2048), (8192, 8192, 2048)]
     if len(sys.argv) > 1 and sys.argv[1] == "small":
         shapes = shapes[:2]
-    cfgs = [dict(), dict(LOCOV_B200_CLUSTER="0"), dict(LOCOV_B200_CM="1", LOCOV_B200_CN="1", LOCOV_B200_BN="256"),
-            dict(LOCOV_B200_CM="1", LOCOV_B200_CN="1", LOCOV_B200_BN="128"), dict(LOCOV_B200_CM="1", LOCOV_B200_CN="1", LOCOV_B200_BN="64"),
-            dict(LOCOV_B200_CM="1", LOCOV_B200_CN="1", LOCOV_B200_BN="256", LOCOV_B200_STAGES="2"),
-            dict(LOCOV_B200_CM="1", LOCOV_B200_CN="1", LOCOV_B200_BN="128", LOCOV_B200_STAGES="2"),
-            dict(LOCOV_B200_CM="2", LOCOV_B200_CN="4", LOCOV_B200_BN="192"), dict(LOCOV_B200_CM="2", LOCOV_B200_CN="2", LOCOV_B200_BN="256"),
-            dict(LOCOV_B200_CM="1", LOCOV_B200_CN="4", LOCOV_B200_BN="192"), dict(LOCOV_B200_CM="1", LOCOV_B200_CN="1", LOCOV_B200_BN="192")]
+    cfgs = [dict(), dict(LOCOV_B200_SMEMKB="110"), dict(LOCOV_B200_SMEMKB="160"), dict(LOCOV_B200_2CTA="0")]
+    for bn in (128, 192, 256):
+        cfgs.append(dict(LOCOV_B200_BN=str(bn)))
     for shp in shapes:
         for cfg in cfgs:
             env = dict(os.environ, **cfg)
