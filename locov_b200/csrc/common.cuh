@@ -333,11 +333,16 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ uint16_t f32_to_bf16_rn(float x) {   // round-to-nearest-even, NaN preserved
-    uint32_t u = __float_as_uint(x);
-    if ((u & 0x7F800000u) == 0x7F800000u && (u & 0x007FFFFFu)) return static_cast<uint16_t>((u >> 16) | 0x40);
-    u += 0x7FFFu + ((u >> 16) & 1u);
-    return static_cast<uint16_t>(u >> 16);
+__device__ __forceinline__ uint16_t f32_to_bf16_rn(float x) {   // round-to-nearest-even: one F2FP instruction
+    uint16_t h;
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(x));
+    return h;
+}
+// two floats -> packed bf16x2 (`a` in the low half, `b` in the high half), one instruction
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
 }
 __device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float(static_cast<uint32_t>(h) << 16); }
 __device__ __forceinline__ void split_bf16(float x, uint16_t &hi, uint16_t &lo) {

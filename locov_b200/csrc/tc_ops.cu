@@ -74,13 +74,13 @@ struct EpiLinear {
             if (p.out_hi != nullptr && gc0 < p.n_bf16) {
                 const int cb = min(cols_valid, p.n_bf16 - gc0);
                 uint32_t hp[16], lp[16];
+                const bool want_lo = p.out_lo != nullptr;          // warp-uniform
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    uint16_t h0, l0, h1, l1;
-                    split_bf16(v[2 * j], h0, l0);
-                    split_bf16(v[2 * j + 1], h1, l1);
-                    hp[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                    lp[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                    hp[j] = pack_bf16x2_rn(v[2 * j], v[2 * j + 1]);
+                    lp[j] = 0u;
+                    if (want_lo)
+                        lp[j] = pack_bf16x2_rn(v[2 * j] - __uint_as_float(hp[j] << 16), v[2 * j + 1] - __uint_as_float(hp[j] & 0xFFFF0000u));
                 }
                 uint16_t *dh = p.out_hi + (int64_t)grow * p.ld_bf16 + gc0;     // 64-byte aligned: base 16 B, ld % 8, gc0 % 32
                 uint16_t *dl = p.out_lo ? p.out_lo + (int64_t)grow * p.ld_bf16 + gc0 : nullptr;
