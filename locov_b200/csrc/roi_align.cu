@@ -442,6 +442,82 @@ __device__ __noinline__ void pool_bin_row(const char *fb, const MergedEntry *yt,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Column-walk form of a bin row (the common case: adaptive sampling grid with GW = ceil(bin_w) <= 3).
+// The gw samples of a bin are < 1 px apart and span < bin_w <= GW px, so the merged taps of bin pw lie in the GW + 1
+// consecutive columns [base(pw), base(pw) + GW], and base(pw) is non-decreasing.  The row is therefore a single
+// left-to-right walk over CONSECUTIVE feature columns with a sliding window of GW + 1 vertically pooled columns in
+// registers: per bin a 4-float dense weight vector and an advance count (both built once per roi — the x structure is the
+// same for all bin rows and channel slabs).  No per-tap table lookups, index compares or cache-slot branches, and the loads
+// of the next column are always issued one advance ahead of their use (they are unconditional), which is what hides the
+// L2 latency the bin-driven walk above exposes (profiles/README.md: long-scoreboard stalls, 45 % issue utilisation).
+// ------------------------------------------------------------------------------------------------
+struct WalkBin {
+    float w[4];      // dense weights of columns base .. base + 3 (zero beyond GW)
+};
+
+template <int GW, int NY>
+__device__ __noinline__ void walk_bin_row(const char *fb, const MergedEntry *yt, const WalkBin *xw, const int *xadv, int x0_bytes,
+                                           int colstride, int xlast_bytes, int PW, float inv_cnt, float *trow, int rstep) {
+    int yo[NY];
+    float yw[NY];
+#pragma unroll
+    for (int k = 0; k < NY; ++k) { yo[k] = yt[k].idx; yw[k] = yt[k].w; }
+    Quad u[GW + 1];
+    Quad raw[NY];
+#pragma unroll
+    for (int k = 0; k <= GW; ++k) { u[k].lo = make_float2(0.f, 0.f); u[k].hi = u[k].lo; }
+    int sb = x0_bytes;                                  // byte offset of the next column of the stream
+    {
+        const char *p = fb + min(sb, xlast_bytes);
+#pragma unroll
+        for (int k = 0; k < NY; ++k) raw[k] = ldg_quad(p + yo[k]);
+    }
+    auto bin = [&](int pw) -> Quad {
+        int a = xadv[pw];
+#pragma unroll 1
+        for (; a > 0; --a) {
+#pragma unroll
+            for (int k = 0; k < GW; ++k) u[k] = u[k + 1];
+            Quad t = quad_mul(yw[0], raw[0]);
+#pragma unroll
+            for (int k = 1; k < NY; ++k) quad_fma(t, yw[k], raw[k]);
+            u[GW] = t;
+            sb += colstride;
+            const char *p = fb + min(sb, xlast_bytes);  // columns past the last one carry zero weight: clamp the address
+#pragma unroll
+            for (int k = 0; k < NY; ++k) raw[k] = ldg_quad(p + yo[k]);
+        }
+        const float4 w = *reinterpret_cast<const float4 *>(xw[pw].w);
+        Quad acc = quad_mul(w.x, u[0]);
+        quad_fma(acc, w.y, u[1]);
+        if (GW >= 2) quad_fma(acc, w.z, u[GW >= 2 ? 2 : 0]);
+        if (GW >= 3) quad_fma(acc, w.w, u[GW >= 3 ? 3 : 0]);
+        return quad_mul(inv_cnt, acc);
+    };
+#pragma unroll 1
+    for (int pw = 0; pw < PW; pw += 2) {               // PW is even on this path (paired 8-byte tile stores)
+        const Quad a = bin(pw);
+        const Quad b = bin(pw + 1);
+        *reinterpret_cast<float2 *>(trow + pw) = make_float2(a.lo.x, b.lo.x);
+        *reinterpret_cast<float2 *>(trow + pw + rstep) = make_float2(a.lo.y, b.lo.y);
+        *reinterpret_cast<float2 *>(trow + pw + 2 * rstep) = make_float2(a.hi.x, b.hi.x);
+        *reinterpret_cast<float2 *>(trow + pw + 3 * rstep) = make_float2(a.hi.y, b.hi.y);
+    }
+}
+
+template <int GW>
+__device__ __forceinline__ bool walk_dispatch(int ny, const char *fb, const MergedEntry *yt, const WalkBin *xw, const int *xadv,
+                                              int x0_bytes, int colstride, int xlast_bytes, int PW, float inv_cnt, float *trow, int rstep) {
+    switch (ny) {                                      // warp-uniform
+        case 1: walk_bin_row<GW, 1>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
+        case 2: walk_bin_row<GW, 2>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
+        case 3: walk_bin_row<GW, 3>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
+        case 4: walk_bin_row<GW, 4>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
+        default: return false;
+    }
+}
+
 template <bool PAIR>
 __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const float *__restrict__ feat,   // [N,H,W,C]
                                                                         const float *__restrict__ rois, int C, int H, int W,
@@ -453,7 +529,11 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
     MergedEntry *xtab = ytab + RA_TAB;
     int *ycnt = reinterpret_cast<int *>(xtab + RA_TAB);      // [32]
     int *xcnt = ycnt + 32;                                    // [32]
-    float *tile = reinterpret_cast<float *>(xcnt + 32);       // [RV_CC][tstride]
+    int *xadv = xcnt + 32;                                    // [32] column-walk advance counts
+    int *xbase = xadv + 32;                                   // [32] first column of each bin (-1: no sample inside the map)
+    int *walk_hdr = xbase + 32;                               // [4]  {-, first column of the walk, -, -}
+    WalkBin *xw = reinterpret_cast<WalkBin *>(walk_hdr + 4);  // [32] dense per-bin column weights (16-byte aligned)
+    float *tile = reinterpret_cast<float *>(xw + 32);         // [RV_CC][tstride]
 
     const int r = blockIdx.x / nchunks;
     const int chunk = blockIdx.x - r * nchunks;               // this CTA pools `slabs` consecutive 128-channel slabs
@@ -466,12 +546,54 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
     const bool tables_fit = !empty && (long long)PH * ystride <= RA_TAB && (long long)PW * xstride <= RA_TAB;
     const float inv_cnt = __fdiv_rn(1.0f, (float)max(g.gh * g.gw, 1));
 
+    // column-walk program, part 1 (by the thread that built the bin's merged list): first column and dense weights
+    const bool walk_try = tables_fit && PAIR && sampling_ratio <= 0 && g.gw >= 1 && g.gw <= 3;
+    bool walk_bad_a = false;
     if (tables_fit) {
         const int t = threadIdx.x;
         if (t < PH) ycnt[t] = build_merged(ytab + t * ystride, g.sh, g.bh, t, g.gh, H, W * C * 4);
-        else if (t >= 32 && t < 32 + PW) xcnt[t - 32] = build_merged(xtab + (t - 32) * xstride, g.sw, g.bw, t - 32, g.gw, W, C * 4, true);
+        else if (t >= 32 && t < 32 + PW) {
+            const int pw = t - 32;
+            const MergedEntry *xt = xtab + pw * xstride;
+            const int nx = build_merged(xtab + pw * xstride, g.sw, g.bw, pw, g.gw, W, C * 4, true);
+            xcnt[pw] = nx;
+            if (walk_try) {
+                const int colbytes = C * 4;
+                float w[4] = {0.f, 0.f, 0.f, 0.f};
+                int base = -1;
+                if (nx > 0) {
+                    base = (xt[0].idx & ~1) / colbytes;                              // (bit 0 of the byte offset is the parity tag)
+                    for (int j = 0; j < nx; ++j) {
+                        const int d = (xt[j].idx & ~1) / colbytes - base;
+                        if (d < 0 || d > g.gw) walk_bad_a = true;
+                        else w[d] += xt[j].w;
+                    }
+                }
+                xbase[pw] = base;
+                xw[pw].w[0] = w[0]; xw[pw].w[1] = w[1]; xw[pw].w[2] = w[2]; xw[pw].w[3] = w[3];
+            }
+        }
     }
+    if (threadIdx.x == 0) walk_hdr[1] = 0;
     __syncthreads();
+    // column-walk program (see walk_bin_row), part 2: advance counts from the bases of the preceding bins
+    bool walk_bad = !walk_try;
+    if (walk_try && threadIdx.x >= 32 && threadIdx.x < 32 + PW) {
+        const int pw = threadIdx.x - 32;
+        walk_bad = walk_bad_a;
+        const int base = xbase[pw];
+        int adv = 0;
+        if (base >= 0) {
+            int prev = -1;
+            for (int q = pw - 1; q >= 0 && prev < 0; --q) prev = xbase[q];
+            if (prev < 0) { adv = g.gw + 1; walk_hdr[1] = base; }      // first non-empty bin primes the whole window
+            else adv = base - prev;
+            if (adv < 0 || adv > g.gw + 1) walk_bad = true;
+        }
+        xadv[pw] = adv;
+    }
+    const bool walk_ok = __syncthreads_and(walk_bad ? 0 : 1) != 0;
+    const int walk_x0 = walk_hdr[1] * C * 4, walk_colstride = C * 4, walk_xlast = (W - 1) * C * 4;
 
     const int cl = 4 * lane;
     float *t0 = tile + (size_t)lane * tstride;                 // rows lane, 32 + lane, 64 + lane, 96 + lane
@@ -496,6 +618,13 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
                 const MergedEntry *yt = ytab + ph * ystride;
                 const int ny = ycnt[ph];
                 float *trow = t0 + ph * PW;
+                if (PAIR && walk_ok) {                         // CTA-uniform: column walk (GW = sampling grid width of this roi)
+                    bool done;
+                    if (g.gw == 1) done = walk_dispatch<1>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
+                    else if (g.gw == 2) done = walk_dispatch<2>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
+                    else done = walk_dispatch<3>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
+                    if (done) continue;
+                }
                 switch (ny) {                                  // warp-uniform
                     case 1: pool_bin_row<1, PAIR>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
                     case 2: pool_bin_row<2, PAIR>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
@@ -673,7 +802,8 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
         int slabs = 1;
         while (slabs < 4 && nslab % (slabs * 2) == 0 && (long long)R * (nslab / (slabs * 2)) >= 8ll * 2 * 148) slabs *= 2;
         const int nchunks = nslab / slabs;
-        const size_t smem = 2 * RA_TAB * sizeof(MergedEntry) + 64 * sizeof(int) + (size_t)RV_CC * tstride * sizeof(float);
+        const size_t smem = 2 * RA_TAB * sizeof(MergedEntry) + (64 + 64 + 4) * sizeof(int) + 32 * sizeof(WalkBin) +
+                            (size_t)RV_CC * tstride * sizeof(float);
         LOCO_REQUIRE(smem <= 200 * 1024, LOCO_E_UNSUPPORTED, "roi_align_fwd: output size %dx%d needs %zu B of shared memory", PH, PW, smem);
         LOCO_REQUIRE((long long)R * nchunks < (1ll << 31), LOCO_E_UNSUPPORTED, "roi_align_fwd: too many (roi, channel-slab) tiles");
         static thread_local size_t smem_set[2] = {0, 0};
