@@ -20,6 +20,8 @@
 //   * results are staged in a [32][PH*PW] shared-memory tile (odd stride: conflict-free column writes)
 //     and streamed out as fully coalesced 128-byte st.global.cs rows (evict-first keeps the feature
 //     map resident in the 126 MB L2).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace loco {
@@ -523,7 +525,7 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
                                                                         const float *__restrict__ rois, int C, int H, int W,
                                                                         int PH, int PW, float scale, int sampling_ratio,
                                                                         int aligned, int nchunks, int slabs, int tstride,
-                                                                        float *__restrict__ out) {
+                                                                        int bulk_out, float *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MergedEntry *ytab = reinterpret_cast<MergedEntry *>(smem_raw);
     MergedEntry *xtab = ytab + RA_TAB;
@@ -655,8 +657,30 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
                     store_bin(ph * PW + pw, acc);
                 }
         }
+        if (bulk_out) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // tile writes -> visible to the copy engine
         __syncthreads();
 
+        const int cc_b = min(RV_CC, C - c0);
+        if (bulk_out) {
+            // write-out by the copy engine: every channel's PH*PW floats are one dense, 16-byte aligned run both in the tile
+            // (tstride == PH*PW) and in the NCHW output, so thread `row` hands its row to cp.async.bulk (evict-first in L2,
+            // like st.global.cs) — no LDS / STG instructions, no LSU wavefronts, and the warps are free as soon as the
+            // copies are queued.  (The generic-proxy tile writes were fenced before the barrier above.)
+            if (threadIdx.x < RV_CC) {
+                const int row = threadIdx.x, ch = 4 * (row & 31) + (row >> 5);
+                if (ch < cc_b) {
+                    uint64_t pol;
+                    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+                    const uint32_t src = smem_u32(tile + (size_t)row * tstride);
+                    float *dst = out + ((size_t)r * C + c0 + ch) * PHW;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                                 ::"l"(dst), "r"(src), "r"((uint32_t)(PHW * 4)), "l"(pol) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile may be overwritten / the CTA may exit
+            }
+            continue;
+        }
         // coalesced streaming write-out of the [cc, PH*PW] slab (contiguous in the NCHW output).  Thread = (channel
         // within a group of `cpi`, position); cpi is a multiple of 4 whenever possible so that stepping to the next
         // channel group is a constant stride in the (row-permuted) tile as well as in global memory.
@@ -794,8 +818,14 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
                     PHW <= RV_THREADS;
     if (v4) {
         const bool pair = (PW % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+        // copy-engine write-out needs dense 16-byte aligned channel rows (PH*PW % 4 == 0: 14x14 yes, 7x7 no); its tile
+        // stride PH*PW = 0 (mod 4) makes the paired 8-byte tile stores 2-way bank conflicted, which costs less than the
+        // LDS + STG write-out loop it removes (LOCOV_B200_ROI_BULK=0 restores the loop for A/B measurements)
+        static const bool bulk_allowed = []() { const char *e = getenv("LOCOV_B200_ROI_BULK"); return !(e != nullptr && e[0] == '0'); }();
+        const int bulk_out = (pair && bulk_allowed && PHW % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
         int tstride;
-        if (pair) { tstride = PHW; while (tstride % 4 != 2) ++tstride; }     // S = 2 (mod 4): conflict-free STS.64 columns
+        if (bulk_out) tstride = PHW;
+        else if (pair) { tstride = PHW; while (tstride % 4 != 2) ++tstride; }     // S = 2 (mod 4): conflict-free STS.64 columns
         else tstride = PHW | 1;
         const int nslab = (C + RV_CC - 1) / RV_CC;
         // each CTA pools `slabs` consecutive slabs with one set of tap tables, as long as the grid keeps >= 8 waves
@@ -814,10 +844,10 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
         }
         if (pair)
             roi_align_fwd_v4_kernel<true><<<R * nchunks, RV_THREADS, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio,
-                                                                                 aligned, nchunks, slabs, tstride, out);
+                                                                                 aligned, nchunks, slabs, tstride, bulk_out, out);
         else
             roi_align_fwd_v4_kernel<false><<<R * nchunks, RV_THREADS, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio,
-                                                                                  aligned, nchunks, slabs, tstride, out);
+                                                                                  aligned, nchunks, slabs, tstride, bulk_out, out);
         count_launch();
         LOCO_CUDA(cudaGetLastError());
         return LOCO_OK;
