@@ -666,8 +666,11 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
             // (tstride == PH*PW) and in the NCHW output, so thread `row` hands its row to cp.async.bulk (evict-first in L2,
             // like st.global.cs) — no LDS / STG instructions, no LSU wavefronts, and the warps are free as soon as the
             // copies are queued.  (The generic-proxy tile writes were fenced before the barrier above.)
-            if (threadIdx.x < RV_CC) {
-                const int row = threadIdx.x, ch = 4 * (row & 31) + (row >> 5);
+            // (the copy instruction takes warp-uniform operands, so a warp issues its lanes' copies one after the other:
+            //  spread the 128 rows over all warps — lane i of warp w takes row w + RV_WARPS * i — instead of 4 full warps)
+            const int row = warp + RV_WARPS * lane;
+            if (row < RV_CC) {
+                const int ch = 4 * (row & 31) + (row >> 5);
                 if (ch < cc_b) {
                     uint64_t pol;
                     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
