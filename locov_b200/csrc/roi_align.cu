@@ -458,7 +458,7 @@ struct WalkBin {
     float w[4];      // dense weights of columns base .. base + 3 (zero beyond GW)
 };
 
-template <int GW, int NY>
+template <int GW, int NY, bool PAIR>
 __device__ __noinline__ void walk_bin_row(const char *fb, const MergedEntry *yt, const WalkBin *xw, const int *xadv, int x0_bytes,
                                            int colstride, int xlast_bytes, int PW, float inv_cnt, float *trow, int rstep) {
     int yo[NY];
@@ -497,30 +497,38 @@ __device__ __noinline__ void walk_bin_row(const char *fb, const MergedEntry *yt,
         if (GW >= 3) quad_fma(acc, w.w, u[GW >= 3 ? 3 : 0]);
         return quad_mul(inv_cnt, acc);
     };
+    if (PAIR) {
 #pragma unroll 1
-    for (int pw = 0; pw < PW; pw += 2) {               // PW is even on this path (paired 8-byte tile stores)
-        const Quad a = bin(pw);
-        const Quad b = bin(pw + 1);
-        *reinterpret_cast<float2 *>(trow + pw) = make_float2(a.lo.x, b.lo.x);
-        *reinterpret_cast<float2 *>(trow + pw + rstep) = make_float2(a.lo.y, b.lo.y);
-        *reinterpret_cast<float2 *>(trow + pw + 2 * rstep) = make_float2(a.hi.x, b.hi.x);
-        *reinterpret_cast<float2 *>(trow + pw + 3 * rstep) = make_float2(a.hi.y, b.hi.y);
+        for (int pw = 0; pw < PW; pw += 2) {           // even PW: paired 8-byte tile stores
+            const Quad a = bin(pw);
+            const Quad b = bin(pw + 1);
+            *reinterpret_cast<float2 *>(trow + pw) = make_float2(a.lo.x, b.lo.x);
+            *reinterpret_cast<float2 *>(trow + pw + rstep) = make_float2(a.lo.y, b.lo.y);
+            *reinterpret_cast<float2 *>(trow + pw + 2 * rstep) = make_float2(a.hi.x, b.hi.x);
+            *reinterpret_cast<float2 *>(trow + pw + 3 * rstep) = make_float2(a.hi.y, b.hi.y);
+        }
+    } else {
+#pragma unroll 1
+        for (int pw = 0; pw < PW; ++pw) {
+            const Quad a = bin(pw);
+            trow[pw] = a.lo.x; trow[pw + rstep] = a.lo.y; trow[pw + 2 * rstep] = a.hi.x; trow[pw + 3 * rstep] = a.hi.y;
+        }
     }
 }
 
-template <int GW>
+template <int GW, bool PAIR>
 __device__ __forceinline__ bool walk_dispatch(int ny, const char *fb, const MergedEntry *yt, const WalkBin *xw, const int *xadv,
                                               int x0_bytes, int colstride, int xlast_bytes, int PW, float inv_cnt, float *trow, int rstep) {
     switch (ny) {                                      // warp-uniform
-        case 1: walk_bin_row<GW, 1>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
-        case 2: walk_bin_row<GW, 2>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
-        case 3: walk_bin_row<GW, 3>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
-        case 4: walk_bin_row<GW, 4>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
+        case 1: walk_bin_row<GW, 1, PAIR>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
+        case 2: walk_bin_row<GW, 2, PAIR>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
+        case 3: walk_bin_row<GW, 3, PAIR>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
+        case 4: walk_bin_row<GW, 4, PAIR>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
         default: return false;
     }
 }
 
-template <bool PAIR>
+template <bool PAIR, bool MULTI>
 __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const float *__restrict__ feat,   // [N,H,W,C]
                                                                         const float *__restrict__ rois, int C, int H, int W,
                                                                         int PH, int PW, float scale, int sampling_ratio,
@@ -549,7 +557,7 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
     const float inv_cnt = __fdiv_rn(1.0f, (float)max(g.gh * g.gw, 1));
 
     // column-walk program, part 1 (by the thread that built the bin's merged list): first column and dense weights
-    const bool walk_try = tables_fit && PAIR && sampling_ratio <= 0 && g.gw >= 1 && g.gw <= 3;
+    const bool walk_try = tables_fit && sampling_ratio <= 0 && g.gw >= 1 && g.gw <= 3;
     bool walk_bad_a = false;
     if (tables_fit) {
         const int t = threadIdx.x;
@@ -597,34 +605,43 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
     const bool walk_ok = __syncthreads_and(walk_bad ? 0 : 1) != 0;
     const int walk_x0 = walk_hdr[1] * C * 4, walk_colstride = C * 4, walk_xlast = (W - 1) * C * 4;
 
+    // Warp roles: a group of PH warps pools one 128-channel slab (warp = bin row); with PH <= RV_WARPS / 2 (7 x 7 pooling)
+    // several groups work on consecutive slabs at the same time, each into its own tile, so no warp idles.
+    // (MULTI = false is the single-group instantiation: one tile, every warp index is a bin row)
+    const int nconc = MULTI ? max(1, RV_WARPS / PH) : 1;
+    const int wgroup = MULTI ? warp / PH : 0, wrow = warp - wgroup * PH;
+    const int row_step = nconc == 1 ? RV_WARPS : PH;
+    const size_t tile_floats = (size_t)RV_CC * tstride;
     const int cl = 4 * lane;
-    float *t0 = tile + (size_t)lane * tstride;                 // rows lane, 32 + lane, 64 + lane, 96 + lane
+    float *t0 = tile + (wgroup < nconc ? wgroup : 0) * tile_floats + (size_t)lane * tstride;   // rows lane, 32 + lane, 64 + lane, 96 + lane
     const int rstep = 32 * tstride;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto store_bin = [&](int o, const float4 &a) {
         t0[o] = a.x; t0[o + rstep] = a.y; t0[o + 2 * rstep] = a.z; t0[o + 3 * rstep] = a.w;
     };
 
-    for (int sl = 0; sl < slabs; ++sl) {
+    for (int sl0 = 0; sl0 < slabs; sl0 += nconc) {
+        const int sl = sl0 + wgroup;
         const int c0 = (chunk * slabs + sl) * RV_CC;
-        if (c0 >= C) break;
-        const bool active = (c0 + cl) < C;                     // C % 4 == 0: a lane's 4 channels are all in or all out
+        const bool work = wgroup < nconc && sl < slabs && c0 < C;   // warp-uniform
+        const bool active = work && (c0 + cl) < C;             // C % 4 == 0: a lane's 4 channels are all in or all out
         const char *fb = reinterpret_cast<const char *>(feat + (size_t)g.batch * H * W * C + (active ? c0 + cl : 0));
-        if (sl > 0) __syncthreads();                           // the previous slab's write-out has drained the tile
+        if (sl0 > 0) __syncthreads();                          // the previous slabs' write-out has drained the tiles
 
-        if (empty) {
-            for (int ph = warp; ph < PH; ph += RV_WARPS)
+        if (!work) {
+        } else if (empty) {
+            for (int ph = wrow; ph < PH; ph += row_step)
                 for (int pw = 0; pw < PW; ++pw) store_bin(ph * PW + pw, zero4);
         } else if (tables_fit) {
-            for (int ph = warp; ph < PH; ph += RV_WARPS) {
+            for (int ph = wrow; ph < PH; ph += row_step) {
                 const MergedEntry *yt = ytab + ph * ystride;
                 const int ny = ycnt[ph];
                 float *trow = t0 + ph * PW;
-                if (PAIR && walk_ok) {                         // CTA-uniform: column walk (GW = sampling grid width of this roi)
+                if (walk_ok) {                                 // CTA-uniform: column walk (GW = sampling grid width of this roi)
                     bool done;
-                    if (g.gw == 1) done = walk_dispatch<1>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
-                    else if (g.gw == 2) done = walk_dispatch<2>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
-                    else done = walk_dispatch<3>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
+                    if (g.gw == 1) done = walk_dispatch<1, PAIR>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
+                    else if (g.gw == 2) done = walk_dispatch<2, PAIR>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
+                    else done = walk_dispatch<3, PAIR>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
                     if (done) continue;
                 }
                 switch (ny) {                                  // warp-uniform
@@ -637,7 +654,7 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
             }
         } else {
             // rois whose sampling grid exceeds the shared tables: direct taps (rare: > 36 samples per bin and axis)
-            for (int ph = warp; ph < PH; ph += RV_WARPS)
+            for (int ph = wrow; ph < PH; ph += row_step)
                 for (int pw = 0; pw < PW; ++pw) {
                     float4 acc = zero4;
                     for (int iy = 0; iy < g.gh; ++iy) {
@@ -660,58 +677,63 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
         if (bulk_out) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // tile writes -> visible to the copy engine
         __syncthreads();
 
-        const int cc_b = min(RV_CC, C - c0);
-        if (bulk_out) {
-            // write-out by the copy engine: every channel's PH*PW floats are one dense, 16-byte aligned run both in the tile
-            // (tstride == PH*PW) and in the NCHW output, so thread `row` hands its row to cp.async.bulk (evict-first in L2,
-            // like st.global.cs) — no LDS / STG instructions, no LSU wavefronts, and the warps are free as soon as the
-            // copies are queued.  (The generic-proxy tile writes were fenced before the barrier above.)
-            // (the copy instruction takes warp-uniform operands, so a warp issues its lanes' copies one after the other:
-            //  spread the 128 rows over all warps — lane i of warp w takes row w + RV_WARPS * i — instead of 4 full warps)
-            const int row = warp + RV_WARPS * lane;
-            if (row < RV_CC) {
-                const int ch = 4 * (row & 31) + (row >> 5);
-                if (ch < cc_b) {
-                    uint64_t pol;
-                    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-                    const uint32_t src = smem_u32(tile + (size_t)row * tstride);
-                    float *dst = out + ((size_t)r * C + c0 + ch) * PHW;
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                                 ::"l"(dst), "r"(src), "r"((uint32_t)(PHW * 4)), "l"(pol) : "memory");
+        for (int gi = 0; gi < nconc; ++gi) {                   // write out every tile pooled in this pass (all threads)
+            const int sl_g = sl0 + gi;
+            const int c0_g = (chunk * slabs + sl_g) * RV_CC;
+            if (sl_g >= slabs || c0_g >= C) break;
+            const float *tile_g = tile + gi * tile_floats;
+            const int cc = min(RV_CC, C - c0_g);
+            if (bulk_out) {
+                // write-out by the copy engine: every channel's PH*PW floats are one dense, 16-byte aligned run both in the
+                // tile (tstride == PH*PW) and in the NCHW output, so one thread per row hands it to cp.async.bulk
+                // (evict-first in L2, like st.global.cs) — no LDS / STG instructions, no LSU wavefronts.  The copy takes
+                // warp-uniform operands, so a warp issues its lanes' copies one after the other: the 128 rows are spread
+                // over all warps (lane i of warp w takes row w + RV_WARPS * i).  The generic-proxy tile writes were fenced
+                // before the barrier above.
+                const int row = warp + RV_WARPS * lane;
+                if (row < RV_CC) {
+                    const int ch = 4 * (row & 31) + (row >> 5);
+                    if (ch < cc) {
+                        uint64_t pol;
+                        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+                        const uint32_t src = smem_u32(tile_g + (size_t)row * tstride);
+                        float *dst = out + ((size_t)r * C + c0_g + ch) * PHW;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                                     ::"l"(dst), "r"(src), "r"((uint32_t)(PHW * 4)), "l"(pol) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile may be overwritten / the CTA may exit
                 }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile may be overwritten / the CTA may exit
+                continue;
             }
-            continue;
-        }
-        // coalesced streaming write-out of the [cc, PH*PW] slab (contiguous in the NCHW output).  Thread = (channel
-        // within a group of `cpi`, position); cpi is a multiple of 4 whenever possible so that stepping to the next
-        // channel group is a constant stride in the (row-permuted) tile as well as in global memory.
-        const int cc = min(RV_CC, C - c0);
-        float *ob = out + ((size_t)r * C + c0) * PHW;
-        const int words = PAIR ? (PHW >> 1) : PHW;           // 8-byte (PAIR) or 4-byte words per channel
-        int cpi = RV_THREADS / words;
-        if (cpi >= 4) cpi &= ~3;
-        const int chs = threadIdx.x / words, wi = threadIdx.x - chs * words;
-        if (chs < cpi) {
-            if ((cpi & 3) == 0) {
-                const int rinc = (cpi >> 2) * tstride;
-                const float *sp = tile + (size_t)(((chs & 3) << 5) + (chs >> 2)) * tstride + (PAIR ? 2 * wi : wi);
-                float *gp = ob + (size_t)chs * PHW + (PAIR ? 2 * wi : wi);
-                const size_t ginc = (size_t)cpi * PHW;
+            // coalesced streaming write-out of the [cc, PH*PW] slab (contiguous in the NCHW output).  Thread = (channel
+            // within a group of `cpi`, position); cpi is a multiple of 4 whenever possible so that stepping to the next
+            // channel group is a constant stride in the (row-permuted) tile as well as in global memory.
+            float *ob = out + ((size_t)r * C + c0_g) * PHW;
+            const int words = PAIR ? (PHW >> 1) : PHW;           // 8-byte (PAIR) or 4-byte words per channel
+            int cpi = RV_THREADS / words;
+            if (cpi >= 4) cpi &= ~3;
+            const int chs = threadIdx.x / words, wi = threadIdx.x - chs * words;
+            if (chs < cpi) {
+                if ((cpi & 3) == 0) {
+                    const int rinc = (cpi >> 2) * tstride;
+                    const float *sp = tile_g + (size_t)(((chs & 3) << 5) + (chs >> 2)) * tstride + (PAIR ? 2 * wi : wi);
+                    float *gp = ob + (size_t)chs * PHW + (PAIR ? 2 * wi : wi);
+                    const size_t ginc = (size_t)cpi * PHW;
 #pragma unroll 4
-                for (int ch = chs; ch < cc; ch += cpi) {
-                    if (PAIR) __stcs(reinterpret_cast<float2 *>(gp), *reinterpret_cast<const float2 *>(sp));
-                    else __stcs(gp, *sp);
-                    sp += rinc;
-                    gp += ginc;
-                }
-            } else {
-                for (int ch = chs; ch < cc; ch += cpi) {
-                    const int row = ((ch & 3) << 5) + (ch >> 2);
-                    if (PAIR) __stcs(reinterpret_cast<float2 *>(ob + (size_t)ch * PHW) + wi,
-                                     *reinterpret_cast<const float2 *>(tile + (size_t)row * tstride + 2 * wi));
-                    else __stcs(ob + (size_t)ch * PHW + wi, tile[(size_t)row * tstride + wi]);
+                    for (int ch = chs; ch < cc; ch += cpi) {
+                        if (PAIR) __stcs(reinterpret_cast<float2 *>(gp), *reinterpret_cast<const float2 *>(sp));
+                        else __stcs(gp, *sp);
+                        sp += rinc;
+                        gp += ginc;
+                    }
+                } else {
+                    for (int ch = chs; ch < cc; ch += cpi) {
+                        const int row = ((ch & 3) << 5) + (ch >> 2);
+                        if (PAIR) __stcs(reinterpret_cast<float2 *>(ob + (size_t)ch * PHW) + wi,
+                                         *reinterpret_cast<const float2 *>(tile_g + (size_t)row * tstride + 2 * wi));
+                        else __stcs(ob + (size_t)ch * PHW + wi, tile_g[(size_t)row * tstride + wi]);
+                    }
                 }
             }
         }
@@ -834,23 +856,25 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
         // each CTA pools `slabs` consecutive slabs with one set of tap tables, as long as the grid keeps >= 8 waves
         int slabs = 1;
         while (slabs < 4 && nslab % (slabs * 2) == 0 && (long long)R * (nslab / (slabs * 2)) >= 8ll * 2 * 148) slabs *= 2;
+        const int nconc = RV_WARPS / PH > 1 ? RV_WARPS / PH : 1;            // slabs pooled at the same time (see the kernel)
+        while (slabs < nconc && nslab % (slabs * 2) == 0) slabs *= 2;       // keep every warp group busy
         const int nchunks = nslab / slabs;
         const size_t smem = 2 * RA_TAB * sizeof(MergedEntry) + (64 + 64 + 4) * sizeof(int) + 32 * sizeof(WalkBin) +
-                            (size_t)RV_CC * tstride * sizeof(float);
+                            (size_t)nconc * RV_CC * tstride * sizeof(float);
         LOCO_REQUIRE(smem <= 200 * 1024, LOCO_E_UNSUPPORTED, "roi_align_fwd: output size %dx%d needs %zu B of shared memory", PH, PW, smem);
         LOCO_REQUIRE((long long)R * nchunks < (1ll << 31), LOCO_E_UNSUPPORTED, "roi_align_fwd: too many (roi, channel-slab) tiles");
-        static thread_local size_t smem_set[2] = {0, 0};
-        if (smem > 48 * 1024 && smem > smem_set[pair]) {
-            if (pair) LOCO_CUDA(cudaFuncSetAttribute(roi_align_fwd_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else LOCO_CUDA(cudaFuncSetAttribute(roi_align_fwd_v4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            smem_set[pair] = smem;
+        typedef void (*v4_fn)(const float *, const float *, int, int, int, int, int, float, int, int, int, int, int, int, float *);
+        const bool multi = nconc > 1;
+        const v4_fn fn = pair ? (multi ? roi_align_fwd_v4_kernel<true, true> : roi_align_fwd_v4_kernel<true, false>)
+                              : (multi ? roi_align_fwd_v4_kernel<false, true> : roi_align_fwd_v4_kernel<false, false>);
+        static thread_local size_t smem_set[4] = {0, 0, 0, 0};
+        const int vi = (pair ? 2 : 0) + (multi ? 1 : 0);
+        if (smem > 48 * 1024 && smem > smem_set[vi]) {
+            LOCO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set[vi] = smem;
         }
-        if (pair)
-            roi_align_fwd_v4_kernel<true><<<R * nchunks, RV_THREADS, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio,
-                                                                                 aligned, nchunks, slabs, tstride, bulk_out, out);
-        else
-            roi_align_fwd_v4_kernel<false><<<R * nchunks, RV_THREADS, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio,
-                                                                                  aligned, nchunks, slabs, tstride, bulk_out, out);
+        fn<<<R * nchunks, RV_THREADS, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, aligned, nchunks, slabs, tstride,
+                                                  bulk_out, out);
         count_launch();
         LOCO_CUDA(cudaGetLastError());
         return LOCO_OK;
