@@ -304,8 +304,16 @@ def run_b200(args):
         if "peak" in v:
             v["frac"] = v["achieved"] / v["peak"]
     dom = max((k for k in kern if "peak" in kern[k]), key=lambda k: kern[k]["ms"])
+    traffic = None          # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            ent = json.load(fh).get(dom)
+        if ent is not None and not acc:      # captured for the default (reduced-precision) mode only
+            traffic = float(ent["bytes"])
+    except (OSError, ValueError, KeyError):
+        traffic = None
     roofline = {"kernel": dom, "bound": kern[dom]["bound"], "achieved": kern[dom]["achieved"], "peak": kern[dom]["peak"],
-                "unit": kern[dom]["unit"], "frac": kern[dom]["frac"], "traffic": None,
+                "unit": kern[dom]["unit"], "frac": kern[dom]["frac"], "traffic": traffic,
                 "peak_source": f"{pk['source']} (MEASURED_PEAKS.json burst figure: kernel timed alone)",
                 "algorithmic": "2*M*N*K of the un-collapsed GEMM (tensor) / bytes read+written once (hbm); fp32 mode runs 3 bf16 passes for the same algorithmic flops",
                 "kernels": kern}

@@ -48,9 +48,11 @@ def main():
     shapes = [(3200, 768, 2048), (8192, 768, 2048), (32768, 768, 2048), (8192, 8192, 2048)]
     if len(sys.argv) > 1 and sys.argv[1] == "small":
         shapes = shapes[:2]
-    cfgs = [dict(), dict(LOCOV_B200_SMEMKB="110"), dict(LOCOV_B200_SMEMKB="160"), dict(LOCOV_B200_2CTA="0")]
+    cfgs = [dict(), dict(LOCOV_B200_2CTA="0")]
     for bn in (128, 192, 256):
         cfgs.append(dict(LOCOV_B200_BN=str(bn)))
+    for cm, cn, bn in ((1, 2, 192), (1, 4, 192), (2, 2, 192), (2, 2, 256), (1, 2, 256), (2, 1, 256), (1, 3, 256)):
+        cfgs.append(dict(LOCOV_B200_2CTA="0", LOCOV_B200_CLUSTER="1", LOCOV_B200_CM=str(cm), LOCOV_B200_CN=str(cn), LOCOV_B200_BN=str(bn)))
     for shp in shapes:
         for cfg in cfgs:
             env = dict(os.environ, **cfg)

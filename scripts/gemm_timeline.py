@@ -53,7 +53,9 @@ def main():
     M, N, K = 3200, 768, 2048
     x = torch.randn(M, K, device=dev)
     w = torch.randn(N, K, device=dev) * 0.01
-    print("# LOCOV_B200_PF =", os.environ.get("LOCOV_B200_PF", "(default)"))
+    print("# LOCOV_B200_PF =", os.environ.get("LOCOV_B200_PF", "(default)"), " LOCOV_B200_DEBUG =", os.environ.get("LOCOV_B200_DEBUG", "0"))
+    if "--lsm-only" in sys.argv:
+        return lsm_case()
     report("projection tf32 3200x768x2048 (bf16 out), operands cold (HBM)", lambda: ops.linear_tf32_fwd(x, w, None, want_f32=False, n_bf16=N))
     report("projection tf32 3200x768x2048 (bf16 out), operands L2-resident", lambda: ops.linear_tf32_fwd(x, w, None, want_f32=False, n_bf16=N), cold=False)
     xa, wa = ops.split_bf16(x, False), ops.split_bf16(w, False)
@@ -64,6 +66,13 @@ def main():
     x8 = torch.randn(8192, K, device=dev)
     x8a = ops.split_bf16(x8, False)
     report("linear bf16 8192x768x2048", lambda: ops.linear_fwd(x8a, wa, None, want_f32=False, n_bf16=N))
+    lsm_case()
+    e5 = ops.split_bf16(torch.randn(8000, 768, device=dev) * 0.3, False)
+    c5 = ops.split_bf16(torch.randn(1204, 768, device=dev) * 0.05, False)
+    report("box_score 8000 x 1204", lambda: ops.box_score(e5, c5))
+
+
+def lsm_case():
     B, T, RG, D = 32, 20, 100, 768
     cap = ops.split_bf16(torch.randn(B * T, D, device=dev) * 0.05, False)
     emb = ops.split_bf16(torch.randn(B * RG, D, device=dev) * 0.5, False)
@@ -72,9 +81,6 @@ def main():
     w2r = torch.empty(B, B, device=dev)
     r2w = torch.empty(B, B, device=dev)
     report("lsm_pair B=32 T=20 Rg=100", lambda: ops.lsm_pair(cap, mc, emb, mr, 0.1, out_w2r=w2r, out_r2w=r2w))
-    e5 = ops.split_bf16(torch.randn(8000, 768, device=dev) * 0.3, False)
-    c5 = ops.split_bf16(torch.randn(1204, 768, device=dev) * 0.05, False)
-    report("box_score 8000 x 1204", lambda: ops.box_score(e5, c5))
 
 
 if __name__ == "__main__":
