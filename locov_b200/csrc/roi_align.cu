@@ -4,22 +4,22 @@
 //   /root/reference/ovr/modeling/roi_heads/roi_emb_heads.py:182-187 (ROIPooler construction)
 //   /root/reference/ovr/modeling/roi_heads/roi_emb_heads.py:243-245 (self.pooler(features, boxes))
 //
-// Design (B200, HBM-write bound: out is R*C*PH*PW*4 B, the feature map is L2 resident):
+// Design (B200, HBM-write bound: out is R*C*PH*PW*4 B, the feature map is L2 resident) — DESIGN.md 4.1:
 //   * features are consumed channels-last ([N,H,W,C]); an NCHW input is transposed once per call by
 //     nchw_to_nhwc_kernel into caller-provided workspace (<4 % of the traffic at the configs).
-//   * one CTA = (roi, 32-channel slab).  Lane = channel, so every tap load is one coalesced 128-byte
-//     request and all control flow (adaptive sample counts, skipped taps) is warp-uniform.
+//   * vectorised kernel (roi_align_fwd_v4_kernel): one CTA = (roi, 1-4 slabs of 128 channels), warp = bin row,
+//     lane = 4 consecutive channels (128-bit taps), so all control flow (adaptive sample counts, skipped
+//     taps) is warp-uniform.  Generic kernel (any C / alignment): one channel per lane, 32-channel slabs.
 //   * the per-roi sampling tables (y taps, x taps) are computed ONCE per CTA with explicitly rounded
 //     fp32 intrinsics (__fmul_rn/__fadd_rn/__fdiv_rn: no FMA contraction) so that coordinates and
 //     integer tap indices are bit-identical to the CPU reference arithmetic.
 //   * bilinear pooling is evaluated separably with MERGED tap lists: per bin and axis the weights of the
 //     samples are summed per distinct feature row / column first (samples are < 1 px apart by
-//     construction of the adaptive grid), so each pixel of a bin's footprint is loaded once — the
-//     L2 -> SM fabric of a B200 moves about as much as HBM, and 4 loads per sample made the kernel
-//     L2-bound at 12 % of the HBM roofline (profiles/README.md).
-//   * results are staged in a [32][PH*PW] shared-memory tile (odd stride: conflict-free column writes)
-//     and streamed out as fully coalesced 128-byte st.global.cs rows (evict-first keeps the feature
-//     map resident in the 126 MB L2).
+//     construction of the adaptive grid), so each pixel of a bin's footprint is loaded once per bin row.
+//     The common case walks consecutive feature columns with a sliding register window (walk_bin_row).
+//   * results are staged in a [128][PH*PW] shared-memory tile and leave through the copy engine
+//     (cp.async.bulk per channel row, evict-first so the feature map stays in the 126 MB L2) or, for pooled
+//     sizes whose rows are not 16-byte multiples, as coalesced st.global.cs rows.
 #include <cstdlib>
 
 #include "common.cuh"

@@ -625,9 +625,9 @@ static int fill_maps(TcMaps &maps, const uint16_t *a_hi, const uint16_t *a_lo, u
     return LOCO_OK;
 }
 
-// Thread-block clusters with TMA multicast are implemented (tc_gemm.cuh) but OFF by default: on B200 they measured
-// no gain for these shapes (profiles/README.md — the kernels are bound by per-tile fixed cost and the tensor pipe, not by
-// L2 -> SM operand traffic).  LOCOV_B200_CLUSTER=1 enables them for A/B measurements.
+// Thread-block clusters with TMA multicast are implemented (tc_gemm.cuh) but OFF by default: re-swept after every change of
+// the core (profiles/README.md §1), they have not beaten CTA pairs / single-CTA tiles at any shape of the path.
+// LOCOV_B200_CLUSTER=1 enables them for A/B measurements.
 static bool clusters_enabled() {
     static int v = -1;
     if (v < 0) {
