@@ -461,6 +461,8 @@ struct WalkBin {
 template <int GW, int NY, bool PAIR>
 __device__ __noinline__ void walk_bin_row(const char *fb, const MergedEntry *yt, const WalkBin *xw, const int *xadv, int x0_bytes,
                                            int colstride, int xlast_bytes, int PW, float inv_cnt, float *trow, int rstep) {
+    // xlast_bytes = byte offset of the LAST column the walk consumes: the look-ahead load past it is redirected to it
+    // (an L1 hit instead of a new 512-byte line per bin row: rows of small rois are only 3-15 columns long)
     int yo[NY];
     float yw[NY];
 #pragma unroll
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
     int *xcnt = ycnt + 32;                                    // [32]
     int *xadv = xcnt + 32;                                    // [32] column-walk advance counts
     int *xbase = xadv + 32;                                   // [32] first column of each bin (-1: no sample inside the map)
-    int *walk_hdr = xbase + 32;                               // [4]  {-, first column of the walk, -, -}
+    int *walk_hdr = xbase + 32;                               // [4]  {-, first column of the walk, last column, -}
     WalkBin *xw = reinterpret_cast<WalkBin *>(walk_hdr + 4);  // [32] dense per-bin column weights (16-byte aligned)
     float *tile = reinterpret_cast<float *>(xw + 32);         // [RV_CC][tstride]
 
@@ -584,7 +586,7 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
             }
         }
     }
-    if (threadIdx.x == 0) walk_hdr[1] = 0;
+    if (threadIdx.x == 0) { walk_hdr[1] = 0; walk_hdr[2] = 0; }
     __syncthreads();
     // column-walk program (see walk_bin_row), part 2: advance counts from the bases of the preceding bins
     bool walk_bad = !walk_try;
@@ -599,11 +601,12 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
             if (prev < 0) { adv = g.gw + 1; walk_hdr[1] = base; }      // first non-empty bin primes the whole window
             else adv = base - prev;
             if (adv < 0 || adv > g.gw + 1) walk_bad = true;
+            atomicMax(&walk_hdr[2], base + g.gw);                     // last column the walk consumes
         }
         xadv[pw] = adv;
     }
     const bool walk_ok = __syncthreads_and(walk_bad ? 0 : 1) != 0;
-    const int walk_x0 = walk_hdr[1] * C * 4, walk_colstride = C * 4, walk_xlast = (W - 1) * C * 4;
+    const int walk_x0 = walk_hdr[1] * C * 4, walk_colstride = C * 4, walk_xlast = min(W - 1, walk_hdr[2]) * C * 4;
 
     // Warp roles: a group of PH warps pools one 128-channel slab (warp = bin row); with PH <= RV_WARPS / 2 (7 x 7 pooling)
     // several groups work on consecutive slabs at the same time, each into its own tile, so no warp idles.
