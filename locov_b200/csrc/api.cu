@@ -93,6 +93,15 @@ unsigned long long *debug_timeline_buffer(int ctas) {
     return g_timeline;
 }
 
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("LOCOV_B200_PDL");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
 int current_device_sm_count() {
     static int cached[64] = {0};
     int dev = 0;

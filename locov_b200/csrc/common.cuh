@@ -47,6 +47,43 @@ void count_launch(int n = 1);   // bumps the library-wide kernel-launch counter 
 // ------------------------------------------------------------------------------------------------
 // device side
 // ------------------------------------------------------------------------------------------------
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// Every kernel of the library starts with pdl_trigger(); pdl_wait(); and is launched through launch_kernel() with the
+// programmatic-stream-serialization attribute: the next kernel of the stream is scheduled while this one still runs, does
+// its set-up (barrier init, TMEM allocation, tensor-map prefetch) and blocks in griddepcontrol.wait until this grid has
+// completed and flushed — the 1-2 us launch gap between the short dependent kernels of the path disappears.  All global
+// reads of produced data and all global writes come after pdl_wait().  LOCOV_B200_PDL=0 launches without the attribute
+// (the device-side instructions are then no-ops).
+bool pdl_enabled();      // api.cu
+
+#if defined(__CUDACC__)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    unsigned n = 0;
+    if (cluster > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)cluster;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 #if defined(__CUDACC__)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -59,6 +96,8 @@ __device__ __forceinline__ uint32_t lane_id() {
     return l;
 }
 
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint64_t global_timer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -13,6 +13,8 @@ namespace loco {
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float *__restrict__ src, int64_t rows, int64_t cols,
                                                          int64_t src_ld, uint16_t *__restrict__ hi,
                                                          uint16_t *__restrict__ lo, int64_t dst_ld) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t quads_per_row = dst_ld / 4;      // dst_ld % 8 == 0
     const int64_t total = rows * quads_per_row;
     const bool vec_ok = (src_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
@@ -44,6 +46,8 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float *__restrict
 __global__ void __launch_bounds__(256) split_bf16_t_kernel(const float *__restrict__ src, int rows, int cols, int64_t src_ld,
                                                            uint16_t *__restrict__ hi, uint16_t *__restrict__ lo,
                                                            int64_t dst_ld) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -70,6 +74,8 @@ __global__ void __launch_bounds__(256) split_bf16_t_kernel(const float *__restri
 __global__ void __launch_bounds__(256) lsm_masks_kernel(const int64_t *__restrict__ att, const int64_t *__restrict__ spe, int64_t n_cap,
                                                         const void *__restrict__ reg, int reg_kind, int64_t n_reg,
                                                         float *__restrict__ cap_mask, float *__restrict__ reg_mask) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cap + n_reg; i += (int64_t)gridDim.x * blockDim.x) {
         if (i < n_cap) {
             cap_mask[i] = (float)(att[i] * (1 - spe[i]));
@@ -87,6 +93,8 @@ __global__ void __launch_bounds__(256) lsm_masks_kernel(const int64_t *__restric
 // ---- 16-bit transpose: dst[c, r] = src[r, c] (bf16 operands for the backward GEMMs) ---------------------------
 __global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t *__restrict__ src, int rows, int cols, int64_t src_ld,
                                                           uint16_t *__restrict__ dst, int64_t dst_ld) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ uint16_t tile[32][34];
     const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -110,6 +118,8 @@ __global__ void __launch_bounds__(256) box_ce_kernel(const float *__restrict__ l
                                                      float *__restrict__ loss_sum, float grad_scale,
                                                      float *__restrict__ dl_f32, uint16_t *__restrict__ dl_bf16,
                                                      int64_t ld_bf16) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     float local = 0.f;
@@ -182,6 +192,8 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
                                                        const float *__restrict__ reg_mask, int Rg, float *__restrict__ out4_all,
                                                        float *__restrict__ dcap_all, float *__restrict__ dimg_all,
                                                        float *__restrict__ scratch) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];
     float *red = sm;                 // [32]
     float *cap_empty = sm + 32;      // [Bc] 1 if the caption has no valid word
@@ -370,14 +382,14 @@ int loco_split_bf16(const float *src, int64_t rows, int64_t cols, int64_t src_ld
         LOCO_REQUIRE(dst_ld >= cols, LOCO_E_BADARG, "split_bf16: dst_ld < cols");
         const int64_t total = rows * (dst_ld / 4);
         const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-        split_bf16_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, src_ld, hi, lo, dst_ld);
+        LOCO_CUDA(launch_kernel(split_bf16_kernel, dim3(blocks), dim3(256), 0, st, 1, src, rows, cols, src_ld, hi, lo, dst_ld));
     count_launch();
     } else {
         LOCO_REQUIRE(dst_ld >= rows, LOCO_E_BADARG, "split_bf16: transposed dst_ld < rows");
         LOCO_REQUIRE(rows < (1ll << 31) && cols < (1ll << 31), LOCO_E_UNSUPPORTED, "split_bf16: matrix too large to transpose");
         dim3 grid((unsigned)((dst_ld + 31) / 32), (unsigned)((cols + 31) / 32));
         LOCO_REQUIRE(grid.y <= 65535, LOCO_E_UNSUPPORTED, "split_bf16: too many columns to transpose");
-        split_bf16_t_kernel<<<grid, 256, 0, st>>>(src, (int)rows, (int)cols, src_ld, hi, lo, dst_ld);
+        LOCO_CUDA(launch_kernel(split_bf16_t_kernel, grid, dim3(256), 0, st, 1, src, (int)rows, (int)cols, src_ld, hi, lo, dst_ld));
     count_launch();
     }
     LOCO_CUDA(cudaGetLastError());
@@ -392,8 +404,8 @@ int loco_lsm_masks(const int64_t *attention_mask, const int64_t *special_tokens_
                  "lsm_masks: null pointer");
     const int64_t total = n_cap + n_reg;
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    lsm_masks_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(attention_mask, special_tokens_mask, n_cap, region_mask,
-                                                                            region_kind, n_reg, cap_mask, reg_mask);
+    LOCO_CUDA(launch_kernel(lsm_masks_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, attention_mask, special_tokens_mask,
+                            n_cap, region_mask, region_kind, n_reg, cap_mask, reg_mask));
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;
@@ -408,7 +420,7 @@ int loco_transpose_bf16(const uint16_t *src, int64_t rows, int64_t cols, int64_t
     LOCO_REQUIRE(rows < (1ll << 31) && cols < (1ll << 31), LOCO_E_UNSUPPORTED, "transpose_bf16: matrix too large");
     dim3 grid((unsigned)((dst_ld + 31) / 32), (unsigned)((cols + 31) / 32));
     LOCO_REQUIRE(grid.y <= 65535, LOCO_E_UNSUPPORTED, "transpose_bf16: too many columns");
-    transpose16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, (int)rows, (int)cols, src_ld, dst, dst_ld);
+    LOCO_CUDA(launch_kernel(transpose16_kernel, grid, dim3(256), 0, static_cast<cudaStream_t>(stream), 1, src, (int)rows, (int)cols, src_ld, dst, dst_ld));
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;
@@ -424,8 +436,8 @@ int loco_box_ce_fwd_bwd(const float *logits, int64_t ld_logits, const float *lse
     const int wpb = 8;
     int blocks = (R + wpb - 1) / wpb;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    box_ce_kernel<<<blocks, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld_logits, lse, labels, R, K1, scale, loss_sum,
-                                                                             grad_scale, dlogits_f32, dlogits_bf16, ld_bf16);
+    LOCO_CUDA(launch_kernel(box_ce_kernel, dim3(blocks), dim3(wpb * 32), 0, static_cast<cudaStream_t>(stream), 1, logits, ld_logits, lse, labels, R, K1,
+                            scale, loss_sum, grad_scale, dlogits_f32, dlogits_bf16, ld_bf16));
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;
@@ -448,13 +460,13 @@ int loco_pair_ce(float *pw, int nmat, int64_t mat_stride, int64_t ld, int Bc, in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (nblk == 1) {
         const size_t staged = base + (size_t)Bc * (Bi + 1) * sizeof(float);
-        pair_ce_kernel<true><<<dim3(nmat, 1), 1024, staged, st>>>(pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T, reg_mask, Rg, out4,
-                                                                  dpw_caption, dpw_image, nullptr);
+        LOCO_CUDA(launch_kernel(pair_ce_kernel<true>, dim3(nmat, 1), dim3(1024), staged, st, 1, pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T,
+                                reg_mask, Rg, out4, dpw_caption, dpw_image, static_cast<float *>(nullptr)));
     } else {
         LOCO_REQUIRE(workspace != nullptr, LOCO_E_BADARG, "pair_ce: B > 32 needs loco_pair_ce_workspace_bytes() of ZERO-INITIALISED workspace "
                      "(the kernel leaves it zeroed again)");
-        pair_ce_kernel<false><<<dim3(nmat, nblk), 1024, base, st>>>(pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T, reg_mask, Rg, out4,
-                                                                    dpw_caption, dpw_image, static_cast<float *>(workspace));
+        LOCO_CUDA(launch_kernel(pair_ce_kernel<false>, dim3(nmat, nblk), dim3(1024), base, st, 1, pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T,
+                                reg_mask, Rg, out4, dpw_caption, dpw_image, static_cast<float *>(workspace)));
     }
     count_launch();
     LOCO_CUDA(cudaGetLastError());

@@ -290,6 +290,8 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
     tc_fence_before();
     if (csize > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers must be initialised before any remote signal
     tc_fence_after();
+    pdl_trigger();                                                                // the next kernel may start its own set-up
+    pdl_wait();                                                                   // operands / masks of the previous kernel are complete
     if (tl && threadIdx.x == 0) tl[1] = global_timer_ns();                       // setup done (barriers, TMEM, cluster sync)
     const uint32_t tmem_base = *tmem_slot;
     const int iters_per_chunk = core.num_k_blocks * core.passes;
@@ -392,26 +394,13 @@ int tc_launch(const TcMaps &maps, const TcCore &core_in, const typename Epi::Par
         LOCO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<Epi, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         configured = 227 * 1024;
     }
-    if (core.cm * core.cn == 1) {
-        tc_gemm_kernel<Epi, PAIR><<<grid, 64 + 32 * Epi::kEpiWarps, smem_bytes, st>>>(maps, core, ep);
-    } else {
-        LOCO_REQUIRE(core.cm * core.cn <= 8 && grid % (core.cm * core.cn) == 0, LOCO_E_BADARG, "bad cluster %dx%d for grid %d", core.cm, core.cn, grid);
+    const int csize = core.cm * core.cn;
+    if (csize > 1) {
+        LOCO_REQUIRE(csize <= 8 && grid % csize == 0, LOCO_E_BADARG, "bad cluster %dx%d for grid %d", core.cm, core.cn, grid);
         LOCO_REQUIRE(TC_BLOCK_M % core.cn == 0 && (TC_BLOCK_M / core.cn) % 8 == 0 && core.block_n % core.cm == 0 && (core.block_n / core.cm) % 8 == 0,
                      LOCO_E_BADARG, "cluster %dx%d does not slice a 128x%d tile on 8-row boundaries", core.cm, core.cn, core.block_n);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3(64 + 32 * Epi::kEpiWarps);
-        cfg.dynamicSmemBytes = smem_bytes;
-        cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = (unsigned)(core.cm * core.cn);
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        LOCO_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<Epi, PAIR>, maps, core, ep));
     }
+    LOCO_CUDA(launch_kernel(tc_gemm_kernel<Epi, PAIR>, dim3((unsigned)grid), dim3(64 + 32 * Epi::kEpiWarps), smem_bytes, st, csize, maps, core, ep));
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;

@@ -212,6 +212,8 @@ struct EpiScore {
 __global__ void __launch_bounds__(256) box_score_finalize_kernel(const float *__restrict__ logits, float *__restrict__ probs, int64_t ld,
                                                                  int R, int K1, const float4 *__restrict__ part, int groups,
                                                                  float *__restrict__ lse, int64_t *__restrict__ argmax_fg) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < R; row += gridDim.x * wpb) {
@@ -820,8 +822,8 @@ int loco_box_score_fwd(const uint16_t *E_hi, const uint16_t *E_lo, int64_t lde, 
         int blocks = (R + 7) / 8;
         const int cap = current_device_sm_count() * 8;
         if (blocks > cap) blocks = cap;
-        box_score_finalize_kernel<<<blocks, 256, 0, st>>>(logits, probs, ld_logits, R, K1,
-                                                          groups > 1 ? static_cast<const float4 *>(workspace) : nullptr, groups, lse, argmax_fg);
+        LOCO_CUDA(launch_kernel(box_score_finalize_kernel, dim3(blocks), dim3(256), 0, st, 1, logits, probs, ld_logits, R, K1,
+                                groups > 1 ? static_cast<const float4 *>(workspace) : static_cast<const float4 *>(nullptr), groups, lse, argmax_fg));
         count_launch();
         LOCO_CUDA(cudaGetLastError());
     }
