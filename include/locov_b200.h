@@ -158,6 +158,15 @@ int loco_lsm_masks(const int64_t *attention_mask, const int64_t *special_tokens_
                    const void *region_mask, int region_kind, int64_t n_reg, float *cap_mask,
                    float *reg_mask, void *stream);
 
+/* ---- LSM input preparation (masks + caption operand in one launch) ---------------------------------------
+ * Replaces: grounding_head.py:94-96,101,105-106 (as loco_lsm_masks) and the fp32 -> bf16 (hi / lo) conversion of the caption
+ * word embeddings input_caption[TEXT_INPUT] [rows = B*T, cols = D] that the pair GEMM consumes (grounding_head.py:116-147
+ * feeds them to torch.bmm as fp32).  cap_lo may be NULL (reduced-precision mode).  dst_ld % 8 == 0, pad columns zeroed. */
+int loco_lsm_prep(const float *cap, int64_t rows, int64_t cols, int64_t cap_ld, uint16_t *cap_hi, uint16_t *cap_lo,
+                  int64_t dst_ld, const int64_t *attention_mask, const int64_t *special_tokens_mask, int64_t n_cap,
+                  const void *region_mask, int region_kind, int64_t n_reg, float *cap_mask, float *reg_mask,
+                  void *stream);
+
 /* ---- LSM pair scoring ------------------------------------------------------------------------------
  * Replaces: grounding_head.py:116-256 — B^2 .repeat() replication, torch.bmm, torch.where mask fill,
  *           two F.softmax passes, masked weighted sums (all ATen/cuBLAS launches over [B^2,T,Rg]).

@@ -37,6 +37,7 @@ SIGNATURES = {
     "loco_box_score_fwd": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "loco_box_ce_fwd_bwd": (_i, [_vp, _i64, _vp, _vp, _i, _i, _f, _vp, _f, _vp, _vp, _i64, _vp]),
     "loco_lsm_masks": (_i, [_vp, _vp, _i64, _vp, _i, _i64, _vp, _vp, _vp]),
+    "loco_lsm_prep": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i, _i64, _vp, _vp, _vp]),
     "loco_lsm_pair_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "loco_lsm_pair_fwd": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _i64, _vp, _vp]),
     "loco_lsm_pair_bwd": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _i64, _vp, _vp, _i64,

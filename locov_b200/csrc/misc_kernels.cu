@@ -9,6 +9,47 @@
 namespace loco {
 
 // ---- fp32 -> bf16 hi/lo -------------------------------------------------------------------------------
+// one destination quad (4 columns) of the fp32 -> bf16 hi/lo split
+__device__ __forceinline__ void split_quad(const float *__restrict__ src, int64_t cols, int64_t src_ld, uint16_t *__restrict__ hi,
+                                           uint16_t *__restrict__ lo, int64_t dst_ld, int64_t quads_per_row, bool vec_ok, int64_t idx) {
+    const int64_t r = idx / quads_per_row;
+    const int64_t c = (idx - r * quads_per_row) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const float *s = src + r * src_ld + c;
+    if (c + 3 < cols && vec_ok) {
+        const float4 f = __ldg(reinterpret_cast<const float4 *>(s));
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (c + j < cols) v[j] = __ldg(s + j);
+    }
+    uint16_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_bf16(v[j], h[j], l[j]);
+    uint2 ph, pl;
+    ph.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16); ph.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
+    pl.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16); pl.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
+    *reinterpret_cast<uint2 *>(hi + r * dst_ld + c) = ph;
+    if (lo != nullptr) *reinterpret_cast<uint2 *>(lo + r * dst_ld + c) = pl;
+}
+
+// one element of the LSM masks: caption_mask = attention * (1 - special) (grounding_head.py:94-101), region mask -> fp32 (:105-106)
+__device__ __forceinline__ void mask_item(const int64_t *__restrict__ att, const int64_t *__restrict__ spe, int64_t n_cap,
+                                          const void *__restrict__ reg, int reg_kind, float *__restrict__ cap_mask,
+                                          float *__restrict__ reg_mask, int64_t i) {
+    if (i < n_cap) {
+        cap_mask[i] = (float)(att[i] * (1 - spe[i]));
+    } else {
+        const int64_t j = i - n_cap;
+        float v;
+        if (reg_kind == 0) v = (float)static_cast<const uint8_t *>(reg)[j];
+        else if (reg_kind == 1) v = static_cast<const float *>(reg)[j];
+        else v = (float)static_cast<const int64_t *>(reg)[j];
+        reg_mask[j] = v;
+    }
+}
+
 // One thread per 4 destination columns; pad columns [cols, dst_ld) are written as zeros.
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float *__restrict__ src, int64_t rows, int64_t cols,
                                                          int64_t src_ld, uint16_t *__restrict__ hi,
@@ -19,26 +60,25 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float *__restrict
     const int64_t total = rows * quads_per_row;
     const bool vec_ok = (src_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = idx / quads_per_row;
-        const int64_t c = (idx - r * quads_per_row) * 4;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        const float *s = src + r * src_ld + c;
-        if (c + 3 < cols && vec_ok) {
-            const float4 f = __ldg(reinterpret_cast<const float4 *>(s));
-            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (c + j < cols) v[j] = __ldg(s + j);
-        }
-        uint16_t h[4], l[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) split_bf16(v[j], h[j], l[j]);
-        uint2 ph, pl;
-        ph.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16); ph.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
-        pl.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16); pl.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
-        *reinterpret_cast<uint2 *>(hi + r * dst_ld + c) = ph;
-        if (lo != nullptr) *reinterpret_cast<uint2 *>(lo + r * dst_ld + c) = pl;
+        split_quad(src, cols, src_ld, hi, lo, dst_ld, quads_per_row, vec_ok, idx);
+    }
+}
+
+// ---- LSM input preparation in ONE launch: caption embeddings -> bf16 operand (hi / lo) and both masks -> fp32.
+// (the two jobs are independent; separate launches cost more in launch gaps than in work at the BASELINE shapes)
+__global__ void __launch_bounds__(256) lsm_prep_kernel(const float *__restrict__ cap, int64_t rows, int64_t cols, int64_t cap_ld,
+                                                       uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, int64_t dst_ld,
+                                                       const int64_t *__restrict__ att, const int64_t *__restrict__ spe, int64_t n_cap,
+                                                       const void *__restrict__ reg, int reg_kind, int64_t n_reg,
+                                                       float *__restrict__ cap_mask, float *__restrict__ reg_mask) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t quads_per_row = dst_ld / 4;
+    const int64_t nq = rows * quads_per_row, total = nq + n_cap + n_reg;
+    const bool vec_ok = (cap_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(cap) & 15) == 0);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        if (idx < nq) split_quad(cap, cols, cap_ld, hi, lo, dst_ld, quads_per_row, vec_ok, idx);
+        else mask_item(att, spe, n_cap, reg, reg_kind, cap_mask, reg_mask, idx - nq);
     }
 }
 
@@ -76,18 +116,8 @@ __global__ void __launch_bounds__(256) lsm_masks_kernel(const int64_t *__restric
                                                         float *__restrict__ cap_mask, float *__restrict__ reg_mask) {
     pdl_trigger();
     pdl_wait();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cap + n_reg; i += (int64_t)gridDim.x * blockDim.x) {
-        if (i < n_cap) {
-            cap_mask[i] = (float)(att[i] * (1 - spe[i]));
-        } else {
-            const int64_t j = i - n_cap;
-            float v;
-            if (reg_kind == 0) v = (float)static_cast<const uint8_t *>(reg)[j];
-            else if (reg_kind == 1) v = static_cast<const float *>(reg)[j];
-            else v = (float)static_cast<const int64_t *>(reg)[j];
-            reg_mask[j] = v;
-        }
-    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cap + n_reg; i += (int64_t)gridDim.x * blockDim.x)
+        mask_item(att, spe, n_cap, reg, reg_kind, cap_mask, reg_mask, i);
 }
 
 // ---- 16-bit transpose: dst[c, r] = src[r, c] (bf16 operands for the backward GEMMs) ---------------------------
@@ -406,6 +436,24 @@ int loco_lsm_masks(const int64_t *attention_mask, const int64_t *special_tokens_
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
     LOCO_CUDA(launch_kernel(lsm_masks_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, attention_mask, special_tokens_mask,
                             n_cap, region_mask, region_kind, n_reg, cap_mask, reg_mask));
+    count_launch();
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+int loco_lsm_prep(const float *cap, int64_t rows, int64_t cols, int64_t cap_ld, uint16_t *cap_hi, uint16_t *cap_lo, int64_t dst_ld,
+                  const int64_t *attention_mask, const int64_t *special_tokens_mask, int64_t n_cap, const void *region_mask,
+                  int region_kind, int64_t n_reg, float *cap_mask, float *reg_mask, void *stream) {
+    LOCO_REQUIRE(rows > 0 && cols > 0 && cap_ld >= cols && n_cap > 0 && n_reg > 0 && region_kind >= 0 && region_kind <= 2, LOCO_E_BADARG,
+                 "lsm_prep: bad shape rows=%lld cols=%lld n_cap=%lld n_reg=%lld", (long long)rows, (long long)cols, (long long)n_cap, (long long)n_reg);
+    LOCO_REQUIRE(cap && cap_hi && attention_mask && special_tokens_mask && region_mask && cap_mask && reg_mask, LOCO_E_BADARG, "lsm_prep: null pointer");
+    LOCO_REQUIRE(dst_ld % 8 == 0 && dst_ld >= cols, LOCO_E_ALIGN, "lsm_prep: dst_ld %lld must be a multiple of 8 and >= cols", (long long)dst_ld);
+    LOCO_REQUIRE((reinterpret_cast<uintptr_t>(cap_hi) & 15) == 0 && (!cap_lo || (reinterpret_cast<uintptr_t>(cap_lo) & 15) == 0), LOCO_E_ALIGN,
+                 "lsm_prep: destination must be 16-byte aligned");
+    const int64_t total = rows * (dst_ld / 4) + n_cap + n_reg;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    LOCO_CUDA(launch_kernel(lsm_prep_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, cap, rows, cols, cap_ld, cap_hi, cap_lo,
+                            dst_ld, attention_mask, special_tokens_mask, n_cap, region_mask, region_kind, n_reg, cap_mask, reg_mask));
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;

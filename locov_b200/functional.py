@@ -281,12 +281,13 @@ class _LsmHead(Function):
     A slice whose alignment is switched off is zero and carries no gradient."""
 
     @staticmethod
-    def forward(ctx, feats, w, b, cap, cap_mask, reg_mask, inv_temp, alignment, precision, want_w2r, want_r2w):
+    def forward(ctx, feats, w, b, cap, cap_mask, reg_mask, inv_temp, alignment, precision, want_w2r, want_r2w, cap_op):
         acc = _acc(precision)
         bi, rg, v = feats.shape
         bc, t, d = cap.shape
         emb_op = project_regions(feats.reshape(bi * rg, v), w, b, d, acc)
-        cap_op = ops.split_bf16(cap.reshape(bc * t, d), acc)
+        if cap_op is None or (cap_op.lo is None) == acc or cap_op.rows != bc * t or cap_op.cols != d:
+            cap_op = ops.split_bf16(cap.reshape(bc * t, d), acc)    # (not prepared by ops.lsm_prep, or for another mode)
         stack = new_pair_stack(bc, bi, feats.device, want_w2r and want_r2w)
         ops.lsm_pair(cap_op, cap_mask, emb_op, reg_mask, inv_temp, alignment, want_w2r, want_r2w, stack[0], stack[1])
         ctx.ops_saved = (emb_op, cap_op)
@@ -320,18 +321,19 @@ class _LsmHead(Function):
             db = demb.sum(0)
         if need_cap:
             dcap = dcap.reshape(cap_shape)
-        return dx, dw, db, (dcap if need_cap else None), None, None, None, None, None, None, None
+        return dx, dw, db, (dcap if need_cap else None), None, None, None, None, None, None, None, None
 
 
 def lsm_head(feats, w, b, cap, cap_mask, reg_mask, temperature, alignment="softmax", precision="fp32",
-             want_w2r=True, want_r2w=True):
+             want_w2r=True, want_r2w=True, cap_op=None):
     """Stacked pair distance matrices [2, Bc, Bi] = (w2r, r2w) (rows = captions, cols = images) before the
-    empty-pair guard; the slice of a switched-off alignment is zero."""
+    empty-pair guard; the slice of a switched-off alignment is zero.  ``cap_op`` = the caption operand when
+    ``ops.lsm_prep`` already produced it together with the masks (same values as ``cap``)."""
     amode = {"softmax": ops.ALIGN_SOFTMAX, "hardmax": ops.ALIGN_HARDMAX}.get(alignment)
     if amode is None:
         raise NotImplementedError(f"alignment {alignment!r} is not implemented on the B200 path")
     return _LsmHead.apply(feats, w, b, cap, cap_mask, reg_mask, 1.0 / float(temperature), amode, precision,
-                          bool(want_w2r), bool(want_r2w))
+                          bool(want_w2r), bool(want_r2w), cap_op)
 
 
 class _PairCE(Function):

@@ -68,7 +68,14 @@ class GroundingHead(LoggedModule):
         att, spe = input_caption["attention_mask"], input_caption["special_tokens_mask"]
         region_features = input_image["region_features"]
         region_mask = input_image["region_mask"]
-        if att.is_cuda and att.dtype == torch.int64 and spe.dtype == torch.int64 and region_mask.dtype in ops._REG_KIND:
+        sharded = self.shard_captions and self.process_group is not None
+        cap_op = None
+        masks_on_device = att.is_cuda and att.dtype == torch.int64 and spe.dtype == torch.int64 and region_mask.dtype in ops._REG_KIND
+        if masks_on_device and not sharded and caption_emb.is_cuda and caption_emb.dim() == 3:
+            # grounding_head.py:94-106 and the caption operand of the pair GEMM in one launch
+            cap32 = caption_emb.to(torch.float32).contiguous()
+            cap_op, caption_mask, region_mask = ops.lsm_prep(cap32.reshape(-1, cap32.shape[-1]), self.precision == "fp32", att, spe, region_mask)
+        elif masks_on_device:
             caption_mask, region_mask = ops.lsm_masks(att, spe, region_mask)       # grounding_head.py:94-106, one launch
         else:
             caption_mask = (att * (1 - spe)).to(torch.float32)
@@ -81,14 +88,14 @@ class GroundingHead(LoggedModule):
         self.log("region_mask", region_mask)
         batch_size = region_features.shape[0]
 
-        if self.shard_captions and self.process_group is not None:
+        if sharded:
             from .. import parallel
             return parallel.sharded_grounding_forward(self, region_features, region_mask, caption_emb, caption_mask)
 
         pw = LF.lsm_head(region_features.to(torch.float32).contiguous(), self.v2l_projection.weight,
                          self.v2l_projection.bias, caption_emb.to(torch.float32).contiguous(), caption_mask,
                          region_mask, self.temperature, self.alignment, self.precision,
-                         want_w2r=self.align_words, want_r2w=self.align_regions)
+                         want_w2r=self.align_words, want_r2w=self.align_regions, cap_op=cap_op)
         assert pw.shape == (2, batch_size, batch_size)
         losses, other_info, dists = self._pair_outputs(pw, caption_mask, region_mask)
         self.log_dict(losses)

@@ -280,6 +280,30 @@ def lsm_masks(attention_mask: torch.Tensor, special_tokens_mask: torch.Tensor, r
     return cap_mask, reg_mask
 
 
+def lsm_prep(cap2d: torch.Tensor, accurate: bool, attention_mask: torch.Tensor, special_tokens_mask: torch.Tensor,
+             region_mask: torch.Tensor):
+    """Caption embeddings [B*T, D] fp32 -> Bf16Operand, plus (caption_mask, region_mask) as in ``lsm_masks`` — one launch."""
+    _need_cuda(cap2d, attention_mask, special_tokens_mask, region_mask)
+    if cap2d.dim() != 2 or cap2d.dtype != torch.float32:
+        raise LocoError("lsm_prep: expects 2-D fp32 caption embeddings")
+    if attention_mask.dtype != torch.int64 or special_tokens_mask.dtype != torch.int64 or region_mask.dtype not in _REG_KIND:
+        raise LocoError("lsm_prep: expects int64 token masks and a uint8/bool/fp32/int64 region mask")
+    if cap2d.stride(1) != 1:
+        cap2d = cap2d.contiguous()
+    att, spe, reg = attention_mask.contiguous(), special_tokens_mask.contiguous(), region_mask.contiguous()
+    rows, cols = cap2d.shape
+    ld = _round_up(max(cols, 1), 8)
+    hi = torch.empty((rows, ld), dtype=torch.bfloat16, device=cap2d.device)
+    lo = torch.empty((rows, ld), dtype=torch.bfloat16, device=cap2d.device) if accurate else None
+    cap_mask = torch.empty(att.shape, dtype=torch.float32, device=att.device)
+    reg_mask = torch.empty(reg.shape, dtype=torch.float32, device=att.device)
+    lib = _lib.load()
+    _lib.check(lib.loco_lsm_prep(_p(cap2d), rows, cols, cap2d.stride(0), _p(hi), _p(lo) if accurate else None, ld, _p(att), _p(spe),
+                                 att.numel(), _p(reg), _REG_KIND[reg.dtype], reg.numel(), _p(cap_mask), _p(reg_mask), _stream(cap2d)),
+               "loco_lsm_prep")
+    return Bf16Operand(hi, lo, rows, cols), cap_mask, reg_mask
+
+
 def lsm_pair(cap: Bf16Operand, cap_mask: torch.Tensor, emb: Bf16Operand, reg_mask: torch.Tensor, inv_temperature: float,
              alignment: int = ALIGN_SOFTMAX, want_w2r: bool = True, want_r2w: bool = True,
              out_w2r: Optional[torch.Tensor] = None, out_r2w: Optional[torch.Tensor] = None):

@@ -172,3 +172,23 @@ def test_pair_ce_kernel_all_batch_sizes(cuda_device, B):
         (gc,) = torch.autograd.grad(ce_cap, ref_in, retain_graph=True)
         (gi,) = torch.autograd.grad(ce_img, ref_in)
         assert relerr(dcap[k].cpu(), gc) < 1e-4 and relerr(dimg[k].cpu(), gi) < 1e-4
+
+
+@pytest.mark.parametrize("accurate", [False, True])
+@pytest.mark.parametrize("reg_dtype", [torch.uint8, torch.float32, torch.int64])
+def test_lsm_prep_equals_masks_plus_split(cuda_device, accurate, reg_dtype):
+    """The fused input-preparation launch is bit-identical to loco_lsm_masks + loco_split_bf16 (ragged D: pad columns zero)."""
+    from locov_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    b, t, rg, d = 5, 7, 9, 100                       # d % 8 != 0: padded operand row stride
+    cap = (torch.randn(b * t, d, generator=g) * 0.05).to(cuda_device)
+    att = (torch.rand(b, t, generator=g) > 0.3).long().to(cuda_device)
+    spe = (torch.rand(b, t, generator=g) > 0.7).long().to(cuda_device)
+    reg = (torch.rand(b, rg, generator=g) > 0.2).to(reg_dtype).to(cuda_device)
+    op, cm, rm = ops.lsm_prep(cap, accurate, att, spe, reg)
+    ref_op = ops.split_bf16(cap, accurate)
+    cm2, rm2 = ops.lsm_masks(att, spe, reg)
+    assert torch.equal(op.hi, ref_op.hi) and op.ld == ref_op.ld and (op.rows, op.cols) == (ref_op.rows, ref_op.cols)
+    assert (op.lo is None) == (not accurate) and (op.lo is None or torch.equal(op.lo, ref_op.lo))
+    assert torch.equal(cm, cm2) and torch.equal(rm, rm2)
+    assert torch.equal(cm.cpu(), (att * (1 - spe)).float().cpu())
