@@ -8,7 +8,7 @@ mkdir -p $O
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches_bench.csv \
     python bench.py --steps 8 --warmup 3 --no-cpu-baseline --e2e-steps 2 > $O/${TAG}_launches_bench.log 2>&1
 # 2. full capture of the LSM step kernels (graph replays of the timed region: skip the eager warm-up launches)
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:tc_gemm|pair_ce|lsm_masks|split_bf16' -s 60 -c 12 \
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:tc_gemm|pair_ce|lsm_prep' -s 4 -c 12 \
     -o $O/${TAG}_bench -f python bench.py --steps 8 --warmup 3 --no-cpu-baseline --e2e-steps 2 > $O/${TAG}_ncu_bench.log 2>&1
 # 3. launch list of the per-kernel bench (RoIAlign + box predictor chain, configs 1/3/5)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_launches_kernels.csv \
