@@ -71,7 +71,7 @@ class GroundingHead(LoggedModule):
         sharded = self.shard_captions and self.process_group is not None
         cap_op = None
         masks_on_device = att.is_cuda and att.dtype == torch.int64 and spe.dtype == torch.int64 and region_mask.dtype in ops._REG_KIND
-        if masks_on_device and not sharded and caption_emb.is_cuda and caption_emb.dim() == 3:
+        if masks_on_device and caption_emb.is_cuda and caption_emb.dim() == 3:
             # grounding_head.py:94-106 and the caption operand of the pair GEMM in one launch
             cap32 = caption_emb.to(torch.float32).contiguous()
             cap_op, caption_mask, region_mask = ops.lsm_prep(cap32.reshape(-1, cap32.shape[-1]), self.precision == "fp32", att, spe, region_mask)
@@ -90,7 +90,7 @@ class GroundingHead(LoggedModule):
 
         if sharded:
             from .. import parallel
-            return parallel.sharded_grounding_forward(self, region_features, region_mask, caption_emb, caption_mask)
+            return parallel.sharded_grounding_forward(self, region_features, region_mask, caption_emb, caption_mask, cap_op=cap_op)
 
         pw = LF.lsm_head(region_features.to(torch.float32).contiguous(), self.v2l_projection.weight,
                          self.v2l_projection.bias, caption_emb.to(torch.float32).contiguous(), caption_mask,

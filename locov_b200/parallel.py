@@ -63,13 +63,9 @@ class _GatherBlocks(Function):
     def forward(ctx, block, nreg_loc, group):
         w, r = dist.get_world_size(group), dist.get_rank(group)
         n, b, bl = block.shape
-        msg = torch.cat([block.reshape(-1), nreg_loc.reshape(-1).to(block.dtype)])
-        parts = msg.new_empty((w * msg.numel(),))          # dim-0 concatenation (the layout every backend accepts)
-        dist.all_gather_into_tensor(parts, msg, group=group)
-        parts = parts.view(w, msg.numel())
+        parts, nreg_all = gather_packed([block.reshape(1, n, b, bl), nreg_loc.reshape(-1).to(block.dtype)], group)
         ctx.cols = (r * bl, (r + 1) * bl)
-        full = parts[:, :n * b * bl].reshape(w, n, b, bl).permute(1, 2, 0, 3).reshape(n, b, w * bl).contiguous()
-        nreg_all = parts[:, n * b * bl:].reshape(w * bl).contiguous()
+        full = parts.permute(1, 2, 0, 3).reshape(n, b, w * bl)          # [w, n, b, bl] -> [n, b, w * bl]: one copy
         ctx.mark_non_differentiable(nreg_all)
         return full, nreg_all
 
@@ -93,20 +89,18 @@ def global_pair_outputs(head, blocks, cap_mask_all, reg_mask_loc, group):
 
 
 def gather_packed(tensors, group):
-    """all-gather several equally-shaped-per-rank tensors with ONE collective (byte-packed message);
-    returns the dim-0 concatenations."""
+    """all-gather several per-rank tensors (equal shapes on every rank) along dim 0 as ONE coalesced collective: on NCCL
+    the all-gathers are grouped (one launch) and land directly in their dense destinations — no pack / unpack copies."""
     w = dist.get_world_size(group)
-    flat = [t.contiguous().view(torch.uint8).reshape(-1) for t in tensors]
-    sizes = [f.numel() for f in flat]
-    msg = torch.cat(flat) if len(flat) > 1 else flat[0]
-    parts = msg.new_empty((w * msg.numel(),))
-    dist.all_gather_into_tensor(parts, msg, group=group)
-    parts = parts.view(w, msg.numel())
-    outs, off = [], 0
-    for t, n in zip(tensors, sizes):
-        chunk = parts[:, off:off + n].contiguous().view(t.dtype)
-        outs.append(chunk.reshape((w * t.shape[0],) + tuple(t.shape[1:])))
-        off += n
+    ins = [t.contiguous() for t in tensors]
+    outs = [t.new_empty((w * t.shape[0],) + tuple(t.shape[1:])) for t in ins]
+    if len(ins) > 1 and ins[0].is_cuda:
+        with dist._coalescing_manager(group=group):
+            for o, i in zip(outs, ins):
+                dist.all_gather_into_tensor(o, i, group=group)
+    else:
+        for o, i in zip(outs, ins):
+            dist.all_gather_into_tensor(o, i, group=group)
     return outs
 
 
@@ -114,19 +108,21 @@ class _ShardedLsm(Function):
     """Local regions x ALL captions -> ([B, B_loc] w2r block, r2w block)."""
 
     @staticmethod
-    def forward(ctx, feats, w, b, cap_loc, cap_mask_loc, reg_mask, inv_temp, alignment, precision, want_w2r, want_r2w, group):
+    def forward(ctx, feats, w, b, cap_loc, cap_mask_loc, reg_mask, inv_temp, alignment, precision, want_w2r, want_r2w, group, cap_op):
         acc = LF._acc(precision)
         bi, rg, v = feats.shape
         bl, t, d = cap_loc.shape
         dev = feats.device
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev)
-        # 1. caption operands: split locally (bf16 hi [+lo]), all-gather on the side stream
-        cap_op = ops.split_bf16(cap_loc.reshape(bl * t, d), acc)
+        # 1. caption operands: split locally (bf16 hi [+lo]; already done by ops.lsm_prep when the module could fuse it
+        #    with the mask preparation), all-gather on the side stream
+        if cap_op is None or (cap_op.lo is None) == acc or cap_op.rows != bl * t or cap_op.cols != d:
+            cap_op = ops.split_bf16(cap_loc.reshape(bl * t, d), acc)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             parts = [cap_op.hi, cap_mask_loc] + ([cap_op.lo] if acc else [])
-            got = gather_packed(parts, group)                 # one NCCL all-gather for operands + masks
+            got = gather_packed(parts, group)                 # one grouped NCCL all-gather for operands + masks
             hi_all, mask_all = got[0], got[1]
             lo_all = got[2] if acc else None
             for x in parts + got:
@@ -166,16 +162,16 @@ class _ShardedLsm(Function):
             dw, _ = ops.linear_fwd(ops.transpose_operand(g_op), ops.transpose_operand(x_op), None, want_f32=True)
         if has_b and ctx.needs_input_grad[2]:
             db = demb.sum(0)
-        return dx, dw, db, None, None, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None, None, None
 
 
-def sharded_grounding_forward(head, region_features, region_mask, caption_emb, caption_mask):
+def sharded_grounding_forward(head, region_features, region_mask, caption_emb, caption_mask, cap_op=None):
     group = head.process_group
     amode = {"softmax": ops.ALIGN_SOFTMAX, "hardmax": ops.ALIGN_HARDMAX}[head.alignment]
     blocks, mask_all = _ShardedLsm.apply(
         region_features.to(torch.float32).contiguous(), head.v2l_projection.weight, head.v2l_projection.bias,
         caption_emb.to(torch.float32).contiguous(), caption_mask, region_mask, 1.0 / float(head.temperature), amode,
-        head.precision, bool(head.align_words), bool(head.align_regions), group)
+        head.precision, bool(head.align_words), bool(head.align_regions), group, cap_op)
     losses, info, dists = global_pair_outputs(head, blocks, mask_all, region_mask, group)
     head.log_dict(losses)
     head.log_dict(info)
