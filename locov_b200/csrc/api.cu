@@ -93,6 +93,23 @@ unsigned long long *debug_timeline_buffer(int ctas) {
     return g_timeline;
 }
 
+int make_tmap_roi_out(CUtensorMap *map, const float *out, uint64_t R, uint64_t C, uint64_t PHW) {
+    encode_tiled_fn fn = get_encode_fn();
+    LOCO_REQUIRE(fn != nullptr, LOCO_E_DRIVER, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    LOCO_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && C % 4 == 0 && PHW >= 1 && PHW <= 256 && (PHW * 4) % 16 == 0 && R >= 1, LOCO_E_ALIGN,
+                 "pooled output is not addressable by a TMA store (base %p, C=%llu, PH*PW=%llu)", (const void *)out, (unsigned long long)C,
+                 (unsigned long long)PHW);
+    cuuint64_t dims[4] = {PHW, 4, C / 4, R};
+    cuuint64_t strides[3] = {PHW * 4, 4 * PHW * 4, C * PHW * 4};        // bytes, dimensions 1..3
+    cuuint32_t box[4] = {(cuuint32_t)PHW, 1, 32, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(out), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LOCO_REQUIRE(r == CUDA_SUCCESS, LOCO_E_DRIVER, "cuTensorMapEncodeTiled (pooled output) failed with CUresult %d (R=%llu C=%llu PHW=%llu)", (int)r,
+                 (unsigned long long)R, (unsigned long long)C, (unsigned long long)PHW);
+    return LOCO_OK;
+}
+
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) {

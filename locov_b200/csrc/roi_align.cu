@@ -18,9 +18,10 @@
 //     construction of the adaptive grid), so each pixel of a bin's footprint is loaded once per bin row.
 //     The common case walks consecutive feature columns with a sliding register window (walk_bin_row).
 //   * results are staged in a [128][PH*PW] shared-memory tile and leave through the copy engine
-//     (cp.async.bulk per channel row, evict-first so the feature map stays in the 126 MB L2) or, for pooled
+//     (four TMA tensor stores per slab, evict-first so the feature map stays in the 126 MB L2) or, for pooled
 //     sizes whose rows are not 16-byte multiples, as coalesced st.global.cs rows.
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -338,6 +339,9 @@ __global__ void __launch_bounds__(RA_THREADS, 3) roi_align_fwd_generic_kernel(co
 constexpr int RV_WARPS = 14;
 constexpr int RV_THREADS = RV_WARPS * 32;
 constexpr int RV_CC = 128;
+// shared-memory layout of the vectorised kernel: tap tables (2 x RA_TAB entries), 4 x 32 ints + 4 header ints, 32 walk
+// weight vectors, then the tile on the next 128-byte boundary
+constexpr int RV_TILE_OFFSET = ((2 * RA_TAB * 8 + (128 + 4) * 4 + 32 * 16) + 127) / 128 * 128;
 
 __device__ __forceinline__ float4 ldg128(const char *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ void fma4(float4 &a, float w, const float4 &v) {
@@ -535,8 +539,9 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
                                                                         const float *__restrict__ rois, int C, int H, int W,
                                                                         int PH, int PW, float scale, int sampling_ratio,
                                                                         int aligned, int nchunks, int slabs, int tstride,
-                                                                        int bulk_out, float *__restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+                                                                        int bulk_out, float *__restrict__ out,
+                                                                        const __grid_constant__ CUtensorMap omap) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     MergedEntry *ytab = reinterpret_cast<MergedEntry *>(smem_raw);
     MergedEntry *xtab = ytab + RA_TAB;
     int *ycnt = reinterpret_cast<int *>(xtab + RA_TAB);      // [32]
@@ -545,7 +550,7 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
     int *xbase = xadv + 32;                                   // [32] first column of each bin (-1: no sample inside the map)
     int *walk_hdr = xbase + 32;                               // [4]  {-, first column of the walk, last column, -}
     WalkBin *xw = reinterpret_cast<WalkBin *>(walk_hdr + 4);  // [32] dense per-bin column weights (16-byte aligned)
-    float *tile = reinterpret_cast<float *>(xw + 32);         // [RV_CC][tstride]
+    float *tile = reinterpret_cast<float *>(smem_raw + RV_TILE_OFFSET);   // [RV_CC][tstride], 128-byte aligned (TMA store source)
 
     const int r = blockIdx.x / nchunks;
     const int chunk = blockIdx.x - r * nchunks;               // this CTA pools `slabs` consecutive 128-channel slabs
@@ -687,22 +692,20 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
             const float *tile_g = tile + gi * tile_floats;
             const int cc = min(RV_CC, C - c0_g);
             if (bulk_out) {
-                // write-out by the copy engine: every channel's PH*PW floats are one dense, 16-byte aligned run both in the
-                // tile (tstride == PH*PW) and in the NCHW output, so one thread per row hands it to cp.async.bulk
-                // (evict-first in L2, like st.global.cs) — no LDS / STG instructions, no LSU wavefronts.  The copy takes
-                // warp-uniform operands, so a warp issues its lanes' copies one after the other: the 128 rows are spread
-                // over all warps (lane i of warp w takes row w + RV_WARPS * i).  The generic-proxy tile writes were fenced
-                // before the barrier above.
-                const int row = warp + RV_WARPS * lane;
-                if (row < RV_CC) {
-                    const int ch = 4 * (row & 31) + (row >> 5);
-                    if (ch < cc) {
-                        uint64_t pol;
-                        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-                        const uint32_t src = smem_u32(tile_g + (size_t)row * tstride);
-                        float *dst = out + ((size_t)r * C + c0_g + ch) * PHW;
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                                     ::"l"(dst), "r"(src), "r"((uint32_t)(PHW * 4)), "l"(pol) : "memory");
+                // write-out by the copy engine: the tile rows j*32 .. j*32+31 (dense, tstride == PH*PW) hold channels 4*l + j of
+                // the slab, which is exactly one box of the 4-D output map — four TMA tensor stores per slab (evict-first in
+                // L2, like st.global.cs), issued by one thread: no LDS / STG instructions, no LSU wavefronts.  (128 per-row
+                // cp.async.bulk copies were measured first: their per-lane issue loop alone drew 19 % of the stall samples.)
+                // The generic-proxy tile writes were fenced before the barrier above; channels past C are clipped by the map.
+                if (threadIdx.x == 0) {
+                    uint64_t pol;
+                    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t src = smem_u32(tile_g + (size_t)j * 32 * tstride);
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+                                     ::"l"(reinterpret_cast<uint64_t>(&omap)), "r"(src), "r"(0), "r"(j), "r"(c0_g >> 2), "r"(r), "l"(pol)
+                                     : "memory");
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile may be overwritten / the CTA may exit
@@ -862,11 +865,16 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
         const int nconc = RV_WARPS / PH > 1 ? RV_WARPS / PH : 1;            // slabs pooled at the same time (see the kernel)
         while (slabs < nconc && nslab % (slabs * 2) == 0) slabs *= 2;       // keep every warp group busy
         const int nchunks = nslab / slabs;
-        const size_t smem = 2 * RA_TAB * sizeof(MergedEntry) + (64 + 64 + 4) * sizeof(int) + 32 * sizeof(WalkBin) +
-                            (size_t)nconc * RV_CC * tstride * sizeof(float);
+        const size_t smem = (size_t)RV_TILE_OFFSET + (size_t)nconc * RV_CC * tstride * sizeof(float);
+        CUtensorMap omap;
+        memset(&omap, 0, sizeof(omap));
+        if (bulk_out) {
+            const int rc = make_tmap_roi_out(&omap, out, (uint64_t)R, (uint64_t)C, (uint64_t)PHW);
+            if (rc != LOCO_OK) return rc;
+        }
         LOCO_REQUIRE(smem <= 200 * 1024, LOCO_E_UNSUPPORTED, "roi_align_fwd: output size %dx%d needs %zu B of shared memory", PH, PW, smem);
         LOCO_REQUIRE((long long)R * nchunks < (1ll << 31), LOCO_E_UNSUPPORTED, "roi_align_fwd: too many (roi, channel-slab) tiles");
-        typedef void (*v4_fn)(const float *, const float *, int, int, int, int, int, float, int, int, int, int, int, int, float *);
+        typedef void (*v4_fn)(const float *, const float *, int, int, int, int, int, float, int, int, int, int, int, int, float *, const CUtensorMap);
         const bool multi = nconc > 1;
         const v4_fn fn = pair ? (multi ? roi_align_fwd_v4_kernel<true, true> : roi_align_fwd_v4_kernel<true, false>)
                               : (multi ? roi_align_fwd_v4_kernel<false, true> : roi_align_fwd_v4_kernel<false, false>);
@@ -877,7 +885,7 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
             smem_set[vi] = smem;
         }
         fn<<<R * nchunks, RV_THREADS, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, aligned, nchunks, slabs, tstride,
-                                                  bulk_out, out);
+                                                  bulk_out, out, omap);
         count_launch();
         LOCO_CUDA(cudaGetLastError());
         return LOCO_OK;
