@@ -76,11 +76,15 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
                        const float *rois, int R, int PH, int PW, float spatial_scale,
                        int sampling_ratio, int aligned, float *out, void *workspace, void *stream);
 
-/* Backward of the above (torchvision roi_align_backward semantics).  dfeat [N,C,H,W] fp32 must be
- * zero-filled by the caller; contributions are accumulated with atomic adds. */
+/* Backward of the above (torchvision roi_align_backward semantics): dfeat [N,C,H,W] fp32 = gradient w.r.t. the feature
+ * map.  With `workspace` (loco_roi_align_bwd_workspace_bytes() bytes, 16-byte aligned, contents ignored) and C % 4 == 0 the
+ * gradient is accumulated channels-last with 128-bit vector atomics and transposed into dfeat, which is then fully
+ * overwritten; without it (NULL) contributions are added to dfeat with scalar atomics and dfeat must be zero-filled by
+ * the caller.  Passing a zero-filled dfeat is correct in both cases. */
+int64_t loco_roi_align_bwd_workspace_bytes(int N, int C, int H, int W, int R);
 int loco_roi_align_bwd(const float *dout, int N, int C, int H, int W, const float *rois, int R,
                        int PH, int PW, float spatial_scale, int sampling_ratio, int aligned,
-                       float *dfeat, void *stream);
+                       float *dfeat, void *workspace, void *stream);
 
 /* Debug/parity entry: for every roi r, bin (ph,pw) and sample (iy,ix) with iy,ix < max_grid writes
  *   grid_hw [R,2] int32            (gh, gw) — the adaptive sample counts

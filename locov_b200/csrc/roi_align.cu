@@ -747,6 +747,179 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
 }
 
 // ------------------------------------------------------------------------------------------------
+// backward, vectorised: the adjoint of the column walk.  One CTA = (roi, slabs of 128 channels), warp = bin row, lane = 4
+// consecutive channels of a CHANNELS-LAST gradient map (workspace, transposed to NCHW afterwards): the upstream
+// gradient slab [128][PH*PW] is staged in shared memory (coalesced reads), a bin row scatters it along x into a sliding window
+// of GW + 1 column accumulators in registers (dense per-bin weights, the same tables as the forward walk), and every
+// finished column is added to the map with one 128-bit vector atomic per row tap (red.global.add.v4.f32: 512 contiguous
+// bytes per warp) — against four scalar atomics per sample, bin and channel in the per-element kernel below
+// (torchvision's scheme).  Rois the walk cannot take (fixed sampling ratio, GW > 3, oversized tables) are left to that
+// kernel through the `handled` flags.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_quad(char *p, float w, const Quad &t) {
+    atomicAdd(reinterpret_cast<float4 *>(p), make_float4(w * t.lo.x, w * t.lo.y, w * t.hi.x, w * t.hi.y));
+}
+
+struct WalkBin8 {
+    float w[8];      // dense weights of columns base .. base + 7 (zero beyond GW): sampling grids up to 7 wide
+};
+
+template <int GW>
+__device__ __noinline__ void walk_bin_row_bwd(char *gb, const MergedEntry *yt, int ny, const WalkBin8 *xw, const int *xadv, int x0_bytes,
+                                               int colstride, int xlast_bytes, int PW, float inv_cnt, const float *trow, int rstep) {
+    Quad acc[GW + 1];
+#pragma unroll
+    for (int k = 0; k <= GW; ++k) { acc[k].lo = make_float2(0.f, 0.f); acc[k].hi = acc[k].lo; }
+    int cb = x0_bytes - (GW + 1) * colstride;           // byte offset of window column 0 (columns before x0 are phantoms)
+    auto emit = [&](int col_bytes, const Quad &t) {
+        if (col_bytes < x0_bytes || col_bytes > xlast_bytes) return;     // warp-uniform
+        for (int k = 0; k < ny; ++k) red_add_quad(gb + yt[k].idx + col_bytes, yt[k].w, t);
+    };
+#pragma unroll 1
+    for (int pw = 0; pw < PW; ++pw) {
+        int a = xadv[pw];
+#pragma unroll 1
+        for (; a > 0; --a) {
+            emit(cb, acc[0]);
+#pragma unroll
+            for (int k = 0; k < GW; ++k) acc[k] = acc[k + 1];
+            acc[GW].lo = make_float2(0.f, 0.f);
+            acc[GW].hi = acc[GW].lo;
+            cb += colstride;
+        }
+        Quad g;
+        g.lo = make_float2(trow[pw], trow[pw + rstep]);
+        g.hi = make_float2(trow[pw + 2 * rstep], trow[pw + 3 * rstep]);
+        g = quad_mul(inv_cnt, g);
+        const float4 wa = *reinterpret_cast<const float4 *>(xw[pw].w);
+        const float4 wb = *reinterpret_cast<const float4 *>(xw[pw].w + 4);
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int k = 0; k <= GW; ++k) quad_fma(acc[k], wv[k], g);
+    }
+#pragma unroll
+    for (int k = 0; k <= GW; ++k) emit(cb + k * colstride, acc[k]);
+}
+
+__global__ void __launch_bounds__(RV_THREADS, 2) roi_align_bwd_v4_kernel(const float *__restrict__ dout, const float *__restrict__ rois, int C,
+                                                                        int H, int W, int PH, int PW, float scale, int sampling_ratio,
+                                                                        int aligned, int nchunks, int slabs, float *__restrict__ dfeat_nhwc,
+                                                                        unsigned char *__restrict__ handled) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MergedEntry *ytab = reinterpret_cast<MergedEntry *>(smem_raw);
+    MergedEntry *xtab = ytab + RA_TAB;
+    int *ycnt = reinterpret_cast<int *>(xtab + RA_TAB);
+    int *xcnt = ycnt + 32;
+    int *xadv = xcnt + 32;
+    int *xbase = xadv + 32;
+    int *walk_hdr = xbase + 32;
+    WalkBin8 *xw = reinterpret_cast<WalkBin8 *>(walk_hdr + 4);
+    float *tile = reinterpret_cast<float *>(xw + 32);         // [RV_CC][PH*PW | 1]: odd pitch, conflict-free lane-per-row reads
+
+    const int r = blockIdx.x / nchunks;
+    const int chunk = blockIdx.x - r * nchunks;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int PHW = PH * PW, pitch = PHW | 1;
+
+    const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, aligned, PH, PW, sampling_ratio);
+    const bool empty = (g.gh <= 0 || g.gw <= 0);
+    if (empty) {                                              // no sample: zero gradient
+        if (chunk == 0 && threadIdx.x == 0) handled[r] = 1;
+        return;
+    }
+    const int ystride = g.gh + 2, xstride = g.gw + 2;
+    const bool walk_try = sampling_ratio <= 0 && g.gw >= 1 && g.gw <= 7 && PH <= RV_WARPS && (long long)PH * ystride <= RA_TAB &&
+                          (long long)PW * xstride <= RA_TAB;
+    if (!walk_try) return;                                    // CTA-uniform: left to the per-element kernel
+    const float inv_cnt = __fdiv_rn(1.0f, (float)max(g.gh * g.gw, 1));
+
+    bool walk_bad_a = false;
+    {
+        const int t = threadIdx.x;
+        if (t < PH) ycnt[t] = build_merged(ytab + t * ystride, g.sh, g.bh, t, g.gh, H, W * C * 4);
+        else if (t >= 32 && t < 32 + PW) {
+            const int pw = t - 32;
+            const MergedEntry *xt = xtab + pw * xstride;
+            const int nx = build_merged(xtab + pw * xstride, g.sw, g.bw, pw, g.gw, W, C * 4, true);
+            xcnt[pw] = nx;
+            const int colbytes = C * 4;
+            float w[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int base = -1;
+            if (nx > 0) {
+                base = (xt[0].idx & ~1) / colbytes;
+                for (int j = 0; j < nx; ++j) {
+                    const int d = (xt[j].idx & ~1) / colbytes - base;
+                    if (d < 0 || d > g.gw) walk_bad_a = true;
+                    else w[d] += xt[j].w;
+                }
+            }
+            xbase[pw] = base;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) xw[pw].w[d] = w[d];
+        }
+    }
+    if (threadIdx.x == 0) { walk_hdr[1] = 0; walk_hdr[2] = 0; }
+    __syncthreads();
+    bool walk_bad = false;
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + PW) {
+        const int pw = threadIdx.x - 32;
+        walk_bad = walk_bad_a;
+        const int base = xbase[pw];
+        int adv = 0;
+        if (base >= 0) {
+            int prev = -1;
+            for (int q = pw - 1; q >= 0 && prev < 0; --q) prev = xbase[q];
+            if (prev < 0) { adv = g.gw + 1; walk_hdr[1] = base; }
+            else adv = base - prev;
+            if (adv < 0 || adv > g.gw + 1) walk_bad = true;
+            atomicMax(&walk_hdr[2], base + g.gw);
+        }
+        xadv[pw] = adv;
+    }
+    if (__syncthreads_and(walk_bad ? 0 : 1) == 0) return;     // CTA-uniform
+    if (chunk == 0 && threadIdx.x == 0) handled[r] = 1;
+    const int x0_bytes = walk_hdr[1] * C * 4, colstride = C * 4, xlast_bytes = min(W - 1, walk_hdr[2]) * C * 4;
+    const int rstep = 32 * pitch;
+
+    for (int sl = 0; sl < slabs; ++sl) {
+        const int c0 = (chunk * slabs + sl) * RV_CC;
+        if (c0 >= C) break;
+        const int cc = min(RV_CC, C - c0);
+        if (sl > 0) __syncthreads();                          // every warp is done with the previous slab's tile
+        // stage dout[r, c0 : c0 + cc, :, :] (one contiguous run) as tile[(ch & 3) * 32 + (ch >> 2)][bin]
+        const float *src = dout + ((size_t)r * C + c0) * PHW;
+        {
+            int ch = threadIdx.x / PHW, b = threadIdx.x - ch * PHW;
+            const int dch = RV_THREADS / PHW, db = RV_THREADS - dch * PHW;
+            for (int e = threadIdx.x; e < cc * PHW; e += RV_THREADS) {
+                tile[(size_t)(((ch & 3) << 5) + (ch >> 2)) * pitch + b] = __ldg(src + e);
+                ch += dch; b += db;
+                if (b >= PHW) { b -= PHW; ++ch; }
+            }
+        }
+        __syncthreads();
+        const bool active = (c0 + 4 * lane) < C;
+        if (warp < PH && active) {
+            char *gb = reinterpret_cast<char *>(dfeat_nhwc + (size_t)g.batch * H * W * C + c0 + 4 * lane);
+            const MergedEntry *yt = ytab + warp * ystride;
+            const float *trow = tile + (size_t)lane * pitch + warp * PW;
+            const int ny = ycnt[warp];
+            if (ny > 0) {
+                switch (g.gw) {                               // CTA-uniform
+                    case 1: walk_bin_row_bwd<1>(gb, yt, ny, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); break;
+                    case 2: walk_bin_row_bwd<2>(gb, yt, ny, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); break;
+                    case 3: walk_bin_row_bwd<3>(gb, yt, ny, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); break;
+                    case 4: walk_bin_row_bwd<4>(gb, yt, ny, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); break;
+                    case 5: walk_bin_row_bwd<5>(gb, yt, ny, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); break;
+                    case 6: walk_bin_row_bwd<6>(gb, yt, ny, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); break;
+                    default: walk_bin_row_bwd<7>(gb, yt, ny, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); break;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward (atomic scatter; one thread per (r, c, ph, pw))
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) roi_align_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ rois,
@@ -761,6 +934,36 @@ __global__ void __launch_bounds__(256) roi_align_bwd_kernel(const float *__restr
         const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, aligned, PH, PW, sampling_ratio);
         if (g.gh <= 0 || g.gw <= 0) continue;
         const float gv = dout[idx] / (float)max(g.gh * g.gw, 1);
+        float *plane = dfeat + ((size_t)g.batch * C + c) * H * W;
+        for (int iy = 0; iy < g.gh; ++iy) {
+            const Tap ty = make_tap(sample_coord(g.sh, g.bh, ph, iy, g.gh), H);
+            if (ty.lo < 0) continue;
+            for (int ix = 0; ix < g.gw; ++ix) {
+                const Tap tx = make_tap(sample_coord(g.sw, g.bw, pw, ix, g.gw), W);
+                if (tx.lo < 0) continue;
+                atomicAdd(plane + ty.lo * W + tx.lo, gv * ty.wl * tx.wl);
+                atomicAdd(plane + ty.lo * W + tx.hi, gv * ty.wl * tx.wh);
+                atomicAdd(plane + ty.hi * W + tx.lo, gv * ty.wh * tx.wl);
+                atomicAdd(plane + ty.hi * W + tx.hi, gv * ty.wh * tx.wh);
+            }
+        }
+    }
+}
+
+// the rois the vectorised backward declined (one CTA per roi; a handled roi costs one flag load)
+__global__ void __launch_bounds__(256) roi_align_bwd_rest_kernel(const float *__restrict__ dout, const float *__restrict__ rois, int C, int H,
+                                                                 int W, int PH, int PW, float scale, int sampling_ratio, int aligned,
+                                                                 float *__restrict__ dfeat, const unsigned char *__restrict__ handled) {
+    const int r = blockIdx.x;
+    if (handled[r]) return;
+    const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, aligned, PH, PW, sampling_ratio);
+    if (g.gh <= 0 || g.gw <= 0) return;
+    const int PHW = PH * PW;
+    const float inv = 1.0f / (float)max(g.gh * g.gw, 1);
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < C * PHW; e += gridDim.y * blockDim.x) {
+        const int c = e / PHW, b = e - c * PHW;
+        const int ph = b / PW, pw = b - ph * PW;
+        const float gv = dout[(size_t)r * C * PHW + e] * inv;
         float *plane = dfeat + ((size_t)g.batch * C + c) * H * W;
         for (int iy = 0; iy < g.gh; ++iy) {
             const Tap ty = make_tap(sample_coord(g.sh, g.bh, ph, iy, g.gh), H);
@@ -908,15 +1111,60 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
     return LOCO_OK;
 }
 
+int64_t loco_roi_align_bwd_workspace_bytes(int N, int C, int H, int W, int R) {
+    if (C % 4 != 0) return 0;                                 // the vectorised path needs 4-channel lanes
+    return (int64_t)N * C * H * W * (int64_t)sizeof(float) + (((int64_t)R + 255) / 256) * 256;
+}
+
 int loco_roi_align_bwd(const float *dout, int N, int C, int H, int W, const float *rois, int R, int PH, int PW,
-                       float spatial_scale, int sampling_ratio, int aligned, float *dfeat, void *stream) {
+                       float spatial_scale, int sampling_ratio, int aligned, float *dfeat, void *workspace, void *stream) {
     LOCO_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0 && R >= 0, LOCO_E_BADARG, "roi_align_bwd: bad shape");
     if (R == 0) return LOCO_OK;
     LOCO_REQUIRE(dout && rois && dfeat, LOCO_E_BADARG, "roi_align_bwd: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t total = (size_t)R * C * PH * PW;
     const int blocks = (int)min((size_t)148 * 32, (total + 255) / 256);
-    roi_align_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dout, rois, C, H, W, PH, PW, spatial_scale,
-                                                                               sampling_ratio, aligned, total, dfeat);
+    const int PHW = PH * PW;
+    const size_t smem = 2 * RA_TAB * sizeof(MergedEntry) + (128 + 4) * sizeof(int) + 32 * sizeof(WalkBin8) + (size_t)RV_CC * (PHW | 1) * sizeof(float);
+    static const bool v4_allowed = []() { const char *e = getenv("LOCOV_B200_ROI_BWD_V4"); return !(e != nullptr && e[0] == '0'); }();
+    const bool v4 = v4_allowed && workspace != nullptr && C % 4 == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && PH <= 32 && PW <= 32 &&
+                    (long long)H * W * C * 4 < (1ll << 31) && smem <= 110 * 1024 && (long long)R * ((C + RV_CC - 1) / RV_CC) < (1ll << 31) &&
+                    N <= 65535;
+    if (!v4) {       // per-element scatter straight into the NCHW gradient (zero-filled by the caller)
+        roi_align_bwd_kernel<<<blocks, 256, 0, st>>>(dout, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, aligned, total, dfeat);
+        count_launch();
+        LOCO_CUDA(cudaGetLastError());
+        return LOCO_OK;
+    }
+    // channels-last accumulation map + per-roi "handled" flags live in the workspace
+    float *ws = static_cast<float *>(workspace);
+    const size_t map_bytes = (size_t)N * C * H * W * sizeof(float);
+    unsigned char *handled = static_cast<unsigned char *>(workspace) + map_bytes;
+    LOCO_CUDA(cudaMemsetAsync(workspace, 0, map_bytes + (size_t)R, st));
+    const int nslab = (C + RV_CC - 1) / RV_CC;
+    int slabs = 1;
+    while (slabs < 4 && nslab % (slabs * 2) == 0 && (long long)R * (nslab / (slabs * 2)) >= 8ll * 2 * 148) slabs *= 2;
+    const int nchunks = nslab / slabs;
+    static thread_local size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        LOCO_CUDA(cudaFuncSetAttribute(roi_align_bwd_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    roi_align_bwd_v4_kernel<<<R * nchunks, RV_THREADS, smem, st>>>(dout, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, aligned, nchunks, slabs,
+                                                                   ws, handled);
+    count_launch();
+    LOCO_CUDA(cudaGetLastError());
+    // [N][HW][C] -> [N][C][HW]: the forward's transpose with the roles of the two axes swapped (this ASSIGNS dfeat)
+    {
+        const int HW = H * W;
+        dim3 grid((C + 31) / 32, (HW + 31) / 32, N);
+        LOCO_REQUIRE(grid.y <= 65535, LOCO_E_UNSUPPORTED, "roi_align_bwd: feature map too large for the transpose grid");
+        nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(ws, dfeat, HW, C);
+        count_launch();
+        LOCO_CUDA(cudaGetLastError());
+    }
+    // whatever the vectorised kernel declined
+    roi_align_bwd_rest_kernel<<<dim3((unsigned)R, 32), 256, 0, st>>>(dout, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, aligned, dfeat, handled);
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;

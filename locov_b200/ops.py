@@ -91,10 +91,13 @@ def roi_align_backward(dout: torch.Tensor, feat_shape, rois: torch.Tensor, spati
     dout = dout.to(torch.float32).contiguous()
     rois = rois.to(torch.float32).contiguous()
     r, _, ph, pw = dout.shape
-    dfeat = torch.zeros(feat_shape, dtype=torch.float32, device=dout.device)
     lib = _lib.load()
+    nbytes = int(lib.loco_roi_align_bwd_workspace_bytes(n, c, h, w, r))
+    ws = _workspace(dout.device, nbytes, "roi_align_bwd") if nbytes > 0 else None
+    # vectorised path: dfeat is fully overwritten; scalar path (C % 4 != 0): accumulated into a zero-filled map
+    dfeat = (torch.empty if ws is not None else torch.zeros)(feat_shape, dtype=torch.float32, device=dout.device)
     _lib.check(lib.loco_roi_align_bwd(_p(dout), n, c, h, w, _p(rois), r, ph, pw, float(spatial_scale),
-                                      int(sampling_ratio), int(bool(aligned)), _p(dfeat), _stream(dout)),
+                                      int(sampling_ratio), int(bool(aligned)), _p(dfeat), _p(ws), _stream(dout)),
                "loco_roi_align_bwd")
     return dfeat
 

@@ -88,6 +88,24 @@ def roi_case(name, n, c, h, w, per_img, ps, scale):
                           "GB/s": nbytes / ms / 1e6, "frac_of_hbm": nbytes / ms / 1e6 / PK["hbm_gbs"]}), flush=True)
 
 
+def roi_bwd_case(name, n, c, h, w, per_img, ps, scale):
+    """RoIAlign backward (gradient w.r.t. the feature map): ours vs torchvision's CUDA backward, same upstream gradient."""
+    import torchvision
+    feat = torch.randn(n, c, h, w, device=dev)
+    rois = rois_for(n, per_img)
+    r = rois.shape[0]
+    dout = torch.randn(r, c, ps, ps, device=dev)
+    nbytes = dout.numel() * 4 + feat.numel() * 4 * 2          # read dout once, read-modify-write the gradient map
+
+    def tv():
+        torch.ops.torchvision._roi_align_backward(dout, rois, scale, ps, ps, n, c, h, w, 0, True)
+
+    for tag, f in (("b200", lambda: ops.roi_align_backward(dout, feat.shape, rois, scale)), ("torchvision-cuda", tv)):
+        ms = timeit(f, iters=5)
+        print(json.dumps({"kernel": "roi_align_bwd", "case": name, "impl": tag, "R": r, "C": c, "out": ps, "ms": ms, "algorithmic_MB": nbytes / 1e6,
+                          "GB/s": nbytes / ms / 1e6, "frac_of_hbm": nbytes / ms / 1e6 / PK["hbm_gbs"]}), flush=True)
+
+
 def box_case(name, r, k, precision, bwd=False):
     from oracle import box_head
     x, we, be, wb, bb, cls, gt = box_head.make_box_inputs(r, k, seed=3)
@@ -153,6 +171,9 @@ if __name__ == "__main__":
     if "--box-only" not in sys.argv:
       roi_case("cfg1 faithful [2,1024,50,76]->[1024,1024,14,14]", 2, 1024, 50, 76, 512, 14, 1 / 16)
       roi_case("cfg1 literal [2,2048,25,38]->[1024,2048,7,7]", 2, 2048, 25, 38, 512, 7, 1 / 32)
+    if "--roi-bwd" in sys.argv:
+        roi_bwd_case("cfg1 faithful bwd [1024,1024,14,14]->[2,1024,50,76]", 2, 1024, 50, 76, 512, 14, 1 / 16)
+        sys.exit(0)
     if "--roi-only" in sys.argv:
         sys.exit(0)
     if "--box-only" not in sys.argv:

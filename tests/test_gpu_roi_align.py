@@ -89,15 +89,18 @@ def test_empty_and_module_interface(cuda_device):
     assert relerr(got, ref) < 1e-5
 
 
-def test_backward_vs_oracle(cuda_device):
+@pytest.mark.parametrize("c,ps,sr", [(24, 7, 0), (136, 14, 0), (22, 7, 0), (40, 6, 2)])
+def test_backward_vs_oracle(cuda_device, c, ps, sr):
+    """c % 4 == 0: channels-last vector-atomic kernel (adjoint column walk; c = 136 spans two 128-channel slabs);
+    c = 22 and the fixed sampling ratio: per-element scatter (directly, resp. through the `handled` flags)."""
     torch.manual_seed(5)
-    feat = torch.randn(2, 24, 25, 38, device=cuda_device, requires_grad=True)
-    rois = torch.cat([_rois(2, 40, 400, 608, seed=9), EDGE[:4]]).to(cuda_device)
-    pool = M.ROIAlign(7, 1 / 16, 0, True)
+    feat = torch.randn(2, c, 25, 38, device=cuda_device, requires_grad=True)
+    rois = torch.cat([_rois(2, 40, 400, 608, seed=9), EDGE]).to(cuda_device)      # EDGE[-1] has a 6-wide sampling grid
+    pool = M.ROIAlign(ps, 1 / 16, sr, True)
     out = pool(feat, rois)
     dout = torch.randn_like(out)
     out.backward(dout)
-    ref = ora.roi_align_bwd(dout.cpu().numpy(), (2, 24, 25, 38), rois.cpu().numpy(), 1 / 16, 0, True)
+    ref = ora.roi_align_bwd(dout.cpu().numpy(), (2, c, 25, 38), rois.cpu().numpy(), 1 / 16, sr, True)
     assert relerr(feat.grad.cpu(), ref) < 1e-4
 
 
