@@ -888,7 +888,30 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_bwd_v4_kernel(const f
         if (sl > 0) __syncthreads();                          // every warp is done with the previous slab's tile
         // stage dout[r, c0 : c0 + cc, :, :] (one contiguous run) as tile[(ch & 3) * 32 + (ch >> 2)][bin]
         const float *src = dout + ((size_t)r * C + c0) * PHW;
-        {
+        if (PHW % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            // 128-bit loads, seven in flight per thread before the first is stored (the loop is latency bound otherwise:
+            // 43 % of the kernel's stall samples sat on the store that waits for its own load)
+            const int nvec = PHW >> 2, total = cc * nvec;
+            const int dch = RV_THREADS / nvec, dq = RV_THREADS - dch * nvec;
+            int ch = threadIdx.x / nvec, q = threadIdx.x - ch * nvec;
+            for (int e0 = threadIdx.x; e0 < total; e0 += 7 * RV_THREADS) {
+                float4 v[7];
+#pragma unroll
+                for (int u = 0; u < 7; ++u) {
+                    const int e = e0 + u * RV_THREADS;
+                    v[u] = (e < total) ? __ldg(reinterpret_cast<const float4 *>(src) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 7; ++u) {
+                    if (e0 + u * RV_THREADS < total) {
+                        float *d = tile + (size_t)(((ch & 3) << 5) + (ch >> 2)) * pitch + 4 * q;
+                        d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+                    }
+                    ch += dch; q += dq;
+                    if (q >= nvec) { q -= nvec; ++ch; }
+                }
+            }
+        } else {
             int ch = threadIdx.x / PHW, b = threadIdx.x - ch * PHW;
             const int dch = RV_THREADS / PHW, db = RV_THREADS - dch * PHW;
             for (int e = threadIdx.x; e < cc * PHW; e += RV_THREADS) {
