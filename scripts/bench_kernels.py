@@ -178,6 +178,8 @@ if __name__ == "__main__":
     if "--roi-bwd" in sys.argv:
         roi_bwd_case("cfg1 faithful bwd [1024,1024,14,14]->[2,1024,50,76]", 2, 1024, 50, 76, 512, 14, 1 / 16)
         sys.exit(0)
+    if "--box-only" not in sys.argv:
+        roi_bwd_case("cfg1 faithful bwd [1024,1024,14,14]->[2,1024,50,76]", 2, 1024, 50, 76, 512, 14, 1 / 16)
     if "--roi-only" in sys.argv:
         sys.exit(0)
     if "--box-only" not in sys.argv:
