@@ -85,7 +85,7 @@ def global_pair_outputs(head, blocks, cap_mask_all, reg_mask_loc, group):
     guard only needs to know WHICH images have no valid region, so the per-image counts travel with the blocks
     and stand in for the region mask ([B, 1])."""
     full, nreg_all = assemble_blocks(blocks, reg_mask_loc.to(torch.float32).sum(1), group)
-    return head._pair_outputs(full, cap_mask_all, (nreg_all > 0).to(torch.float32).reshape(-1, 1))
+    return head._pair_outputs(full, cap_mask_all, nreg_all.reshape(-1, 1))     # a [B, 1] "mask" whose row sum is the count
 
 
 def gather_packed(tensors, group):
