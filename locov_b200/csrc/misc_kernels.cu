@@ -242,11 +242,19 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
     const float *mat = STAGED ? tile : pw;
 
     float mx = -FLT_MAX;
-    for (int idx = tid; idx < Bc * Bi; idx += nt) {
-        const int c = idx / Bi, i = idx - c * Bi;
-        const float v = pw[(int64_t)c * ld + i];
-        if (STAGED) tile[c * (Bi + 1) + i] = v;
-        mx = fmaxf(mx, v);
+    if (STAGED) {
+        for (int idx = tid; idx < Bc * Bi; idx += nt) {
+            const int c = idx / Bi, i = idx - c * Bi;
+            const float v = pw[(int64_t)c * ld + i];
+            tile[c * (Bi + 1) + i] = v;
+            mx = fmaxf(mx, v);
+        }
+    } else {
+        // every CTA scans the whole (L2-resident) matrix: warp = row, lane = column — coalesced, no index divisions
+        for (int c = warp; c < Bc; c += nwarp) {
+            const float *row = pw + (int64_t)c * ld;
+            for (int i = lane; i < Bi; i += 32) mx = fmaxf(mx, row[i]);
+        }
     }
     for (int c = warp; c < Bc; c += nwarp) {
         float s = 0.f;
@@ -290,6 +298,70 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
     const int i_end2 = (blk == nblk - 1) ? Bi : i_end;
 
     // choose caption: per image column i, log-softmax over the rows of -pw; target row = i + diag_off
+    if (!STAGED) {
+        // matrix in global memory (B > 32): lane = column of this CTA's strip, warps stride over the rows, so that every
+        // access is a coalesced 128-byte row segment (a warp walking one column touches 32 sectors per load: 20 of the
+        // 45 us of this kernel at B = 256).  Per-warp partial statistics are combined over the warps in a fixed order.
+        float *px = tile;                  // [nwarp][33] partial max / partial sums
+        float *py = px + 32 * 33;          // [nwarp][33] partial minima
+        int *pz = reinterpret_cast<int *>(py + 32 * 33);   // [nwarp][33] partial argmin
+        float *col_m = reinterpret_cast<float *>(pz + 32 * 33), *col_s = col_m + 32;
+        const int i = i_beg + lane;
+        const bool col_on = i < i_end2;
+        const int tgt = i + diag_off;
+        float m = -FLT_MAX, best = FLT_MAX;
+        int arg = 0x7fffffff;
+        if (col_on)
+            for (int c = warp; c < Bc; c += nwarp) {
+                const float v = val(c, i);
+                m = fmaxf(m, -v);
+                if (v < best) { best = v; arg = c; }        // rows visited in increasing order: first minimum
+            }
+        px[warp * 33 + lane] = m; py[warp * 33 + lane] = best; pz[warp * 33 + lane] = arg;
+        __syncthreads();
+        if (warp == 0) {
+            float mm = -FLT_MAX, bb = FLT_MAX;
+            int aa = 0x7fffffff;
+            for (int w = 0; w < nwarp; ++w) {
+                mm = fmaxf(mm, px[w * 33 + lane]);
+                const float ob = py[w * 33 + lane];
+                const int oa = pz[w * 33 + lane];
+                if (ob < bb || (ob == bb && oa < aa)) { bb = ob; aa = oa; }
+            }
+            col_m[lane] = mm;
+            pz[lane] = aa;                 // (row 0 of pz now holds the column argmin: read below by warp 0 only)
+        }
+        __syncthreads();
+        const float cm = col_m[lane];
+        float s = 0.f;
+        if (col_on)
+            for (int c = warp; c < Bc; c += nwarp) s += expf(-val(c, i) - cm);
+        px[warp * 33 + lane] = s;          // (the partial maxima in px were consumed before the barrier above)
+        __syncthreads();
+        if (warp == 0) {
+            float ss = 0.f;
+            for (int w = 0; w < nwarp; ++w) ss += px[w * 33 + lane];
+            col_s[lane] = ss;
+            float l = 0.f, a = 0.f;
+            if (col_on && tgt < Bc) {
+                l = (cm + logf(ss)) + val(tgt, i);
+                a = (pz[lane] == tgt) ? 1.f : 0.f;
+            }
+            l = warp_sum(l);
+            a = warp_sum(a);
+            if (lane == 0) { acc[0 * 32 + 0] += l; acc[2 * 32 + 0] += a; }
+        }
+        __syncthreads();
+        if (dcap != nullptr && col_on) {
+            const float cs = col_s[lane];
+            for (int c = warp; c < Bc; c += nwarp) {
+                float g = 0.f;
+                if (tgt < Bc && !(cap_empty[c] > 0.f && img_empty[i] > 0.f))
+                    g = (((c == tgt) ? 1.f : 0.f) - expf(-val(c, i) - cm) / cs) * inv;
+                dcap[(int64_t)c * Bi + i] = g;
+            }
+        }
+    } else
     for (int i = i_beg + warp; i < i_end2; i += nwarp) {
         float m = -FLT_MAX, best = FLT_MAX;
         int arg = 0x7fffffff;
@@ -513,7 +585,8 @@ int loco_pair_ce(float *pw, int nmat, int64_t mat_stride, int64_t ld, int Bc, in
     } else {
         LOCO_REQUIRE(workspace != nullptr, LOCO_E_BADARG, "pair_ce: B > 32 needs loco_pair_ce_workspace_bytes() of ZERO-INITIALISED workspace "
                      "(the kernel leaves it zeroed again)");
-        LOCO_CUDA(launch_kernel(pair_ce_kernel<false>, dim3(nmat, nblk), dim3(1024), base, st, 1, pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T,
+        const size_t strip = base + (size_t)(3 * 32 * 33 + 64) * sizeof(float);      // per-warp partial statistics of the column pass
+        LOCO_CUDA(launch_kernel(pair_ce_kernel<false>, dim3(nmat, nblk), dim3(1024), strip, st, 1, pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T,
                                 reg_mask, Rg, out4, dpw_caption, dpw_image, static_cast<float *>(workspace)));
     }
     count_launch();
