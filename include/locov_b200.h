@@ -146,6 +146,24 @@ int loco_box_score_fwd(const uint16_t *E_hi, const uint16_t *E_lo, int64_t lde, 
                        float *logits, float *probs, int64_t ld_logits, float *lse,
                        int64_t *argmax_fg, void *workspace, void *stream);
 
+/* Softmax statistics of an EXISTING score matrix (no GEMM in front): the outputs of the loco_box_score_fwd epilogue for
+ * logits that did not come out of it.
+ * Replaces: Detectron2 FastRCNNOutputLayers.predict_probs F.softmax / .losses F.cross_entropy's log_softmax (ATen) on the
+ *           score matrices of box_emb_head.py:204-212 when NORMALIZE_EMB_PRED / STANDARDIZE_EMB_PRED put a row-wise
+ *           normalisation between the two GEMMs, or when the caller passes its own scores to losses / inference.
+ * logits [R,K1] fp32 (ld_logits).  Outputs (each may be NULL, at least one required): lse [R]; argmax_fg [R] int64 over the
+ * first K1-1 columns (first maximum); probs [R,K1] (ld_probs). */
+int loco_box_softmax(const float *logits, int64_t ld_logits, int R, int K1, float *lse, int64_t *argmax_fg,
+                     float *probs, int64_t ld_probs, void *stream);
+
+/* Row-wise normalisation of the projected embeddings, forward and backward.
+ * Replaces: logged_module.py:55-72 normalize_vec (F.normalize p=2) / standardize_vec ((x - mean) / (std + 1e-12), unbiased
+ *           std) called at box_emb_head.py:207-210 between emb_pred and cls_score, and at :228-234 on the class matrix.
+ * x [rows, cols] fp32 (ldx); mode 0 = L2 normalise, 1 = standardise.  dy == NULL: out = normalised rows.
+ * dy [rows, cols] (lddy) given: out = gradient with respect to x (x is the forward input). */
+int loco_row_normalize(const float *x, int64_t ldx, int rows, int cols, int mode, const float *dy, int64_t lddy,
+                       float *out, int64_t ldo, void *stream);
+
 /* Cross-entropy over the scored logits (Detectron2 FastRCNNOutputLayers.losses: F.cross_entropy mean).
  * labels [R] int64 in [0,K1).  loss_sum: 1 fp32, accumulated (caller zero-fills) with sum_r(lse_r -
  * logit[r,label_r]) * scale.  dlogits (may be NULL): [R,K1] (softmax - onehot) * grad_scale written

@@ -36,6 +36,8 @@ SIGNATURES = {
     "loco_linear_tf32_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _i, _i64, _vp]),
     "loco_box_score_workspace_bytes": (_i64, [_i, _i]),
     "loco_box_score_fwd": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "loco_box_softmax": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _i64, _vp]),
+    "loco_row_normalize": (_i, [_vp, _i64, _i, _i, _i, _vp, _i64, _vp, _i64, _vp]),
     "loco_box_ce_fwd_bwd": (_i, [_vp, _i64, _vp, _vp, _i, _i, _f, _vp, _f, _vp, _vp, _i64, _vp]),
     "loco_lsm_masks": (_i, [_vp, _vp, _i64, _vp, _i, _i64, _vp, _vp, _vp]),
     "loco_lsm_prep": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i, _i64, _vp, _vp, _vp]),
@@ -64,11 +66,15 @@ def load():
         if _lib is not None:
             return _lib
         path = _build.lib_path()
-        if not os.path.exists(path):
+        # build() is a no-op while the stamp matches the sources; after a source / header edit the library is rebuilt
+        # before it is bound, so the ctypes signatures below can never meet a stale binary (ABI drift)
+        if not _build.is_current():
             try:
                 _build.build()
             except Exception as e:  # no fallback: fail loudly
-                raise LocoError(f"liblocov_b200.so is missing and could not be built: {e}") from e
+                if not os.path.exists(path):
+                    raise LocoError(f"liblocov_b200.so is missing and could not be built: {e}") from e
+                raise LocoError(f"liblocov_b200.so is older than its sources and could not be rebuilt: {e}") from e
         try:
             lib = ctypes.CDLL(path)
         except OSError as e:

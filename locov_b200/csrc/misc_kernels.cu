@@ -180,6 +180,98 @@ __global__ void __launch_bounds__(256) box_ce_kernel(const float *__restrict__ l
     }
 }
 
+// ---- row softmax statistics over given logits (no GEMM in front) ----------------------------------------------------
+// One warp per RoI row: log-sum-exp over the K1 columns, first-maximum argmax over the K1 - 1 foreground columns and, when
+// requested, the probabilities — the same outputs as the scoring epilogue, for logits that did not come out of it
+// (NORMALIZE_EMB_PRED / STANDARDIZE_EMB_PRED, or a caller-modified score matrix handed to losses / inference).
+__global__ void __launch_bounds__(256) box_softmax_kernel(const float *__restrict__ logits, int64_t ld, int R, int K1, float *__restrict__ lse,
+                                                          int64_t *__restrict__ argmax_fg, float *__restrict__ probs, int64_t ld_probs) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += gridDim.x * wpb) {
+        const float *row = logits + (int64_t)r * ld;
+        float m = -FLT_MAX, best = -FLT_MAX;
+        int arg = 0x7fffffff;
+        for (int c = lane; c < K1; c += 32) {
+            const float v = row[c];
+            m = fmaxf(m, v);
+            if (c < K1 - 1 && v > best) { best = v; arg = c; }       // columns visited in increasing order per lane
+        }
+        m = warp_max(m);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        float s = 0.f;
+        for (int c = lane; c < K1; c += 32) s += expf(row[c] - m);
+        s = warp_sum(s);
+        const float l = m + logf(s);
+        if (lane == 0) {
+            if (lse != nullptr) lse[r] = l;
+            if (argmax_fg != nullptr) argmax_fg[r] = (int64_t)(arg == 0x7fffffff ? 0 : arg);
+        }
+        if (probs != nullptr)
+            for (int c = lane; c < K1; c += 32) probs[(int64_t)r * ld_probs + c] = expf(row[c] - l);
+    }
+}
+
+// ---- row-wise L2 normalisation / standardisation of the projected embeddings (logged_module.py:55-72) ---------------
+// mode 0: y = x / max(||x||_2, 1e-12)        (F.normalize)
+// mode 1: y = (x - mean) / (std + 1e-12), std with Bessel's correction (torch.std default)
+// One warp per row.  Backward (dy -> dx) in the same kernel when `dy` is given: x is the forward INPUT.
+__global__ void __launch_bounds__(256) row_normalize_kernel(const float *__restrict__ x, int64_t ldx, int rows, int cols, int mode,
+                                                            const float *__restrict__ dy, int64_t lddy, float *__restrict__ out, int64_t ldo) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+        const float *xr = x + (int64_t)r * ldx;
+        float *o = out + (int64_t)r * ldo;
+        float s1 = 0.f;
+        for (int c = lane; c < cols; c += 32) s1 += xr[c];
+        s1 = warp_sum(s1);
+        const float mean = mode == 1 ? s1 / (float)cols : 0.f;
+        float s2 = 0.f;
+        for (int c = lane; c < cols; c += 32) { const float d = xr[c] - mean; s2 = fmaf(d, d, s2); }
+        s2 = warp_sum(s2);
+        if (mode == 0) {
+            const float nrm = sqrtf(s2), den = fmaxf(nrm, 1e-12f);
+            if (dy == nullptr) {
+                for (int c = lane; c < cols; c += 32) o[c] = xr[c] / den;
+            } else {
+                const float *g = dy + (int64_t)r * lddy;
+                float dot = 0.f;
+                for (int c = lane; c < cols; c += 32) dot = fmaf(g[c], xr[c], dot);
+                dot = warp_sum(dot);
+                // y = x / den; den = ||x|| unless clamped (then it is a constant)
+                const float k = nrm > 1e-12f ? dot / (den * den * den) : 0.f;
+                for (int c = lane; c < cols; c += 32) o[c] = g[c] / den - xr[c] * k;
+            }
+        } else {
+            const float sd = cols > 1 ? sqrtf(s2 / (float)(cols - 1)) : nanf("");
+            const float den = sd + 1e-12f;
+            if (dy == nullptr) {
+                for (int c = lane; c < cols; c += 32) o[c] = (xr[c] - mean) / den;
+            } else {
+                const float *g = dy + (int64_t)r * lddy;
+                float gs = 0.f, gc = 0.f;
+                for (int c = lane; c < cols; c += 32) { gs += g[c]; gc = fmaf(g[c], xr[c] - mean, gc); }
+                gs = warp_sum(gs);
+                gc = warp_sum(gc);
+                // dL/dc = g/den - (sum g c) / den^2 * c / (sd (n-1));  dx = dL/dc - mean(dL/dc), and sum(c) = 0
+                const float k = sd > 0.f ? gc / (den * den * sd * (float)(cols - 1)) : 0.f;
+                const float gm = gs / ((float)cols * den);
+                for (int c = lane; c < cols; c += 32) o[c] = g[c] / den - (xr[c] - mean) * k - gm;
+            }
+        }
+    }
+}
+
 // ---- pair-matrix losses (single CTA; the matrix is at most a few hundred KB) ----------------------------------
 // Both reductions return the block-wide result to EVERY thread (broadcast through red[0]).
 __device__ __forceinline__ float block_reduce_max(float v, float *red) {
@@ -558,6 +650,36 @@ int loco_box_ce_fwd_bwd(const float *logits, int64_t ld_logits, const float *lse
     if (blocks > 148 * 8) blocks = 148 * 8;
     LOCO_CUDA(launch_kernel(box_ce_kernel, dim3(blocks), dim3(wpb * 32), 0, static_cast<cudaStream_t>(stream), 1, logits, ld_logits, lse, labels, R, K1,
                             scale, loss_sum, grad_scale, dlogits_f32, dlogits_bf16, ld_bf16));
+    count_launch();
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+int loco_box_softmax(const float *logits, int64_t ld_logits, int R, int K1, float *lse, int64_t *argmax_fg, float *probs,
+                     int64_t ld_probs, void *stream) {
+    LOCO_REQUIRE(R >= 0 && K1 >= 1 && ld_logits >= K1, LOCO_E_BADARG, "box_softmax: bad shape R=%d K1=%d ld=%lld", R, K1, (long long)ld_logits);
+    if (R == 0) return LOCO_OK;
+    LOCO_REQUIRE(logits && (lse || argmax_fg || probs), LOCO_E_BADARG, "box_softmax: null pointer / no output requested");
+    LOCO_REQUIRE(probs == nullptr || ld_probs >= K1, LOCO_E_BADARG, "box_softmax: ld_probs < K1");
+    int blocks = (R + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    LOCO_CUDA(launch_kernel(box_softmax_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, logits, ld_logits, R, K1, lse,
+                            argmax_fg, probs, ld_probs));
+    count_launch();
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+int loco_row_normalize(const float *x, int64_t ldx, int rows, int cols, int mode, const float *dy, int64_t lddy, float *out, int64_t ldo,
+                       void *stream) {
+    LOCO_REQUIRE(rows >= 0 && cols >= 1 && ldx >= cols && ldo >= cols && (mode == 0 || mode == 1), LOCO_E_BADARG,
+                 "row_normalize: bad arguments rows=%d cols=%d mode=%d", rows, cols, mode);
+    if (rows == 0) return LOCO_OK;
+    LOCO_REQUIRE(x && out && (dy == nullptr || lddy >= cols), LOCO_E_BADARG, "row_normalize: null pointer or lddy < cols");
+    int blocks = (rows + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    LOCO_CUDA(launch_kernel(row_normalize_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, x, ldx, rows, cols, mode, dy, lddy,
+                            out, ldo));
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;

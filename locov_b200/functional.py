@@ -41,7 +41,15 @@ def _acc(precision: str) -> bool:
 # Parameters are aliased between modules (v2l_projection <-> emb_pred weight tying), so the cache is
 # keyed on storage identity + version counter, never on the module.
 # ------------------------------------------------------------------------------------------------
+# Freshness rule: a shadow is served only while (a) the SAME tensor object is alive, (b) its autograd version counter is
+# unchanged and (c) the tensor does not require grad.  (c) closes the hole the version counter leaves: an in-place update
+# through ``param.data`` (EMA helpers, hand-written SGD, weight surgery) does NOT bump ``param._version``; a trainable
+# parameter changes every step anyway, so its shadow is simply re-converted on every call (one 3 us HBM pass for the
+# 768 x 2048 projection).  Frozen tensors (requires_grad False: the class-embedding matrix, FREEZE_EMB_PRED weights) keep
+# their shadow; after editing one of those through ``.data`` call ``clear_weight_cache()``, or set
+# LOCOV_B200_WEIGHT_CACHE=0 to disable caching altogether.
 _wcache = {}
+WEIGHT_CACHE = os.environ.get("LOCOV_B200_WEIGHT_CACHE", "1") != "0"
 
 
 def weight_operand(w: torch.Tensor, accurate: bool, transpose: bool = False, tag: str = "") -> ops.Bf16Operand:
@@ -50,9 +58,9 @@ def weight_operand(w: torch.Tensor, accurate: bool, transpose: bool = False, tag
     ver = w._version
     # identity check through a weak reference: a freed parameter's address (and version count) can be
     # re-used by a new tensor, which must never be served the old shadow.
-    if ent is not None and ent[0] == ver and ent[2]() is w:
+    if WEIGHT_CACHE and not w.requires_grad and ent is not None and ent[0] == ver and ent[2]() is w:
         return ent[1]
-    reuse = ent[1] if (ent is not None and ent[2]() is w) else None
+    reuse = ent[1] if (ent is not None and ent[2]() is w and not torch.cuda.is_current_stream_capturing()) else None
     op = ops.split_bf16(w.detach(), accurate, transpose=transpose, out=reuse)
     _wcache[key] = (ver, op, weakref.ref(w))
     if len(_wcache) > 256:      # parameters re-created by set_class_embeddings: drop dead / oldest shadows
@@ -62,7 +70,9 @@ def weight_operand(w: torch.Tensor, accurate: bool, transpose: bool = False, tag
 
 
 def clear_weight_cache():
+    """Drop every cached bf16 weight shadow (call after modifying a FROZEN weight through ``.data``)."""
     _wcache.clear()
+    _cat_cache.clear()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -215,7 +225,7 @@ def _cat_weight(w_emb, w_box):
     ver = (w_emb._version, w_box._version)
     ent = _cat_cache.get(key)
     alive = ent is not None and ent[2]() is w_emb and ent[3]() is w_box
-    if alive and ent[0] == ver:
+    if alive and ent[0] == ver and WEIGHT_CACHE and not (w_emb.requires_grad or w_box.requires_grad):
         return ent[1]
     if alive:
         cat = ent[1]
@@ -235,6 +245,62 @@ def box_predict(x, w_emb, b_emb, w_box, b_box, w_cls, b_cls=None, precision="fp3
     aux = []
     scores, deltas = _BoxPredict.apply(x, w_emb, b_emb, w_box, b_box, w_cls, b_cls, precision, want_probs, aux)
     return scores, deltas, aux[0]
+
+
+class _BoxScore(Function):
+    """scores = e · W_cls^T + b_cls with the fused softmax statistics, for embeddings that are NOT the direct output of the
+    projection GEMM (a row-wise normalisation sits in between: box_emb_head.py:207-211)."""
+
+    @staticmethod
+    def forward(ctx, e, w_cls, b_cls, precision, want_probs, aux_box):
+        acc = _acc(precision)
+        e_op = ops.split_bf16(e.contiguous(), acc)
+        logits, probs, lse, arg = ops.box_score(e_op, weight_operand(w_cls, acc), b_cls, want_probs)
+        aux_box.append(BoxScoreAux(lse, probs, arg))
+        ctx.save_for_backward(w_cls)
+        ctx.precision = precision
+        return logits
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dscores):
+        (w_cls,) = ctx.saved_tensors
+        acc = _acc(ctx.precision)
+        de = None
+        if ctx.needs_input_grad[0]:
+            de, _ = ops.linear_fwd(ops.split_bf16(dscores.contiguous(), acc), weight_operand(w_cls, acc, transpose=True), None, want_f32=True)
+        return de, None, None, None, None, None
+
+
+def box_score(e, w_cls, b_cls=None, precision="fp32", want_probs=True):
+    """Returns (scores, BoxScoreAux); the class matrix is a frozen input (box_emb_head.py:233-236)."""
+    aux = []
+    scores = _BoxScore.apply(e, w_cls, b_cls, precision, want_probs, aux)
+    return scores, aux[0]
+
+
+class _RowNormalize(Function):
+    """normalize_vec / standardize_vec (logged_module.py:55-72) on the rows of a 2-D tensor, forward and backward on the device."""
+
+    @staticmethod
+    def forward(ctx, x, mode):
+        ctx.save_for_backward(x)
+        ctx.mode = mode
+        return ops.row_normalize(x, mode)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.row_normalize(x, ctx.mode, dy=dy.contiguous()), None
+
+
+def normalize_rows(x):
+    return _RowNormalize.apply(x.to(torch.float32).contiguous(), ops.NORM_L2)
+
+
+def standardize_rows(x):
+    return _RowNormalize.apply(x.to(torch.float32).contiguous(), ops.NORM_STANDARDIZE)
 
 
 class _BoxCE(Function):

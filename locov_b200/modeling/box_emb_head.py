@@ -8,14 +8,16 @@ Kept: constructor keywords, ``from_config`` keys, parameter names and layouts (`
 New: the three GEMMs run on the tcgen05 kernels with softmax / log-sum-exp / argmax fused into the
 scoring epilogue (locov_b200.functional.box_predict); ``losses`` re-uses the fused statistics.
 """
+import contextlib
 import math
 from typing import Dict, List, Tuple, Union
 
 import torch
 from torch import nn
-from torch.nn import functional as F
 
 from .. import functional as LF
+from .. import ops
+from .configurable import configurable
 from .logged_module import normalize_vec, standardize_vec
 from .registry import BOX_PREDICTORS
 from .structures import Boxes, Instances, ShapeSpec
@@ -99,6 +101,11 @@ def fast_rcnn_inference_single_image(boxes, scores, image_shape, score_thresh, n
 
 @BOX_PREDICTORS.register()
 class EmbeddingFastRCNNOutputLayers(nn.Module):
+    """Constructible both ways the reference's class is (box_emb_head.py:67-177): ``cls(input_shape, *, box2box_transform=...,
+    ...)`` with explicit arguments, or ``cls(cfg, input_shape)`` — what ``build_box_predictor`` does (:249) — which goes
+    through ``from_config``."""
+
+    @configurable
     def __init__(self, input_shape, *, box2box_transform=None, num_classes: int = 80, test_score_thresh: float = 0.0,
                  test_nms_thresh: float = 0.5, test_topk_per_image: int = 100, cls_agnostic_bbox_reg: bool = False,
                  smooth_l1_beta: float = 0.0, box_reg_loss_type: str = "smooth_l1",
@@ -106,9 +113,6 @@ class EmbeddingFastRCNNOutputLayers(nn.Module):
                  freeze_emb_pred: bool = True, normalize_emb: bool = False, standardize_emb: bool = False,
                  detach_cls_predictor: bool = False, precision: str = "fp32"):
         super().__init__()
-        if not isinstance(input_shape, int) and not hasattr(input_shape, "channels"):
-            # (cfg, input_shape) calling convention of @configurable / build_box_predictor
-            raise TypeError("use EmbeddingFastRCNNOutputLayers.from_cfg(cfg, input_shape) to build from a config")
         if isinstance(input_shape, int):
             input_shape = ShapeSpec(channels=input_shape)
         num_inputs = input_shape.channels * (input_shape.width or 1) * (input_shape.height or 1)
@@ -121,9 +125,9 @@ class EmbeddingFastRCNNOutputLayers(nn.Module):
         self.test_nms_thresh = test_nms_thresh
         self.test_topk_per_image = test_topk_per_image
         self.box_reg_loss_type = box_reg_loss_type
-        if isinstance(loss_weight, float):
-            loss_weight = {"loss_cls": loss_weight, "loss_box_reg": loss_weight}
-        self.loss_weight = dict(loss_weight)
+        if isinstance(loss_weight, (int, float)):
+            loss_weight = {"loss_cls": float(loss_weight), "loss_box_reg": float(loss_weight)}
+        self.loss_weight = dict(loss_weight)      # a missing key weighs 1.0 (Detectron2: loss_weight.get(k, 1.0))
         self.precision = precision
 
         box_dim = len(self.box2box_transform.weights)
@@ -169,18 +173,14 @@ class EmbeddingFastRCNNOutputLayers(nn.Module):
             "normalize_emb": cfg.MODEL.ROI_BOX_HEAD.NORMALIZE_EMB_PRED,
             "standardize_emb": cfg.MODEL.ROI_BOX_HEAD.STANDARDIZE_EMB_PRED,
             "detach_cls_predictor": cfg.MODEL.ROI_HEADS.DETACH_CLASS_PREDICTOR,
+            # the one key this package adds (optional): tensor-core operand mode, "fp32" (reference numerics) or "bf16"
+            "precision": getattr(getattr(cfg.MODEL, "B200", None), "PRECISION", "fp32"),
         }
 
     @classmethod
     def from_cfg(cls, cfg, input_shape):
-        kw = cls.from_config(cfg, input_shape)
-        shape = kw.pop("input_shape")
-        lw = kw["loss_weight"]
-        kw["loss_weight"] = {"loss_cls": 1.0, **lw}
-        b200 = getattr(cfg.MODEL, "B200", None)
-        if b200 is not None and hasattr(b200, "PRECISION"):
-            kw["precision"] = b200.PRECISION
-        return cls(shape, **kw)
+        """Explicit spelling of ``cls(cfg, input_shape)`` (kept from round 1)."""
+        return cls(cfg, input_shape)
 
     # ---- forward (box_emb_head.py:179-212) ------------------------------------------------------------
     def forward(self, x):
@@ -207,23 +207,37 @@ class EmbeddingFastRCNNOutputLayers(nn.Module):
         return scores, deltas
 
     def _forward_unfused(self, x):
-        """NORMALIZE_EMB_PRED / STANDARDIZE_EMB_PRED (both off in the shipped configs, config.py:131,133):
-        the row-wise normalisation sits between the two GEMMs, so they run as separate kernels."""
+        """NORMALIZE_EMB_PRED / STANDARDIZE_EMB_PRED (both off in the shipped configs, config.py:131,133): the row-wise
+        normalisation sits between the two GEMMs, so projection, normalisation and scoring are three launches — the
+        scoring one still carries the fused softmax statistics."""
         deltas = LF.linear(x, self.bbox_pred.weight, self.bbox_pred.bias, self.precision)
-        ctx = torch.no_grad() if self.detach_cls_predictor else torch.enable_grad()
-        with ctx:
+        with (torch.no_grad() if self.detach_cls_predictor else contextlib.nullcontext()):
             xs = x.detach() if self.detach_cls_predictor else x
-            scores = self.forward_cls_prediction(xs)
-        self._aux = None
+            scores, aux = self._scores_unfused(xs)
+        self._aux = (scores, aux)
         return scores, deltas
 
-    def forward_cls_prediction(self, x):
+    def _scores_unfused(self, x):
         e = LF.linear(x, self.emb_pred.weight, self.emb_pred.bias, self.precision)
         if self.normalize_emb:
-            e = normalize_vec(e, dim=1)
+            e = LF.normalize_rows(e)
         if self.standardize_emb:
-            e = standardize_vec(e, dim=1)
-        return LF.linear(e, self.cls_score.weight, self.cls_score.bias, self.precision)
+            e = LF.standardize_rows(e)
+        return LF.box_score(e, self.cls_score.weight, self.cls_score.bias, self.precision, want_probs=not self.training)
+
+    def forward_cls_prediction(self, x):
+        """box_emb_head.py:204-212 (scores only)."""
+        if x.dim() > 2:
+            x = torch.flatten(x, start_dim=1)
+        x = x.to(torch.float32).contiguous()
+        if self.normalize_emb or self.standardize_emb:
+            scores, aux = self._scores_unfused(x)
+        else:
+            ep, bp, cs = self.emb_pred, self.bbox_pred, self.cls_score
+            scores, _, aux = LF.box_predict(x, ep.weight, ep.bias, bp.weight, bp.bias, cs.weight, cs.bias, self.precision,
+                                            want_probs=not self.training)
+        self._aux = (scores, aux)
+        return scores
 
     # ---- text matrix (box_emb_head.py:214-236) ----------------------------------------------------------
     def set_class_embeddings(self, embs):
@@ -237,10 +251,12 @@ class EmbeddingFastRCNNOutputLayers(nn.Module):
             embs = torch.tensor(embs, device=device, dtype=torch.float32)
         if self.normalize_emb or self.standardize_emb:
             assert embs.shape[1] == self.emb_dim, "The embedding dimension has to match the one saved in the model"
+        # one-off preparation of the text matrix: on the device when the module already lives there (the reference calls this
+        # after .to(device), trainer.py:365-407), with the host formulas of logged_module.py:55-72 while it is still on the CPU
         if self.normalize_emb:
-            embs = normalize_vec(embs, dim=1)
+            embs = LF.normalize_rows(embs) if embs.is_cuda else normalize_vec(embs, dim=1)
         if self.standardize_emb:
-            embs = standardize_vec(embs, dim=1)
+            embs = LF.standardize_rows(embs) if embs.is_cuda else standardize_vec(embs, dim=1)
         self.cls_score.weight.data = embs
         self.cls_score.bias.data = torch.zeros_like(self.cls_score.bias.data)
         self.cls_score.weight.requires_grad = False
@@ -248,10 +264,17 @@ class EmbeddingFastRCNNOutputLayers(nn.Module):
         self._aux = None
 
     # ---- Detectron2 FastRCNNOutputLayers behaviour ------------------------------------------------------
-    def _fused_aux(self, scores):
+    def _fused_aux(self, scores, want_probs=False):
+        """Softmax statistics of ``scores``: the ones the scoring epilogue produced when ``scores`` is the tensor the last
+        forward returned, otherwise computed from the given matrix by one bandwidth kernel (loco_box_softmax)."""
         if self._aux is not None and self._aux[0] is scores:
-            return self._aux[1]
-        return None
+            aux = self._aux[1]
+            if not want_probs or aux.probs is not None:
+                return aux
+        lse, arg, probs = ops.box_softmax(scores.detach().to(torch.float32), want_probs=want_probs)
+        aux = LF.BoxScoreAux(lse, probs, arg)
+        self._aux = (scores, aux)
+        return aux
 
     def losses(self, predictions, proposals):
         scores, proposal_deltas = predictions
@@ -262,43 +285,38 @@ class EmbeddingFastRCNNOutputLayers(nn.Module):
             gt_boxes = _cat([_box_tensor(p.gt_boxes if p.has("gt_boxes") else p.proposal_boxes) for p in proposals], 0)
         else:
             proposal_boxes = gt_boxes = torch.empty((0, 4), device=proposal_deltas.device)
-        aux = self._fused_aux(scores)
         if scores.shape[0] == 0:
             loss_cls = scores.sum() * 0.0
-        elif aux is not None and scores.is_cuda:
-            loss_cls = LF.box_cross_entropy(scores, aux.lse, gt_classes)
         else:
-            loss_cls = F.cross_entropy(scores, gt_classes, reduction="mean")
+            loss_cls = LF.box_cross_entropy(scores, self._fused_aux(scores).lse, gt_classes)
         losses = {"loss_cls": loss_cls,
                   "loss_box_reg": self.box_reg_loss(proposal_boxes, gt_boxes, proposal_deltas, gt_classes)}
         return {k: v * self.loss_weight.get(k, 1.0) for k, v in losses.items()}
 
     def box_reg_loss(self, proposal_boxes, gt_boxes, pred_deltas, gt_classes):
+        """Detectron2 box_reg_loss (smooth-L1 over the foreground rows, summed, / max(R, 1)) as a masked sum over ALL rows:
+        no ``nonzero`` (a host synchronisation per step in the stock implementation), same value and gradients."""
         box_dim = proposal_boxes.shape[1]
-        fg_inds = torch.nonzero((gt_classes >= 0) & (gt_classes < self.num_classes), as_tuple=True)[0]
-        fg_pred_deltas = pred_deltas[fg_inds] if pred_deltas.shape[1] == box_dim else \
-            pred_deltas.view(-1, self.num_classes, box_dim)[fg_inds, gt_classes[fg_inds]]
         if self.box_reg_loss_type != "smooth_l1":
             raise NotImplementedError(f"box_reg_loss_type {self.box_reg_loss_type!r} (shipped configs use smooth_l1)")
-        tgt = self.box2box_transform.get_deltas(proposal_boxes[fg_inds], gt_boxes[fg_inds])
-        if self.smooth_l1_beta < 1e-5:
-            loss = torch.abs(fg_pred_deltas - tgt).sum()
-        else:
-            n = torch.abs(fg_pred_deltas - tgt)
-            loss = torch.where(n < self.smooth_l1_beta, 0.5 * n ** 2 / self.smooth_l1_beta, n - 0.5 * self.smooth_l1_beta).sum()
+        assert pred_deltas.shape[1] == box_dim, "class-agnostic box regression only (box_emb_head.py:137)"
+        fg = ((gt_classes >= 0) & (gt_classes < self.num_classes))[:, None]
+        tgt = self.box2box_transform.get_deltas(proposal_boxes, gt_boxes)
+        tgt = torch.where(fg, tgt, torch.zeros_like(tgt))          # background rows may hold degenerate gt boxes (log of <= 0)
+        n = torch.abs(pred_deltas - tgt)
+        if self.smooth_l1_beta >= 1e-5:
+            n = torch.where(n < self.smooth_l1_beta, 0.5 * n ** 2 / self.smooth_l1_beta, n - 0.5 * self.smooth_l1_beta)
+        loss = torch.where(fg, n, torch.zeros_like(n)).sum()
         return loss / max(gt_classes.numel(), 1.0)
 
     def predict_probs(self, predictions, proposals):
         scores, _ = predictions
-        aux = self._fused_aux(scores)
-        probs = aux.probs if (aux is not None and aux.probs is not None) else F.softmax(scores, dim=-1)
-        return probs.split([len(p) for p in proposals], dim=0)
+        return self._fused_aux(scores, want_probs=True).probs.split([len(p) for p in proposals], dim=0)
 
     def predict_classes(self, predictions):
         """Per-RoI argmax over the K foreground columns (int64), from the fused epilogue."""
         scores, _ = predictions
-        aux = self._fused_aux(scores)
-        return aux.argmax_fg if aux is not None else F.softmax(scores, -1)[:, :-1].argmax(1)
+        return self._fused_aux(scores).argmax_fg
 
     def predict_boxes(self, predictions, proposals):
         if not len(proposals):
@@ -324,4 +342,4 @@ def build_box_predictor(cfg, input_shape):
     if name not in BOX_PREDICTORS:
         raise KeyError(f"box predictor {name!r} is not part of the B200 region-text path "
                        f"(available: {sorted(BOX_PREDICTORS)})")
-    return BOX_PREDICTORS[name].from_cfg(cfg, input_shape)
+    return BOX_PREDICTORS[name](cfg, input_shape)

@@ -14,15 +14,24 @@ import torch
 from torch import nn
 
 from .box_emb_head import build_box_predictor
+from .configurable import configurable
 from .poolers import ROIPooler
 from .registry import ROI_HEADS_REGISTRY
+from .res5 import build_res5_block
 
 
 @ROI_HEADS_REGISTRY.register()
 class EmbeddingRes5ROIHeads(nn.Module):
+    """Constructible both ways the reference's class is (roi_emb_heads.py:129-214): with explicit keyword arguments, or as
+    ``EmbeddingRes5ROIHeads(cfg, input_shape)`` — the call Detectron2's ``build_roi_heads`` makes — which goes through
+    ``from_config``.  Keyword arguments of Detectron2's ``ROIHeads`` base (``num_classes``, ``batch_size_per_image``,
+    ``positive_fraction``, ``proposal_matcher``, ``proposal_append_gt``) are accepted and kept as attributes."""
+
+    @configurable
     def __init__(self, *, in_features: List[str], pooler: ROIPooler, res5: nn.Module, box_predictor: nn.Module,
                  mask_head: Optional[nn.Module] = None, output_shape: Optional[int] = 0,
-                 proposal_sampler: Optional[Callable] = None, num_classes: Optional[int] = None, **kwargs):
+                 proposal_sampler: Optional[Callable] = None, num_classes: Optional[int] = None, batch_size_per_image: int = 512,
+                 positive_fraction: float = 0.25, proposal_matcher=None, proposal_append_gt: bool = True):
         super().__init__()
         if mask_head is not None:
             raise NotImplementedError("mask heads are dead code in the reference (roi_emb_heads.py:206,268: un-imported helpers)")
@@ -35,24 +44,52 @@ class EmbeddingRes5ROIHeads(nn.Module):
         self.box_predictor = box_predictor
         self.mask_on = False
         self.num_classes = num_classes
+        self.batch_size_per_image = batch_size_per_image
+        self.positive_fraction = positive_fraction
+        self.proposal_matcher = proposal_matcher
+        self.proposal_append_gt = proposal_append_gt
         self.proposal_sampler = proposal_sampler
 
     @classmethod
-    def from_cfg(cls, cfg, input_shape, res5: nn.Module, out_channels: int = None, proposal_sampler=None):
-        """Mirror of from_config (:168-214); ``res5`` is supplied by the caller (Detectron2's
-        ``_build_res5_block`` result) because the conv stage is outside this package's scope."""
-        in_features = cfg.MODEL.ROI_HEADS.IN_FEATURES
+    def from_config(cls, cfg, input_shape, res5: Optional[nn.Module] = None, out_channels: Optional[int] = None,
+                    proposal_sampler: Optional[Callable] = None):
+        """roi_emb_heads.py:168-214.  ``res5`` may be injected (e.g. a channels-last / bf16 variant of the stage); by default it
+        is built by ``_build_res5_block`` exactly as the reference does."""
+        roi = cfg.MODEL.ROI_HEADS
+        in_features = roi.IN_FEATURES
         assert not cfg.MODEL.KEYPOINT_ON
         assert len(in_features) == 1
+        if getattr(cfg.MODEL, "MASK_ON", False):
+            raise NotImplementedError("MODEL.MASK_ON: the reference's mask path calls un-imported helpers (roi_emb_heads.py:206)")
         stride = input_shape[in_features[0]].stride
-        pooler = ROIPooler(output_size=cfg.MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION, scales=(1.0 / stride,),
-                           sampling_ratio=cfg.MODEL.ROI_BOX_HEAD.POOLER_SAMPLING_RATIO,
-                           pooler_type=cfg.MODEL.ROI_BOX_HEAD.POOLER_TYPE)
-        if out_channels is None:
+        ret = {
+            "in_features": in_features,
+            "num_classes": roi.NUM_CLASSES,
+            "batch_size_per_image": roi.BATCH_SIZE_PER_IMAGE,
+            "positive_fraction": roi.POSITIVE_FRACTION,
+            "proposal_append_gt": getattr(roi, "PROPOSAL_APPEND_GT", True),
+            "proposal_sampler": proposal_sampler,
+            "pooler": ROIPooler(output_size=cfg.MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION, scales=(1.0 / stride,),
+                                sampling_ratio=cfg.MODEL.ROI_BOX_HEAD.POOLER_SAMPLING_RATIO,
+                                pooler_type=cfg.MODEL.ROI_BOX_HEAD.POOLER_TYPE),
+        }
+        if res5 is None:
+            res5, out_channels = cls._build_res5_block(cfg)
+        elif out_channels is None:
             out_channels = cfg.MODEL.RESNETS.RES2_OUT_CHANNELS * 8
-        return cls(in_features=in_features, pooler=pooler, res5=res5,
-                   box_predictor=build_box_predictor(cfg, input_shape=out_channels), output_shape=out_channels,
-                   proposal_sampler=proposal_sampler, num_classes=cfg.MODEL.ROI_HEADS.NUM_CLASSES)
+        ret["res5"] = res5
+        ret["box_predictor"] = build_box_predictor(cfg, input_shape=out_channels)
+        ret["output_shape"] = out_channels
+        return ret
+
+    @classmethod
+    def from_cfg(cls, cfg, input_shape, res5: Optional[nn.Module] = None, out_channels: Optional[int] = None, proposal_sampler=None):
+        """Explicit spelling of ``cls(cfg, input_shape, ...)`` (kept from round 1)."""
+        return cls(cfg, input_shape, res5=res5, out_channels=out_channels, proposal_sampler=proposal_sampler)
+
+    @classmethod
+    def _build_res5_block(cls, cfg):
+        return build_res5_block(cfg)
 
     def label_and_sample_proposals(self, proposals, targets):
         if self.proposal_sampler is None:

@@ -4,6 +4,7 @@ PyTorch is used for device memory and streams only; every computation below is a
 liblocov_b200.so.  All functions require CUDA tensors and raise ``LocoError`` on failure — there is
 no eager/CPU fallback.
 """
+import threading
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -40,8 +41,13 @@ def _round_up(x, m):
 _ws_cache = {}
 
 
+def _ws_key(device, tag):
+    # scratch is private to a (device, stream, host thread): two streams or the autograd thread never share tickets / scratch
+    return (device.index, tag, torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
+
+
 def _workspace(device, nbytes, tag):
-    key = (device.index, tag)
+    key = _ws_key(device, tag)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
@@ -51,12 +57,17 @@ def _workspace(device, nbytes, tag):
 
 def _zero_workspace(device, nbytes, tag):
     """Scratch that is zero-initialised once and that the kernels leave zeroed (ticket counters)."""
-    key = (device.index, tag, "zero")
+    key = _ws_key(device, tag) + ("zero",)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.zeros(max(int(nbytes), 16), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
+
+
+def _drop_zero_workspace(device, tag):
+    """After a failed launch the ticket counters may be non-zero: forget the buffer (a fresh zeroed one is made next call)."""
+    _ws_cache.pop(_ws_key(device, tag) + ("zero",), None)
 
 
 def roi_align(feat: torch.Tensor, rois: torch.Tensor, output_size, spatial_scale: float, sampling_ratio: int = 0,
@@ -94,8 +105,9 @@ def roi_align_backward(dout: torch.Tensor, feat_shape, rois: torch.Tensor, spati
     lib = _lib.load()
     nbytes = int(lib.loco_roi_align_bwd_workspace_bytes(n, c, h, w, r))
     ws = _workspace(dout.device, nbytes, "roi_align_bwd") if nbytes > 0 else None
-    # vectorised path: dfeat is fully overwritten; scalar path (C % 4 != 0): accumulated into a zero-filled map
-    dfeat = (torch.empty if ws is not None else torch.zeros)(feat_shape, dtype=torch.float32, device=dout.device)
+    # always zero-filled: the vectorised path overwrites it, but the library may decline that path (R == 0, pooled sizes whose
+    # staging exceeds shared memory, LOCOV_B200_ROI_BWD_V4=0, huge maps) and accumulate with scalar atomics instead
+    dfeat = torch.zeros(feat_shape, dtype=torch.float32, device=dout.device)
     _lib.check(lib.loco_roi_align_bwd(_p(dout), n, c, h, w, _p(rois), r, ph, pw, float(spatial_scale),
                                       int(sampling_ratio), int(bool(aligned)), _p(dfeat), _p(ws), _stream(dout)),
                "loco_roi_align_bwd")
@@ -266,6 +278,43 @@ def box_ce(logits: torch.Tensor, lse: torch.Tensor, labels: torch.Tensor, want_g
     return loss, dl, dlb
 
 
+def box_softmax(logits: torch.Tensor, want_probs: bool = False):
+    """Softmax statistics of an existing score matrix [R,K1]: returns (lse [R], argmax_fg [R] i64, probs or None)."""
+    _need_cuda(logits)
+    if logits.dim() != 2 or logits.dtype != torch.float32:
+        raise LocoError("box_softmax: expects a 2-D fp32 score matrix")
+    if logits.stride(1) != 1:
+        logits = logits.contiguous()
+    r, k1 = logits.shape
+    dev = logits.device
+    lse = torch.empty((r,), dtype=torch.float32, device=dev)
+    arg = torch.empty((r,), dtype=torch.int64, device=dev)
+    probs = torch.empty((r, k1), dtype=torch.float32, device=dev) if want_probs else None
+    _lib.check(_lib.load().loco_box_softmax(_p(logits), logits.stride(0) if r else k1, r, k1, _p(lse), _p(arg), _p(probs), k1, _stream(logits)),
+               "loco_box_softmax")
+    return lse, arg, probs
+
+
+NORM_L2, NORM_STANDARDIZE = 0, 1
+
+
+def row_normalize(x: torch.Tensor, mode: int, dy: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Row-wise L2 normalisation (mode 0) / standardisation (mode 1) of x [rows, cols]; with ``dy`` the gradient w.r.t. x."""
+    _need_cuda(x, dy)
+    if x.dim() != 2 or x.dtype != torch.float32:
+        raise LocoError("row_normalize: expects a 2-D fp32 tensor")
+    x = x if x.stride(1) == 1 else x.contiguous()
+    if dy is not None:
+        dy = dy.to(torch.float32)
+        dy = dy if dy.stride(1) == 1 else dy.contiguous()
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().loco_row_normalize(_p(x), x.stride(0) if rows else cols, rows, cols, int(mode), _p(dy),
+                                              (dy.stride(0) if rows else cols) if dy is not None else 0, _p(out), cols, _stream(x)),
+               "loco_row_normalize")
+    return out
+
+
 _REG_KIND = {torch.uint8: 0, torch.bool: 0, torch.float32: 1, torch.int64: 2}
 
 
@@ -405,9 +454,11 @@ def pair_ce(pw: torch.Tensor, cap_mask: torch.Tensor, reg_mask: torch.Tensor, di
     dimg = torch.empty((nmat, bc, bi), dtype=torch.float32, device=pw.device) if want_grad else None
     lib = _lib.load()
     ws = _zero_workspace(pw.device, lib.loco_pair_ce_workspace_bytes(nmat, bc, bi), "pair_ce") if max(bc, bi) > 32 else None
-    _lib.check(lib.loco_pair_ce(_p(pw3), nmat, pw3.stride(0), pw3.stride(1), bc, bi, int(diag_offset), _p(cap_mask),
-                                cap_mask.shape[1], _p(reg_mask), reg_mask.shape[1], _p(out), _p(dcap), _p(dimg), _p(ws),
-                                _stream(pw)), "loco_pair_ce")
+    rc = lib.loco_pair_ce(_p(pw3), nmat, pw3.stride(0), pw3.stride(1), bc, bi, int(diag_offset), _p(cap_mask),
+                          cap_mask.shape[1], _p(reg_mask), reg_mask.shape[1], _p(out), _p(dcap), _p(dimg), _p(ws), _stream(pw))
+    if rc != 0 and ws is not None:
+        _drop_zero_workspace(pw.device, "pair_ce")
+    _lib.check(rc, "loco_pair_ce")
     if single:
         out = out[0]
         dcap = dcap[0] if want_grad else None

@@ -125,8 +125,10 @@ class _ShardedLsm(Function):
             got = gather_packed(parts, group)                 # one grouped NCCL all-gather for operands + masks
             hi_all, mask_all = got[0], got[1]
             lo_all = got[2] if acc else None
-            for x in parts + got:
-                x.record_stream(side)
+            for x in parts:
+                x.record_stream(side)          # allocated on the main stream, read by the side stream
+        for x in got:
+            x.record_stream(main)              # allocated on the side stream, consumed on the main stream
         # 2. projection of the local regions overlaps the gather
         emb_op = LF.project_regions(feats.reshape(bi * rg, v), w, b, d, acc)
         main.wait_stream(side)

@@ -7,8 +7,12 @@ Follows /root/reference/ovr/modeling/roi_heads/box_emb_head.py:
 and the Detectron2 behaviour the class inherits (un-vendored, version unpinned):
 FastRCNNOutputLayers.losses (cross_entropy mean over all R; smooth-L1 over fg / R) and
 .predict_probs / fast_rcnn_inference (softmax, drop background column, per-RoI argmax).
-The reference class cannot be imported without Detectron2 and the reference holds no golden vectors
-for it: parity unpinned beyond torch's own F.linear / F.cross_entropy / F.softmax primitives.
+PINNED (round 2): the reference class IS importable once the handful of Detectron2 symbols it touches are stubbed
+(oracle/d2_stubs.py restates them; oracle/ref_loader.load_reference_box_head executes the reference's own
+box_emb_head.py unmodified).  tests/golden/box_*.npz hold the outputs of that real class — forward, probabilities,
+losses, gradients, inference, normalise / standardise variants, re-set class embeddings, detached classifier — and
+tests/test_oracle_box.py checks this restatement against every one of them (and against the live class when
+/root/reference is present).  The reference itself ships no tests or golden vectors for this path.
 """
 import torch
 import torch.nn.functional as F
@@ -101,3 +105,39 @@ def make_box_inputs(R, K, V=2048, D=768, seed=1992, bg_frac=0.25):
     gt = torch.randint(0, K, (R,), generator=g)
     gt[torch.rand(R, generator=g) < bg_frac] = K
     return x, w_emb, b_emb, w_box, b_box, cls, gt
+
+
+def make_proposals(n_img, per_img, K, seed=1992, image_size=(320, 480), bg_frac=0.25):
+    """Seeded proposals with labels for Detectron2's ``losses`` / ``inference``: per image a dict
+    {proposal_boxes [Ri,4], gt_boxes [Ri,4], gt_classes [Ri] int64 in [0,K] (K = background)}, boxes inside the image,
+    at least 8 px wide / high (SURVEY.md §8d box distribution, scaled to the image)."""
+    g = torch.Generator().manual_seed(seed)
+    h, w = image_size
+    out = []
+    for _ in range(n_img):
+        cx = torch.rand(per_img, generator=g) * w
+        cy = torch.rand(per_img, generator=g) * h
+        s = 16.0 * (min(h, w) / 16.0) ** torch.rand(per_img, generator=g)
+        a = 0.5 * 4.0 ** torch.rand(per_img, generator=g)
+        bw, bh = s * a.sqrt(), s / a.sqrt()
+        x1 = (cx - bw / 2).clamp(0, w - 9)
+        y1 = (cy - bh / 2).clamp(0, h - 9)
+        x2 = torch.minimum((cx + bw / 2).clamp(0, w), x1 + bw).clamp_min(0)
+        y2 = torch.minimum((cy + bh / 2).clamp(0, h), y1 + bh).clamp_min(0)
+        x2 = torch.maximum(x2, x1 + 8)
+        y2 = torch.maximum(y2, y1 + 8)
+        prop = torch.stack([x1, y1, x2, y2], 1)
+        gtb = prop + torch.randn(per_img, 4, generator=g) * 2.0
+        gtb[:, 2:] = torch.maximum(gtb[:, 2:], gtb[:, :2] + 4)
+        gt = torch.randint(0, K, (per_img,), generator=g)
+        gt[torch.rand(per_img, generator=g) < bg_frac] = K
+        out.append({"proposal_boxes": prop, "gt_boxes": gtb, "gt_classes": gt})
+    return out
+
+
+def instances_from(props, image_size, Instances, Boxes, device=None):
+    """Wrap ``make_proposals`` output in an Instances / Boxes implementation (Detectron2's, the oracle's restatement
+    or the drop-in package's stand-ins)."""
+    mv = (lambda t: t.to(device)) if device is not None else (lambda t: t)
+    return [Instances(image_size, proposal_boxes=Boxes(mv(p["proposal_boxes"])), gt_boxes=Boxes(mv(p["gt_boxes"])),
+                      gt_classes=mv(p["gt_classes"])) for p in props]

@@ -26,6 +26,13 @@ for ps in (14, 7):
     ref = torch.from_numpy(ora.roi_align_fwd(feat.numpy(), rois.numpy(), ps, 1 / 16, 0, True))
     err = float(((out - ref).abs() / ref.abs().clamp(min=ref.pow(2).mean().sqrt())).max())
     assert err < 1e-4, ("roi_align", ps, err)
+fg = feat[:, :24].to(dev).requires_grad_(True)
+out = M.ROIAlign(7, 1 / 16, 0, True)(fg, rois.to(dev))
+dout = torch.randn(out.shape, generator=g).to(dev)
+out.backward(dout)
+ref = torch.from_numpy(ora.roi_align_bwd(dout.cpu().numpy(), (2, 24, 25, 38), rois.numpy(), 1 / 16, 0, True))
+err = float(((fg.grad.cpu() - ref).abs() / ref.abs().clamp(min=ref.pow(2).mean().sqrt())).max())
+assert err < 1e-4, ("roi_align_bwd", err)
 ii, ic, w, b = lsm_head.make_lsm_inputs(B=5, Rg=40, T=9, V=256, D=768, seed=3, gain=5.0, ragged_regions=True)
 for precision, tol in (("fp32", 1e-4), ("bf16", 2e-2)):
     cfg = M.get_cfg("lsm"); cfg.MODEL.B200.PRECISION = precision
@@ -42,7 +49,7 @@ print("env path ok")
 """
 
 
-@pytest.mark.parametrize("env", [{"LOCOV_B200_PDL": "0"}, {"LOCOV_B200_ROI_BULK": "0"}, {"LOCOV_B200_2CTA": "0"},
+@pytest.mark.parametrize("env", [{"LOCOV_B200_PDL": "0"}, {"LOCOV_B200_ROI_BULK": "0"}, {"LOCOV_B200_ROI_BWD_V4": "0"}, {"LOCOV_B200_2CTA": "0"},
                                  {"LOCOV_B200_2CTA": "0", "LOCOV_B200_CLUSTER": "1", "LOCOV_B200_CM": "1", "LOCOV_B200_CN": "2"}])
 def test_alternative_paths_meet_the_parity_bars(cuda_device, env):
     r = subprocess.run([sys.executable, "-c", _CHECK % {"root": ROOT}], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)

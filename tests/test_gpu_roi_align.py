@@ -104,6 +104,29 @@ def test_backward_vs_oracle(cuda_device, c, ps, sr):
     assert relerr(feat.grad.cpu(), ref) < 1e-4
 
 
+@pytest.mark.parametrize("ps", [16, 28])
+def test_backward_large_pooled_sizes(cuda_device, ps):
+    """Pooled sizes whose gradient staging exceeds shared memory (15 x 15 and above): the library declines the vectorised
+    kernel and accumulates with scalar atomics into the (zero-filled) map — same result."""
+    torch.manual_seed(ps)
+    feat = torch.randn(1, 8, 25, 38, device=cuda_device, requires_grad=True)
+    rois = torch.cat([_rois(1, 12, 400, 608, seed=ps), EDGE[:3] * torch.tensor([0, 1, 1, 1, 1.0])]).to(cuda_device)
+    out = M.ROIAlign(ps, 1 / 16, 0, True)(feat, rois)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    ref = ora.roi_align_bwd(dout.cpu().numpy(), (1, 8, 25, 38), rois.cpu().numpy(), 1 / 16, 0, True)
+    assert relerr(feat.grad.cpu(), ref) < 1e-4
+
+
+def test_backward_without_rois_is_zero(cuda_device):
+    g = ops.roi_align_backward(torch.zeros(0, 8, 7, 7, device=cuda_device), (2, 8, 20, 30), torch.zeros(0, 5, device=cuda_device), 1 / 16)
+    assert g.shape == (2, 8, 20, 30) and float(g.abs().max()) == 0.0
+    feat = torch.randn(2, 8, 20, 30, device=cuda_device, requires_grad=True)
+    out = M.ROIAlign(7, 1 / 16, 0, True)(feat, torch.zeros(0, 5, device=cuda_device))
+    out.sum().backward()
+    assert float(feat.grad.abs().max()) == 0.0
+
+
 def test_full_size_properties(cuda_device):
     """BASELINE config 1 size (2 x 512 RoIs, [2,1024,50,76] -> [1024,1024,14,14]): linearity and
     agreement with the oracle on a channel subset (the oracle is scalar C: a subset keeps it in seconds)."""
@@ -116,6 +139,10 @@ def test_full_size_properties(cuda_device):
     assert torch.equal(b, 2.0 * a)                       # exact: scaling by 2 commutes with every rounding
     ones = ops.roi_align(torch.ones_like(f[:, :32]), r, 14, 1 / 16)
     assert float((ones - 1).abs().max()) < 1e-5           # in-image boxes: bilinear weights sum to one
-    sub = [0, 1, 511, 512, 1023]
+    # every channel against the oracle for a spread of RoIs (all 1024 channels x 64 RoIs), a channel subset for all RoIs
+    pick = torch.arange(0, 1024, 16)
+    ref = torch.from_numpy(ora.roi_align_fwd(feat.numpy(), rois[pick].numpy(), 14, 1 / 16, 0, True))
+    assert relerr(a[pick].cpu(), ref) < 1e-4
+    sub = [0, 1, 127, 128, 511, 512, 1023]
     ref = torch.from_numpy(ora.roi_align_fwd(feat[:, sub].numpy(), rois.numpy(), 14, 1 / 16, 0, True))
     assert relerr(a[:, sub].cpu(), ref) < 1e-4

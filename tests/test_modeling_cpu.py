@@ -79,3 +79,60 @@ def test_pooler_box_format():
     from locov_b200.modeling.poolers import convert_boxes_to_pooler_format
     r = convert_boxes_to_pooler_format([M.Boxes(torch.ones(2, 4)), M.Boxes(torch.zeros(0, 4)), M.Boxes(2 * torch.ones(1, 4))])
     assert r.tolist() == [[0, 1, 1, 1, 1], [0, 1, 1, 1, 1], [2, 2, 2, 2, 2]]
+
+
+# ---- the (cfg, input_shape) construction path Detectron2's build_roi_heads / the reference's build_box_predictor use ----
+from oracle import box_cases  # noqa: E402
+from util import load_golden  # noqa: E402
+
+
+def _small_cfg(stage, cls_name):
+    cfg = M.get_cfg(stage)
+    cfg.MODEL.RESNETS.RES2_OUT_CHANNELS = 8
+    cfg.MODEL.RESNETS.WIDTH_PER_GROUP = 2
+    cfg.MODEL.ROI_BOX_HEAD.EMB_DIM = 32
+    cfg.MODEL.ROI_HEADS.NAME = cls_name
+    cfg.MODEL.ROI_HEADS.NUM_CLASSES = box_cases.ROI_SHAPE["K"]
+    return cfg
+
+
+def test_heads_are_constructible_the_way_the_registries_call_them():
+    """``ROI_HEADS_REGISTRY.get(name)(cfg, input_shape)`` (Detectron2 build_roi_heads) and
+    ``BOX_EMBEDDING_PREDICTORS[name](cfg, input_shape)`` (box_emb_head.py:249)."""
+    for stage, name in (("stt", "EmbeddingRes5ROIHeads"), ("lsm", "EmbeddingProposalsRes5ROIHeads")):
+        cfg = _small_cfg(stage, name)
+        heads = M.ROI_HEADS_REGISTRY.get(cfg.MODEL.ROI_HEADS.NAME)(cfg, {"res4": M.ShapeSpec(channels=32, stride=16)})
+        assert type(heads).__name__ == name and heads.in_features == ["res4"] and heads.output_shape == 64
+        assert heads.num_classes == 6 and heads.batch_size_per_image == cfg.MODEL.ROI_HEADS.BATCH_SIZE_PER_IMAGE
+        assert heads.pooler.output_size == (14, 14) and heads.pooler.level_poolers[0].spatial_scale == 1 / 16
+        assert len(heads.res5) == 3 and heads.res5[0].stride == 2 and heads.res5[0].shortcut is not None and heads.res5[1].shortcut is None
+        assert type(heads.box_predictor).__name__ == "EmbeddingFastRCNNOutputLayers" and heads.box_predictor.emb_dim == 32
+    bp = M.BOX_PREDICTORS["EmbeddingFastRCNNOutputLayers"](M.get_cfg("stt"), M.ShapeSpec(channels=2048))
+    assert bp.emb_pred.weight.shape == (768, 2048) and bp.loss_weight == {"loss_box_reg": 1.0} and bp.precision == "fp32"
+    bp = M.EmbeddingFastRCNNOutputLayers(M.get_cfg("stt"), 2048, precision="bf16")       # keyword override next to a cfg
+    assert bp.precision == "bf16"
+    bp = M.EmbeddingFastRCNNOutputLayers(64, cls_agnostic_bbox_reg=True, emb_dim=16)    # explicit-argument form
+    assert bp.emb_pred.weight.shape == (16, 64)
+    # explicit-argument form of the ROI heads with an injected res5
+    heads = M.EmbeddingRes5ROIHeads(in_features=["res4"], pooler=M.ROIPooler(7, (1 / 16,), 0, "ROIAlignV2"), res5=torch.nn.Identity(),
+                                    box_predictor=bp, num_classes=3)
+    assert heads.num_classes == 3 and isinstance(heads.res5, torch.nn.Identity)
+
+
+@pytest.mark.parametrize("case", sorted(box_cases.ROI_CASES))
+def test_reference_state_dicts_load_strictly(case):
+    """The state_dict the REAL reference ROI heads produced (tests/golden/roiheads_*.npz) loads with identical keys."""
+    z = load_golden("roiheads_" + case)
+    cls_name, stage, _ = box_cases.ROI_CASES[case]
+    heads = M.ROI_HEADS_REGISTRY.get(cls_name)(_small_cfg(stage, cls_name), {"res4": M.ShapeSpec(channels=32, stride=16)})
+    heads.box_predictor.set_class_embeddings(torch.from_numpy(z["cls"]))
+    sd = {k[len("state::"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("state::")}
+    assert sorted(sd) == sorted(heads.state_dict().keys())
+    heads.load_state_dict(sd, strict=True)
+
+
+def test_box_predictor_state_keys_match_the_reference_class():
+    z = load_golden("box_k65_infer")
+    bp = M.build_box_predictor(M.get_cfg("stt"), 2048)
+    bp.set_class_embeddings(torch.zeros(66, 768))
+    assert sorted(bp.state_dict().keys()) == sorted(z["state_keys"].tolist())

@@ -62,3 +62,16 @@ def frob_relerr(a, b):
     a = torch.as_tensor(a).double()
     b = torch.as_tensor(b).double()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def golden_box(name):
+    """-> (case dict, seeded inputs, golden arrays) for a tests/golden/box_*.npz case; checks the regenerated inputs against the
+    checksums stored when the real reference class ran on them."""
+    from oracle import box_cases
+    z = load_golden("box_" + name)
+    c = box_cases.BOX_CASES[name]
+    d = box_cases.box_case_inputs(c)
+    for key, t in (("x", d["x"]), ("w_emb", d["w_emb"]), ("cls", d["cls"])):
+        cs = np.array([float(t.double().sum()), float(t.double().abs().sum())])
+        assert np.allclose(cs, z["checksum_" + key], rtol=1e-9), f"seeded input {key} drifted from the golden run"
+    return c, d, z
