@@ -220,6 +220,9 @@ __device__ __forceinline__ void mma_issue_loop(const TcCore &core, unsigned char
 //   __device__ void begin(const Params&, const TcCore&, int cta, int row, int lane, int q, unsigned char *smem);
 //   __device__ void chunk(const Params&, const TcCore&, int cta, int chunk, uint32_t taddr, ...same...);
 //   __device__ void finish(const Params&, const TcCore&, int cta, ...same...);
+//   static constexpr bool kHasPrefetch;  true: prefetch(const Params&, const TcCore&, int cta, int chunk, row, lane, q, smem) runs before the
+//                                        wait for the chunk's accumulator (masks / per-tile inputs load under the MMAs)
+//   static constexpr bool kSelfRelease;  true: chunk() itself arrives on the accumulator-empty barrier (members release_bar / release_local)
 // PAIR = true is the CTA-pair (cta_group::2) instantiation: a kernel containing cta_group::2 instructions can only be
 // launched as a cluster of two, so it is a separate instantiation from the single-CTA / multicast-cluster one.
 template <class Epi, bool PAIR = false>
@@ -295,7 +298,9 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
     if (tl && threadIdx.x == 0) tl[1] = global_timer_ns();                       // setup done (barriers, TMEM, cluster sync)
     const uint32_t tmem_base = *tmem_slot;
     const int iters_per_chunk = core.num_k_blocks * core.passes;
-    const int nchunks = core.total_tiles > 0 ? max(0, (core.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) : core.chunks;
+    // persistent mode: unit u (a CTA, or a CTA pair) of U launched units processes tiles u, u + U, ...
+    const int unit = pair ? (int)blockIdx.x / 2 : (int)blockIdx.x, units = pair ? (int)gridDim.x / 2 : (int)gridDim.x;
+    const int nchunks = core.total_tiles > 0 ? max(0, (core.total_tiles - unit + units - 1) / units) : core.chunks;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -356,14 +361,24 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
         for (int ch = 0; ch < nchunks; ++ch) {
             const int acc = ch % core.acc_stages;
             const uint32_t acc_phase = (uint32_t)(ch / core.acc_stages) & 1u;
+            if constexpr (Epi::kHasPrefetch) epi.prefetch(ep, core, cta, ch, row, lane, q, epi_smem);   // per-tile inputs of the epilogue, loaded
+                                                                                                          // while the tile's MMAs still run
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             if (tl && ch == nchunks - 1 && threadIdx.x == 64) tl[4] = global_timer_ns();   // last accumulator complete
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * core.block_n);
-            epi.chunk(ep, core, cta, ch, taddr, row, lane, q, epi_smem);
-            tc_fence_before();
-            if constexpr (pair) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));   // the leader's MMA thread waits for both CTAs
-            else mbar_arrive(&tempty[acc]);
+            if constexpr (Epi::kSelfRelease) {
+                // the policy frees the accumulator itself as soon as its last tcgen05.ld has completed (every epilogue thread
+                // arrives exactly once per chunk), so the MMAs of the tile after next can start under the rest of the epilogue
+                epi.release_bar = pair ? mapa_u32(smem_u32(&tempty[acc]), 0) : 0u;
+                epi.release_local = &tempty[acc];
+                epi.chunk(ep, core, cta, ch, taddr, row, lane, q, epi_smem);
+            } else {
+                epi.chunk(ep, core, cta, ch, taddr, row, lane, q, epi_smem);
+                tc_fence_before();
+                if constexpr (pair) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));   // the leader's MMA thread waits for both CTAs
+                else mbar_arrive(&tempty[acc]);
+            }
         }
         epi.finish(ep, core, cta, row, lane, q, epi_smem);
         if (tl && threadIdx.x == 64) tl[5] = global_timer_ns();                  // epilogue done

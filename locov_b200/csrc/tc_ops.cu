@@ -20,6 +20,7 @@ constexpr float LSM_PAD = -3.0e38f;    // padding columns of a tile: exp2(LSM_PA
 struct EpiLinear {
     static constexpr int kEpiWarps = 4;
     static constexpr int kMinBlocks = 1;
+    static constexpr bool kHasPrefetch = false, kSelfRelease = false;
     struct Params {
         const float *bias;
         float *out_f32;
@@ -110,6 +111,7 @@ struct EpiLinear {
 struct EpiScore {
     static constexpr int kEpiWarps = 4;
     static constexpr int kMinBlocks = 1;
+    static constexpr bool kHasPrefetch = false, kSelfRelease = false;
     struct Params {
         const float *bias;
         float *logits;
@@ -335,6 +337,7 @@ template <bool BWD>
 struct EpiLsm {
     static constexpr int kEpiWarps = 8;
     static constexpr int kMinBlocks = 2;      // two CTAs per SM: one tile's epilogue overlaps the other's loads / MMAs
+    static constexpr bool kHasPrefetch = false, kSelfRelease = false;
     static constexpr int kThreads = 32 * kEpiWarps;
     typedef LsmParams Params;
     static __device__ __forceinline__ void coords(const Params &p, const TcCore &, int cta, int, int &row_a, int &row_b) {
@@ -601,6 +604,254 @@ struct EpiLsm {
                     if (dl) dl[r] = l;
                 }
             }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// LSM pair FORWARD epilogue, second generation (softmax alignment): persistent CTA pairs.
+//
+// A CTA pair (tcgen05 cta_group::2, M = 256) owns the similarity tile of 2 x `per_tile` captions (CTA rm holds the word rows of
+// caption group 2*gp + rm) x `ipt` consecutive images (image j of the tile = accumulator columns [j*Rg, j*Rg + Rg)): the region
+// operand of the images is staged ONCE for both caption groups (each CTA loads half of it), so the bytes an SM pulls from L2 per
+// MAC drop to 0.6x of the single-CTA 128 x 128 tile the first generation used — that kernel was bound by TMA ingest (30 KB per
+// 224-cycle k block), not by the tensor pipe.  Pairs are persistent (pair p takes tiles p, p + P, ...) with two accumulator stages
+// in tensor memory, so the epilogue of tile k runs under the MMAs of tile k + 1, and it frees its accumulator right after its last
+// tcgen05.ld so that tile k + 2 can start under the rest of it.
+//
+// Epilogue = two independent halves of four warps (TMEM lane quarters 0-3 each); half h takes the images j = h, h + 2, ... of
+// the tile.  Per image:
+//   row pass    (thread = word row)  : ONE sweep over the image's Rg accumulator columns with an online softmax (running max,
+//                                      rescaled sums) -> attention-pooled f_t (w2r); the scaled similarities (log2 units) are
+//                                      parked in the half's private shared-memory sub-tile with conflict-free 128-bit stores
+//   column pass (thread = region)    : per caption, softmax over its T words down the parked column -> h_r (r2w), reduced over the
+//                                      regions with a fixed-order shuffle tree per warp
+//   finish      (thread = caption)   : fixed-order sums of the T row values / the four warp partials -> the two scalars of the pair
+// Masks of the NEXT tile are fetched by prefetch() while its MMAs still run.  All reductions have a fixed order that depends
+// only on (caption, image): any block of the pair matrix is bit-identical to the same block computed in another tiling / shard.
+// ------------------------------------------------------------------------------------------------
+struct LsmFwdParams {
+    const float *cap_mask;   // [Bc, T]
+    const float *reg_mask;   // [Bi, Rg]
+    float *out_w2r, *out_r2w;   // [Bc, Bi] (ld_out), each may be null
+    int64_t ld_out;
+    int Bc, T, Bi, Rg;
+    int per_tile;            // captions per CTA (one 128-row half of the pair tile)
+    int ipt;                 // images per tile
+    int slots;               // images per epilogue half = ceil(ipt / 2)
+    int lds;                 // parked sub-tile row stride (floats): multiple of 4, lds / 4 odd (conflict-free 128-bit row stores)
+    int rb;                  // region-bias stride per image slot = round_up(Rg, 32)
+    int npairs;              // CTA pairs launched
+    int tiles_i;             // image tiles = ceil(Bi / ipt)
+    float inv_temp;
+};
+
+struct EpiLsmFwd {
+    static constexpr int kEpiWarps = 8;
+    static constexpr int kMinBlocks = 1;
+    static constexpr bool kHasPrefetch = true, kSelfRelease = true;
+    typedef LsmFwdParams Params;
+    uint32_t release_bar;        // set by the core: shared::cluster address of the leader's accumulator-empty barrier
+    uint64_t *release_local;
+
+    struct Tile { int rm, gp, it, c_first, ncap, nrows; };
+    static __device__ __forceinline__ Tile decode(const Params &p, int cta, int ch) {
+        Tile t;
+        t.rm = cta / p.npairs;
+        const int tile = (cta - t.rm * p.npairs) + ch * p.npairs;
+        t.gp = tile / p.tiles_i;
+        t.it = tile - t.gp * p.tiles_i;
+        t.c_first = (2 * t.gp + t.rm) * p.per_tile;
+        t.ncap = max(0, min(p.per_tile, p.Bc - t.c_first));
+        t.nrows = t.ncap * p.T;
+        return t;
+    }
+    static __device__ __forceinline__ void coords(const Params &p, const TcCore &, int cta, int ch, int &row_a, int &row_b) {
+        const Tile t = decode(p, cta, ch);
+        row_a = t.c_first * p.T;                 // word rows of this CTA's caption group (A operand; rows past Bc*T are zero-filled)
+        row_b = t.it * p.ipt * p.Rg;             // region rows of the tile's images (B operand; the core adds this CTA's half)
+    }
+    // per-half shared memory (floats)
+    struct Half {
+        float *park, *rbias, *cbias, *rowval, *colpart, *capnw, *nreg;
+    };
+    static __host__ __device__ __forceinline__ size_t half_floats(int nrows_max, int lds, int slots, int rb) {
+        return (size_t)nrows_max * lds + (size_t)slots * rb + 128 + 128 + 4 * LSM_MAX_PER_TILE + LSM_MAX_PER_TILE + 16;
+    }
+    static __device__ __forceinline__ Half carve(const Params &p, unsigned char *smem, int half) {
+        const int nrows_max = p.per_tile * p.T;
+        float *b = reinterpret_cast<float *>(smem) + (size_t)half * ((half_floats(nrows_max, p.lds, p.slots, p.rb) + 3) & ~(size_t)3);
+        Half h;
+        h.park = b; b += (size_t)nrows_max * p.lds;
+        h.rbias = b; b += (size_t)p.slots * p.rb;
+        h.cbias = b; b += 128;
+        h.rowval = b; b += 128;
+        h.colpart = b; b += 4 * LSM_MAX_PER_TILE;
+        h.capnw = b; b += LSM_MAX_PER_TILE;
+        h.nreg = b;
+        return h;
+    }
+    __device__ __forceinline__ void begin(const Params &, const TcCore &, int, int, int, int, unsigned char *) {}
+    __device__ __forceinline__ void finish(const Params &, const TcCore &, int, int, int, int, unsigned char *) {}
+
+    // masks of tile `ch` -> additive biases in the half's shared memory, word / region counts (all before the accumulator is awaited)
+    __device__ __forceinline__ void prefetch(const Params &p, const TcCore &, int cta, int ch, int row, int lane, int, unsigned char *smem) {
+        const int et = threadIdx.x - 64, half = et >> 7, ht = et & 127, hw = (et >> 5) & 3;
+        const Half h = carve(p, smem, half);
+        const Tile t = decode(p, cta, ch);
+        named_bar_sync(2 + half, 128);                         // the half has finished reading the previous tile's buffers
+        const float mc = (row < t.nrows) ? __ldg(p.cap_mask + (int64_t)t.c_first * p.T + row) : 0.f;
+        h.cbias[row] = (mc > 0.f) ? 0.f : LSM_FILL;
+        for (int s = 0; s < p.slots; ++s) {
+            const int i = t.it * p.ipt + half + 2 * s;
+            const bool img_on = (half + 2 * s < p.ipt) && i < p.Bi;
+            for (int r = ht; r < p.rb; r += 128)
+                h.rbias[s * p.rb + r] = (r < p.Rg && img_on) ? ((__ldg(p.reg_mask + (int64_t)i * p.Rg + r) > 0.f) ? 0.f : LSM_FILL) : LSM_PAD;
+        }
+        named_bar_sync(2 + half, 128);
+        if (ht < t.ncap) {                                     // valid words of caption ht (fixed order)
+            float nw = 0.f;
+            for (int w = 0; w < p.T; ++w) nw += (h.cbias[ht * p.T + w] == 0.f) ? 1.f : 0.f;
+            h.capnw[ht] = nw;
+        }
+        for (int s = hw; s < p.slots; s += 4) {                // valid regions of the half's images: one warp each
+            float nr = 0.f;
+            for (int r = lane; r < p.Rg; r += 32) nr += (h.rbias[s * p.rb + r] == 0.f) ? 1.f : 0.f;
+            nr = warp_sum(nr);
+            if (lane == 0) h.nreg[s] = nr;
+        }
+    }
+
+    // 32 (or 16) accumulator columns of this thread's row: park the scaled values, fold them into the running softmax statistics
+    template <int W>
+    __device__ __forceinline__ void fold(const float (&v)[W], int valid, float scale2, const float *rb, float *prow, int lds_left, float &m, float &d,
+                                         float &n) {
+        float sv[W], x[W];
+        float bm = -FLT_MAX;
+#pragma unroll
+        for (int j = 0; j < W; j += 4) {
+            const float4 r4 = *reinterpret_cast<const float4 *>(rb + j);
+            // columns past the image (valid < W only in the tail block) may hold anything, NaN patterns included: select, never multiply
+            sv[j] = (j < valid) ? v[j] * scale2 : 0.f;
+            sv[j + 1] = (j + 1 < valid) ? v[j + 1] * scale2 : 0.f;
+            sv[j + 2] = (j + 2 < valid) ? v[j + 2] * scale2 : 0.f;
+            sv[j + 3] = (j + 3 < valid) ? v[j + 3] * scale2 : 0.f;
+            if (j < lds_left) *reinterpret_cast<float4 *>(prow + j) = make_float4(sv[j], sv[j + 1], sv[j + 2], sv[j + 3]);
+            x[j] = sv[j] + r4.x; x[j + 1] = sv[j + 1] + r4.y; x[j + 2] = sv[j + 2] + r4.z; x[j + 3] = sv[j + 3] + r4.w;
+            bm = fmaxf(bm, fmaxf(fmaxf(x[j], x[j + 1]), fmaxf(x[j + 2], x[j + 3])));
+        }
+        const float m_new = fmaxf(m, bm);
+        const float corr = ex2_ftz(m - m_new);
+        float d0 = d * corr, d1 = 0.f, n0 = n * corr, n1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < W; j += 2) {
+            const float e0 = ex2_ftz(x[j] - m_new), e1 = ex2_ftz(x[j + 1] - m_new);
+            d0 += e0; n0 = fmaf(e0, sv[j], n0);
+            d1 += e1; n1 = fmaf(e1, sv[j + 1], n1);
+        }
+        m = m_new;
+        d = d0 + d1;
+        n = n0 + n1;
+    }
+
+    __device__ __forceinline__ void release_acc() {
+        tc_fence_before();
+        mbar_arrive_cluster(release_bar);
+    }
+
+    __device__ __forceinline__ void chunk(const Params &p, const TcCore &core, int cta, int ch, uint32_t taddr, int row, int lane, int,
+                                          unsigned char *smem) {
+        const int et = threadIdx.x - 64, half = et >> 7, ht = et & 127, hw = (et >> 5) & 3;
+        const Half h = carve(p, smem, half);
+        const Tile t = decode(p, cta, ch);
+        const int T = p.T, Rg = p.Rg, lds = p.lds;
+        int nslots = 0;                                         // images this half really has in this tile
+        for (int s = 0; s < p.slots; ++s)
+            if (half + 2 * s < p.ipt && t.it * p.ipt + half + 2 * s < p.Bi) nslots = s + 1;
+        if (t.ncap == 0 || nslots == 0 || core.debug_mode == 3) {   // padding half of the last pair / nothing for this half
+            release_acc();
+            return;
+        }
+        const float scale2 = p.inv_temp * LSM_LOG2E;
+        const bool row_on = h.cbias[row] == 0.f;
+        const int nfull = Rg >> 5, rem = Rg & 31;
+        for (int s = 0; s < nslots; ++s) {
+            const int j = half + 2 * s, i = t.it * p.ipt + j;
+            const float *rb = h.rbias + s * p.rb;
+            // ---- row pass ------------------------------------------------------------------------------------------
+            {
+                const uint32_t tcol = taddr + (uint32_t)(j * Rg);
+                float *prow = h.park + (size_t)min(row, max(t.nrows - 1, 0)) * lds;      // rows past the valid ones alias the last valid row:
+                const int keep = row < t.nrows ? lds : 0;                              // ... and store nothing
+                float m = -FLT_MAX, d = 0.f, n = 0.f;
+                for (int b = 0; b < nfull; ++b) {
+                    float v[32];
+                    tmem_ld32(tcol + (uint32_t)(b * 32), v);
+                    fold<32>(v, 32, scale2, rb + b * 32, prow + b * 32, keep - b * 32, m, d, n);
+                }
+                if (rem > 16) {
+                    float v[32];
+                    tmem_ld32(tcol + (uint32_t)(nfull * 32), v);
+                    fold<32>(v, rem, scale2, rb + nfull * 32, prow + nfull * 32, keep - nfull * 32, m, d, n);
+                } else if (rem > 0) {
+                    float v[16];
+                    tmem_ld16(tcol + (uint32_t)(nfull * 32), v);
+                    fold<16>(v, rem, scale2, rb + nfull * 32, prow + nfull * 32, keep - nfull * 32, m, d, n);
+                }
+                if (s == nslots - 1) release_acc();                                   // last tcgen05.ld of this thread for this tile
+                h.rowval[row] = row_on ? (n / d) * LSM_LN2 : 0.f;
+            }
+            named_bar_sync(2 + half, 128);
+            // ---- column pass: thread = region, softmax over the T words of each caption ------------------------------------
+            if (core.debug_mode != 4 && p.out_r2w != nullptr) {
+                const int r = min(ht, Rg - 1);
+                const bool r_on = ht < Rg && rb[r] == 0.f;
+                for (int cl = 0; cl < t.ncap; ++cl) {
+                    const float *col = h.park + (size_t)cl * T * lds + r;
+                    const float *cb = h.cbias + cl * T;
+                    float c0 = -FLT_MAX, c1 = -FLT_MAX, c2 = -FLT_MAX, c3 = -FLT_MAX;
+                    int w = 0;
+                    for (; w + 3 < T; w += 4) {
+                        c0 = fmaxf(c0, col[(size_t)w * lds] + cb[w]);
+                        c1 = fmaxf(c1, col[(size_t)(w + 1) * lds] + cb[w + 1]);
+                        c2 = fmaxf(c2, col[(size_t)(w + 2) * lds] + cb[w + 2]);
+                        c3 = fmaxf(c3, col[(size_t)(w + 3) * lds] + cb[w + 3]);
+                    }
+                    for (; w < T; ++w) c0 = fmaxf(c0, col[(size_t)w * lds] + cb[w]);
+                    const float ncmx = -fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
+                    float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f;
+                    for (w = 0; w + 1 < T; w += 2) {
+                        const float s0 = col[(size_t)w * lds], s1 = col[(size_t)(w + 1) * lds];
+                        const float e0 = ex2_ftz((s0 + ncmx) + cb[w]), e1 = ex2_ftz((s1 + ncmx) + cb[w + 1]);
+                        d0 += e0; n0 = fmaf(e0, s0, n0);
+                        d1 += e1; n1 = fmaf(e1, s1, n1);
+                    }
+                    if (w < T) {
+                        const float s0 = col[(size_t)w * lds];
+                        const float e0 = ex2_ftz((s0 + ncmx) + cb[w]);
+                        d0 += e0; n0 = fmaf(e0, s0, n0);
+                    }
+                    float hv = r_on ? (n0 + n1) / (d0 + d1) * LSM_LN2 : 0.f;
+                    hv = warp_sum(hv);
+                    if (lane == 0) h.colpart[hw * LSM_MAX_PER_TILE + cl] = hv;
+                }
+            }
+            named_bar_sync(2 + half, 128);
+            // ---- finish: thread = caption ------------------------------------------------------------------------------
+            if (ht < t.ncap) {
+                const int c = t.c_first + ht;
+                if (p.out_w2r != nullptr) {
+                    float a = 0.f;
+                    for (int w = 0; w < T; ++w) a += h.rowval[ht * T + w];
+                    p.out_w2r[(int64_t)c * p.ld_out + i] = -a / fmaxf(h.capnw[ht], 1.f);
+                }
+                if (p.out_r2w != nullptr) {
+                    const float b = ((h.colpart[ht] + h.colpart[LSM_MAX_PER_TILE + ht]) + h.colpart[2 * LSM_MAX_PER_TILE + ht]) +
+                                    h.colpart[3 * LSM_MAX_PER_TILE + ht];
+                    p.out_r2w[(int64_t)c * p.ld_out + i] = -b / fmaxf(h.nreg[s], 1.f);
+                }
+            }
+            if (s + 1 < nslots) named_bar_sync(2 + half, 128);      // park / rowval / colpart are rewritten by the next image
         }
     }
 };
