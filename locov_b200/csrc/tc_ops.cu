@@ -639,7 +639,9 @@ struct LsmFwdParams {
     int per_tile;            // captions per CTA (one 128-row half of the pair tile)
     int ipt;                 // images per tile
     int slots;               // images per epilogue half = ceil(ipt / 2)
-    int lds;                 // parked sub-tile row stride (floats): multiple of 4, lds / 4 odd (conflict-free 128-bit row stores)
+    int halves;              // epilogue halves with a shared-memory allocation (1 when ipt == 1)
+    int Tp;                  // words per caption in the parked layout = round_up(T, 4): a caption's column segment is whole float4s
+    int ldt;                 // parked sub-tile row stride (floats): >= per_tile * Tp, multiple of 4, ldt / 4 odd (conflict-free 128-bit loads)
     int rb;                  // region-bias stride per image slot = round_up(Rg, 32)
     int npairs;              // CTA pairs launched
     int tiles_i;             // image tiles = ceil(Bi / ipt)
@@ -650,6 +652,7 @@ struct EpiLsmFwd {
     static constexpr int kEpiWarps = 8;
     static constexpr int kMinBlocks = 1;
     static constexpr bool kHasPrefetch = true, kSelfRelease = true;
+    static constexpr int kCbt = 192;       // >= per_tile * Tp (per_tile <= 16, per_tile * T <= 128, Tp <= T + 3)
     typedef LsmFwdParams Params;
     uint32_t release_bar;        // set by the core: shared::cluster address of the leader's accumulator-empty barrier
     uint64_t *release_local;
@@ -671,37 +674,50 @@ struct EpiLsmFwd {
         row_a = t.c_first * p.T;                 // word rows of this CTA's caption group (A operand; rows past Bc*T are zero-filled)
         row_b = t.it * p.ipt * p.Rg;             // region rows of the tile's images (B operand; the core adds this CTA's half)
     }
-    // per-half shared memory (floats)
+    // per-half shared memory
     struct Half {
-        float *park, *rbias, *cbias, *rowval, *colpart, *capnw, *nreg;
+        float *park;        // [Rg][ldt]   RAW similarities of the image being processed, TRANSPOSED: region-major, a caption's words
+                            //             contiguous at [cl * Tp, cl * Tp + T)
+        float *rbias;       // [slots][rb] additive region mask: 0 valid, LSM_FILL masked, LSM_PAD past the image
+        float *cbt;         // [kCbt]      additive word mask in the parked layout: 0 valid, LSM_FILL masked, LSM_PAD for the pad words
+        float *rowval;      // [128]       f_t of the accumulator row (0 for a masked word)
+        float *colpart;     // [4][16]     per-warp partial sums of h_r per caption
+        float *capnw;       // [16]        valid words per caption
+        float *nreg;        // [16]        valid regions per image slot
+        int *ncols;         // [16]        accumulator columns of the image that can matter (last valid region + 1; Rg when none is valid)
     };
-    static __host__ __device__ __forceinline__ size_t half_floats(int nrows_max, int lds, int slots, int rb) {
-        return (size_t)nrows_max * lds + (size_t)slots * rb + 128 + 128 + 4 * LSM_MAX_PER_TILE + LSM_MAX_PER_TILE + 16;
+    static __host__ __device__ __forceinline__ size_t half_floats(int Rg, int ldt, int slots, int rb) {
+        return (size_t)Rg * ldt + (size_t)slots * rb + kCbt + 128 + 4 * LSM_MAX_PER_TILE + LSM_MAX_PER_TILE + 16 + 16;
     }
     static __device__ __forceinline__ Half carve(const Params &p, unsigned char *smem, int half) {
-        const int nrows_max = p.per_tile * p.T;
-        float *b = reinterpret_cast<float *>(smem) + (size_t)half * ((half_floats(nrows_max, p.lds, p.slots, p.rb) + 3) & ~(size_t)3);
+        float *b = reinterpret_cast<float *>(smem) + (size_t)half * ((half_floats(p.Rg, p.ldt, p.slots, p.rb) + 3) & ~(size_t)3);
         Half h;
-        h.park = b; b += (size_t)nrows_max * p.lds;
+        h.park = b; b += (size_t)p.Rg * p.ldt;
         h.rbias = b; b += (size_t)p.slots * p.rb;
-        h.cbias = b; b += 128;
+        h.cbt = b; b += kCbt;
         h.rowval = b; b += 128;
         h.colpart = b; b += 4 * LSM_MAX_PER_TILE;
         h.capnw = b; b += LSM_MAX_PER_TILE;
-        h.nreg = b;
+        h.nreg = b; b += 16;
+        h.ncols = reinterpret_cast<int *>(b);
         return h;
     }
     __device__ __forceinline__ void begin(const Params &, const TcCore &, int, int, int, int, unsigned char *) {}
     __device__ __forceinline__ void finish(const Params &, const TcCore &, int, int, int, int, unsigned char *) {}
 
-    // masks of tile `ch` -> additive biases in the half's shared memory, word / region counts (all before the accumulator is awaited)
+    // masks of tile `ch` -> additive biases and counts in the half's shared memory (all before the accumulator is awaited)
     __device__ __forceinline__ void prefetch(const Params &p, const TcCore &, int cta, int ch, int row, int lane, int, unsigned char *smem) {
         const int et = threadIdx.x - 64, half = et >> 7, ht = et & 127, hw = (et >> 5) & 3;
+        if (half >= p.halves) return;
         const Half h = carve(p, smem, half);
         const Tile t = decode(p, cta, ch);
         named_bar_sync(2 + half, 128);                         // the half has finished reading the previous tile's buffers
-        const float mc = (row < t.nrows) ? __ldg(p.cap_mask + (int64_t)t.c_first * p.T + row) : 0.f;
-        h.cbias[row] = (mc > 0.f) ? 0.f : LSM_FILL;
+        if (row < t.nrows) {
+            const int cl = row / p.T, w = row - cl * p.T;
+            h.cbt[cl * p.Tp + w] = (__ldg(p.cap_mask + (int64_t)t.c_first * p.T + row) > 0.f) ? 0.f : LSM_FILL;
+        }
+        if (ht < t.ncap)
+            for (int w = p.T; w < p.Tp; ++w) h.cbt[ht * p.Tp + w] = LSM_PAD;
         for (int s = 0; s < p.slots; ++s) {
             const int i = t.it * p.ipt + half + 2 * s;
             const bool img_on = (half + 2 * s < p.ipt) && i < p.Bi;
@@ -709,49 +725,117 @@ struct EpiLsmFwd {
                 h.rbias[s * p.rb + r] = (r < p.Rg && img_on) ? ((__ldg(p.reg_mask + (int64_t)i * p.Rg + r) > 0.f) ? 0.f : LSM_FILL) : LSM_PAD;
         }
         named_bar_sync(2 + half, 128);
-        if (ht < t.ncap) {                                     // valid words of caption ht (fixed order)
+        if (ht < t.ncap) {                                     // valid words of caption ht
             float nw = 0.f;
-            for (int w = 0; w < p.T; ++w) nw += (h.cbias[ht * p.T + w] == 0.f) ? 1.f : 0.f;
+            for (int w = 0; w < p.T; ++w) nw += (h.cbt[ht * p.Tp + w] == 0.f) ? 1.f : 0.f;
             h.capnw[ht] = nw;
         }
-        for (int s = hw; s < p.slots; s += 4) {                // valid regions of the half's images: one warp each
+        for (int s = hw; s < p.slots; s += 4) {                // the half's images: one warp each
             float nr = 0.f;
-            for (int r = lane; r < p.Rg; r += 32) nr += (h.rbias[s * p.rb + r] == 0.f) ? 1.f : 0.f;
+            int last = 0;
+            for (int r = lane; r < p.Rg; r += 32)
+                if (h.rbias[s * p.rb + r] == 0.f) { nr += 1.f; last = r + 1; }
             nr = warp_sum(nr);
-            if (lane == 0) h.nreg[s] = nr;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+            if (lane == 0) {
+                h.nreg[s] = nr;
+                h.ncols[s] = last > 0 ? last : p.Rg;           // none valid: uniform over all Rg regions, every column matters
+            }
         }
+        named_bar_sync(2 + half, 128);                         // counts are read by every thread of the half in chunk()
     }
 
-    // 32 (or 16) accumulator columns of this thread's row: park the scaled values, fold them into the running softmax statistics
-    template <int W>
-    __device__ __forceinline__ void fold(const float (&v)[W], int valid, float scale2, const float *rb, float *prow, int lds_left, float &m, float &d,
-                                         float &n) {
-        float sv[W], x[W];
+    // W accumulator columns of this thread's row, RAW units (c = inv_temp * log2 e turns them into log2 units inside the FFMA that
+    // feeds MUFU.EX2): park them transposed, fold them into the running softmax statistics (m: running max of the biased raw
+    // values, d: sum of 2^((x - m) c), n: sum of those weights times the raw value).
+    // TAIL: only the first `valid` columns belong to the image (the others may hold anything, NaN patterns included: select, never
+    // multiply).  MASKED: add the region bias (an image whose regions are all valid needs none in its full blocks).
+    template <int W, bool TAIL, bool MASKED>
+    __device__ __forceinline__ void fold(const uint32_t (&v)[32], int valid, float c, const float *rb, float *pp, int ldt, bool store, float &m,
+                                         float &d, float &n) {
+        float a[W], x[W];
         float bm = -FLT_MAX;
 #pragma unroll
         for (int j = 0; j < W; j += 4) {
-            const float4 r4 = *reinterpret_cast<const float4 *>(rb + j);
-            // columns past the image (valid < W only in the tail block) may hold anything, NaN patterns included: select, never multiply
-            sv[j] = (j < valid) ? v[j] * scale2 : 0.f;
-            sv[j + 1] = (j + 1 < valid) ? v[j + 1] * scale2 : 0.f;
-            sv[j + 2] = (j + 2 < valid) ? v[j + 2] * scale2 : 0.f;
-            sv[j + 3] = (j + 3 < valid) ? v[j + 3] * scale2 : 0.f;
-            if (j < lds_left) *reinterpret_cast<float4 *>(prow + j) = make_float4(sv[j], sv[j + 1], sv[j + 2], sv[j + 3]);
-            x[j] = sv[j] + r4.x; x[j + 1] = sv[j + 1] + r4.y; x[j + 2] = sv[j + 2] + r4.z; x[j + 3] = sv[j + 3] + r4.w;
+            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MASKED || TAIL) r4 = *reinterpret_cast<const float4 *>(rb + j);
+            const float rbj[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float raw = __uint_as_float(v[j + u]);
+                a[j + u] = TAIL ? ((j + u < valid) ? raw : 0.f) : raw;
+                if (store && (!TAIL || j + u < valid)) pp[(size_t)(j + u) * ldt] = a[j + u];
+                x[j + u] = (MASKED || TAIL) ? a[j + u] + rbj[u] : a[j + u];
+            }
             bm = fmaxf(bm, fmaxf(fmaxf(x[j], x[j + 1]), fmaxf(x[j + 2], x[j + 3])));
         }
         const float m_new = fmaxf(m, bm);
-        const float corr = ex2_ftz(m - m_new);
+        const float corr = ex2_ftz((m - m_new) * c);
         float d0 = d * corr, d1 = 0.f, n0 = n * corr, n1 = 0.f;
 #pragma unroll
         for (int j = 0; j < W; j += 2) {
-            const float e0 = ex2_ftz(x[j] - m_new), e1 = ex2_ftz(x[j + 1] - m_new);
-            d0 += e0; n0 = fmaf(e0, sv[j], n0);
-            d1 += e1; n1 = fmaf(e1, sv[j + 1], n1);
+            // (x - m) * c, NOT fma(x, c, -m * c): with every region masked x == m == LSM_FILL and the difference must be exactly 0
+            // (the rounding error of m * c alone is ~1e22 at that magnitude)
+            const float e0 = ex2_ftz((x[j] - m_new) * c), e1 = ex2_ftz((x[j + 1] - m_new) * c);
+            d0 += e0; n0 = fmaf(e0, a[j], n0);
+            d1 += e1; n1 = fmaf(e1, a[j + 1], n1);
         }
         m = m_new;
         d = d0 + d1;
         n = n0 + n1;
+    }
+
+    // softmax over one caption's words down a parked column (NQ float4 quads; the last one holds `tlast` real words):
+    // returns sum_t softmax_t * raw similarity
+    template <int NQ>
+    static __device__ __forceinline__ float col_caption(const float *base, const float *cb, int tlast, float c) {
+        float a[4 * NQ], x[4 * NQ];
+        float mx = -FLT_MAX;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const float4 v = *reinterpret_cast<const float4 *>(base + 4 * q);
+            const float4 b = *reinterpret_cast<const float4 *>(cb + 4 * q);
+            a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+            if (q == NQ - 1) {                                  // pad words were never parked: select them away
+                if (tlast < 2) a[4 * q + 1] = 0.f;
+                if (tlast < 3) a[4 * q + 2] = 0.f;
+                if (tlast < 4) a[4 * q + 3] = 0.f;
+            }
+            x[4 * q] = a[4 * q] + b.x; x[4 * q + 1] = a[4 * q + 1] + b.y; x[4 * q + 2] = a[4 * q + 2] + b.z; x[4 * q + 3] = a[4 * q + 3] + b.w;
+            mx = fmaxf(mx, fmaxf(fmaxf(x[4 * q], x[4 * q + 1]), fmaxf(x[4 * q + 2], x[4 * q + 3])));
+        }
+        float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4 * NQ; j += 2) {
+            const float e0 = ex2_ftz((x[j] - mx) * c), e1 = ex2_ftz((x[j + 1] - mx) * c);      // (exact 0 for an all-masked caption)
+            d0 += e0; n0 = fmaf(e0, a[j], n0);
+            d1 += e1; n1 = fmaf(e1, a[j + 1], n1);
+        }
+        return (n0 + n1) / (d0 + d1);
+    }
+    // any number of quads (T > 32): two sweeps over the column segment
+    static __device__ __forceinline__ float col_caption_long(const float *base, const float *cb, int nq, int tlast, float c) {
+        float mx = -FLT_MAX;
+        for (int q = 0; q < nq; ++q) {
+            float4 v = *reinterpret_cast<const float4 *>(base + 4 * q);
+            const float4 b = *reinterpret_cast<const float4 *>(cb + 4 * q);
+            if (q == nq - 1) { if (tlast < 2) v.y = 0.f; if (tlast < 3) v.z = 0.f; if (tlast < 4) v.w = 0.f; }
+            mx = fmaxf(mx, fmaxf(fmaxf(v.x + b.x, v.y + b.y), fmaxf(v.z + b.z, v.w + b.w)));
+        }
+        float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f;
+        for (int q = 0; q < nq; ++q) {
+            float4 v = *reinterpret_cast<const float4 *>(base + 4 * q);
+            const float4 b = *reinterpret_cast<const float4 *>(cb + 4 * q);
+            if (q == nq - 1) { if (tlast < 2) v.y = 0.f; if (tlast < 3) v.z = 0.f; if (tlast < 4) v.w = 0.f; }
+            const float e0 = ex2_ftz(((v.x + b.x) - mx) * c), e1 = ex2_ftz(((v.y + b.y) - mx) * c);
+            const float e2 = ex2_ftz(((v.z + b.z) - mx) * c), e3 = ex2_ftz(((v.w + b.w) - mx) * c);
+            d0 += e0; n0 = fmaf(e0, v.x, n0);
+            d1 += e1; n1 = fmaf(e1, v.y, n1);
+            d0 += e2; n0 = fmaf(e2, v.z, n0);
+            d1 += e3; n1 = fmaf(e3, v.w, n1);
+        }
+        return (n0 + n1) / (d0 + d1);
     }
 
     __device__ __forceinline__ void release_acc() {
@@ -759,81 +843,98 @@ struct EpiLsmFwd {
         mbar_arrive_cluster(release_bar);
     }
 
+    // block k of an image's columns: k < nb are full 32-column blocks, block nb (if any) is the tail, read 16 or 32 columns wide
+    static __device__ __forceinline__ void blk_issue(int k, int nb, int tw, uint32_t tcol, uint32_t (&buf)[32]) {
+        const uint32_t adr = tcol + (uint32_t)(k * 32);
+        if (k < nb || tw == 32) tmem_ld_async<32>(adr, buf);
+        else tmem_ld_async<16>(adr, buf);
+    }
+    static __device__ __forceinline__ void blk_fence(int k, int nb, int tw, uint32_t (&buf)[32]) {
+        if (k < nb || tw == 32) tmem_ld_fence<32>(buf);
+        else tmem_ld_fence<16>(buf);
+    }
+
     __device__ __forceinline__ void chunk(const Params &p, const TcCore &core, int cta, int ch, uint32_t taddr, int row, int lane, int,
                                           unsigned char *smem) {
         const int et = threadIdx.x - 64, half = et >> 7, ht = et & 127, hw = (et >> 5) & 3;
-        const Half h = carve(p, smem, half);
         const Tile t = decode(p, cta, ch);
-        const int T = p.T, Rg = p.Rg, lds = p.lds;
+        const int T = p.T, Rg = p.Rg, ldt = p.ldt, Tp = p.Tp;
         int nslots = 0;                                         // images this half really has in this tile
-        for (int s = 0; s < p.slots; ++s)
-            if (half + 2 * s < p.ipt && t.it * p.ipt + half + 2 * s < p.Bi) nslots = s + 1;
+        if (half < p.halves)
+            for (int s = 0; s < p.slots; ++s)
+                if (half + 2 * s < p.ipt && t.it * p.ipt + half + 2 * s < p.Bi) nslots = s + 1;
         if (t.ncap == 0 || nslots == 0 || core.debug_mode == 3) {   // padding half of the last pair / nothing for this half
             release_acc();
             return;
         }
-        const float scale2 = p.inv_temp * LSM_LOG2E;
-        const bool row_on = h.cbias[row] == 0.f;
-        const int nfull = Rg >> 5, rem = Rg & 31;
+        const Half h = carve(p, smem, half);
+        const float c2 = p.inv_temp * LSM_LOG2E;
+        const bool row_in = row < t.nrows;
+        const int rcl = row / T;
+        const int pcol = rcl * Tp + (row - rcl * T);            // this row's position in the parked (padded) word layout
+        const bool row_on = row_in && h.cbt[pcol] == 0.f;
+        const int nq = Tp >> 2, tlast = T - 4 * (nq - 1);
         for (int s = 0; s < nslots; ++s) {
             const int j = half + 2 * s, i = t.it * p.ipt + j;
             const float *rb = h.rbias + s * p.rb;
-            // ---- row pass ------------------------------------------------------------------------------------------
+            const int ncols = h.ncols[s];
+            // ---- row pass: one software-pipelined sweep over the image's accumulator columns -----------------------------------
             {
                 const uint32_t tcol = taddr + (uint32_t)(j * Rg);
-                float *prow = h.park + (size_t)min(row, max(t.nrows - 1, 0)) * lds;      // rows past the valid ones alias the last valid row:
-                const int keep = row < t.nrows ? lds : 0;                              // ... and store nothing
+                const int nb = ncols >> 5, rem = ncols & 31;
+                const int tw = rem == 0 ? 0 : (rem <= 16 ? 16 : 32);
+                const int nblk = nb + (tw > 0 ? 1 : 0);
+                const bool masked = h.nreg[s] != (float)Rg;
                 float m = -FLT_MAX, d = 0.f, n = 0.f;
-                for (int b = 0; b < nfull; ++b) {
-                    float v[32];
-                    tmem_ld32(tcol + (uint32_t)(b * 32), v);
-                    fold<32>(v, 32, scale2, rb + b * 32, prow + b * 32, keep - b * 32, m, d, n);
-                }
-                if (rem > 16) {
-                    float v[32];
-                    tmem_ld32(tcol + (uint32_t)(nfull * 32), v);
-                    fold<32>(v, rem, scale2, rb + nfull * 32, prow + nfull * 32, keep - nfull * 32, m, d, n);
-                } else if (rem > 0) {
-                    float v[16];
-                    tmem_ld16(tcol + (uint32_t)(nfull * 32), v);
-                    fold<16>(v, rem, scale2, rb + nfull * 32, prow + nfull * 32, keep - nfull * 32, m, d, n);
+                uint32_t cur[32], nxt[32];
+                blk_issue(0, nb, tw, tcol, cur);
+                blk_fence(0, nb, tw, cur);
+                for (int k = 0; k < nblk; ++k) {
+                    if (k + 1 < nblk) blk_issue(k + 1, nb, tw, tcol, nxt);       // in flight while block k is folded
+                    float *pp = h.park + (size_t)(k * 32) * ldt + pcol;
+                    const float *rbk = rb + k * 32;
+                    if (k < nb) {
+                        if (masked) fold<32, false, true>(cur, 32, c2, rbk, pp, ldt, row_in, m, d, n);
+                        else fold<32, false, false>(cur, 32, c2, rbk, pp, ldt, row_in, m, d, n);
+                    } else if (tw == 32) fold<32, true, true>(cur, rem, c2, rbk, pp, ldt, row_in, m, d, n);
+                    else fold<16, true, true>(cur, rem, c2, rbk, pp, ldt, row_in, m, d, n);
+                    if (k + 1 < nblk) {
+                        blk_fence(k + 1, nb, tw, nxt);
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) cur[u] = nxt[u];
+                    }
                 }
                 if (s == nslots - 1) release_acc();                                   // last tcgen05.ld of this thread for this tile
-                h.rowval[row] = row_on ? (n / d) * LSM_LN2 : 0.f;
+                h.rowval[row] = row_on ? (n / d) * p.inv_temp : 0.f;
             }
             named_bar_sync(2 + half, 128);
-            // ---- column pass: thread = region, softmax over the T words of each caption ------------------------------------
+            // ---- column pass: thread = region, softmax over the T words of each caption down the parked column ----------------------
             if (core.debug_mode != 4 && p.out_r2w != nullptr) {
-                const int r = min(ht, Rg - 1);
-                const bool r_on = ht < Rg && rb[r] == 0.f;
-                for (int cl = 0; cl < t.ncap; ++cl) {
-                    const float *col = h.park + (size_t)cl * T * lds + r;
-                    const float *cb = h.cbias + cl * T;
-                    float c0 = -FLT_MAX, c1 = -FLT_MAX, c2 = -FLT_MAX, c3 = -FLT_MAX;
-                    int w = 0;
-                    for (; w + 3 < T; w += 4) {
-                        c0 = fmaxf(c0, col[(size_t)w * lds] + cb[w]);
-                        c1 = fmaxf(c1, col[(size_t)(w + 1) * lds] + cb[w + 1]);
-                        c2 = fmaxf(c2, col[(size_t)(w + 2) * lds] + cb[w + 2]);
-                        c3 = fmaxf(c3, col[(size_t)(w + 3) * lds] + cb[w + 3]);
+                for (int r0 = 0; r0 < ncols; r0 += 128) {
+                    const int r = r0 + ht;
+                    const bool r_on = r < ncols && rb[min(r, ncols - 1)] == 0.f;
+                    const bool warp_on = __any_sync(0xffffffffu, r_on);               // a warp whose regions are all masked has nothing to do
+                    const float *colbase = h.park + (size_t)min(r, ncols - 1) * ldt;
+                    for (int cl = 0; cl < t.ncap; ++cl) {
+                        float hv = 0.f;
+                        if (warp_on) {
+                            const float *base = colbase + cl * Tp, *cb = h.cbt + cl * Tp;
+                            float v;
+                            switch (nq) {
+                                case 1: v = col_caption<1>(base, cb, tlast, c2); break;
+                                case 2: v = col_caption<2>(base, cb, tlast, c2); break;
+                                case 3: v = col_caption<3>(base, cb, tlast, c2); break;
+                                case 4: v = col_caption<4>(base, cb, tlast, c2); break;
+                                case 5: v = col_caption<5>(base, cb, tlast, c2); break;
+                                case 6: v = col_caption<6>(base, cb, tlast, c2); break;
+                                case 7: v = col_caption<7>(base, cb, tlast, c2); break;
+                                case 8: v = col_caption<8>(base, cb, tlast, c2); break;
+                                default: v = col_caption_long(base, cb, nq, tlast, c2); break;
+                            }
+                            hv = warp_sum(r_on ? v * p.inv_temp : 0.f);
+                        }
+                        if (lane == 0) h.colpart[hw * LSM_MAX_PER_TILE + cl] = (r0 == 0 ? 0.f : h.colpart[hw * LSM_MAX_PER_TILE + cl]) + hv;
                     }
-                    for (; w < T; ++w) c0 = fmaxf(c0, col[(size_t)w * lds] + cb[w]);
-                    const float ncmx = -fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
-                    float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f;
-                    for (w = 0; w + 1 < T; w += 2) {
-                        const float s0 = col[(size_t)w * lds], s1 = col[(size_t)(w + 1) * lds];
-                        const float e0 = ex2_ftz((s0 + ncmx) + cb[w]), e1 = ex2_ftz((s1 + ncmx) + cb[w + 1]);
-                        d0 += e0; n0 = fmaf(e0, s0, n0);
-                        d1 += e1; n1 = fmaf(e1, s1, n1);
-                    }
-                    if (w < T) {
-                        const float s0 = col[(size_t)w * lds];
-                        const float e0 = ex2_ftz((s0 + ncmx) + cb[w]);
-                        d0 += e0; n0 = fmaf(e0, s0, n0);
-                    }
-                    float hv = r_on ? (n0 + n1) / (d0 + d1) * LSM_LN2 : 0.f;
-                    hv = warp_sum(hv);
-                    if (lane == 0) h.colpart[hw * LSM_MAX_PER_TILE + cl] = hv;
                 }
             }
             named_bar_sync(2 + half, 128);
@@ -1117,6 +1218,74 @@ static int lsm_launch(bool bwd, const uint16_t *cap_hi, const uint16_t *cap_lo, 
     return bwd ? tc_launch<EpiLsm<true>>(maps, core, p, grid, smem, st) : tc_launch<EpiLsm<false>>(maps, core, p, grid, smem, st);
 }
 
+// LOCOV_B200_LSM_V2=0 keeps the first-generation forward kernel (one CTA per (caption group, image) tile) for A/B runs.
+static bool lsm_v2_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("LOCOV_B200_LSM_V2");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+// second-generation forward (softmax alignment): persistent CTA pairs, see EpiLsmFwd.  Returns LOCO_E_UNSUPPORTED (without an
+// error message of its own) when no tile shape fits shared / tensor memory: the caller then uses the first-generation kernel.
+static int lsm_fwd2_launch(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ldcap, const uint16_t *emb_hi, const uint16_t *emb_lo,
+                           int64_t ldemb, int D, LsmFwdParams &p, cudaStream_t st, bool *declined) {
+    *declined = false;
+    const int sms = current_device_sm_count();
+    p.per_tile = TC_BLOCK_M / p.T;
+    if (p.per_tile > LSM_MAX_PER_TILE) p.per_tile = LSM_MAX_PER_TILE;
+    if (p.per_tile > p.Bc) p.per_tile = p.Bc;
+    p.Tp = tc_round_up(p.T, 4);
+    p.ldt = tc_round_up(p.per_tile * p.Tp, 4);
+    if (((p.ldt / 4) & 1) == 0) p.ldt += 4;
+    p.rb = tc_round_up(p.Rg, 32);
+    // images per tile: as many as fit 256 accumulator columns (two accumulator stages = 512 TMEM columns), at most 16; fewer when the
+    // epilogue's reads would leave the allocation or the parked sub-tiles leave too little shared memory for the operand ring
+    int ipt = 256 / p.Rg;
+    if (ipt < 1) ipt = 1;
+    if (ipt > p.Bi) ipt = p.Bi;
+    if (ipt > 16) ipt = 16;
+    if (const char *e = getenv("LOCOV_B200_LSM_IPT")) { const int v = atoi(e); if (v >= 1 && v <= ipt) ipt = v; }   // developer sweep knob
+    const int groups = (p.Bc + p.per_tile - 1) / p.per_tile;
+    TcCore core;
+    size_t smem = 0;
+    for (;; --ipt) {
+        if (ipt < 1) { *declined = true; return LOCO_E_UNSUPPORTED; }
+        p.ipt = ipt;
+        p.slots = (ipt + 1) / 2;
+        p.halves = ipt > 1 ? 2 : 1;
+        p.tiles_i = (p.Bi + ipt - 1) / ipt;
+        const long long total = (long long)((groups + 1) / 2) * p.tiles_i;
+        LOCO_REQUIRE(total < (1ll << 30), LOCO_E_UNSUPPORTED, "lsm_pair: too many tiles");
+        core = TcCore{};
+        core.block_n = tc_round_up(ipt * p.Rg, 16);
+        core.cm = 2; core.cn = 1; core.two_cta = 1;
+        int npairs = sms / 2;
+        if (npairs > total) npairs = (int)total;
+        if (npairs < 1) npairs = 1;
+        p.npairs = npairs;
+        core.clusters_n = npairs;                       // virtual CTA index = rm * npairs + pair (see tc_gemm_kernel)
+        core.total_tiles = (int)total;
+        core.single_wave = 1;
+        const int chunks = (int)((total + npairs - 1) / npairs);
+        const size_t half = (EpiLsmFwd::half_floats(p.Rg, p.ldt, p.slots, p.rb) + 3) & ~(size_t)3;
+        const size_t epi = (size_t)p.halves * half * sizeof(float) + 16;
+        if (epi > 200 * 1024) continue;
+        smem = tc_finalize(core, D, cap_lo ? 3 : 1, chunks > 1 ? chunks : 2, (int)epi);     // (>= 2: two accumulator stages whenever they fit)
+        // every accumulator column the epilogue reads must lie inside the allocation (worst case: the last image read as 32-wide blocks)
+        const int reach = (core.acc_stages - 1) * core.block_n + (ipt - 1) * p.Rg + tc_round_up(p.Rg, 32);
+        while (core.tmem_cols < reach && core.tmem_cols < 512) core.tmem_cols <<= 1;
+        if (reach > core.tmem_cols || core.stages < 2 || smem > 227 * 1024) continue;
+        break;
+    }
+    TcMaps maps;
+    int rc = fill_maps(maps, cap_hi, cap_lo, (uint64_t)p.Bc * p.T, ldcap, emb_hi, emb_lo, (uint64_t)p.Bi * p.Rg, ldemb, D, core);
+    if (rc != LOCO_OK) return rc;
+    return tc_launch<EpiLsmFwd, true>(maps, core, p, 2 * p.npairs, smem, st);
+}
+
 int loco_lsm_pair_fwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ldcap, const float *cap_mask,
                       const uint16_t *emb_hi, const uint16_t *emb_lo, int64_t ldemb, const float *reg_mask, int Bc, int T,
                       int Bi, int Rg, int D, float inv_temperature, int alignment, float *d_w2r, float *d_r2w,
@@ -1127,6 +1296,17 @@ int loco_lsm_pair_fwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ld
     LOCO_REQUIRE(alignment == LOCO_ALIGN_SOFTMAX || alignment == LOCO_ALIGN_HARDMAX, LOCO_E_UNSUPPORTED, "lsm_pair_fwd: alignment %d not implemented", alignment);
     LOCO_REQUIRE(d_w2r || d_r2w, LOCO_E_BADARG, "lsm_pair_fwd: no output requested");
     LOCO_REQUIRE(ld_out >= Bi, LOCO_E_BADARG, "lsm_pair_fwd: ld_out < Bi");
+    if (alignment == LOCO_ALIGN_SOFTMAX && lsm_v2_enabled() && current_device_sm_count() >= 2) {
+        LOCO_REQUIRE(cap_hi && emb_hi && cap_mask && reg_mask, LOCO_E_BADARG, "lsm_pair_fwd: null pointer");
+        LOCO_REQUIRE((cap_lo == nullptr) == (emb_lo == nullptr), LOCO_E_BADARG, "lsm_pair_fwd: cap_lo and emb_lo must both be given or both be NULL");
+        LOCO_REQUIRE(T > 0 && Rg > 0 && D > 0, LOCO_E_BADARG, "lsm_pair_fwd: bad shape T=%d Rg=%d D=%d", T, Rg, D);
+        LsmFwdParams q = {};
+        q.cap_mask = cap_mask; q.reg_mask = reg_mask; q.out_w2r = d_w2r; q.out_r2w = d_r2w; q.ld_out = ld_out;
+        q.Bc = Bc; q.T = T; q.Bi = Bi; q.Rg = Rg; q.inv_temp = inv_temperature;
+        bool declined = false;
+        const int rc2 = lsm_fwd2_launch(cap_hi, cap_lo, ldcap, emb_hi, emb_lo, ldemb, D, q, static_cast<cudaStream_t>(stream), &declined);
+        if (!declined) return rc2;        // (declined: no tile shape fits — the first-generation kernel below takes it)
+    }
     LsmParams p = {};
     p.cap_mask = cap_mask; p.reg_mask = reg_mask; p.out_w2r = d_w2r; p.out_r2w = d_r2w; p.ld_out = ld_out;
     p.Bc = Bc; p.T = T; p.Bi = Bi; p.Rg = Rg; p.inv_temp = inv_temperature; p.hardmax = (alignment == LOCO_ALIGN_HARDMAX);
