@@ -55,8 +55,9 @@ const char *loco_last_error(void);      /* thread-local; never NULL */
 int loco_device_check(int device);      /* LOCO_OK iff `device` is compute capability 10.x */
 int loco_sm_count(int device);          /* number of SMs (148 on B200) or <0 */
 long long loco_launch_count(void);      /* kernels this library has launched so far (process-wide, monotonic) */
-/* developer probe (env LOCOV_B200_TIMELINE=1): copies the per-CTA phase stamps (8 x uint64 nanoseconds per CTA: entry, setup
- * done, first operand stage landed, last MMA issued, last accumulator complete, epilogue done, exit, unused) of the most recent
+/* developer probe (env LOCOV_B200_TIMELINE=1): copies the per-CTA phase stamps (16 x uint64 nanoseconds per CTA: entry, setup
+ * done, first operand stage landed, last MMA issued, last accumulator complete, epilogue done, exit, unused, then 8 policy-defined
+ * stamps inside the epilogue) of the most recent
  * tensor-core launch to `host`; returns the number of CTAs copied (0 when the probe is off).  Synchronises the device. */
 int loco_debug_timeline_read(unsigned long long *host, int max_ctas);
 

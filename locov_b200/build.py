@@ -13,13 +13,15 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIBDIR = os.path.join(HERE, "lib")
+# developer experiments: LOCOV_B200_LIBDIR builds / loads a variant library in another directory (relative to the package),
+# LOCOV_B200_NVCC_EXTRA adds compiler flags (e.g. -DLOCOV_EXP=3) to it
+LIBDIR = os.path.join(HERE, os.environ.get("LOCOV_B200_LIBDIR", "lib"))
 LIBNAME = "liblocov_b200.so"
 SOURCES = ["api.cu", "roi_align.cu", "misc_kernels.cu", "tc_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("LOCOV_B200_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

@@ -75,7 +75,7 @@ int make_tmap_f32_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t
     return make_tmap_2d(map, base, rows, cols, ld_elems, box_rows, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4);
 }
 
-// Developer probe: with LOCOV_B200_TIMELINE=1 every tensor-core kernel writes 8 globaltimer stamps per CTA (entry, setup
+// Developer probe: with LOCOV_B200_TIMELINE=1 every tensor-core kernel writes up to 16 globaltimer stamps per CTA (entry, setup
 // done, first stage landed, last MMA issued, last accumulator complete, epilogue done, exit) into this buffer; the most
 // recent launch overwrites it.  Read back with loco_debug_timeline_read().
 static unsigned long long *g_timeline = nullptr;
@@ -88,7 +88,7 @@ unsigned long long *debug_timeline_buffer(int ctas) {
         enabled = (e != nullptr && e[0] == '1') ? 1 : 0;
     }
     if (!enabled || ctas > kTimelineMaxCtas) return nullptr;
-    if (g_timeline == nullptr && cudaMalloc(&g_timeline, (size_t)kTimelineMaxCtas * 8 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+    if (g_timeline == nullptr && cudaMalloc(&g_timeline, (size_t)kTimelineMaxCtas * 16 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
     g_timeline_ctas = ctas;
     return g_timeline;
 }
@@ -160,7 +160,7 @@ int loco_device_check(int device) {
 int loco_debug_timeline_read(unsigned long long *host, int max_ctas) {
     if (loco::g_timeline == nullptr || host == nullptr) return 0;
     const int n = loco::g_timeline_ctas < max_ctas ? loco::g_timeline_ctas : max_ctas;
-    if (cudaMemcpy(host, loco::g_timeline, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (cudaMemcpy(host, loco::g_timeline, (size_t)n * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return n;
 }
 

@@ -195,6 +195,13 @@ __device__ __forceinline__ void cluster_sync_all() {      // every thread of eve
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution-only rendezvous of the cluster (no memory ordering of its own): the set-up sync is ordered by fence.mbarrier_init.release.cluster,
+// the exit sync only keeps a CTA alive while peers may still signal its barriers.  The release / acquire form above costs a GPU-scope
+// memory barrier per warp (~0.5 us of the ~1 us set-up the phase timeline shows).
+__device__ __forceinline__ void cluster_sync_relaxed() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 
 // ---- tcgen05 / TMEM ---------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {   // whole warp, ncols pow2 >= 32
@@ -281,6 +288,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {      // arrive on a (possibly remote) mbarrier
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Same with CTA-scope release: enough when the arrival publishes no shared / global data to the other CTA — the accumulator-empty
+// signal orders tensor-memory reads, which tcgen05.fence::before_thread_sync covers — and avoids the cluster-scope memory barrier.
+__device__ __forceinline__ void mbar_arrive_cluster_cta(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // 2-D tile load into THIS CTA's shared memory whose completion is signalled on an mbarrier of either CTA of the pair
 // (`bar_cluster_addr` = shared::cluster address, normally the leader's barrier).

@@ -54,7 +54,7 @@ struct TcCore {
                         // A and HALF of the B tile (no multicast); the leader CTA (rank 0) issues the MMAs
     int epi_overlay;    // 1: the epilogue scratch overlays the operand ring (legal only with chunks == 1: the ring is
                         // dead once the accumulator barrier fired — every load of this tile has landed and been consumed)
-    unsigned long long *timeline;   // developer probe (LOCOV_B200_TIMELINE=1): per CTA 8 globaltimer stamps, NULL otherwise
+    unsigned long long *timeline;   // developer probe (LOCOV_B200_TIMELINE=1): per CTA 16 globaltimer stamps (0-6 set by the core, 8-15 free for the epilogue policy), NULL otherwise
     int prefetch;       // > 0: the producer prefetches the A panel into L2 in bursts of `prefetch` consecutive k blocks, one burst
                         // ahead of the loads: a 128-byte-wide k block touches every row's DRAM page for 128 bytes only; a burst
                         // turns that into `prefetch` x 128 contiguous bytes per row while the page is open
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int k_elems = core.tf32 ? TC_BLOCK_K / 2 : TC_BLOCK_K;
-    unsigned long long *tl = core.timeline ? core.timeline + (size_t)blockIdx.x * 8 : nullptr;
+    unsigned long long *tl = core.timeline ? core.timeline + (size_t)blockIdx.x * 16 : nullptr;
     if (tl && threadIdx.x == 0) tl[0] = global_timer_ns();                       // CTA entry
 
     // cluster geometry -> virtual CTA index handed to the epilogue policy
@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
         else tmem_alloc(tmem_slot, (uint32_t)core.tmem_cols);
     }
     tc_fence_before();
-    if (csize > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers must be initialised before any remote signal
+    __syncthreads();                                               // TMEM address / barrier words visible inside the CTA
+    if (csize > 1) cluster_sync_relaxed();                         // peers' barriers must be initialised (fence.mbarrier_init above) before any remote signal
     tc_fence_after();
     pdl_trigger();                                                                // the next kernel may start its own set-up
     pdl_wait();                                                                   // operands / masks of the previous kernel are complete
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
             } else {
                 epi.chunk(ep, core, cta, ch, taddr, row, lane, q, epi_smem);
                 tc_fence_before();
-                if constexpr (pair) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));   // the leader's MMA thread waits for both CTAs
+                if constexpr (pair) mbar_arrive_cluster_cta(mapa_u32(smem_u32(&tempty[acc]), 0));   // the leader's MMA thread waits for both CTAs
                 else mbar_arrive(&tempty[acc]);
             }
         }
@@ -384,7 +385,8 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
         if (tl && threadIdx.x == 64) tl[5] = global_timer_ns();                  // epilogue done
     }
     tc_fence_before();
-    if (csize > 1) cluster_sync_all(); else __syncthreads();      // no CTA may exit while peers still signal its barriers
+    __syncthreads();
+    if (csize > 1) cluster_sync_relaxed();                         // no CTA may exit while peers still signal its barriers
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();

@@ -648,6 +648,17 @@ struct LsmFwdParams {
     float inv_temp;
 };
 
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+#ifndef LOCOV_EXP
+#define LOCOV_EXP 0
+#endif
+// developer experiments (build with LOCOV_B200_NVCC_EXTRA=-DLOCOV_EXP=n): results are garbage, timings show what a piece costs
+__device__ __forceinline__ float exp_col(float x) { return (LOCOV_EXP == 1 || LOCOV_EXP == 3 || LOCOV_EXP == 6) ? x : ex2_ftz(x); }     // no MUFU in the column pass
+__device__ __forceinline__ float exp_row(float x) { return (LOCOV_EXP == 2 || LOCOV_EXP == 3 || LOCOV_EXP == 6) ? x : ex2_ftz(x); }     // no MUFU in the row pass
+
+// LDT > 0: the parked sub-tile's row stride is this compile-time constant (every transposed store is one STS with an immediate
+// offset); LDT == 0: run-time stride p.ldt (caption groups whose padded word count exceeds the constant).
+template <int LDT>
 struct EpiLsmFwd {
     static constexpr int kEpiWarps = 8;
     static constexpr int kMinBlocks = 1;
@@ -656,8 +667,13 @@ struct EpiLsmFwd {
     typedef LsmFwdParams Params;
     uint32_t release_bar;        // set by the core: shared::cluster address of the leader's accumulator-empty barrier
     uint64_t *release_local;
-
+    // per-tile state computed by prefetch() (before the accumulator is awaited) and used by chunk(): no integer divisions,
+    // mask reads or tile decoding between the arrival of the accumulator and the first tcgen05.ld
     struct Tile { int rm, gp, it, c_first, ncap, nrows; };
+    Tile tile_;
+    int pcol_, nslots_;
+    bool row_in_, row_on_;
+
     static __device__ __forceinline__ Tile decode(const Params &p, int cta, int ch) {
         Tile t;
         t.rm = cta / p.npairs;
@@ -674,21 +690,25 @@ struct EpiLsmFwd {
         row_a = t.c_first * p.T;                 // word rows of this CTA's caption group (A operand; rows past Bc*T are zero-filled)
         row_b = t.it * p.ipt * p.Rg;             // region rows of the tile's images (B operand; the core adds this CTA's half)
     }
-    // per-half shared memory
+    // per-half shared memory.  All additive masks are in LOG2 units (pre-multiplied by c = inv_temp * log2 e), so one packed FFMA
+    // turns two raw accumulator values into two masked softmax arguments.
     struct Half {
         float *park;        // [Rg][ldt]   RAW similarities of the image being processed, TRANSPOSED: region-major, a caption's words
                             //             contiguous at [cl * Tp, cl * Tp + T)
-        float *rbias;       // [slots][rb] additive region mask: 0 valid, LSM_FILL masked, LSM_PAD past the image
-        float *cbt;         // [kCbt]      additive word mask in the parked layout: 0 valid, LSM_FILL masked, LSM_PAD for the pad words
+        float *rbias;       // [slots][rb] additive region mask: 0 valid, LSM_FILL * c masked, LSM_PAD * c past the image
+        float *cbt;         // [kCbt]      additive word mask in the parked layout: 0 valid, LSM_FILL * c masked, LSM_PAD * c for the pad words
         float *rowval;      // [128]       f_t of the accumulator row (0 for a masked word)
         float *colpart;     // [4][16]     per-warp partial sums of h_r per caption
         float *capnw;       // [16]        valid words per caption
         float *nreg;        // [16]        valid regions per image slot
         int *ncols;         // [16]        accumulator columns of the image that can matter (last valid region + 1; Rg when none is valid)
+        int *capq;          // [16]        float4 quads of a caption's parked column segment that can matter (up to its last valid word)
+        float *hbuf;        // [16][128]   h_r of (caption, region thread), summed per caption in the finish phase
     };
     static __host__ __device__ __forceinline__ size_t half_floats(int Rg, int ldt, int slots, int rb) {
-        return (size_t)Rg * ldt + (size_t)slots * rb + kCbt + 128 + 4 * LSM_MAX_PER_TILE + LSM_MAX_PER_TILE + 16 + 16;
+        return (size_t)Rg * ldt + (size_t)slots * rb + kCbt + 128 + 4 * LSM_MAX_PER_TILE + LSM_MAX_PER_TILE + 16 + 16 + 16 + LSM_MAX_PER_TILE * 128;
     }
+    static __device__ __forceinline__ int stride(const Params &p) { return LDT > 0 ? LDT : p.ldt; }
     static __device__ __forceinline__ Half carve(const Params &p, unsigned char *smem, int half) {
         float *b = reinterpret_cast<float *>(smem) + (size_t)half * ((half_floats(p.Rg, p.ldt, p.slots, p.rb) + 3) & ~(size_t)3);
         Half h;
@@ -699,7 +719,9 @@ struct EpiLsmFwd {
         h.colpart = b; b += 4 * LSM_MAX_PER_TILE;
         h.capnw = b; b += LSM_MAX_PER_TILE;
         h.nreg = b; b += 16;
-        h.ncols = reinterpret_cast<int *>(b);
+        h.ncols = reinterpret_cast<int *>(b); b += 16;
+        h.capq = reinterpret_cast<int *>(b); b += 16;
+        h.hbuf = b;
         return h;
     }
     __device__ __forceinline__ void begin(const Params &, const TcCore &, int, int, int, int, unsigned char *) {}
@@ -708,27 +730,41 @@ struct EpiLsmFwd {
     // masks of tile `ch` -> additive biases and counts in the half's shared memory (all before the accumulator is awaited)
     __device__ __forceinline__ void prefetch(const Params &p, const TcCore &, int cta, int ch, int row, int lane, int, unsigned char *smem) {
         const int et = threadIdx.x - 64, half = et >> 7, ht = et & 127, hw = (et >> 5) & 3;
+        const Tile t = decode(p, cta, ch);
+        tile_ = t;
+        nslots_ = 0;                                            // images this half really has in this tile
+        if (half < p.halves)
+            for (int s = 0; s < p.slots; ++s)
+                if (half + 2 * s < p.ipt && t.it * p.ipt + half + 2 * s < p.Bi) nslots_ = s + 1;
+        row_in_ = row < t.nrows;
+        row_on_ = false;
+        const int rcl = row / p.T;
+        pcol_ = rcl * p.Tp + (row - rcl * p.T);                 // this row's position in the parked (padded) word layout
         if (half >= p.halves) return;
         const Half h = carve(p, smem, half);
-        const Tile t = decode(p, cta, ch);
+        const float c2 = p.inv_temp * LSM_LOG2E;
+        const float fill2 = LSM_FILL * c2, pad2 = LSM_PAD * c2;
         named_bar_sync(2 + half, 128);                         // the half has finished reading the previous tile's buffers
-        if (row < t.nrows) {
-            const int cl = row / p.T, w = row - cl * p.T;
-            h.cbt[cl * p.Tp + w] = (__ldg(p.cap_mask + (int64_t)t.c_first * p.T + row) > 0.f) ? 0.f : LSM_FILL;
+        if (row_in_) {
+            row_on_ = __ldg(p.cap_mask + (int64_t)t.c_first * p.T + row) > 0.f;
+            h.cbt[pcol_] = row_on_ ? 0.f : fill2;
         }
         if (ht < t.ncap)
-            for (int w = p.T; w < p.Tp; ++w) h.cbt[ht * p.Tp + w] = LSM_PAD;
+            for (int w = p.T; w < p.Tp; ++w) h.cbt[ht * p.Tp + w] = pad2;
         for (int s = 0; s < p.slots; ++s) {
             const int i = t.it * p.ipt + half + 2 * s;
             const bool img_on = (half + 2 * s < p.ipt) && i < p.Bi;
             for (int r = ht; r < p.rb; r += 128)
-                h.rbias[s * p.rb + r] = (r < p.Rg && img_on) ? ((__ldg(p.reg_mask + (int64_t)i * p.Rg + r) > 0.f) ? 0.f : LSM_FILL) : LSM_PAD;
+                h.rbias[s * p.rb + r] = (r < p.Rg && img_on) ? ((__ldg(p.reg_mask + (int64_t)i * p.Rg + r) > 0.f) ? 0.f : fill2) : pad2;
         }
         named_bar_sync(2 + half, 128);
         if (ht < t.ncap) {                                     // valid words of caption ht
             float nw = 0.f;
-            for (int w = 0; w < p.T; ++w) nw += (h.cbt[ht * p.Tp + w] == 0.f) ? 1.f : 0.f;
+            int last = 0;
+            for (int w = 0; w < p.T; ++w)
+                if (h.cbt[ht * p.Tp + w] == 0.f) { nw += 1.f; last = w + 1; }
             h.capnw[ht] = nw;
+            h.capq[ht] = last > 0 ? (last + 3) >> 2 : (p.Tp >> 2);       // no valid word: uniform over all T words
         }
         for (int s = hw; s < p.slots; s += 4) {                // the half's images: one warp each
             float nr = 0.f;
@@ -746,90 +782,145 @@ struct EpiLsmFwd {
         named_bar_sync(2 + half, 128);                         // counts are read by every thread of the half in chunk()
     }
 
-    // W accumulator columns of this thread's row, RAW units (c = inv_temp * log2 e turns them into log2 units inside the FFMA that
-    // feeds MUFU.EX2): park them transposed, fold them into the running softmax statistics (m: running max of the biased raw
-    // values, d: sum of 2^((x - m) c), n: sum of those weights times the raw value).
+    // W accumulator columns of this thread's row (RAW units): park them transposed and fold them into the running softmax statistics
+    // (m: running max of the masked log2-domain values, d: sum of 2^(x - m), n: sum of those weights times the RAW value), two
+    // columns per instruction with Blackwell's packed fp32x2 arithmetic (the epilogue is issue- and MUFU-bound).
     // TAIL: only the first `valid` columns belong to the image (the others may hold anything, NaN patterns included: select, never
     // multiply).  MASKED: add the region bias (an image whose regions are all valid needs none in its full blocks).
     template <int W, bool TAIL, bool MASKED>
     __device__ __forceinline__ void fold(const uint32_t (&v)[32], int valid, float c, const float *rb, float *pp, int ldt, bool store, float &m,
-                                         float &d, float &n) {
-        float a[W], x[W];
+                                         float2 &d, float2 &n) {
+        float2 a[W / 2], x[W / 2];
+        const float2 cc = f2(c, c);
         float bm = -FLT_MAX;
 #pragma unroll
         for (int j = 0; j < W; j += 4) {
             float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (MASKED || TAIL) r4 = *reinterpret_cast<const float4 *>(rb + j);
-            const float rbj[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float raw = __uint_as_float(v[j + u]);
-                a[j + u] = TAIL ? ((j + u < valid) ? raw : 0.f) : raw;
-                if (store && (!TAIL || j + u < valid)) pp[(size_t)(j + u) * ldt] = a[j + u];
-                x[j + u] = (MASKED || TAIL) ? a[j + u] + rbj[u] : a[j + u];
+            for (int u = 0; u < 2; ++u) {
+                const int k = j + 2 * u;
+                float2 raw = f2(__uint_as_float(v[k]), __uint_as_float(v[k + 1]));
+                if (TAIL) {
+                    if (k >= valid) raw.x = 0.f;
+                    if (k + 1 >= valid) raw.y = 0.f;
+                }
+                a[k >> 1] = raw;
+                if (store && LOCOV_EXP != 4 && LOCOV_EXP != 6) {
+                    if (!TAIL || k < valid) pp[(size_t)k * ldt] = raw.x;
+                    if (!TAIL || k + 1 < valid) pp[(size_t)(k + 1) * ldt] = raw.y;
+                }
+                x[k >> 1] = (MASKED || TAIL) ? __ffma2_rn(raw, cc, u == 0 ? f2(r4.x, r4.y) : f2(r4.z, r4.w)) : __fmul2_rn(raw, cc);
+                bm = fmaxf(bm, fmaxf(x[k >> 1].x, x[k >> 1].y));
             }
-            bm = fmaxf(bm, fmaxf(fmaxf(x[j], x[j + 1]), fmaxf(x[j + 2], x[j + 3])));
         }
         const float m_new = fmaxf(m, bm);
-        const float corr = ex2_ftz((m - m_new) * c);
-        float d0 = d * corr, d1 = 0.f, n0 = n * corr, n1 = 0.f;
+        const float corr = ex2_ftz(m - m_new);
+        const float2 cr = f2(corr, corr), nm = f2(-m_new, -m_new);
+        float2 d0 = __fmul2_rn(d, cr), n0 = __fmul2_rn(n, cr), d1 = f2(0.f, 0.f), n1 = f2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < W; j += 2) {
-            // (x - m) * c, NOT fma(x, c, -m * c): with every region masked x == m == LSM_FILL and the difference must be exactly 0
-            // (the rounding error of m * c alone is ~1e22 at that magnitude)
-            const float e0 = ex2_ftz((x[j] - m_new) * c), e1 = ex2_ftz((x[j + 1] - m_new) * c);
-            d0 += e0; n0 = fmaf(e0, a[j], n0);
-            d1 += e1; n1 = fmaf(e1, a[j + 1], n1);
+        for (int k = 0; k < W / 2; k += 2) {
+            // x - m: exactly 0 where every region is masked (x == m == the fill)
+            const float2 t0 = __fadd2_rn(x[k], nm), t1 = __fadd2_rn(x[k + 1], nm);
+            const float2 e0 = f2(exp_row(t0.x), exp_row(t0.y)), e1 = f2(exp_row(t1.x), exp_row(t1.y));
+            d0 = __fadd2_rn(d0, e0); n0 = __ffma2_rn(e0, a[k], n0);
+            d1 = __fadd2_rn(d1, e1); n1 = __ffma2_rn(e1, a[k + 1], n1);
         }
         m = m_new;
-        d = d0 + d1;
-        n = n0 + n1;
+        d = __fadd2_rn(d0, d1);
+        n = __fadd2_rn(n0, n1);
     }
 
-    // softmax over one caption's words down a parked column (NQ float4 quads; the last one holds `tlast` real words):
-    // returns sum_t softmax_t * raw similarity
+    // softmax over one caption's words down a parked column (NQ float4 quads; `tlast` real words in the last one):
+    // returns sum_t softmax_t * RAW similarity
     template <int NQ>
     static __device__ __forceinline__ float col_caption(const float *base, const float *cb, int tlast, float c) {
-        float a[4 * NQ], x[4 * NQ];
+        float2 a[2 * NQ], x[2 * NQ];
+        const float2 cc = f2(c, c);
         float mx = -FLT_MAX;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            const float4 v = *reinterpret_cast<const float4 *>(base + 4 * q);
+            float4 v = *reinterpret_cast<const float4 *>(base + 4 * q);
             const float4 b = *reinterpret_cast<const float4 *>(cb + 4 * q);
-            a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
             if (q == NQ - 1) {                                  // pad words were never parked: select them away
-                if (tlast < 2) a[4 * q + 1] = 0.f;
-                if (tlast < 3) a[4 * q + 2] = 0.f;
-                if (tlast < 4) a[4 * q + 3] = 0.f;
+                if (tlast < 2) v.y = 0.f;
+                if (tlast < 3) v.z = 0.f;
+                if (tlast < 4) v.w = 0.f;
             }
-            x[4 * q] = a[4 * q] + b.x; x[4 * q + 1] = a[4 * q + 1] + b.y; x[4 * q + 2] = a[4 * q + 2] + b.z; x[4 * q + 3] = a[4 * q + 3] + b.w;
-            mx = fmaxf(mx, fmaxf(fmaxf(x[4 * q], x[4 * q + 1]), fmaxf(x[4 * q + 2], x[4 * q + 3])));
+            a[2 * q] = f2(v.x, v.y);
+            a[2 * q + 1] = f2(v.z, v.w);
+            x[2 * q] = __ffma2_rn(a[2 * q], cc, f2(b.x, b.y));
+            x[2 * q + 1] = __ffma2_rn(a[2 * q + 1], cc, f2(b.z, b.w));
+            mx = fmaxf(mx, fmaxf(fmaxf(x[2 * q].x, x[2 * q].y), fmaxf(x[2 * q + 1].x, x[2 * q + 1].y)));
         }
-        float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f;
+        const float2 nm = f2(-mx, -mx);
+        float2 d0 = f2(0.f, 0.f), d1 = f2(0.f, 0.f), n0 = f2(0.f, 0.f), n1 = f2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 4 * NQ; j += 2) {
-            const float e0 = ex2_ftz((x[j] - mx) * c), e1 = ex2_ftz((x[j + 1] - mx) * c);      // (exact 0 for an all-masked caption)
-            d0 += e0; n0 = fmaf(e0, a[j], n0);
-            d1 += e1; n1 = fmaf(e1, a[j + 1], n1);
+        for (int k = 0; k < 2 * NQ; k += 2) {
+            const float2 t0 = __fadd2_rn(x[k], nm), t1 = __fadd2_rn(x[k + 1], nm);       // (exactly 0 for an all-masked caption)
+            const float2 e0 = f2(exp_col(t0.x), exp_col(t0.y)), e1 = f2(exp_col(t1.x), exp_col(t1.y));
+            d0 = __fadd2_rn(d0, e0); n0 = __ffma2_rn(e0, a[k], n0);
+            d1 = __fadd2_rn(d1, e1); n1 = __ffma2_rn(e1, a[k + 1], n1);
         }
-        return (n0 + n1) / (d0 + d1);
+        const float2 dd = __fadd2_rn(d0, d1), nn = __fadd2_rn(n0, n1);
+        return __fdividef(nn.x + nn.y, dd.x + dd.y);
     }
-    // any number of quads (T > 32): two sweeps over the column segment
+    // two captions in lockstep: the phases of one (loads, max chain, exponentials) fill the latency gaps of the other — with two epilogue
+    // warps per scheduler there is little else to hide them
+    template <int NQ>
+    static __device__ __forceinline__ void col_caption2(const float *baseA, const float *baseB, const float *cbA, const float *cbB, int tlast, float c,
+                                                        float &outA, float &outB) {
+        float2 a[2][2 * NQ], x[2][2 * NQ];
+        const float2 cc = f2(c, c);
+        float mx[2] = {-FLT_MAX, -FLT_MAX};
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                float4 v = *reinterpret_cast<const float4 *>((z ? baseB : baseA) + 4 * q);
+                const float4 b = *reinterpret_cast<const float4 *>((z ? cbB : cbA) + 4 * q);
+                if (q == NQ - 1) {
+                    if (tlast < 2) v.y = 0.f;
+                    if (tlast < 3) v.z = 0.f;
+                    if (tlast < 4) v.w = 0.f;
+                }
+                a[z][2 * q] = f2(v.x, v.y);
+                a[z][2 * q + 1] = f2(v.z, v.w);
+                x[z][2 * q] = __ffma2_rn(a[z][2 * q], cc, f2(b.x, b.y));
+                x[z][2 * q + 1] = __ffma2_rn(a[z][2 * q + 1], cc, f2(b.z, b.w));
+                mx[z] = fmaxf(mx[z], fmaxf(fmaxf(x[z][2 * q].x, x[z][2 * q].y), fmaxf(x[z][2 * q + 1].x, x[z][2 * q + 1].y)));
+            }
+        }
+        float2 d[2] = {f2(0.f, 0.f), f2(0.f, 0.f)}, n[2] = {f2(0.f, 0.f), f2(0.f, 0.f)};
+#pragma unroll
+        for (int k = 0; k < 2 * NQ; ++k) {
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                const float2 t0 = __fadd2_rn(x[z][k], f2(-mx[z], -mx[z]));
+                const float2 e0 = f2(exp_col(t0.x), exp_col(t0.y));
+                d[z] = __fadd2_rn(d[z], e0);
+                n[z] = __ffma2_rn(e0, a[z][k], n[z]);
+            }
+        }
+        outA = __fdividef(n[0].x + n[0].y, d[0].x + d[0].y);       // 2 ulp: far inside the 1e-4 bar
+        outB = __fdividef(n[1].x + n[1].y, d[1].x + d[1].y);
+    }
+    // any number of quads (more than 8: T > 32): two sweeps over the column segment
     static __device__ __forceinline__ float col_caption_long(const float *base, const float *cb, int nq, int tlast, float c) {
         float mx = -FLT_MAX;
         for (int q = 0; q < nq; ++q) {
             float4 v = *reinterpret_cast<const float4 *>(base + 4 * q);
             const float4 b = *reinterpret_cast<const float4 *>(cb + 4 * q);
             if (q == nq - 1) { if (tlast < 2) v.y = 0.f; if (tlast < 3) v.z = 0.f; if (tlast < 4) v.w = 0.f; }
-            mx = fmaxf(mx, fmaxf(fmaxf(v.x + b.x, v.y + b.y), fmaxf(v.z + b.z, v.w + b.w)));
+            mx = fmaxf(mx, fmaxf(fmaxf(fmaf(v.x, c, b.x), fmaf(v.y, c, b.y)), fmaxf(fmaf(v.z, c, b.z), fmaf(v.w, c, b.w))));
         }
         float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f;
         for (int q = 0; q < nq; ++q) {
             float4 v = *reinterpret_cast<const float4 *>(base + 4 * q);
             const float4 b = *reinterpret_cast<const float4 *>(cb + 4 * q);
             if (q == nq - 1) { if (tlast < 2) v.y = 0.f; if (tlast < 3) v.z = 0.f; if (tlast < 4) v.w = 0.f; }
-            const float e0 = ex2_ftz(((v.x + b.x) - mx) * c), e1 = ex2_ftz(((v.y + b.y) - mx) * c);
-            const float e2 = ex2_ftz(((v.z + b.z) - mx) * c), e3 = ex2_ftz(((v.w + b.w) - mx) * c);
+            const float e0 = ex2_ftz(fmaf(v.x, c, b.x) - mx), e1 = ex2_ftz(fmaf(v.y, c, b.y) - mx);
+            const float e2 = ex2_ftz(fmaf(v.z, c, b.z) - mx), e3 = ex2_ftz(fmaf(v.w, c, b.w) - mx);
             d0 += e0; n0 = fmaf(e0, v.x, n0);
             d1 += e1; n1 = fmaf(e1, v.y, n1);
             d0 += e2; n0 = fmaf(e2, v.z, n0);
@@ -840,7 +931,7 @@ struct EpiLsmFwd {
 
     __device__ __forceinline__ void release_acc() {
         tc_fence_before();
-        mbar_arrive_cluster(release_bar);
+        mbar_arrive_cluster_cta(release_bar);
     }
 
     // block k of an image's columns: k < nb are full 32-column blocks, block nb (if any) is the tail, read 16 or 32 columns wide
@@ -854,25 +945,39 @@ struct EpiLsmFwd {
         else tmem_ld_fence<16>(buf);
     }
 
-    __device__ __forceinline__ void chunk(const Params &p, const TcCore &core, int cta, int ch, uint32_t taddr, int row, int lane, int,
+    template <int NQ>
+    __device__ __forceinline__ void col_pass(const Half &h, const float *colbase, int ncap, int Tp, int tl, float c2, float scale, bool r_on, int ht,
+                                             bool first) {
+        int cl = 0;
+        for (; cl + 1 < ncap; cl += 2) {
+            float vA, vB;
+            col_caption2<NQ>(colbase + cl * Tp, colbase + (cl + 1) * Tp, h.cbt + cl * Tp, h.cbt + (cl + 1) * Tp, tl, c2, vA, vB);
+            float *hb = h.hbuf + cl * 128 + ht;
+            hb[0] = (first ? 0.f : hb[0]) + (r_on ? vA * scale : 0.f);
+            hb[128] = (first ? 0.f : hb[128]) + (r_on ? vB * scale : 0.f);
+        }
+        if (cl < ncap) {
+            const float v = col_caption<NQ>(colbase + cl * Tp, h.cbt + cl * Tp, tl, c2);
+            float *hb = h.hbuf + cl * 128 + ht;
+            hb[0] = (first ? 0.f : hb[0]) + (r_on ? v * scale : 0.f);
+        }
+    }
+
+    __device__ __forceinline__ void chunk(const Params &p, const TcCore &core, int, int, uint32_t taddr, int row, int lane, int,
                                           unsigned char *smem) {
         const int et = threadIdx.x - 64, half = et >> 7, ht = et & 127, hw = (et >> 5) & 3;
-        const Tile t = decode(p, cta, ch);
-        const int T = p.T, Rg = p.Rg, ldt = p.ldt, Tp = p.Tp;
-        int nslots = 0;                                         // images this half really has in this tile
-        if (half < p.halves)
-            for (int s = 0; s < p.slots; ++s)
-                if (half + 2 * s < p.ipt && t.it * p.ipt + half + 2 * s < p.Bi) nslots = s + 1;
+        const Tile t = tile_;
+        const int T = p.T, Rg = p.Rg, ldt = stride(p), Tp = p.Tp;
+        const int nslots = nslots_;
         if (t.ncap == 0 || nslots == 0 || core.debug_mode == 3) {   // padding half of the last pair / nothing for this half
             release_acc();
             return;
         }
         const Half h = carve(p, smem, half);
+        unsigned long long *tl = (core.timeline != nullptr && threadIdx.x == 64) ? core.timeline + (size_t)blockIdx.x * 16 : nullptr;
         const float c2 = p.inv_temp * LSM_LOG2E;
-        const bool row_in = row < t.nrows;
-        const int rcl = row / T;
-        const int pcol = rcl * Tp + (row - rcl * T);            // this row's position in the parked (padded) word layout
-        const bool row_on = row_in && h.cbt[pcol] == 0.f;
+        const bool row_in = row_in_, row_on = row_on_;
+        const int pcol = pcol_;
         const int nq = Tp >> 2, tlast = T - 4 * (nq - 1);
         for (int s = 0; s < nslots; ++s) {
             const int j = half + 2 * s, i = t.it * p.ipt + j;
@@ -885,77 +990,108 @@ struct EpiLsmFwd {
                 const int tw = rem == 0 ? 0 : (rem <= 16 ? 16 : 32);
                 const int nblk = nb + (tw > 0 ? 1 : 0);
                 const bool masked = h.nreg[s] != (float)Rg;
-                float m = -FLT_MAX, d = 0.f, n = 0.f;
+                float m = -FLT_MAX;
+                float2 d = f2(0.f, 0.f), n = f2(0.f, 0.f);
                 uint32_t cur[32], nxt[32];
+                if (tl) tl[8] = global_timer_ns();
                 blk_issue(0, nb, tw, tcol, cur);
                 blk_fence(0, nb, tw, cur);
+#ifdef LOCOV_ROWCLK
+                long long ckf = 0, ckw = 0;
+#endif
                 for (int k = 0; k < nblk; ++k) {
                     if (k + 1 < nblk) blk_issue(k + 1, nb, tw, tcol, nxt);       // in flight while block k is folded
                     float *pp = h.park + (size_t)(k * 32) * ldt + pcol;
                     const float *rbk = rb + k * 32;
+#ifdef LOCOV_ROWCLK
+                    const long long c0 = clock64();
+#endif
                     if (k < nb) {
                         if (masked) fold<32, false, true>(cur, 32, c2, rbk, pp, ldt, row_in, m, d, n);
                         else fold<32, false, false>(cur, 32, c2, rbk, pp, ldt, row_in, m, d, n);
                     } else if (tw == 32) fold<32, true, true>(cur, rem, c2, rbk, pp, ldt, row_in, m, d, n);
                     else fold<16, true, true>(cur, rem, c2, rbk, pp, ldt, row_in, m, d, n);
+#ifdef LOCOV_ROWCLK
+                    const long long c1 = clock64();
+                    ckf += c1 - c0;
+#endif
                     if (k + 1 < nblk) {
                         blk_fence(k + 1, nb, tw, nxt);
 #pragma unroll
                         for (int u = 0; u < 32; ++u) cur[u] = nxt[u];
                     }
+#ifdef LOCOV_ROWCLK
+                    ckw += clock64() - c1;
+#endif
                 }
+#ifdef LOCOV_ROWCLK
+                if (tl) { tl[14] = (unsigned long long)ckf; tl[15] = (unsigned long long)ckw; }
+#endif
+                if (tl) tl[10] = global_timer_ns();
                 if (s == nslots - 1) release_acc();                                   // last tcgen05.ld of this thread for this tile
-                h.rowval[row] = row_on ? (n / d) * p.inv_temp : 0.f;
+                h.rowval[row] = row_on ? __fdividef(n.x + n.y, d.x + d.y) * p.inv_temp : 0.f;
             }
             named_bar_sync(2 + half, 128);
-            // ---- column pass: thread = region, softmax over the T words of each caption down the parked column ----------------------
-            if (core.debug_mode != 4 && p.out_r2w != nullptr) {
+            if (tl) tl[11] = global_timer_ns();
+            // ---- column pass: thread = region, softmax over the T words of each caption down the parked column, two captions at a
+            //      time; the per-(caption, region) results go to shared memory and are summed in the finish phase ------------------
+            const bool do_col = core.debug_mode != 4 && p.out_r2w != nullptr;
+            if (do_col) {
+                int qmax = 1;                                                         // quads up to the last valid word of any caption
+                for (int cl = 0; cl < t.ncap; ++cl) qmax = max(qmax, h.capq[cl]);
+                const int tl4 = qmax == nq ? tlast : 4;
                 for (int r0 = 0; r0 < ncols; r0 += 128) {
                     const int r = r0 + ht;
                     const bool r_on = r < ncols && rb[min(r, ncols - 1)] == 0.f;
-                    const bool warp_on = __any_sync(0xffffffffu, r_on);               // a warp whose regions are all masked has nothing to do
                     const float *colbase = h.park + (size_t)min(r, ncols - 1) * ldt;
-                    for (int cl = 0; cl < t.ncap; ++cl) {
-                        float hv = 0.f;
-                        if (warp_on) {
-                            const float *base = colbase + cl * Tp, *cb = h.cbt + cl * Tp;
-                            float v;
-                            switch (nq) {
-                                case 1: v = col_caption<1>(base, cb, tlast, c2); break;
-                                case 2: v = col_caption<2>(base, cb, tlast, c2); break;
-                                case 3: v = col_caption<3>(base, cb, tlast, c2); break;
-                                case 4: v = col_caption<4>(base, cb, tlast, c2); break;
-                                case 5: v = col_caption<5>(base, cb, tlast, c2); break;
-                                case 6: v = col_caption<6>(base, cb, tlast, c2); break;
-                                case 7: v = col_caption<7>(base, cb, tlast, c2); break;
-                                case 8: v = col_caption<8>(base, cb, tlast, c2); break;
-                                default: v = col_caption_long(base, cb, nq, tlast, c2); break;
+                    if (!__any_sync(0xffffffffu, r_on)) {                             // a warp whose regions are all masked has nothing to do
+                        if (r0 == 0)
+                            for (int cl = 0; cl < t.ncap; ++cl) h.hbuf[cl * 128 + ht] = 0.f;
+                        continue;
+                    }
+                    switch (qmax) {
+                        case 1: col_pass<1>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
+                        case 2: col_pass<2>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
+                        case 3: col_pass<3>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
+                        case 4: col_pass<4>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
+                        case 5: col_pass<5>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
+                        case 6: col_pass<6>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
+                        case 7: col_pass<7>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
+                        case 8: col_pass<8>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
+                        default:
+                            for (int cl = 0; cl < t.ncap; ++cl) {
+                                const float v = col_caption_long(colbase + cl * Tp, h.cbt + cl * Tp, qmax, tl4, c2);
+                                float *hb = h.hbuf + cl * 128 + ht;
+                                hb[0] = (r0 == 0 ? 0.f : hb[0]) + (r_on ? v * p.inv_temp : 0.f);
                             }
-                            hv = warp_sum(r_on ? v * p.inv_temp : 0.f);
-                        }
-                        if (lane == 0) h.colpart[hw * LSM_MAX_PER_TILE + cl] = (r0 == 0 ? 0.f : h.colpart[hw * LSM_MAX_PER_TILE + cl]) + hv;
+                            break;
                     }
                 }
             }
+            if (tl) tl[12] = global_timer_ns();
             named_bar_sync(2 + half, 128);
-            // ---- finish: thread = caption ------------------------------------------------------------------------------
-            if (ht < t.ncap) {
-                const int c = t.c_first + ht;
-                if (p.out_w2r != nullptr) {
-                    float a = 0.f;
-                    for (int w = 0; w < T; ++w) a += h.rowval[ht * T + w];
-                    p.out_w2r[(int64_t)c * p.ld_out + i] = -a / fmaxf(h.capnw[ht], 1.f);
+            if (tl) tl[13] = global_timer_ns();
+            // ---- finish: warp = caption; both sums in a fixed order (lane-strided partials, then the shuffle tree) ------------------------
+            for (int cl = hw; cl < t.ncap; cl += 4) {
+                float a = 0.f, b = 0.f;
+                for (int w = lane; w < T; w += 32) a += h.rowval[cl * T + w];
+                if (do_col) b = (h.hbuf[cl * 128 + lane] + h.hbuf[cl * 128 + 32 + lane]) + (h.hbuf[cl * 128 + 64 + lane] + h.hbuf[cl * 128 + 96 + lane]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
                 }
-                if (p.out_r2w != nullptr) {
-                    const float b = ((h.colpart[ht] + h.colpart[LSM_MAX_PER_TILE + ht]) + h.colpart[2 * LSM_MAX_PER_TILE + ht]) +
-                                    h.colpart[3 * LSM_MAX_PER_TILE + ht];
-                    p.out_r2w[(int64_t)c * p.ld_out + i] = -b / fmaxf(h.nreg[s], 1.f);
+                if (lane == 0) {
+                    const int c = t.c_first + cl;
+                    if (p.out_w2r != nullptr) p.out_w2r[(int64_t)c * p.ld_out + i] = -a / fmaxf(h.capnw[cl], 1.f);
+                    if (p.out_r2w != nullptr) p.out_r2w[(int64_t)c * p.ld_out + i] = -b / fmaxf(h.nreg[s], 1.f);
                 }
             }
-            if (s + 1 < nslots) named_bar_sync(2 + half, 128);      // park / rowval / colpart are rewritten by the next image
+            if (s + 1 < nslots) named_bar_sync(2 + half, 128);      // park / rowval / hbuf are rewritten by the next image
         }
     }
 };
+constexpr int LSM_LDT = 132;      // compile-time parked stride: covers per_tile * round_up(T, 4) <= 132 (T = 20: 120; T = 70: 72; T = 7, 8, 16: 128)
 
 // ------------------------------------------------------------------------------------------------
 // host-side helpers
@@ -1240,6 +1376,8 @@ static int lsm_fwd2_launch(const uint16_t *cap_hi, const uint16_t *cap_lo, int64
     p.Tp = tc_round_up(p.T, 4);
     p.ldt = tc_round_up(p.per_tile * p.Tp, 4);
     if (((p.ldt / 4) & 1) == 0) p.ldt += 4;
+    const bool fixed_ldt = p.ldt <= LSM_LDT;
+    if (fixed_ldt) p.ldt = LSM_LDT;
     p.rb = tc_round_up(p.Rg, 32);
     // images per tile: as many as fit 256 accumulator columns (two accumulator stages = 512 TMEM columns), at most 16; fewer when the
     // epilogue's reads would leave the allocation or the parked sub-tiles leave too little shared memory for the operand ring
@@ -1270,7 +1408,7 @@ static int lsm_fwd2_launch(const uint16_t *cap_hi, const uint16_t *cap_lo, int64
         core.total_tiles = (int)total;
         core.single_wave = 1;
         const int chunks = (int)((total + npairs - 1) / npairs);
-        const size_t half = (EpiLsmFwd::half_floats(p.Rg, p.ldt, p.slots, p.rb) + 3) & ~(size_t)3;
+        const size_t half = (EpiLsmFwd<0>::half_floats(p.Rg, p.ldt, p.slots, p.rb) + 3) & ~(size_t)3;
         const size_t epi = (size_t)p.halves * half * sizeof(float) + 16;
         if (epi > 200 * 1024) continue;
         smem = tc_finalize(core, D, cap_lo ? 3 : 1, chunks > 1 ? chunks : 2, (int)epi);     // (>= 2: two accumulator stages whenever they fit)
@@ -1283,7 +1421,8 @@ static int lsm_fwd2_launch(const uint16_t *cap_hi, const uint16_t *cap_lo, int64
     TcMaps maps;
     int rc = fill_maps(maps, cap_hi, cap_lo, (uint64_t)p.Bc * p.T, ldcap, emb_hi, emb_lo, (uint64_t)p.Bi * p.Rg, ldemb, D, core);
     if (rc != LOCO_OK) return rc;
-    return tc_launch<EpiLsmFwd, true>(maps, core, p, 2 * p.npairs, smem, st);
+    if (fixed_ldt) return tc_launch<EpiLsmFwd<LSM_LDT>, true>(maps, core, p, 2 * p.npairs, smem, st);
+    return tc_launch<EpiLsmFwd<0>, true>(maps, core, p, 2 * p.npairs, smem, st);
 }
 
 int loco_lsm_pair_fwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ldcap, const float *cap_mask,

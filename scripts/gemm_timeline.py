@@ -15,7 +15,7 @@ from locov_b200 import _lib, ops  # noqa: E402
 dev = torch.device("cuda:0")
 lib = _lib.load()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-NAMES = ["entry", "setup", "stage0", "mma_end", "acc_done", "epi_done", "exit"]
+NAMES = ["entry", "setup", "stage0", "mma_end", "acc_done", "epi_done", "exit", "-", "e8", "e9", "e10", "e11", "e12", "e13", "e14", "e15"]
 
 
 def report(tag, fn, reps=5, cold=True):
@@ -26,9 +26,9 @@ def report(tag, fn, reps=5, cold=True):
         torch.cuda.synchronize()
         fn()
         torch.cuda.synchronize()
-        buf = np.zeros(8192 * 8, dtype=np.uint64)
+        buf = np.zeros(8192 * 16, dtype=np.uint64)
         n = lib.loco_debug_timeline_read(buf.ctypes.data_as(ctypes.c_void_p), 8192)
-        t = buf[: n * 8].reshape(n, 8).astype(np.int64)
+        t = buf[: n * 16].reshape(n, 16).astype(np.int64)
         rows.append(t)
     t = rows[-1]
     t0 = t[:, 0].min()
@@ -39,6 +39,9 @@ def report(tag, fn, reps=5, cold=True):
         v = v[v > 0] - t0
         if len(v):
             print(f"   {nm:9s} n={len(v):4d}  min {1e-3 * v.min():7.2f}  median {1e-3 * np.median(v):7.2f}  max {1e-3 * v.max():7.2f} us")
+    if (t[:, 15] > 0).any():
+        print(f"   raw e14 (cycles inside fold) median {np.median(t[:, 14]):.0f}   e15 (cycles in the TMEM fence + copy) median {np.median(t[:, 15]):.0f}   "
+              f"ns of the row pass median {np.median(t[:, 10] - t[:, 8]):.0f}")
     issuers = t[:, 3] > 0
     if issuers.any():
         ml = (t[issuers, 3] - t[issuers, 2]) * 1e-3
