@@ -173,6 +173,28 @@ int loco_box_ce_fwd_bwd(const float *logits, int64_t ld_logits, const float *lse
                         int R, int K1, float scale, float *loss_sum, float grad_scale,
                         float *dlogits_f32, uint16_t *dlogits_bf16, int64_t ld_bf16, void *stream);
 
+/* Class-agnostic box-regression loss and its gradient in one launch.
+ * Replaces: Detectron2 FastRCNNOutputLayers.box_reg_loss reached from roi_emb_heads.py:266,347 (foreground mask, nonzero — a host
+ *           synchronisation —, Box2BoxTransform.get_deltas, fvcore smooth_l1_loss(sum) / max(R, 1): ~15 ATen launches forward and as
+ *           many in autograd's backward).
+ * deltas [R,4] fp32 (ld_deltas): predicted (dx, dy, dw, dh); proposal_boxes, gt_boxes [R,4] fp32 contiguous (x1, y1, x2, y2);
+ * labels [R] int64 (foreground: 0 <= label < K); reg_weights4_host: the 4 BBOX_REG_WEIGHTS (HOST pointer);
+ * loss[0] = scale * sum_fg smooth_l1_beta(deltas - target) (beta < 1e-5: plain L1), overwritten; ddeltas [R,4] (ld_ddeltas) or NULL:
+ * d loss / d deltas (zero rows for background).  workspace: loco_box_reg_loss_workspace_bytes(R) bytes, ZERO-INITIALISED once (left
+ * zeroed by every launch); partial sums are added in block order: deterministic. */
+int64_t loco_box_reg_loss_workspace_bytes(int R);
+int loco_box_reg_loss(const float *deltas, int64_t ld_deltas, const float *proposal_boxes, const float *gt_boxes,
+                      const int64_t *labels, int R, int K, const float *reg_weights4_host, float smooth_l1_beta, float scale,
+                      float *loss, float *ddeltas, int64_t ld_ddeltas, void *workspace, void *stream);
+
+/* Weight / bias gradient of a linear layer with very few outputs: dw[j, v] = sum_r dy[r, j] * x[r, v], db[j] = sum_r dy[r, j], J <= 8.
+ * Replaces: autograd's addmm backward for bbox_pred (box_emb_head.py:196; [4 x R] . [R x 2048] through cuBLAS) — here x is streamed
+ *           once from HBM with no transposed copy.  dy [R,J] fp32 (ld_dy), x [R,V] fp32 (ld_x % 4 == 0, 16-byte aligned), dw [J,V]
+ * contiguous, db [J] or NULL.  workspace: loco_skinny_grad_workspace_bytes(R, J, V) bytes.  Deterministic (fixed chunk order). */
+int64_t loco_skinny_grad_workspace_bytes(int R, int J, int V);
+int loco_skinny_grad(const float *dy, int64_t ld_dy, const float *x, int64_t ld_x, int R, int J, int V, float *dw, float *db,
+                     void *workspace, void *stream);
+
 /* ---- LSM masks -------------------------------------------------------------------------------------
  * Replaces: grounding_head.py:94-96,101,105-106 (attention_mask * (1 - special_tokens_mask), two .to(float32)).
  * attention_mask / special_tokens_mask: n_cap int64 values; region_mask: n_reg values of kind

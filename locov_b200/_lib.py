@@ -39,6 +39,10 @@ SIGNATURES = {
     "loco_box_softmax": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _i64, _vp]),
     "loco_row_normalize": (_i, [_vp, _i64, _i, _i, _i, _vp, _i64, _vp, _i64, _vp]),
     "loco_box_ce_fwd_bwd": (_i, [_vp, _i64, _vp, _vp, _i, _i, _f, _vp, _f, _vp, _vp, _i64, _vp]),
+    "loco_box_reg_loss_workspace_bytes": (_i64, [_i]),
+    "loco_box_reg_loss": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _c.POINTER(_f), _f, _f, _vp, _vp, _i64, _vp, _vp]),
+    "loco_skinny_grad_workspace_bytes": (_i64, [_i, _i, _i]),
+    "loco_skinny_grad": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "loco_lsm_masks": (_i, [_vp, _vp, _i64, _vp, _i, _i64, _vp, _vp, _vp]),
     "loco_lsm_prep": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i, _i64, _vp, _vp, _vp]),
     "loco_lsm_pair_workspace_bytes": (_i64, [_i, _i, _i, _i]),

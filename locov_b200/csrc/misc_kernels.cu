@@ -556,6 +556,134 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
     }
 }
 
+// ---- class-agnostic box regression loss (Detectron2 FastRCNNOutputLayers.box_reg_loss, smooth-L1 / L1) -----------------------
+// loss = sum over foreground rows (0 <= gt < K) of smooth_l1(deltas - get_deltas(proposal, gt_box)) * scale, and its gradient
+// with respect to the predicted deltas (zero rows for background), in ONE launch instead of ~30 ATen launches (masks, box
+// transforms, abs / where / sum and their autograd twins): with the GEMMs at tens of microseconds those launches WERE the
+// training step of the box head.  One thread per RoI; per-block partial sums in a fixed order, last block adds the partials
+// in block order (ticket in `scratch`): deterministic.
+__global__ void __launch_bounds__(256) box_reg_loss_kernel(const float *__restrict__ deltas, int64_t ld_d, const float *__restrict__ prop,
+                                                           const float *__restrict__ gtb, const int64_t *__restrict__ labels, int R, int K,
+                                                           float wx, float wy, float ww, float wh, float beta, float scale,
+                                                           float *__restrict__ loss, float *__restrict__ ddeltas, int64_t ld_g,
+                                                           float *__restrict__ scratch) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float red[32];
+    __shared__ int s_last;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    float l = 0.f;
+    if (r < R) {
+        const int64_t y = labels[r];
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        if (y >= 0 && y < K) {
+            const float4 p = *reinterpret_cast<const float4 *>(prop + 4 * (int64_t)r), q = *reinterpret_cast<const float4 *>(gtb + 4 * (int64_t)r);
+            const float sw = p.z - p.x, sh = p.w - p.y, sx = p.x + 0.5f * sw, sy = p.y + 0.5f * sh;
+            const float tw = q.z - q.x, th = q.w - q.y, tx = q.x + 0.5f * tw, ty = q.y + 0.5f * th;
+            const float tgt[4] = {wx * (tx - sx) / sw, wy * (ty - sy) / sh, ww * logf(tw / sw), wh * logf(th / sh)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float df = deltas[(int64_t)r * ld_d + k] - tgt[k], n = fabsf(df);
+                if (beta < 1e-5f) {
+                    l += n;
+                    g[k] = (df > 0.f) ? scale : ((df < 0.f) ? -scale : 0.f);         // sign(0) = 0, as torch.abs' gradient
+                } else if (n < beta) {
+                    l += 0.5f * n * n / beta;
+                    g[k] = df / beta * scale;
+                } else {
+                    l += n - 0.5f * beta;
+                    g[k] = (df > 0.f) ? scale : -scale;
+                }
+            }
+        }
+        if (ddeltas != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ddeltas[(int64_t)r * ld_g + k] = g[k];
+        }
+    }
+    l = block_reduce_sum(l, red);
+    float *parts = scratch + 16;
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(scratch);
+    if (threadIdx.x == 0) parts[blockIdx.x] = l;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        float v = 0.f;
+        for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) v += __ldcg(parts + j);     // (fixed order per thread, then the fixed tree)
+        v = block_reduce_sum(v, red);
+        if (threadIdx.x == 0) {
+            *loss = v * scale;
+            *ticket = 0;            // ready for the next launch
+        }
+    }
+}
+
+// ---- skinny weight gradient: dW[j, v] = sum_r dy[r, j] * x[r, v], db[j] = sum_r dy[r, j]  (J <= 8 output rows) ---------------------
+// The gradient of the class-agnostic box regressor (bbox_pred: 4 x 2048) is a [4 x R] x [R x 2048] product: as a tensor-core GEMM it
+// needs x TRANSPOSED (a 67 MB pass at 8192 RoIs) and wastes 124 of 128 tile rows.  Here x is streamed once (HBM bound, 128-bit
+// loads): block (vc, rc) owns 512 columns x a chunk of rows; partials [row chunks][J][V] are added in chunk order by the second kernel.
+template <int J>
+__global__ void __launch_bounds__(128) skinny_grad_partial_kernel(const float *__restrict__ dy, int64_t ld_dy, const float *__restrict__ x,
+                                                                  int64_t ld_x, int R, int V, int rows_per_chunk, float *__restrict__ part) {
+    pdl_trigger();
+    pdl_wait();
+    const int v0 = (blockIdx.x * 128 + threadIdx.x) * 4;
+    const int r0 = blockIdx.y * rows_per_chunk, r1 = min(R, r0 + rows_per_chunk);
+    float4 acc[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (v0 < V) {
+        for (int r = r0; r < r1; ++r) {
+            float4 xv;
+            if (v0 + 3 < V) xv = __ldg(reinterpret_cast<const float4 *>(x + (int64_t)r * ld_x + v0));
+            else {
+                xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float *xr = x + (int64_t)r * ld_x + v0;
+                xv.x = xr[0];
+                if (v0 + 1 < V) xv.y = xr[1];
+                if (v0 + 2 < V) xv.z = xr[2];
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const float g = __ldg(dy + (int64_t)r * ld_dy + j);           // warp-uniform address: one broadcast load
+                acc[j].x = fmaf(g, xv.x, acc[j].x); acc[j].y = fmaf(g, xv.y, acc[j].y);
+                acc[j].z = fmaf(g, xv.z, acc[j].z); acc[j].w = fmaf(g, xv.w, acc[j].w);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            float *dst = part + ((int64_t)blockIdx.y * J + j) * V + v0;
+            dst[0] = acc[j].x;
+            if (v0 + 1 < V) dst[1] = acc[j].y;
+            if (v0 + 2 < V) dst[2] = acc[j].z;
+            if (v0 + 3 < V) dst[3] = acc[j].w;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) skinny_grad_reduce_kernel(const float *__restrict__ part, int nchunk, int JV, float *__restrict__ dw,
+                                                                 const float *__restrict__ dy, int64_t ld_dy, int R, int J, float *__restrict__ db) {
+    pdl_trigger();
+    pdl_wait();
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < JV) {
+        float v = 0.f;
+        for (int c = 0; c < nchunk; ++c) v += part[(int64_t)c * JV + idx];
+        dw[idx] = v;
+    }
+    if (db != nullptr && blockIdx.x == 0) {           // bias gradient: column sums of dy, warp j sums column j in a fixed order
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (w < J) {
+            float v = 0.f;
+            for (int r = lane; r < R; r += 32) v += dy[(int64_t)r * ld_dy + w];
+            v = warp_sum(v);
+            if (lane == 0) db[w] = v;
+        }
+    }
+}
+
 }  // namespace loco
 
 using namespace loco;
@@ -680,6 +808,72 @@ int loco_row_normalize(const float *x, int64_t ldx, int rows, int cols, int mode
     if (blocks > 148 * 8) blocks = 148 * 8;
     LOCO_CUDA(launch_kernel(row_normalize_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, x, ldx, rows, cols, mode, dy, lddy,
                             out, ldo));
+    count_launch();
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+int64_t loco_box_reg_loss_workspace_bytes(int R) { return (int64_t)(16 + (R + 255) / 256) * (int64_t)sizeof(float); }
+
+int loco_box_reg_loss(const float *deltas, int64_t ld_deltas, const float *proposal_boxes, const float *gt_boxes, const int64_t *labels, int R,
+                      int K, const float *reg_weights4_host, float smooth_l1_beta, float scale, float *loss, float *ddeltas, int64_t ld_ddeltas,
+                      void *workspace, void *stream) {
+    LOCO_REQUIRE(R >= 0 && K >= 0 && ld_deltas >= 4 && (ddeltas == nullptr || ld_ddeltas >= 4), LOCO_E_BADARG, "box_reg_loss: bad shape R=%d", R);
+    LOCO_REQUIRE(loss != nullptr && reg_weights4_host != nullptr, LOCO_E_BADARG, "box_reg_loss: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (R == 0) {
+        LOCO_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+        return LOCO_OK;
+    }
+    LOCO_REQUIRE(deltas && proposal_boxes && gt_boxes && labels && workspace, LOCO_E_BADARG, "box_reg_loss: null pointer");
+    LOCO_REQUIRE(((reinterpret_cast<uintptr_t>(proposal_boxes) | reinterpret_cast<uintptr_t>(gt_boxes)) & 15) == 0, LOCO_E_ALIGN,
+                 "box_reg_loss: box arrays must be 16-byte aligned (contiguous [R,4] fp32)");
+    const int blocks = (R + 255) / 256;
+    LOCO_CUDA(launch_kernel(box_reg_loss_kernel, dim3(blocks), dim3(256), 0, st, 1, deltas, ld_deltas, proposal_boxes, gt_boxes, labels, R, K,
+                            reg_weights4_host[0], reg_weights4_host[1], reg_weights4_host[2], reg_weights4_host[3], smooth_l1_beta, scale, loss, ddeltas,
+                            ld_ddeltas, static_cast<float *>(workspace)));
+    count_launch();
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+static int skinny_chunks(int R) {
+    int c = (R + 255) / 256;
+    if (c > 64) c = 64;
+    return c < 1 ? 1 : c;
+}
+int64_t loco_skinny_grad_workspace_bytes(int R, int J, int V) { return (int64_t)skinny_chunks(R) * J * V * (int64_t)sizeof(float); }
+
+int loco_skinny_grad(const float *dy, int64_t ld_dy, const float *x, int64_t ld_x, int R, int J, int V, float *dw, float *db, void *workspace,
+                     void *stream) {
+    LOCO_REQUIRE(R >= 0 && J >= 1 && J <= 8 && V >= 1 && ld_dy >= J && ld_x >= V, LOCO_E_BADARG, "skinny_grad: bad shape R=%d J=%d V=%d", R, J, V);
+    LOCO_REQUIRE(dw != nullptr, LOCO_E_BADARG, "skinny_grad: null output");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (R == 0) {
+        LOCO_CUDA(cudaMemsetAsync(dw, 0, (size_t)J * V * sizeof(float), st));
+        if (db) LOCO_CUDA(cudaMemsetAsync(db, 0, (size_t)J * sizeof(float), st));
+        return LOCO_OK;
+    }
+    LOCO_REQUIRE(dy && x && workspace, LOCO_E_BADARG, "skinny_grad: null pointer");
+    LOCO_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && ld_x % 4 == 0, LOCO_E_ALIGN, "skinny_grad: x must be 16-byte aligned with ld_x %% 4 == 0");
+    const int nchunk = skinny_chunks(R), rpc = (R + nchunk - 1) / nchunk;
+    dim3 grid((unsigned)((V + 511) / 512), (unsigned)nchunk);
+    float *part = static_cast<float *>(workspace);
+#define LOCO_SKINNY(JJ) LOCO_CUDA(launch_kernel(skinny_grad_partial_kernel<JJ>, grid, dim3(128), 0, st, 1, dy, ld_dy, x, ld_x, R, V, rpc, part))
+    switch (J) {
+        case 1: LOCO_SKINNY(1); break;
+        case 2: LOCO_SKINNY(2); break;
+        case 3: LOCO_SKINNY(3); break;
+        case 4: LOCO_SKINNY(4); break;
+        case 5: LOCO_SKINNY(5); break;
+        case 6: LOCO_SKINNY(6); break;
+        case 7: LOCO_SKINNY(7); break;
+        default: LOCO_SKINNY(8); break;
+    }
+#undef LOCO_SKINNY
+    count_launch();
+    LOCO_CUDA(launch_kernel(skinny_grad_reduce_kernel, dim3((unsigned)((J * V + 255) / 256)), dim3(256), 0, st, 1, static_cast<const float *>(part), nchunk,
+                            J * V, dw, dy, ld_dy, R, J, db));
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;

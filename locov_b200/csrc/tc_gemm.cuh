@@ -40,6 +40,8 @@ struct TcCore {
     int acc_stages;     // TMEM accumulator buffers (1 or 2)
     int tmem_cols;      // allocation: power of two >= 32
     int epi_smem;       // bytes of epilogue scratch
+    int epi_tail;       // bytes of epilogue scratch that never overlay the ring (they follow the barriers even with epi_overlay): buffers the
+                        // policy fills while the tile's operands are still in flight
     // thread-block cluster with TMA multicast (cm x cn CTAs; 1 x 1 = no cluster): CTA (rm, rn) computes tile
     // (tile_m0 + rm, tile_n0 + rn); the A tile of a row is shared by its cn CTAs (each loads 1/cn of it and
     // multicasts), the B tile of a column by its cm CTAs — L2->SM operand traffic drops by the same factors.
@@ -85,7 +87,7 @@ inline size_t tc_finalize(TcCore &core, int K, int passes, int chunks, int epi_s
     if (core.cn < 1) core.cn = 1;
     const size_t stage_bytes = TC_A_BYTES + (size_t)(core.two_cta ? core.block_n / 2 : core.block_n) * 128;
     if (chunks != 1) core.epi_overlay = 0;
-    const long long fixed = 1024 /*alignment slack*/ + 512 /*barriers*/ + (core.epi_overlay ? 0 : (long long)epi_smem);
+    const long long fixed = 1024 /*alignment slack*/ + 512 /*barriers*/ + core.epi_tail + (core.epi_overlay ? 0 : (long long)epi_smem);
     long long budget = core.single_wave ? 225 : 110;                                // two CTAs per SM unless the grid is one wave
     if (const char *e = getenv("LOCOV_B200_SMEMKB")) { const int v = atoi(e); if (v >= 32 && v <= 225) budget = v; }   // developer sweep knob
     int stages = (int)((budget * 1024 - fixed) / (long long)stage_bytes);

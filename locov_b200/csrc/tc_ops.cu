@@ -658,9 +658,16 @@ __device__ __forceinline__ float exp_row(float x) { return (LOCOV_EXP == 2 || LO
 
 // LDT > 0: the parked sub-tile's row stride is this compile-time constant (every transposed store is one STS with an immediate
 // offset); LDT == 0: run-time stride p.ldt (caption groups whose padded word count exceeds the constant).
+//
+// SIXTEEN epilogue warps = four warpgroups of 128 threads, each covering the 128 accumulator rows (TMEM lane quarter = warp & 3).
+// Warpgroup g works on image (g & 1) of the current pair of images ("slot") and, in the row pass, on column half (g >> 1) of that
+// image's accumulator columns; the two warpgroups of an image ("image group", 256 threads, one named barrier) merge their partial
+// row statistics through shared memory, then split the CAPTIONS of the column pass between them.  Four warps per scheduler instead
+// of two: the epilogue is a chain of dependent packed-fp32 / MUFU / shared-memory operations, and with two warps per scheduler every
+// one of those latencies was exposed (issue slots 14 % busy in the r2 profile).
 template <int LDT>
 struct EpiLsmFwd {
-    static constexpr int kEpiWarps = 8;
+    static constexpr int kEpiWarps = 16;
     static constexpr int kMinBlocks = 1;
     static constexpr bool kHasPrefetch = true, kSelfRelease = true;
     static constexpr int kCbt = 192;       // >= per_tile * Tp (per_tile <= 16, per_tile * T <= 128, Tp <= T + 3)
@@ -690,83 +697,92 @@ struct EpiLsmFwd {
         row_a = t.c_first * p.T;                 // word rows of this CTA's caption group (A operand; rows past Bc*T are zero-filled)
         row_b = t.it * p.ipt * p.Rg;             // region rows of the tile's images (B operand; the core adds this CTA's half)
     }
-    // per-half shared memory.  All additive masks are in LOG2 units (pre-multiplied by c = inv_temp * log2 e), so one packed FFMA
-    // turns two raw accumulator values into two masked softmax arguments.
+    // shared memory of one image group.  All additive masks are in LOG2 units (pre-multiplied by c = inv_temp * log2 e), so one packed
+    // FFMA turns two raw accumulator values into two masked softmax arguments.
     struct Half {
         float *park;        // [Rg][ldt]   RAW similarities of the image being processed, TRANSPOSED: region-major, a caption's words
                             //             contiguous at [cl * Tp, cl * Tp + T)
         float *rbias;       // [slots][rb] additive region mask: 0 valid, LSM_FILL * c masked, LSM_PAD * c past the image
         float *cbt;         // [kCbt]      additive word mask in the parked layout: 0 valid, LSM_FILL * c masked, LSM_PAD * c for the pad words
         float *rowval;      // [128]       f_t of the accumulator row (0 for a masked word)
-        float *colpart;     // [4][16]     per-warp partial sums of h_r per caption
+        float *part;        // [2][3][128] partial row statistics (max, sum, weighted sum) of the two column halves
         float *capnw;       // [16]        valid words per caption
         float *nreg;        // [16]        valid regions per image slot
         int *ncols;         // [16]        accumulator columns of the image that can matter (last valid region + 1; Rg when none is valid)
         int *capq;          // [16]        float4 quads of a caption's parked column segment that can matter (up to its last valid word)
         float *hbuf;        // [16][128]   h_r of (caption, region thread), summed per caption in the finish phase
     };
-    static __host__ __device__ __forceinline__ size_t half_floats(int Rg, int ldt, int slots, int rb) {
-        return (size_t)Rg * ldt + (size_t)slots * rb + kCbt + 128 + 4 * LSM_MAX_PER_TILE + LSM_MAX_PER_TILE + 16 + 16 + 16 + LSM_MAX_PER_TILE * 128;
+    // "big" part of an image group's scratch (parked sub-tile + per-region results): may overlay the operand ring when every pair
+    // has a single tile; "small" part (masks, counts, row statistics): filled by prefetch() while operands are in flight, never overlaid
+    static __host__ __device__ __forceinline__ size_t big_floats(int Rg, int ldt, int per_tile) {
+        return ((size_t)Rg * ldt + (size_t)per_tile * 128 + 3) & ~(size_t)3;
+    }
+    static __host__ __device__ __forceinline__ size_t small_floats(int slots, int rb) {
+        return ((size_t)slots * rb + kCbt + 128 + 6 * 128 + LSM_MAX_PER_TILE + 16 + 16 + 16 + 3) & ~(size_t)3;
     }
     static __device__ __forceinline__ int stride(const Params &p) { return LDT > 0 ? LDT : p.ldt; }
-    static __device__ __forceinline__ Half carve(const Params &p, unsigned char *smem, int half) {
-        float *b = reinterpret_cast<float *>(smem) + (size_t)half * ((half_floats(p.Rg, p.ldt, p.slots, p.rb) + 3) & ~(size_t)3);
+    static __device__ __forceinline__ Half carve(const Params &p, const TcCore &core, unsigned char *smem, int img) {
+        // core hands over the ring base when the scratch overlays it, else the first byte after the barriers
+        float *small = reinterpret_cast<float *>(core.epi_overlay ? smem + core.ring_bytes + 512 : smem);
+        float *big = core.epi_overlay ? reinterpret_cast<float *>(smem) : small + 2 * small_floats(p.slots, p.rb);
+        float *b = small + (size_t)img * small_floats(p.slots, p.rb);
         Half h;
-        h.park = b; b += (size_t)p.Rg * p.ldt;
         h.rbias = b; b += (size_t)p.slots * p.rb;
         h.cbt = b; b += kCbt;
         h.rowval = b; b += 128;
-        h.colpart = b; b += 4 * LSM_MAX_PER_TILE;
+        h.part = b; b += 6 * 128;
         h.capnw = b; b += LSM_MAX_PER_TILE;
         h.nreg = b; b += 16;
         h.ncols = reinterpret_cast<int *>(b); b += 16;
-        h.capq = reinterpret_cast<int *>(b); b += 16;
-        h.hbuf = b;
+        h.capq = reinterpret_cast<int *>(b);
+        h.park = big + (size_t)img * big_floats(p.Rg, p.ldt, p.per_tile);
+        h.hbuf = h.park + (size_t)p.Rg * p.ldt;
         return h;
     }
     __device__ __forceinline__ void begin(const Params &, const TcCore &, int, int, int, int, unsigned char *) {}
     __device__ __forceinline__ void finish(const Params &, const TcCore &, int, int, int, int, unsigned char *) {}
 
-    // masks of tile `ch` -> additive biases and counts in the half's shared memory (all before the accumulator is awaited)
-    __device__ __forceinline__ void prefetch(const Params &p, const TcCore &, int cta, int ch, int row, int lane, int, unsigned char *smem) {
-        const int et = threadIdx.x - 64, half = et >> 7, ht = et & 127, hw = (et >> 5) & 3;
+    // masks of tile `ch` -> additive biases and counts in the image group's shared memory (all before the accumulator is awaited)
+    __device__ __forceinline__ void prefetch(const Params &p, const TcCore &core, int cta, int ch, int row, int lane, int, unsigned char *smem) {
+        const int e = (threadIdx.x >> 5) - 2, g = e >> 2, img = g & 1, hcol = g >> 1;
+        const int gt = hcol * 128 + (e & 3) * 32 + lane, gw = hcol * 4 + (e & 3);      // thread / warp index inside the image group
         const Tile t = decode(p, cta, ch);
         tile_ = t;
-        nslots_ = 0;                                            // images this half really has in this tile
-        if (half < p.halves)
+        nslots_ = 0;                                            // images this image group really has in this tile
+        if (img < p.halves)
             for (int s = 0; s < p.slots; ++s)
-                if (half + 2 * s < p.ipt && t.it * p.ipt + half + 2 * s < p.Bi) nslots_ = s + 1;
+                if (img + 2 * s < p.ipt && t.it * p.ipt + img + 2 * s < p.Bi) nslots_ = s + 1;
         row_in_ = row < t.nrows;
         row_on_ = false;
         const int rcl = row / p.T;
         pcol_ = rcl * p.Tp + (row - rcl * p.T);                 // this row's position in the parked (padded) word layout
-        if (half >= p.halves) return;
-        const Half h = carve(p, smem, half);
+        if (img >= p.halves) return;
+        const Half h = carve(p, core, smem, img);
         const float c2 = p.inv_temp * LSM_LOG2E;
         const float fill2 = LSM_FILL * c2, pad2 = LSM_PAD * c2;
-        named_bar_sync(2 + half, 128);                         // the half has finished reading the previous tile's buffers
+        named_bar_sync(2 + img, 256);                          // the image group has finished reading the previous tile's buffers
         if (row_in_) {
             row_on_ = __ldg(p.cap_mask + (int64_t)t.c_first * p.T + row) > 0.f;
-            h.cbt[pcol_] = row_on_ ? 0.f : fill2;
+            if (hcol == 0) h.cbt[pcol_] = row_on_ ? 0.f : fill2;
         }
-        if (ht < t.ncap)
-            for (int w = p.T; w < p.Tp; ++w) h.cbt[ht * p.Tp + w] = pad2;
+        if (gt < t.ncap)
+            for (int w = p.T; w < p.Tp; ++w) h.cbt[gt * p.Tp + w] = pad2;
         for (int s = 0; s < p.slots; ++s) {
-            const int i = t.it * p.ipt + half + 2 * s;
-            const bool img_on = (half + 2 * s < p.ipt) && i < p.Bi;
-            for (int r = ht; r < p.rb; r += 128)
+            const int i = t.it * p.ipt + img + 2 * s;
+            const bool img_on = (img + 2 * s < p.ipt) && i < p.Bi;
+            for (int r = gt; r < p.rb; r += 256)
                 h.rbias[s * p.rb + r] = (r < p.Rg && img_on) ? ((__ldg(p.reg_mask + (int64_t)i * p.Rg + r) > 0.f) ? 0.f : fill2) : pad2;
         }
-        named_bar_sync(2 + half, 128);
-        if (ht < t.ncap) {                                     // valid words of caption ht
+        named_bar_sync(2 + img, 256);
+        if (gt < t.ncap) {                                     // valid words of caption gt
             float nw = 0.f;
             int last = 0;
             for (int w = 0; w < p.T; ++w)
-                if (h.cbt[ht * p.Tp + w] == 0.f) { nw += 1.f; last = w + 1; }
-            h.capnw[ht] = nw;
-            h.capq[ht] = last > 0 ? (last + 3) >> 2 : (p.Tp >> 2);       // no valid word: uniform over all T words
+                if (h.cbt[gt * p.Tp + w] == 0.f) { nw += 1.f; last = w + 1; }
+            h.capnw[gt] = nw;
+            h.capq[gt] = last > 0 ? (last + 3) >> 2 : (p.Tp >> 2);       // no valid word: uniform over all T words
         }
-        for (int s = hw; s < p.slots; s += 4) {                // the half's images: one warp each
+        for (int s = gw; s < p.slots; s += 8) {                // the group's images: one warp each
             float nr = 0.f;
             int last = 0;
             for (int r = lane; r < p.Rg; r += 32)
@@ -779,18 +795,18 @@ struct EpiLsmFwd {
                 h.ncols[s] = last > 0 ? last : p.Rg;           // none valid: uniform over all Rg regions, every column matters
             }
         }
-        named_bar_sync(2 + half, 128);                         // counts are read by every thread of the half in chunk()
+        named_bar_sync(2 + img, 256);                          // counts are read by every thread of the group in chunk()
     }
 
     // W accumulator columns of this thread's row (RAW units): park them transposed and fold them into the running softmax statistics
     // (m: running max of the masked log2-domain values, d: sum of 2^(x - m), n: sum of those weights times the RAW value), two
-    // columns per instruction with Blackwell's packed fp32x2 arithmetic (the epilogue is issue- and MUFU-bound).
+    // columns per instruction with Blackwell's packed fp32x2 arithmetic.
     // TAIL: only the first `valid` columns belong to the image (the others may hold anything, NaN patterns included: select, never
     // multiply).  MASKED: add the region bias (an image whose regions are all valid needs none in its full blocks).
     template <int W, bool TAIL, bool MASKED>
-    __device__ __forceinline__ void fold(const uint32_t (&v)[32], int valid, float c, const float *rb, float *pp, int ldt, bool store, float &m,
+    __device__ __forceinline__ void fold(uint32_t (&v)[32], int valid, float c, const float *rb, float *pp, int ldt, bool store, float &m,
                                          float2 &d, float2 &n) {
-        float2 a[W / 2], x[W / 2];
+        float2 x[W / 2];
         const float2 cc = f2(c, c);
         float bm = -FLT_MAX;
 #pragma unroll
@@ -800,12 +816,11 @@ struct EpiLsmFwd {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int k = j + 2 * u;
-                float2 raw = f2(__uint_as_float(v[k]), __uint_as_float(v[k + 1]));
                 if (TAIL) {
-                    if (k >= valid) raw.x = 0.f;
-                    if (k + 1 >= valid) raw.y = 0.f;
+                    if (k >= valid) v[k] = 0u;
+                    if (k + 1 >= valid) v[k + 1] = 0u;
                 }
-                a[k >> 1] = raw;
+                const float2 raw = f2(__uint_as_float(v[k]), __uint_as_float(v[k + 1]));
                 if (store && LOCOV_EXP != 4 && LOCOV_EXP != 6) {
                     if (!TAIL || k < valid) pp[(size_t)k * ldt] = raw.x;
                     if (!TAIL || k + 1 < valid) pp[(size_t)(k + 1) * ldt] = raw.y;
@@ -823,8 +838,8 @@ struct EpiLsmFwd {
             // x - m: exactly 0 where every region is masked (x == m == the fill)
             const float2 t0 = __fadd2_rn(x[k], nm), t1 = __fadd2_rn(x[k + 1], nm);
             const float2 e0 = f2(exp_row(t0.x), exp_row(t0.y)), e1 = f2(exp_row(t1.x), exp_row(t1.y));
-            d0 = __fadd2_rn(d0, e0); n0 = __ffma2_rn(e0, a[k], n0);
-            d1 = __fadd2_rn(d1, e1); n1 = __ffma2_rn(e1, a[k + 1], n1);
+            d0 = __fadd2_rn(d0, e0); n0 = __ffma2_rn(e0, f2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])), n0);
+            d1 = __fadd2_rn(d1, e1); n1 = __ffma2_rn(e1, f2(__uint_as_float(v[2 * k + 2]), __uint_as_float(v[2 * k + 3])), n1);
         }
         m = m_new;
         d = __fadd2_rn(d0, d1);
@@ -863,47 +878,7 @@ struct EpiLsmFwd {
             d1 = __fadd2_rn(d1, e1); n1 = __ffma2_rn(e1, a[k + 1], n1);
         }
         const float2 dd = __fadd2_rn(d0, d1), nn = __fadd2_rn(n0, n1);
-        return __fdividef(nn.x + nn.y, dd.x + dd.y);
-    }
-    // two captions in lockstep: the phases of one (loads, max chain, exponentials) fill the latency gaps of the other — with two epilogue
-    // warps per scheduler there is little else to hide them
-    template <int NQ>
-    static __device__ __forceinline__ void col_caption2(const float *baseA, const float *baseB, const float *cbA, const float *cbB, int tlast, float c,
-                                                        float &outA, float &outB) {
-        float2 a[2][2 * NQ], x[2][2 * NQ];
-        const float2 cc = f2(c, c);
-        float mx[2] = {-FLT_MAX, -FLT_MAX};
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-#pragma unroll
-            for (int z = 0; z < 2; ++z) {
-                float4 v = *reinterpret_cast<const float4 *>((z ? baseB : baseA) + 4 * q);
-                const float4 b = *reinterpret_cast<const float4 *>((z ? cbB : cbA) + 4 * q);
-                if (q == NQ - 1) {
-                    if (tlast < 2) v.y = 0.f;
-                    if (tlast < 3) v.z = 0.f;
-                    if (tlast < 4) v.w = 0.f;
-                }
-                a[z][2 * q] = f2(v.x, v.y);
-                a[z][2 * q + 1] = f2(v.z, v.w);
-                x[z][2 * q] = __ffma2_rn(a[z][2 * q], cc, f2(b.x, b.y));
-                x[z][2 * q + 1] = __ffma2_rn(a[z][2 * q + 1], cc, f2(b.z, b.w));
-                mx[z] = fmaxf(mx[z], fmaxf(fmaxf(x[z][2 * q].x, x[z][2 * q].y), fmaxf(x[z][2 * q + 1].x, x[z][2 * q + 1].y)));
-            }
-        }
-        float2 d[2] = {f2(0.f, 0.f), f2(0.f, 0.f)}, n[2] = {f2(0.f, 0.f), f2(0.f, 0.f)};
-#pragma unroll
-        for (int k = 0; k < 2 * NQ; ++k) {
-#pragma unroll
-            for (int z = 0; z < 2; ++z) {
-                const float2 t0 = __fadd2_rn(x[z][k], f2(-mx[z], -mx[z]));
-                const float2 e0 = f2(exp_col(t0.x), exp_col(t0.y));
-                d[z] = __fadd2_rn(d[z], e0);
-                n[z] = __ffma2_rn(e0, a[z][k], n[z]);
-            }
-        }
-        outA = __fdividef(n[0].x + n[0].y, d[0].x + d[0].y);       // 2 ulp: far inside the 1e-4 bar
-        outB = __fdividef(n[1].x + n[1].y, d[1].x + d[1].y);
+        return __fdividef(nn.x + nn.y, dd.x + dd.y);            // 2 ulp: far inside the 1e-4 bar
     }
     // any number of quads (more than 8: T > 32): two sweeps over the column segment
     static __device__ __forceinline__ float col_caption_long(const float *base, const float *cb, int nq, int tlast, float c) {
@@ -926,7 +901,23 @@ struct EpiLsmFwd {
             d0 += e2; n0 = fmaf(e2, v.z, n0);
             d1 += e3; n1 = fmaf(e3, v.w, n1);
         }
-        return (n0 + n1) / (d0 + d1);
+        return __fdividef(n0 + n1, d0 + d1);
+    }
+    // one caption's column segment, `q` quads of it (up to the caption's last valid word; the last quad of a whole segment holds `tlast`
+    // real words)
+    static __device__ __forceinline__ float col_any(const float *base, const float *cb, int q, int nq, int tlast, float c2) {
+        const int tl = q == nq ? tlast : 4;
+        switch (q) {
+            case 1: return col_caption<1>(base, cb, tl, c2);
+            case 2: return col_caption<2>(base, cb, tl, c2);
+            case 3: return col_caption<3>(base, cb, tl, c2);
+            case 4: return col_caption<4>(base, cb, tl, c2);
+            case 5: return col_caption<5>(base, cb, tl, c2);
+            case 6: return col_caption<6>(base, cb, tl, c2);
+            case 7: return col_caption<7>(base, cb, tl, c2);
+            case 8: return col_caption<8>(base, cb, tl, c2);
+            default: return col_caption_long(base, cb, q, tl, c2);
+        }
     }
 
     __device__ __forceinline__ void release_acc() {
@@ -934,145 +925,93 @@ struct EpiLsmFwd {
         mbar_arrive_cluster_cta(release_bar);
     }
 
-    // block k of an image's columns: k < nb are full 32-column blocks, block nb (if any) is the tail, read 16 or 32 columns wide
-    static __device__ __forceinline__ void blk_issue(int k, int nb, int tw, uint32_t tcol, uint32_t (&buf)[32]) {
-        const uint32_t adr = tcol + (uint32_t)(k * 32);
-        if (k < nb || tw == 32) tmem_ld_async<32>(adr, buf);
-        else tmem_ld_async<16>(adr, buf);
-    }
-    static __device__ __forceinline__ void blk_fence(int k, int nb, int tw, uint32_t (&buf)[32]) {
-        if (k < nb || tw == 32) tmem_ld_fence<32>(buf);
-        else tmem_ld_fence<16>(buf);
-    }
-
-    template <int NQ>
-    __device__ __forceinline__ void col_pass(const Half &h, const float *colbase, int ncap, int Tp, int tl, float c2, float scale, bool r_on, int ht,
-                                             bool first) {
-        int cl = 0;
-        for (; cl + 1 < ncap; cl += 2) {
-            float vA, vB;
-            col_caption2<NQ>(colbase + cl * Tp, colbase + (cl + 1) * Tp, h.cbt + cl * Tp, h.cbt + (cl + 1) * Tp, tl, c2, vA, vB);
-            float *hb = h.hbuf + cl * 128 + ht;
-            hb[0] = (first ? 0.f : hb[0]) + (r_on ? vA * scale : 0.f);
-            hb[128] = (first ? 0.f : hb[128]) + (r_on ? vB * scale : 0.f);
-        }
-        if (cl < ncap) {
-            const float v = col_caption<NQ>(colbase + cl * Tp, h.cbt + cl * Tp, tl, c2);
-            float *hb = h.hbuf + cl * 128 + ht;
-            hb[0] = (first ? 0.f : hb[0]) + (r_on ? v * scale : 0.f);
-        }
-    }
-
     __device__ __forceinline__ void chunk(const Params &p, const TcCore &core, int, int, uint32_t taddr, int row, int lane, int,
                                           unsigned char *smem) {
-        const int et = threadIdx.x - 64, half = et >> 7, ht = et & 127, hw = (et >> 5) & 3;
+        const int e = (threadIdx.x >> 5) - 2, g = e >> 2, img = g & 1, hcol = g >> 1;
+        const int ht = (e & 3) * 32 + lane, gw = hcol * 4 + (e & 3);
         const Tile t = tile_;
         const int T = p.T, Rg = p.Rg, ldt = stride(p), Tp = p.Tp;
         const int nslots = nslots_;
-        if (t.ncap == 0 || nslots == 0 || core.debug_mode == 3) {   // padding half of the last pair / nothing for this half
+        if (t.ncap == 0 || nslots == 0 || core.debug_mode == 3) {   // padding half of the last pair / nothing for this image group
             release_acc();
             return;
         }
-        const Half h = carve(p, smem, half);
+        const Half h = carve(p, core, smem, img);
         unsigned long long *tl = (core.timeline != nullptr && threadIdx.x == 64) ? core.timeline + (size_t)blockIdx.x * 16 : nullptr;
         const float c2 = p.inv_temp * LSM_LOG2E;
         const bool row_in = row_in_, row_on = row_on_;
         const int pcol = pcol_;
         const int nq = Tp >> 2, tlast = T - 4 * (nq - 1);
         for (int s = 0; s < nslots; ++s) {
-            const int j = half + 2 * s, i = t.it * p.ipt + j;
+            const int j = img + 2 * s, i = t.it * p.ipt + j;
             const float *rb = h.rbias + s * p.rb;
             const int ncols = h.ncols[s];
-            // ---- row pass: one software-pipelined sweep over the image's accumulator columns -----------------------------------
+            // ---- row pass: this warpgroup's column half of the image's accumulator columns ----------------------------------------
             {
                 const uint32_t tcol = taddr + (uint32_t)(j * Rg);
                 const int nb = ncols >> 5, rem = ncols & 31;
                 const int tw = rem == 0 ? 0 : (rem <= 16 ? 16 : 32);
-                const int nblk = nb + (tw > 0 ? 1 : 0);
+                const int nblk = nb + (tw > 0 ? 1 : 0), nsplit = (nblk + 1) >> 1;
+                const int k0 = hcol == 0 ? 0 : nsplit, k1 = hcol == 0 ? nsplit : nblk;
                 const bool masked = h.nreg[s] != (float)Rg;
                 float m = -FLT_MAX;
                 float2 d = f2(0.f, 0.f), n = f2(0.f, 0.f);
-                uint32_t cur[32], nxt[32];
                 if (tl) tl[8] = global_timer_ns();
-                blk_issue(0, nb, tw, tcol, cur);
-                blk_fence(0, nb, tw, cur);
-#ifdef LOCOV_ROWCLK
-                long long ckf = 0, ckw = 0;
-#endif
-                for (int k = 0; k < nblk; ++k) {
-                    if (k + 1 < nblk) blk_issue(k + 1, nb, tw, tcol, nxt);       // in flight while block k is folded
+                for (int k = k0; k < k1; ++k) {
+                    uint32_t cur[32];
+                    const uint32_t adr = tcol + (uint32_t)(k * 32);
                     float *pp = h.park + (size_t)(k * 32) * ldt + pcol;
                     const float *rbk = rb + k * 32;
-#ifdef LOCOV_ROWCLK
-                    const long long c0 = clock64();
-#endif
-                    if (k < nb) {
-                        if (masked) fold<32, false, true>(cur, 32, c2, rbk, pp, ldt, row_in, m, d, n);
-                        else fold<32, false, false>(cur, 32, c2, rbk, pp, ldt, row_in, m, d, n);
-                    } else if (tw == 32) fold<32, true, true>(cur, rem, c2, rbk, pp, ldt, row_in, m, d, n);
-                    else fold<16, true, true>(cur, rem, c2, rbk, pp, ldt, row_in, m, d, n);
-#ifdef LOCOV_ROWCLK
-                    const long long c1 = clock64();
-                    ckf += c1 - c0;
-#endif
-                    if (k + 1 < nblk) {
-                        blk_fence(k + 1, nb, tw, nxt);
-#pragma unroll
-                        for (int u = 0; u < 32; ++u) cur[u] = nxt[u];
+                    if (k < nb || tw == 32) {
+                        tmem_ld_async<32>(adr, cur);
+                        tmem_ld_fence<32>(cur);
+                        if (k < nb) {
+                            if (masked) fold<32, false, true>(cur, 32, c2, rbk, pp, ldt, row_in, m, d, n);
+                            else fold<32, false, false>(cur, 32, c2, rbk, pp, ldt, row_in, m, d, n);
+                        } else fold<32, true, true>(cur, rem, c2, rbk, pp, ldt, row_in, m, d, n);
+                    } else {
+                        tmem_ld_async<16>(adr, cur);
+                        tmem_ld_fence<16>(cur);
+                        fold<16, true, true>(cur, rem, c2, rbk, pp, ldt, row_in, m, d, n);
                     }
-#ifdef LOCOV_ROWCLK
-                    ckw += clock64() - c1;
-#endif
                 }
-#ifdef LOCOV_ROWCLK
-                if (tl) { tl[14] = (unsigned long long)ckf; tl[15] = (unsigned long long)ckw; }
-#endif
                 if (tl) tl[10] = global_timer_ns();
                 if (s == nslots - 1) release_acc();                                   // last tcgen05.ld of this thread for this tile
-                h.rowval[row] = row_on ? __fdividef(n.x + n.y, d.x + d.y) * p.inv_temp : 0.f;
+                float *pt = h.part + hcol * 384 + row;
+                pt[0] = m; pt[128] = d.x + d.y; pt[256] = n.x + n.y;
             }
-            named_bar_sync(2 + half, 128);
+            named_bar_sync(2 + img, 256);
             if (tl) tl[11] = global_timer_ns();
-            // ---- column pass: thread = region, softmax over the T words of each caption down the parked column, two captions at a
-            //      time; the per-(caption, region) results go to shared memory and are summed in the finish phase ------------------
+            if (hcol == 0) {                                                          // merge the two column halves of the row
+                const float m0 = h.part[row], m1 = h.part[384 + row];
+                const float mm = fmaxf(m0, m1), w0 = ex2_ftz(m0 - mm), w1 = ex2_ftz(m1 - mm);
+                const float dd = h.part[128 + row] * w0 + h.part[512 + row] * w1, nn = h.part[256 + row] * w0 + h.part[640 + row] * w1;
+                h.rowval[row] = row_on ? __fdividef(nn, dd) * p.inv_temp : 0.f;
+            }
+            // ---- column pass: thread = region, softmax over the T words of each caption down the parked column; the captions are split
+            //      between the two warpgroups; per-(caption, region) results go to shared memory and are summed in the finish phase ----
             const bool do_col = core.debug_mode != 4 && p.out_r2w != nullptr;
             if (do_col) {
-                int qmax = 1;                                                         // quads up to the last valid word of any caption
-                for (int cl = 0; cl < t.ncap; ++cl) qmax = max(qmax, h.capq[cl]);
-                const int tl4 = qmax == nq ? tlast : 4;
+                const int csplit = (t.ncap + 1) >> 1;
+                const int c_lo = hcol == 0 ? 0 : csplit, c_hi = hcol == 0 ? csplit : t.ncap;
                 for (int r0 = 0; r0 < ncols; r0 += 128) {
                     const int r = r0 + ht;
                     const bool r_on = r < ncols && rb[min(r, ncols - 1)] == 0.f;
                     const float *colbase = h.park + (size_t)min(r, ncols - 1) * ldt;
-                    if (!__any_sync(0xffffffffu, r_on)) {                             // a warp whose regions are all masked has nothing to do
-                        if (r0 == 0)
-                            for (int cl = 0; cl < t.ncap; ++cl) h.hbuf[cl * 128 + ht] = 0.f;
-                        continue;
-                    }
-                    switch (qmax) {
-                        case 1: col_pass<1>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
-                        case 2: col_pass<2>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
-                        case 3: col_pass<3>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
-                        case 4: col_pass<4>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
-                        case 5: col_pass<5>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
-                        case 6: col_pass<6>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
-                        case 7: col_pass<7>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
-                        case 8: col_pass<8>(h, colbase, t.ncap, Tp, tl4, c2, p.inv_temp, r_on, ht, r0 == 0); break;
-                        default:
-                            for (int cl = 0; cl < t.ncap; ++cl) {
-                                const float v = col_caption_long(colbase + cl * Tp, h.cbt + cl * Tp, qmax, tl4, c2);
-                                float *hb = h.hbuf + cl * 128 + ht;
-                                hb[0] = (r0 == 0 ? 0.f : hb[0]) + (r_on ? v * p.inv_temp : 0.f);
-                            }
-                            break;
+                    const bool warp_on = __any_sync(0xffffffffu, r_on);               // a warp whose regions are all masked has nothing to do
+                    for (int cl = c_lo; cl < c_hi; ++cl) {
+                        float v = 0.f;
+                        if (warp_on) v = col_any(colbase + cl * Tp, h.cbt + cl * Tp, h.capq[cl], nq, tlast, c2);
+                        float *hb = h.hbuf + cl * 128 + ht;
+                        hb[0] = (r0 == 0 ? 0.f : hb[0]) + (r_on ? v * p.inv_temp : 0.f);
                     }
                 }
             }
             if (tl) tl[12] = global_timer_ns();
-            named_bar_sync(2 + half, 128);
+            named_bar_sync(2 + img, 256);
             if (tl) tl[13] = global_timer_ns();
             // ---- finish: warp = caption; both sums in a fixed order (lane-strided partials, then the shuffle tree) ------------------------
-            for (int cl = hw; cl < t.ncap; cl += 4) {
+            for (int cl = gw; cl < t.ncap; cl += 8) {
                 float a = 0.f, b = 0.f;
                 for (int w = lane; w < T; w += 32) a += h.rowval[cl * T + w];
                 if (do_col) b = (h.hbuf[cl * 128 + lane] + h.hbuf[cl * 128 + 32 + lane]) + (h.hbuf[cl * 128 + 64 + lane] + h.hbuf[cl * 128 + 96 + lane]);
@@ -1087,7 +1026,7 @@ struct EpiLsmFwd {
                     if (p.out_r2w != nullptr) p.out_r2w[(int64_t)c * p.ld_out + i] = -b / fmaxf(h.nreg[s], 1.f);
                 }
             }
-            if (s + 1 < nslots) named_bar_sync(2 + half, 128);      // park / rowval / hbuf are rewritten by the next image
+            if (s + 1 < nslots) named_bar_sync(2 + img, 256);       // park / rowval / hbuf are rewritten by the next image
         }
     }
 };
@@ -1370,14 +1309,11 @@ static int lsm_fwd2_launch(const uint16_t *cap_hi, const uint16_t *cap_lo, int64
                            int64_t ldemb, int D, LsmFwdParams &p, cudaStream_t st, bool *declined) {
     *declined = false;
     const int sms = current_device_sm_count();
-    p.per_tile = TC_BLOCK_M / p.T;
-    if (p.per_tile > LSM_MAX_PER_TILE) p.per_tile = LSM_MAX_PER_TILE;
-    if (p.per_tile > p.Bc) p.per_tile = p.Bc;
+    int per_max = TC_BLOCK_M / p.T;
+    if (per_max > LSM_MAX_PER_TILE) per_max = LSM_MAX_PER_TILE;
+    if (per_max > p.Bc) per_max = p.Bc;
+    if (per_max < 1) per_max = 1;
     p.Tp = tc_round_up(p.T, 4);
-    p.ldt = tc_round_up(p.per_tile * p.Tp, 4);
-    if (((p.ldt / 4) & 1) == 0) p.ldt += 4;
-    const bool fixed_ldt = p.ldt <= LSM_LDT;
-    if (fixed_ldt) p.ldt = LSM_LDT;
     p.rb = tc_round_up(p.Rg, 32);
     // images per tile: as many as fit 256 accumulator columns (two accumulator stages = 512 TMEM columns), at most 16; fewer when the
     // epilogue's reads would leave the allocation or the parked sub-tiles leave too little shared memory for the operand ring
@@ -1386,15 +1322,28 @@ static int lsm_fwd2_launch(const uint16_t *cap_hi, const uint16_t *cap_lo, int64
     if (ipt > p.Bi) ipt = p.Bi;
     if (ipt > 16) ipt = 16;
     if (const char *e = getenv("LOCOV_B200_LSM_IPT")) { const int v = atoi(e); if (v >= 1 && v <= ipt) ipt = v; }   // developer sweep knob
-    const int groups = (p.Bc + p.per_tile - 1) / p.per_tile;
     TcCore core;
     size_t smem = 0;
+    bool fixed_ldt = false;
     for (;; --ipt) {
         if (ipt < 1) { *declined = true; return LOCO_E_UNSUPPORTED; }
         p.ipt = ipt;
         p.slots = (ipt + 1) / 2;
         p.halves = ipt > 1 ? 2 : 1;
         p.tiles_i = (p.Bi + ipt - 1) / ipt;
+        // captions per CTA: the most that fit 128 accumulator rows — unless fewer still give every pair a single tile: then the epilogue
+        // (the longer half of a lone tile's life) is spread over more SMs
+        p.per_tile = per_max;
+        for (int pt = 1; pt < per_max; ++pt) {
+            const long long tot = (long long)(((p.Bc + pt - 1) / pt + 1) / 2) * p.tiles_i;
+            if (tot <= sms / 2) { p.per_tile = pt; break; }
+        }
+        if (const char *e = getenv("LOCOV_B200_LSM_PT")) { const int v = atoi(e); if (v >= 1 && v <= per_max) p.per_tile = v; }   // developer sweep knob
+        p.ldt = tc_round_up(p.per_tile * p.Tp, 4);
+        if (((p.ldt / 4) & 1) == 0) p.ldt += 4;
+        fixed_ldt = p.ldt <= LSM_LDT;
+        if (fixed_ldt) p.ldt = LSM_LDT;
+        const int groups = (p.Bc + p.per_tile - 1) / p.per_tile;
         const long long total = (long long)((groups + 1) / 2) * p.tiles_i;
         LOCO_REQUIRE(total < (1ll << 30), LOCO_E_UNSUPPORTED, "lsm_pair: too many tiles");
         core = TcCore{};
@@ -1408,10 +1357,14 @@ static int lsm_fwd2_launch(const uint16_t *cap_hi, const uint16_t *cap_lo, int64
         core.total_tiles = (int)total;
         core.single_wave = 1;
         const int chunks = (int)((total + npairs - 1) / npairs);
-        const size_t half = (EpiLsmFwd<0>::half_floats(p.Rg, p.ldt, p.slots, p.rb) + 3) & ~(size_t)3;
-        const size_t epi = (size_t)p.halves * half * sizeof(float) + 16;
-        if (epi > 200 * 1024) continue;
-        smem = tc_finalize(core, D, cap_lo ? 3 : 1, chunks > 1 ? chunks : 2, (int)epi);     // (>= 2: two accumulator stages whenever they fit)
+        const size_t big = 2 * EpiLsmFwd<0>::big_floats(p.Rg, p.ldt, p.per_tile) * sizeof(float);
+        core.epi_tail = (int)(2 * EpiLsmFwd<0>::small_floats(p.slots, p.rb) * sizeof(float) + 16);
+        if (big + core.epi_tail > 200 * 1024) continue;
+        // a lone tile per pair: its parked sub-tiles re-use the operand ring (dead once the accumulator is complete), the ring gets all
+        // of shared memory; several tiles: separate scratch, two accumulator stages
+        core.epi_overlay = chunks == 1 ? 1 : 0;
+        if (const char *e = getenv("LOCOV_B200_LSM_OVERLAY")) { if (e[0] == '0') core.epi_overlay = 0; }
+        smem = tc_finalize(core, D, cap_lo ? 3 : 1, core.epi_overlay ? 1 : (chunks > 1 ? chunks : 2), (int)big);
         // every accumulator column the epilogue reads must lie inside the allocation (worst case: the last image read as 32-wide blocks)
         const int reach = (core.acc_stages - 1) * core.block_n + (ipt - 1) * p.Rg + tc_round_up(p.Rg, 32);
         while (core.tmem_cols < reach && core.tmem_cols < 512) core.tmem_cols <<= 1;

@@ -186,33 +186,51 @@ class _BoxPredict(Function):
         acc = _acc(precision)
         r = x.shape[0]
         dev = x.device
-        # dE = dscores · W_cls   [R, D]
-        g_cat = torch.zeros((r, d + nbox), dtype=torch.float32, device=dev)
-        if dscores is not None:
+        need_x, need_we, need_be, need_wb, need_bb = ctx.needs_input_grad[:5]
+        dx = dwe = dbe = dwb = dbb = None
+        # The upstream gradient of [emb | deltas] as ONE bf16 operand [R, pad8(D + 4)]: dE = dscores . W_cls lands in its first D columns
+        # straight from the GEMM epilogue (no fp32 round trip, no separate split pass), the box gradient goes into the last 4.
+        ldg = (d + nbox + 7) // 8 * 8
+        have_de = dscores is not None and (need_x or need_we or need_be)
+        mk = torch.empty if have_de else torch.zeros              # (the GEMM below overwrites the first D columns of every row)
+        g_hi = mk((r, ldg), dtype=torch.bfloat16, device=dev)
+        g_lo = mk((r, ldg), dtype=torch.bfloat16, device=dev) if acc else None
+        de = None
+        if have_de:
             gs_op = ops.split_bf16(dscores.contiguous(), acc)
             clst_op = weight_operand(w_cls, acc, transpose=True)
-            de, _ = ops.linear_fwd(gs_op, clst_op, None, want_f32=True)
-            g_cat[:, :d] = de
+            de = ops.linear_fwd_into(gs_op, clst_op, None, want_f32=need_we or need_be, out_hi=g_hi, out_lo=g_lo, n_bf16=d)
+            g_hi[:, d:].zero_()
+            if acc:
+                g_lo[:, d:].zero_()
         if ddeltas is not None:
-            g_cat[:, d:] = ddeltas
-        dx = dwe = dbe = dwb = dbb = None
-        w_cat = _cat_weight(w_emb, w_box)
-        if ctx.needs_input_grad[0]:
-            g_op = ops.split_bf16(g_cat, acc)
+            dd = ddeltas.to(torch.float32)
+            g_hi[:, d:d + nbox] = dd
+            if acc:
+                g_lo[:, d:d + nbox] = dd - g_hi[:, d:d + nbox].to(torch.float32)
+        g_op = ops.Bf16Operand(g_hi, g_lo, r, d + nbox)
+        if need_x:
+            w_cat = _cat_weight(w_emb, w_box)
             wt_op = weight_operand(w_cat, acc, transpose=True, tag="cat")
             dx, _ = ops.linear_fwd(g_op, wt_op, None, want_f32=True)
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[3]:
-            gt_op = ops.split_bf16(g_cat, acc, transpose=True)
+        if need_we:
+            # trainable emb_pred (LSM stage): the full [D+4, V] weight gradient as a tensor-core GEMM over transposed operands
             xt_op = ops.split_bf16(x, acc, transpose=True)
-            dw_cat, _ = ops.linear_fwd(gt_op, xt_op, None, want_f32=True)
-            if ctx.needs_input_grad[1]:
-                dwe = dw_cat[:d]
-            if ctx.needs_input_grad[3]:
-                dwb = dw_cat[d:]
-        if ctx.needs_input_grad[2]:
-            dbe = g_cat[:, :d].sum(0)
-        if ctx.needs_input_grad[4]:
-            dbb = g_cat[:, d:].sum(0)
+            dw_cat, _ = ops.linear_fwd(ops.transpose_operand(g_op), xt_op, None, want_f32=True)
+            dwe = dw_cat[:d]
+            if need_wb:
+                dwb = dw_cat[d:d + nbox]
+            if need_bb and ddeltas is not None:
+                dbb = ddeltas.to(torch.float32).sum(0)
+        elif (need_wb or need_bb) and ddeltas is not None:
+            # only the class-agnostic box regressor trains (FREEZE_EMB_PRED, coco_stt.yaml:36): 4 x V gradient, x streamed once
+            dwb, dbb = ops.skinny_grad(ddeltas, x, want_bias=True)
+        if need_be and de is not None:
+            dbe = de.sum(0)
+        if not need_wb:
+            dwb = None
+        if not need_bb:
+            dbb = None
         return dx, dwe, dbe, dwb, dbb, None, None, None, None, None
 
 
@@ -220,20 +238,22 @@ _cat_cache = {}
 
 
 def _cat_weight(w_emb, w_box):
-    """[W_emb; W_box] as one [D+4, V] matrix, rebuilt only when either parameter changed."""
+    """[W_emb; W_box] as one [D+4, V] fp32 matrix.  Each part is re-copied only when ITS parameter may have changed (version counter
+    moved, or the parameter is trainable — see the freshness rule above): with FREEZE_EMB_PRED the 768 x 2048 block is copied once and
+    a training step refreshes only the 4 x 2048 rows of bbox_pred."""
     key = (w_emb.data_ptr(), w_box.data_ptr(), tuple(w_emb.shape), tuple(w_box.shape))
-    ver = (w_emb._version, w_box._version)
     ent = _cat_cache.get(key)
-    alive = ent is not None and ent[2]() is w_emb and ent[3]() is w_box
-    if alive and ent[0] == ver and WEIGHT_CACHE and not (w_emb.requires_grad or w_box.requires_grad):
-        return ent[1]
+    alive = WEIGHT_CACHE and ent is not None and ent[2]() is w_emb and ent[3]() is w_box
+    d = w_emb.shape[0]
     if alive:
-        cat = ent[1]
-        cat[:w_emb.shape[0]].copy_(w_emb.detach())      # in place: bumps cat._version -> bf16 shadow refreshes
-        cat[w_emb.shape[0]:].copy_(w_box.detach())
+        cat, (ve, vb) = ent[1], ent[0]
+        if w_emb.requires_grad or ve != w_emb._version:
+            cat[:d].copy_(w_emb.detach())       # in place: bumps cat._version -> the bf16 shadow of `cat` refreshes
+        if w_box.requires_grad or vb != w_box._version:
+            cat[d:].copy_(w_box.detach())
     else:
         cat = torch.cat([w_emb.detach(), w_box.detach()], 0).to(torch.float32).contiguous()
-    _cat_cache[key] = (ver, cat, weakref.ref(w_emb), weakref.ref(w_box))
+    _cat_cache[key] = ((w_emb._version, w_box._version), cat, weakref.ref(w_emb), weakref.ref(w_box))
     if len(_cat_cache) > 64:
         for k in [k for k, v in _cat_cache.items() if v[2]() is None] or list(_cat_cache)[:32]:
             del _cat_cache[k]
@@ -322,6 +342,29 @@ class _BoxCE(Function):
 
 def box_cross_entropy(logits, lse, labels):
     return _BoxCE.apply(logits, lse, labels)
+
+
+class _BoxRegLoss(Function):
+    """Detectron2 FastRCNNOutputLayers.box_reg_loss (class-agnostic, smooth-L1 / L1, sum over foreground / max(R, 1)) with its gradient
+    from the same launch (reached from roi_emb_heads.py:266,347)."""
+
+    @staticmethod
+    def forward(ctx, deltas, proposal_boxes, gt_boxes, labels, num_classes, reg_weights, beta):
+        r = deltas.shape[0]
+        loss, grad = ops.box_reg_loss(deltas, proposal_boxes, gt_boxes, labels, num_classes, reg_weights, beta, 1.0 / max(r, 1),
+                                      want_grad=ctx.needs_input_grad[0])
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (grad * g if grad is not None else None), None, None, None, None, None, None
+
+
+def box_reg_loss(deltas, proposal_boxes, gt_boxes, labels, num_classes, reg_weights, beta):
+    return _BoxRegLoss.apply(deltas, proposal_boxes, gt_boxes, labels, int(num_classes), tuple(float(w) for w in reg_weights), float(beta))
 
 
 # ------------------------------------------------------------------------------------------------

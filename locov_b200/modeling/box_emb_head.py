@@ -294,20 +294,14 @@ class EmbeddingFastRCNNOutputLayers(nn.Module):
         return {k: v * self.loss_weight.get(k, 1.0) for k, v in losses.items()}
 
     def box_reg_loss(self, proposal_boxes, gt_boxes, pred_deltas, gt_classes):
-        """Detectron2 box_reg_loss (smooth-L1 over the foreground rows, summed, / max(R, 1)) as a masked sum over ALL rows:
-        no ``nonzero`` (a host synchronisation per step in the stock implementation), same value and gradients."""
+        """Detectron2 box_reg_loss (smooth-L1 over the foreground rows, summed, / max(R, 1)): one kernel launch for the loss and
+        its gradient — no ``nonzero`` (a host synchronisation per step in the stock implementation), no chain of small launches."""
         box_dim = proposal_boxes.shape[1]
         if self.box_reg_loss_type != "smooth_l1":
             raise NotImplementedError(f"box_reg_loss_type {self.box_reg_loss_type!r} (shipped configs use smooth_l1)")
-        assert pred_deltas.shape[1] == box_dim, "class-agnostic box regression only (box_emb_head.py:137)"
-        fg = ((gt_classes >= 0) & (gt_classes < self.num_classes))[:, None]
-        tgt = self.box2box_transform.get_deltas(proposal_boxes, gt_boxes)
-        tgt = torch.where(fg, tgt, torch.zeros_like(tgt))          # background rows may hold degenerate gt boxes (log of <= 0)
-        n = torch.abs(pred_deltas - tgt)
-        if self.smooth_l1_beta >= 1e-5:
-            n = torch.where(n < self.smooth_l1_beta, 0.5 * n ** 2 / self.smooth_l1_beta, n - 0.5 * self.smooth_l1_beta)
-        loss = torch.where(fg, n, torch.zeros_like(n)).sum()
-        return loss / max(gt_classes.numel(), 1.0)
+        assert pred_deltas.shape[1] == box_dim == 4, "class-agnostic box regression only (box_emb_head.py:137)"
+        return LF.box_reg_loss(pred_deltas, proposal_boxes, gt_boxes, gt_classes, self.num_classes, self.box2box_transform.weights,
+                               self.smooth_l1_beta)
 
     def predict_probs(self, predictions, proposals):
         scores, _ = predictions

@@ -4,6 +4,7 @@ PyTorch is used for device memory and streams only; every computation below is a
 liblocov_b200.so.  All functions require CUDA tensors and raise ``LocoError`` on failure — there is
 no eager/CPU fallback.
 """
+import ctypes
 import threading
 from dataclasses import dataclass
 from typing import Optional, Tuple
@@ -204,6 +205,23 @@ def linear_fwd(a: Bf16Operand, w: Bf16Operand, bias: Optional[torch.Tensor], wan
     return out_f32, ob
 
 
+def linear_fwd_into(a: Bf16Operand, w: Bf16Operand, bias: Optional[torch.Tensor], want_f32: bool, out_hi: torch.Tensor,
+                    out_lo: Optional[torch.Tensor], n_bf16: int) -> Optional[torch.Tensor]:
+    """``linear_fwd`` whose bf16 output lands in the first ``n_bf16`` columns of caller-owned matrices (row stride = their width):
+    lets a gradient GEMM write one slice of a wider operand.  Returns the fp32 output or None."""
+    if a.cols != w.cols or (a.lo is None) != (w.lo is None):
+        raise LocoError("linear_fwd_into: operand mismatch")
+    m, n, k = a.rows, w.rows, a.cols
+    if n_bf16 > n or out_hi.shape[0] != m or out_hi.stride(1) != 1 or out_hi.stride(0) % 8:
+        raise LocoError("linear_fwd_into: bad destination")
+    out_f32 = torch.empty((m, n), dtype=torch.float32, device=a.hi.device) if want_f32 else None
+    if bias is not None:
+        bias = bias.to(torch.float32).contiguous()
+    _lib.check(_lib.load().loco_linear_fwd(_p(a.hi), _p(a.lo), a.ld, _p(w.hi), _p(w.lo), w.ld, _p(bias), m, n, k, _p(out_f32), n if want_f32 else 0,
+                                           _p(out_hi), _p(out_lo), n_bf16, out_hi.stride(0), _stream(a.hi)), "loco_linear_fwd")
+    return out_f32
+
+
 def linear_tf32_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], want_f32: bool = True, n_bf16: int = 0):
     """out[M,N] = x[M,K] · w[N,K]^T + bias with the fp32 operands read in place as TF32 (no split pass).
     Returns (out_f32 or None, bf16 operand of the first n_bf16 columns or None)."""
@@ -276,6 +294,52 @@ def box_ce(logits: torch.Tensor, lse: torch.Tensor, labels: torch.Tensor, want_g
                                        1.0 / r, _p(dl), _p(dlb), dlb.shape[1] if dlb is not None else 0,
                                        _stream(logits)), "loco_box_ce_fwd_bwd")
     return loss, dl, dlb
+
+
+def box_reg_loss(deltas: torch.Tensor, proposal_boxes: torch.Tensor, gt_boxes: torch.Tensor, labels: torch.Tensor, num_classes: int,
+                 reg_weights, smooth_l1_beta: float, scale: float, want_grad: bool = False):
+    """Class-agnostic box-regression loss (Detectron2 box_reg_loss) in one launch: returns (loss scalar tensor, d loss / d deltas or None)."""
+    _need_cuda(deltas, proposal_boxes, gt_boxes, labels)
+    r = deltas.shape[0]
+    dev = deltas.device
+    if deltas.dim() != 2 or deltas.shape[1] != 4:
+        raise LocoError("box_reg_loss: class-agnostic deltas [R,4] expected")
+    deltas = deltas.to(torch.float32)
+    if deltas.stride(1) != 1:
+        deltas = deltas.contiguous()
+    prop = proposal_boxes.to(torch.float32).contiguous()
+    gtb = gt_boxes.to(torch.float32).contiguous()
+    labels = labels.to(torch.int64).contiguous()
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    grad = torch.empty((r, 4), dtype=torch.float32, device=dev) if want_grad else None
+    lib = _lib.load()
+    ws = _zero_workspace(dev, lib.loco_box_reg_loss_workspace_bytes(r), "box_reg_loss")
+    w4 = (ctypes.c_float * 4)(*[float(v) for v in reg_weights])
+    rc = lib.loco_box_reg_loss(_p(deltas), deltas.stride(0) if r else 4, _p(prop), _p(gtb), _p(labels), r, int(num_classes), w4, float(smooth_l1_beta),
+                               float(scale), _p(loss), _p(grad), 4, _p(ws), _stream(deltas))
+    if rc != 0:
+        _drop_zero_workspace(dev, "box_reg_loss")
+    _lib.check(rc, "loco_box_reg_loss")
+    return loss, grad
+
+
+def skinny_grad(dy: torch.Tensor, x: torch.Tensor, want_bias: bool = True):
+    """dW [J,V] = dy^T . x and db [J] = column sums of dy for a linear layer with J <= 8 outputs (bbox_pred)."""
+    _need_cuda(dy, x)
+    dy = dy.to(torch.float32)
+    if dy.stride(1) != 1:
+        dy = dy.contiguous()
+    if x.stride(1) != 1 or x.stride(0) % 4 or x.data_ptr() % 16:
+        x = x.contiguous()
+    r, j = dy.shape
+    v = x.shape[1]
+    dw = torch.empty((j, v), dtype=torch.float32, device=x.device)
+    db = torch.empty((j,), dtype=torch.float32, device=x.device) if want_bias else None
+    lib = _lib.load()
+    ws = _workspace(x.device, lib.loco_skinny_grad_workspace_bytes(r, j, v), "skinny_grad")
+    _lib.check(lib.loco_skinny_grad(_p(dy), dy.stride(0) if r else j, _p(x), x.stride(0) if r else v, r, j, v, _p(dw), _p(db), _p(ws), _stream(x)),
+               "loco_skinny_grad")
+    return dw, db
 
 
 def box_softmax(logits: torch.Tensor, want_probs: bool = False):
