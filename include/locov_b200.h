@@ -252,6 +252,19 @@ int loco_lsm_pair_bwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ld
                       int64_t ld_g, uint16_t *dst_hi, uint16_t *dst_lo, int64_t ld_dst,
                       uint16_t *ds_hi, uint16_t *ds_lo, int64_t ld_ds, void *stream);
 
+/* ---- peer scatter (multi-GPU exchange of the sharded LSM head) ------------------------------------------------------------------
+ * New versus the reference, whose heads contain no collective: the image-sharded pair matrix of BASELINE configs[3]
+ * needs every rank's caption operands on every rank, and every rank's [B, B_loc] distance block in every rank's [B, B] matrix.
+ * Replaces: the NCCL all-gathers a torch.distributed implementation of that exchange would launch (one collective + stream hand-offs
+ *           per tensor); here the producing rank stores its slice straight into every rank's symmetric buffer over NVLink.
+ * src [rows][row_bytes] (pitch src_pitch, local) -> peer_p + dst_offset (pitch dst_pitch) for each of the n_peers base pointers in the
+ * DEVICE array peers_dev (CUDA symmetric-memory allocations mapped into this process, e.g. torch.distributed._symmetric_memory
+ * buffer_ptrs_dev; this rank's own buffer included).  All byte counts / offsets / pitches are multiples of 4 (16-byte stores when they
+ * all are multiples of 16).  The caller orders the
+ * stores against the consumers with a symmetric-memory barrier. */
+int loco_peer_scatter(const void *src, int64_t src_pitch, int rows, int64_t row_bytes, const void *const *peers_dev, int n_peers,
+                      int64_t dst_pitch, int64_t dst_offset, void *stream);
+
 /* ---- pair-matrix losses ---------------------------------------------------------------------------
  * Replaces: grounding_head.py:240-251 (empty-pair guard), :272-290 (4 CE losses), :354-379 (accuracies).
  * pw: nmat pair matrices [Bc, Bi] fp32 (row stride ld, matrix stride mat_stride elements; nmat = 2

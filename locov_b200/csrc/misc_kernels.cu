@@ -684,6 +684,27 @@ __global__ void __launch_bounds__(256) skinny_grad_reduce_kernel(const float *__
     }
 }
 
+// ---- peer scatter: one local 2-D buffer -> the same place in EVERY rank's symmetric buffer (all-gather by peer stores) --------------------
+// src [rows][row_bytes] (pitch src_pitch) is written to dst_p + dst_offset (pitch dst_pitch) for every peer p of `peers` (device array of
+// `n_peers` base pointers into the ranks' symmetric allocations, this rank's own included): 16-byte stores over NVLink / NVSwitch
+// straight from the producing rank — no NCCL launch, no staging copy.  Ordering against the consumers is the caller's job (a
+// symmetric-memory barrier after this kernel).  One block per (chunk of 16-byte words, peer).
+template <typename W>
+__global__ void __launch_bounds__(256) peer_scatter_kernel(const unsigned char *__restrict__ src, int64_t src_pitch, int rows, int row_words,
+                                                           unsigned char *const *__restrict__ peers, int n_peers, int64_t dst_pitch,
+                                                           int64_t dst_offset) {
+    pdl_trigger();
+    pdl_wait();
+    const int peer = blockIdx.y;
+    unsigned char *dst = peers[peer] + dst_offset;
+    const int64_t total = (int64_t)rows * row_words;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / row_words, w = idx - r * row_words;
+        const W v = *reinterpret_cast<const W *>(src + r * src_pitch + w * (int64_t)sizeof(W));
+        *reinterpret_cast<W *>(dst + r * dst_pitch + w * (int64_t)sizeof(W)) = v;
+    }
+}
+
 }  // namespace loco
 
 using namespace loco;
@@ -874,6 +895,33 @@ int loco_skinny_grad(const float *dy, int64_t ld_dy, const float *x, int64_t ld_
     count_launch();
     LOCO_CUDA(launch_kernel(skinny_grad_reduce_kernel, dim3((unsigned)((J * V + 255) / 256)), dim3(256), 0, st, 1, static_cast<const float *>(part), nchunk,
                             J * V, dw, dy, ld_dy, R, J, db));
+    count_launch();
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+int loco_peer_scatter(const void *src, int64_t src_pitch, int rows, int64_t row_bytes, const void *const *peers_dev, int n_peers, int64_t dst_pitch,
+                      int64_t dst_offset, void *stream) {
+    LOCO_REQUIRE(rows >= 0 && row_bytes >= 0 && n_peers >= 1 && n_peers <= 64, LOCO_E_BADARG, "peer_scatter: bad arguments rows=%d row_bytes=%lld peers=%d", rows,
+                 (long long)row_bytes, n_peers);
+    if (rows == 0 || row_bytes == 0) return LOCO_OK;
+    LOCO_REQUIRE(src && peers_dev, LOCO_E_BADARG, "peer_scatter: null pointer");
+    LOCO_REQUIRE(src_pitch >= row_bytes && dst_pitch >= row_bytes, LOCO_E_BADARG, "peer_scatter: pitch < row_bytes");
+    const int64_t all = row_bytes | src_pitch | dst_pitch | dst_offset | (int64_t)(reinterpret_cast<uintptr_t>(src) & 15);
+    LOCO_REQUIRE(all % 4 == 0, LOCO_E_ALIGN, "peer_scatter: rows, pitches and offsets must be multiples of 4 bytes");
+    const bool wide = all % 16 == 0;           // 16-byte words when everything allows it, 4-byte words otherwise
+    const int wbytes = wide ? 16 : 4;
+    const int64_t total = (int64_t)rows * (row_bytes / wbytes);
+    int blocks = (int)((total + 255) / 256 < 64 ? (total + 255) / 256 : 64);
+    if (blocks < 1) blocks = 1;
+    const dim3 grid((unsigned)blocks, (unsigned)n_peers);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (wide)
+        LOCO_CUDA(launch_kernel(peer_scatter_kernel<uint4>, grid, dim3(256), 0, st, 1, static_cast<const unsigned char *>(src), src_pitch, rows,
+                                (int)(row_bytes / 16), (unsigned char *const *)(peers_dev), n_peers, dst_pitch, dst_offset));
+    else
+        LOCO_CUDA(launch_kernel(peer_scatter_kernel<uint32_t>, grid, dim3(256), 0, st, 1, static_cast<const unsigned char *>(src), src_pitch, rows,
+                                (int)(row_bytes / 4), (unsigned char *const *)(peers_dev), n_peers, dst_pitch, dst_offset));
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;

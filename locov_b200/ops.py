@@ -500,6 +500,20 @@ def lsm_pair_bwd(cap: Bf16Operand, cap_mask: torch.Tensor, emb: Bf16Operand, reg
     return demb, dcap
 
 
+def peer_scatter(src: torch.Tensor, peers_dev: int, n_peers: int, dst_pitch_bytes: int, dst_offset_bytes: int, rows: int = None,
+                 row_bytes: int = None):
+    """Store a local 2-D buffer at the same place in every rank's symmetric buffer (``peers_dev``: device array of base pointers)."""
+    _need_cuda(src)
+    if src.dim() == 1:
+        src = src.reshape(1, -1)
+    if src.dim() != 2 or src.stride(1) != 1:
+        raise LocoError("peer_scatter: expects a 2-D tensor with unit column stride")
+    rows = src.shape[0] if rows is None else rows
+    row_bytes = src.shape[1] * src.element_size() if row_bytes is None else row_bytes
+    _lib.check(_lib.load().loco_peer_scatter(_p(src), src.stride(0) * src.element_size(), int(rows), int(row_bytes), int(peers_dev), int(n_peers),
+                                             int(dst_pitch_bytes), int(dst_offset_bytes), _stream(src)), "loco_peer_scatter")
+
+
 def pair_ce(pw: torch.Tensor, cap_mask: torch.Tensor, reg_mask: torch.Tensor, diag_offset: int = 0,
             want_grad: bool = False):
     """Empty-pair guard (in place on pw) + [CE choose caption, CE choose image, acc caption, acc image].

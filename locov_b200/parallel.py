@@ -14,11 +14,19 @@ Parity definition: for identical global inputs, rank g's block equals columns [g
 of the single-device matrix and the four global losses equal the single-device losses
 (tests/test_parallel_*.py).  The masked fill is a fixed finite constant, never a per-shard minimum.
 
+Exchange: on GPUs of one NVSwitch box both steps are PEER STORES into CUDA symmetric memory (torch.distributed._symmetric_memory
+buffers mapped into every process): the rank that produces a slice (caption operand rows from ``loco_lsm_prep``, its distance block from
+the pair kernel) stores it straight into every rank's gathered buffer (``loco_peer_scatter``) and a symmetric-memory barrier orders the
+stores against the consumers — two small kernels and two barriers per step on ONE stream, no NCCL launch, no stream hand-off, no
+re-layout copy (the blocks land in place in the [2, B, B] matrices).  The NCCL all-gather implementation below remains as the path for
+process groups without symmetric memory (and is what the gloo / CPU test of the exchange logic exercises); LOCOV_B200_SYMM=0 forces it.
+
 Gradient convention: every rank holds the SAME global loss; its autograd path covers only its own
 column block, so summing parameter gradients over ranks gives the single-device gradient (under DDP's
 mean-reduction multiply the loss by the world size).  Caption embeddings are frozen BERT inputs in the
 shipped configuration (coco_lsm.yaml: LANGUAGE_BACKBONE.FREEZE) and receive no gradient here.
 """
+import os
 from typing import Optional
 
 import torch
@@ -167,9 +175,142 @@ class _ShardedLsm(Function):
         return dx, dw, db, None, None, None, None, None, None, None, None, None, None
 
 
+# ------------------------------------------------------------------------------------------------
+# symmetric-memory exchange (peer stores + barriers)
+# ------------------------------------------------------------------------------------------------
+_symm_states = {}
+_symm_disabled = {}
+
+
+class _SymmState:
+    """Symmetric buffers of one (process group, shape) — allocated and exchanged once (collective), reused by every step."""
+
+    def __init__(self, group, dev, bl, t, d, ld, acc):
+        import torch.distributed._symmetric_memory as symm
+        self.w, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        b = self.w * bl
+        self.hi = symm.empty((b * t, ld), dtype=torch.bfloat16, device=dev)
+        self.h_hi = symm.rendezvous(self.hi, group)
+        self.lo = self.h_lo = None
+        if acc:
+            self.lo = symm.empty((b * t, ld), dtype=torch.bfloat16, device=dev)
+            self.h_lo = symm.rendezvous(self.lo, group)
+        self.mask = symm.empty((b, t), dtype=torch.float32, device=dev)
+        self.h_mask = symm.rendezvous(self.mask, group)
+        self.pw = symm.empty((2, b, b), dtype=torch.float32, device=dev)
+        self.h_pw = symm.rendezvous(self.pw, group)
+        self.nreg = symm.empty((b,), dtype=torch.float32, device=dev)
+        self.h_nreg = symm.rendezvous(self.nreg, group)
+        self.hi.zero_()
+        if acc:
+            self.lo.zero_()           # (the pad columns [d, ld) of the operand rows stay zero: only [0, ld) of each row is re-written)
+        self.bl, self.t, self.d, self.ld, self.b = bl, t, d, ld, b
+        torch.cuda.synchronize(dev)
+        self.h_hi.barrier(channel=0)
+
+
+def _symm_state(group, dev, bl, t, d, ld, acc):
+    """The symmetric buffers for this shape, or None when symmetric memory is unavailable for the group (then NCCL is used)."""
+    if os.environ.get("LOCOV_B200_SYMM", "1") == "0" or dist.get_backend(group) != "nccl":
+        return None
+    gkey = id(group)
+    if _symm_disabled.get(gkey):
+        return None
+    key = (gkey, dev.index, bl, t, d, ld, acc)
+    st = _symm_states.get(key)
+    if st is None:
+        try:
+            st = _SymmState(group, dev, bl, t, d, ld, acc)
+        except Exception as e:      # noqa: BLE001  (no fabric / IPC support in this process group: fall back to NCCL, once, loudly)
+            import warnings
+            warnings.warn(f"locov_b200: CUDA symmetric memory is unavailable for this process group ({e}); the sharded LSM head uses NCCL all-gathers")
+            _symm_disabled[gkey] = True
+            return None
+        _symm_states[key] = st
+    return st
+
+
+class _ShardedLsmSymm(Function):
+    """Local regions x ALL captions with the symmetric-memory exchange -> (full [2, B, B] matrices, caption masks [B, T], region counts [B])."""
+
+    @staticmethod
+    def forward(ctx, feats, w, b, cap_loc, cap_mask_loc, reg_mask, inv_temp, alignment, precision, want_w2r, want_r2w, st, cap_op):
+        acc = LF._acc(precision)
+        bi, rg, v = feats.shape
+        bl, t, d = cap_loc.shape
+        dev = feats.device
+        if cap_op is None or (cap_op.lo is None) == acc or cap_op.rows != bl * t or cap_op.cols != d or cap_op.ld != st.ld:
+            cap_op = ops.split_bf16(cap_loc.reshape(bl * t, d), acc)
+        # 1. this rank's caption operand rows and masks -> every rank's gathered buffers
+        row0 = st.rank * bl * t
+        ops.peer_scatter(cap_op.hi, st.h_hi.buffer_ptrs_dev, st.w, st.ld * 2, row0 * st.ld * 2)
+        if acc:
+            ops.peer_scatter(cap_op.lo, st.h_lo.buffer_ptrs_dev, st.w, st.ld * 2, row0 * st.ld * 2)
+        ops.peer_scatter(cap_mask_loc.to(torch.float32).contiguous().reshape(1, -1), st.h_mask.buffer_ptrs_dev, st.w, bl * t * 4, st.rank * bl * t * 4)
+        nreg_loc = reg_mask.to(torch.float32).sum(1)
+        ops.peer_scatter(nreg_loc.reshape(1, -1), st.h_nreg.buffer_ptrs_dev, st.w, bl * 4, st.rank * bl * 4)
+        # 2. projection of the local regions needs no captions: it runs while the peers' stores are in flight
+        emb_op = LF.project_regions(feats.reshape(bi * rg, v), w, b, d, acc)
+        st.h_hi.barrier(channel=0)                      # every rank's slices have landed in this rank's buffers
+        cap_all = ops.Bf16Operand(st.hi, st.lo if acc else None, st.b * t, d)
+        stack = LF.new_pair_stack(st.b, bi, dev, want_w2r and want_r2w)
+        ops.lsm_pair(cap_all, st.mask, emb_op, reg_mask, inv_temp, alignment, want_w2r, want_r2w, stack[0], stack[1])
+        # 3. this rank's [2, B, B_loc] block -> its columns of every rank's [2, B, B] matrices, in place (no re-layout)
+        ops.peer_scatter(stack.reshape(2 * st.b, bi), st.h_pw.buffer_ptrs_dev, st.w, st.b * 4, st.rank * bi * 4)
+        st.h_hi.barrier(channel=1)
+        full = st.pw.clone()                            # the symmetric buffer is rewritten by the next step
+        mask_all = st.mask.clone()
+        nreg_all = st.nreg.clone()
+        ctx.ops_saved = (emb_op, ops.Bf16Operand(st.hi.clone(), st.lo.clone() if acc else None, st.b * t, d) if any(ctx.needs_input_grad[:3]) else None)
+        ctx.save_for_backward(feats, w, mask_all, reg_mask)
+        ctx.meta = (inv_temp, alignment, precision, b is not None, want_w2r, want_r2w, st.rank * bi, bi)
+        ctx.mark_non_differentiable(mask_all, nreg_all)
+        return full, mask_all, nreg_all
+
+    @staticmethod
+    def backward(ctx, g, _gm, _gn):
+        feats, w, mask_all, reg_mask = ctx.saved_tensors
+        emb_op, cap_all = ctx.ops_saved
+        inv_temp, alignment, precision, has_b, want_w2r, want_r2w, c0, bl = ctx.meta
+        acc = LF._acc(precision)
+        bi, rg, v = feats.shape
+        if ctx.needs_input_grad[3]:
+            raise NotImplementedError("sharded LSM: caption embeddings are frozen inputs (LANGUAGE_BACKBONE.FREEZE); "
+                                      "a reduce-scatter of d(captions) is not implemented")
+        g = g[:, :, c0:c0 + bl].contiguous()            # this rank's column block of the (replicated) full gradient: no communication
+        demb, _ = ops.lsm_pair_bwd(cap_all, mask_all, emb_op, reg_mask, inv_temp, alignment,
+                                   g[0] if want_w2r else None, g[1] if want_r2w else None, False)
+        dx = dw = db = None
+        g_op = ops.split_bf16(demb, acc)
+        if ctx.needs_input_grad[0]:
+            dx, _ = ops.linear_fwd(g_op, LF.weight_operand(w, acc, transpose=True), None, want_f32=True)
+            dx = dx.reshape(bi, rg, v)
+        if ctx.needs_input_grad[1]:
+            x_op = ops.split_bf16(feats.reshape(bi * rg, v), acc)
+            dw, _ = ops.linear_fwd(ops.transpose_operand(g_op), ops.transpose_operand(x_op), None, want_f32=True)
+        if has_b and ctx.needs_input_grad[2]:
+            db = demb.sum(0)
+        return dx, dw, db, None, None, None, None, None, None, None, None, None, None
+
+
 def sharded_grounding_forward(head, region_features, region_mask, caption_emb, caption_mask, cap_op=None):
     group = head.process_group
     amode = {"softmax": ops.ALIGN_SOFTMAX, "hardmax": ops.ALIGN_HARDMAX}[head.alignment]
+    st = None
+    if region_features.is_cuda and caption_emb.dim() == 3:
+        bl, t, d = caption_emb.shape
+        st = _symm_state(group, region_features.device, bl, t, d, (d + 7) // 8 * 8, head.precision == "fp32")
+    if st is not None:
+        full, mask_all, nreg_all = _ShardedLsmSymm.apply(
+            region_features.to(torch.float32).contiguous(), head.v2l_projection.weight, head.v2l_projection.bias,
+            caption_emb.to(torch.float32).contiguous(), caption_mask, region_mask, 1.0 / float(head.temperature), amode,
+            head.precision, bool(head.align_words), bool(head.align_regions), st, cap_op)
+        losses, info, dists = head._pair_outputs(full, mask_all, nreg_all.reshape(-1, 1))      # [B, 1] "mask" whose row sum is the region count
+        head.log_dict(losses)
+        head.log_dict(info)
+        if head.return_dist:
+            return info, losses, dists
+        return info, losses
     blocks, mask_all = _ShardedLsm.apply(
         region_features.to(torch.float32).contiguous(), head.v2l_projection.weight, head.v2l_projection.bias,
         caption_emb.to(torch.float32).contiguous(), caption_mask, region_mask, 1.0 / float(head.temperature), amode,

@@ -1,0 +1,20 @@
+#!/bin/bash
+# multi-GPU pass: sharded parity (both exchange paths, small + bench shape), then the N-GPU bench line
+N=${1:-2}
+mkdir -p gpurun_out
+for mode in "1 small" "0 small" "1 bench"; do
+  set -- $mode
+  LOCOV_B200_SYMM=$1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 scripts/check_sharded_nccl.py $2 2>&1 | grep -E "parity|err|Error|error|warn" | tail -8
+done
+for symm in 1 0; do
+  LOCOV_B200_SYMM=$symm timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 500 --warmup 20 --no-workloads > gpurun_out/r2g_bench_n${N}_symm$symm.json 2> gpurun_out/r2g_bench_n${N}_symm$symm.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/r2g_bench_n${N}_symm$symm.json').read().strip().split('\n')[-1])
+    print('N=${N} symm=$symm', 'ms_per_step', round(d['ms_per_step'],4), {k: round(v['ms_per_step'],4) for k,v in d['precisions'].items()}, 'launches', d['gpu_launches_per_step'], 'e2e', round(d['e2e']['ms_per_step'],3))
+    print('   kernels', {k: round(v,4) for k,v in d['precisions'][d['config']['precision']]['kernels_ms'].items()})
+except Exception as e:
+    print('bench parse failed', e); print(open('gpurun_out/r2g_bench_n${N}_symm$symm.err').read()[-1500:])
+PY
+done
