@@ -252,18 +252,26 @@ int loco_lsm_pair_bwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ld
                       int64_t ld_g, uint16_t *dst_hi, uint16_t *dst_lo, int64_t ld_dst,
                       uint16_t *ds_hi, uint16_t *ds_lo, int64_t ld_ds, void *stream);
 
-/* ---- peer scatter (multi-GPU exchange of the sharded LSM head) ------------------------------------------------------------------
+/* ---- peer exchange (multi-GPU step of the sharded LSM head) ------------------------------------------------------------------------
  * New versus the reference, whose heads contain no collective: the image-sharded pair matrix of BASELINE configs[3]
  * needs every rank's caption operands on every rank, and every rank's [B, B_loc] distance block in every rank's [B, B] matrix.
  * Replaces: the NCCL all-gathers a torch.distributed implementation of that exchange would launch (one collective + stream hand-offs
- *           per tensor); here the producing rank stores its slice straight into every rank's symmetric buffer over NVLink.
- * src [rows][row_bytes] (pitch src_pitch, local) -> peer_p + dst_offset (pitch dst_pitch) for each of the n_peers base pointers in the
- * DEVICE array peers_dev (CUDA symmetric-memory allocations mapped into this process, e.g. torch.distributed._symmetric_memory
- * buffer_ptrs_dev; this rank's own buffer included).  All byte counts / offsets / pitches are multiples of 4 (16-byte stores when they
- * all are multiples of 16).  The caller orders the
- * stores against the consumers with a symmetric-memory barrier. */
-int loco_peer_scatter(const void *src, int64_t src_pitch, int rows, int64_t row_bytes, const void *const *peers_dev, int n_peers,
-                      int64_t dst_pitch, int64_t dst_offset, void *stream);
+ *           per tensor) AND the barrier after them: the producing rank stores its slices straight into every rank's symmetric buffer
+ *           over NVLink and the same launch ends with a cross-GPU flag barrier.
+ * nseg <= 4 segments (HOST arrays of length nseg): src[k] [rows[k]][row_bytes[k]] (pitch src_pitch[k], local device memory) is written
+ * to peer_p + dst_offset[k] (pitch dst_pitch[k]) for each of the n_peers base pointers in the DEVICE array peers_dev (CUDA
+ * symmetric-memory allocations mapped into this process, e.g. torch.distributed._symmetric_memory buffer_ptrs_dev; this rank's own
+ * buffer included).  All byte counts / offsets / pitches are multiples of 4 (16-byte stores when they all are multiples of 16).
+ * mode: bit 0 = store the segments (nseg > 0), bit 1 = SIGNAL: after the stores, set flag word [channel][rank] of every peer, bit 2 =
+ * WAIT: spin until every peer has set this rank's flag words [channel][peer], then clear them — when a launch with the WAIT bit
+ * completes, every peer's slices of this exchange have landed here.  (flag_peers_dev: DEVICE array of n_peers pointers to symmetric
+ * uint32[16][n_peers] buffers, zero-initialised once; ticket_dev: one zero-initialised uint32 of local device memory.)  SIGNAL and WAIT
+ * may be split over two launches (store + signal, independent work, then a WAIT-only launch with nseg = 0) so that the wait for the
+ * slowest peer overlaps that work.  Consecutive exchanges must alternate channels.  A segment whose source IS this rank's own
+ * destination (slice produced in place) is not copied to itself. */
+int loco_peer_exchange(int nseg, const void *const *src, const int64_t *src_pitch, const int *rows, const int64_t *row_bytes,
+                       const int64_t *dst_pitch, const int64_t *dst_offset, const void *const *peers_dev, int n_peers,
+                       const void *const *flag_peers_dev, int rank, int channel, int mode, void *ticket_dev, void *stream);
 
 /* ---- pair-matrix losses ---------------------------------------------------------------------------
  * Replaces: grounding_head.py:240-251 (empty-pair guard), :272-290 (4 CE losses), :354-379 (accuracies).

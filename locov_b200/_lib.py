@@ -49,7 +49,8 @@ SIGNATURES = {
     "loco_lsm_pair_fwd": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _i64, _vp, _vp]),
     "loco_lsm_pair_bwd": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _i64, _vp, _vp, _i64,
                                 _vp, _vp, _i64, _vp]),
-    "loco_peer_scatter": (_i, [_vp, _i64, _i, _i64, _vp, _i, _i64, _i64, _vp]),
+    "loco_peer_exchange": (_i, [_i, _c.POINTER(_vp), _c.POINTER(_i64), _c.POINTER(_i), _c.POINTER(_i64), _c.POINTER(_i64), _c.POINTER(_i64), _vp, _i, _vp, _i, _i,
+                                _i, _vp, _vp]),
     "loco_pair_ce_workspace_bytes": (_i64, [_i, _i, _i]),
     "loco_pair_ce": (_i, [_vp, _i, _i64, _i64, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -689,20 +689,71 @@ __global__ void __launch_bounds__(256) skinny_grad_reduce_kernel(const float *__
 // `n_peers` base pointers into the ranks' symmetric allocations, this rank's own included): 16-byte stores over NVLink / NVSwitch
 // straight from the producing rank — no NCCL launch, no staging copy.  Ordering against the consumers is the caller's job (a
 // symmetric-memory barrier after this kernel).  One block per (chunk of 16-byte words, peer).
+struct PeerSegs {
+    const unsigned char *src[4];
+    long long src_pitch[4], dst_pitch[4], dst_offset[4];
+    int rows[4], row_words[4];
+    int nseg;
+};
+
+__device__ __forceinline__ void st_release_sys_u32(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// wait for the flag words [channel][peer] of THIS rank (set by the peers' signals), then clear them for the next round
+__device__ __forceinline__ void peer_wait_flags(unsigned int *const *flag_peers, int n_peers, int rank, int channel) {
+    if ((int)threadIdx.x < n_peers) {
+        unsigned int *mine = flag_peers[rank] + channel * n_peers + threadIdx.x;
+        const uint64_t t0 = global_timer_ns();
+        while (*reinterpret_cast<volatile unsigned int *>(mine) == 0u)      // (relaxed polling; the system-scope fence below is the acquire)
+            if (global_timer_ns() - t0 > 2000000000ull) { printf("locov_b200: rank %d timed out waiting for peer %d (channel %d)\n", rank, (int)threadIdx.x, channel); __trap(); }
+        *mine = 0u;
+    }
+    __threadfence_system();
+}
+
+// Up to four local 2-D buffers -> the same places of every rank's symmetric buffer, then (mode & 2) a SIGNAL to every peer and (mode & 4)
+// a WAIT for every peer's signal in the same launch: every block fences its peer stores at system scope and takes a ticket; the last
+// block stores 1 (release, system scope) into flag word [channel][this rank] of every peer and, when asked to, spins (acquire) on its own
+// flag words [channel][peer] and clears them.  A flag word has one writer (its peer) and is cleared by its reader before that peer can
+// signal the same channel again (the two exchanges of a step alternate channels and each needs the other side's previous signal), so
+// plain stores suffice and CUDA-graph replays need no sequence numbers.  Waits are bounded (2 s, then trap): a missing peer surfaces
+// as a CUDA error, never as a hung GPU.
 template <typename W>
-__global__ void __launch_bounds__(256) peer_scatter_kernel(const unsigned char *__restrict__ src, int64_t src_pitch, int rows, int row_words,
-                                                           unsigned char *const *__restrict__ peers, int n_peers, int64_t dst_pitch,
-                                                           int64_t dst_offset) {
+__global__ void __launch_bounds__(256) peer_scatter_kernel(const PeerSegs segs, unsigned char *const *__restrict__ peers, int n_peers,
+                                                           unsigned int *const *__restrict__ flag_peers, int rank, int channel, int mode,
+                                                           unsigned int *__restrict__ ticket) {
     pdl_trigger();
     pdl_wait();
-    const int peer = blockIdx.y;
-    unsigned char *dst = peers[peer] + dst_offset;
-    const int64_t total = (int64_t)rows * row_words;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = idx / row_words, w = idx - r * row_words;
-        const W v = *reinterpret_cast<const W *>(src + r * src_pitch + w * (int64_t)sizeof(W));
-        *reinterpret_cast<W *>(dst + r * dst_pitch + w * (int64_t)sizeof(W)) = v;
+    if (segs.nseg > 0) {
+        const int peer = blockIdx.y, sg = blockIdx.z;
+        unsigned char *dst = peers[peer] + segs.dst_offset[sg];
+        const unsigned char *src = segs.src[sg];
+        const int row_words = segs.row_words[sg];
+        const long long sp = segs.src_pitch[sg], dp = segs.dst_pitch[sg];
+        const int64_t total = (int64_t)segs.rows[sg] * row_words;
+        if (dst + 0 != src || sp != dp)       // (a slice produced in place in this rank's own buffer needs no copy to itself)
+            for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+                const int64_t r = idx / row_words, w = idx - r * row_words;
+                const W v = *reinterpret_cast<const W *>(src + r * sp + w * (int64_t)sizeof(W));
+                *reinterpret_cast<W *>(dst + r * dp + w * (int64_t)sizeof(W)) = v;
+            }
     }
+    if ((mode & 6) == 0) return;
+    __shared__ int s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y * gridDim.z - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if (threadIdx.x == 0) *ticket = 0;                       // ready for the next launch
+    if ((mode & 2) && (int)threadIdx.x < n_peers) st_release_sys_u32(flag_peers[threadIdx.x] + channel * n_peers + rank, 1u);
+    if (mode & 4) peer_wait_flags(flag_peers, n_peers, rank, channel);
 }
 
 }  // namespace loco
@@ -900,28 +951,47 @@ int loco_skinny_grad(const float *dy, int64_t ld_dy, const float *x, int64_t ld_
     return LOCO_OK;
 }
 
-int loco_peer_scatter(const void *src, int64_t src_pitch, int rows, int64_t row_bytes, const void *const *peers_dev, int n_peers, int64_t dst_pitch,
-                      int64_t dst_offset, void *stream) {
-    LOCO_REQUIRE(rows >= 0 && row_bytes >= 0 && n_peers >= 1 && n_peers <= 64, LOCO_E_BADARG, "peer_scatter: bad arguments rows=%d row_bytes=%lld peers=%d", rows,
-                 (long long)row_bytes, n_peers);
-    if (rows == 0 || row_bytes == 0) return LOCO_OK;
-    LOCO_REQUIRE(src && peers_dev, LOCO_E_BADARG, "peer_scatter: null pointer");
-    LOCO_REQUIRE(src_pitch >= row_bytes && dst_pitch >= row_bytes, LOCO_E_BADARG, "peer_scatter: pitch < row_bytes");
-    const int64_t all = row_bytes | src_pitch | dst_pitch | dst_offset | (int64_t)(reinterpret_cast<uintptr_t>(src) & 15);
-    LOCO_REQUIRE(all % 4 == 0, LOCO_E_ALIGN, "peer_scatter: rows, pitches and offsets must be multiples of 4 bytes");
+int loco_peer_exchange(int nseg, const void *const *src, const int64_t *src_pitch, const int *rows, const int64_t *row_bytes, const int64_t *dst_pitch,
+                       const int64_t *dst_offset, const void *const *peers_dev, int n_peers, const void *const *flag_peers_dev, int rank, int channel,
+                       int mode, void *ticket_dev, void *stream) {
+    LOCO_REQUIRE(nseg >= 0 && nseg <= 4 && n_peers >= 1 && n_peers <= 64 && rank >= 0 && rank < n_peers, LOCO_E_BADARG, "peer_exchange: bad arguments nseg=%d peers=%d rank=%d",
+                 nseg, n_peers, rank);
+    LOCO_REQUIRE(nseg == 0 || (src && src_pitch && rows && row_bytes && dst_pitch && dst_offset && peers_dev), LOCO_E_BADARG, "peer_exchange: null pointer");
+    LOCO_REQUIRE((mode & ~7) == 0 && ((mode & 1) != 0) == (nseg > 0) && mode != 0, LOCO_E_BADARG, "peer_exchange: mode %d does not match %d segments", mode, nseg);
+    LOCO_REQUIRE((mode & 6) == 0 || (flag_peers_dev != nullptr && ticket_dev != nullptr && channel >= 0 && channel < 16), LOCO_E_BADARG,
+                 "peer_exchange: signal / wait need flag buffers, a ticket word and 0 <= channel < 16");
+    PeerSegs segs = {};
+    segs.nseg = nseg;
+    int64_t all = 0, max_words = 1;
+    for (int k = 0; k < nseg; ++k) {
+        LOCO_REQUIRE(rows[k] >= 0 && row_bytes[k] >= 0 && (rows[k] == 0 || row_bytes[k] == 0 || src[k] != nullptr), LOCO_E_BADARG, "peer_exchange: bad segment %d", k);
+        LOCO_REQUIRE(src_pitch[k] >= row_bytes[k] && dst_pitch[k] >= row_bytes[k], LOCO_E_BADARG, "peer_exchange: pitch < row_bytes in segment %d", k);
+        all |= row_bytes[k] | src_pitch[k] | dst_pitch[k] | dst_offset[k] | (int64_t)(reinterpret_cast<uintptr_t>(src[k]) & 15);
+    }
+    LOCO_REQUIRE(all % 4 == 0, LOCO_E_ALIGN, "peer_exchange: rows, pitches and offsets must be multiples of 4 bytes");
     const bool wide = all % 16 == 0;           // 16-byte words when everything allows it, 4-byte words otherwise
     const int wbytes = wide ? 16 : 4;
-    const int64_t total = (int64_t)rows * (row_bytes / wbytes);
-    int blocks = (int)((total + 255) / 256 < 64 ? (total + 255) / 256 : 64);
-    if (blocks < 1) blocks = 1;
-    const dim3 grid((unsigned)blocks, (unsigned)n_peers);
+    for (int k = 0; k < nseg; ++k) {
+        segs.src[k] = static_cast<const unsigned char *>(src[k]);
+        segs.src_pitch[k] = src_pitch[k]; segs.dst_pitch[k] = dst_pitch[k]; segs.dst_offset[k] = dst_offset[k];
+        segs.rows[k] = rows[k]; segs.row_words[k] = (int)(row_bytes[k] / wbytes);
+        const int64_t words = (int64_t)rows[k] * segs.row_words[k];
+        if (words > max_words) max_words = words;
+    }
+    // enough blocks to keep NVLink busy (a few hundred KB per peer), few enough that the grid is one wave beside the GEMMs
+    int cap = 512 / (n_peers * (nseg > 0 ? nseg : 1));
+    if (cap < 4) cap = 4;
+    if (cap > 64) cap = 64;
+    int blocks = (int)((max_words + 511) / 512 < cap ? (max_words + 511) / 512 : cap);
+    if (blocks < 1 || nseg == 0) blocks = 1;
+    const dim3 grid((unsigned)blocks, nseg > 0 ? (unsigned)n_peers : 1u, nseg > 0 ? (unsigned)nseg : 1u);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (wide)
-        LOCO_CUDA(launch_kernel(peer_scatter_kernel<uint4>, grid, dim3(256), 0, st, 1, static_cast<const unsigned char *>(src), src_pitch, rows,
-                                (int)(row_bytes / 16), (unsigned char *const *)(peers_dev), n_peers, dst_pitch, dst_offset));
+        LOCO_CUDA(launch_kernel(peer_scatter_kernel<uint4>, grid, dim3(256), 0, st, 1, segs, (unsigned char *const *)(peers_dev), n_peers,
+                                (unsigned int *const *)(flag_peers_dev), rank, channel, mode, static_cast<unsigned int *>(ticket_dev)));
     else
-        LOCO_CUDA(launch_kernel(peer_scatter_kernel<uint32_t>, grid, dim3(256), 0, st, 1, static_cast<const unsigned char *>(src), src_pitch, rows,
-                                (int)(row_bytes / 4), (unsigned char *const *)(peers_dev), n_peers, dst_pitch, dst_offset));
+        LOCO_CUDA(launch_kernel(peer_scatter_kernel<uint32_t>, grid, dim3(256), 0, st, 1, segs, (unsigned char *const *)(peers_dev), n_peers,
+                                (unsigned int *const *)(flag_peers_dev), rank, channel, mode, static_cast<unsigned int *>(ticket_dev)));
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;

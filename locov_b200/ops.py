@@ -500,18 +500,36 @@ def lsm_pair_bwd(cap: Bf16Operand, cap_mask: torch.Tensor, emb: Bf16Operand, reg
     return demb, dcap
 
 
-def peer_scatter(src: torch.Tensor, peers_dev: int, n_peers: int, dst_pitch_bytes: int, dst_offset_bytes: int, rows: int = None,
-                 row_bytes: int = None):
-    """Store a local 2-D buffer at the same place in every rank's symmetric buffer (``peers_dev``: device array of base pointers)."""
-    _need_cuda(src)
-    if src.dim() == 1:
-        src = src.reshape(1, -1)
-    if src.dim() != 2 or src.stride(1) != 1:
-        raise LocoError("peer_scatter: expects a 2-D tensor with unit column stride")
-    rows = src.shape[0] if rows is None else rows
-    row_bytes = src.shape[1] * src.element_size() if row_bytes is None else row_bytes
-    _lib.check(_lib.load().loco_peer_scatter(_p(src), src.stride(0) * src.element_size(), int(rows), int(row_bytes), int(peers_dev), int(n_peers),
-                                             int(dst_pitch_bytes), int(dst_offset_bytes), _stream(src)), "loco_peer_scatter")
+PEER_STORE, PEER_SIGNAL, PEER_WAIT = 1, 2, 4
+
+
+def peer_exchange(segments, peers_dev: int, n_peers: int, flag_peers_dev: int = 0, rank: int = 0, channel: int = 0, mode: int = PEER_STORE,
+                  ticket: torch.Tensor = None, device: torch.device = None):
+    """Store up to four local 2-D buffers at the same places of every rank's symmetric buffer and / or signal the peers and / or wait for
+    their signals (``mode`` bits PEER_STORE | PEER_SIGNAL | PEER_WAIT), in one launch.  ``segments``: list of (src tensor [rows, cols]
+    with unit column stride, dst_pitch_bytes, dst_offset_bytes); ``peers_dev`` / ``flag_peers_dev``: device arrays of base pointers
+    (symmetric memory)."""
+    n = len(segments)
+    if n > 4:
+        raise LocoError("peer_exchange: at most 4 segments")
+    srcs = []
+    for t, _, _ in segments:
+        _need_cuda(t)
+        t2 = t.reshape(1, -1) if t.dim() == 1 else t
+        if t2.dim() != 2 or t2.stride(1) != 1:
+            raise LocoError("peer_exchange: segments must be 2-D with unit column stride")
+        srcs.append(t2)
+    m = max(n, 1)
+    vp = (ctypes.c_void_p * m)(*[t.data_ptr() for t in srcs])
+    sp = (ctypes.c_int64 * m)(*[t.stride(0) * t.element_size() if t.shape[0] > 1 else t.shape[1] * t.element_size() for t in srcs])
+    rows = (ctypes.c_int * m)(*[t.shape[0] for t in srcs])
+    rb = (ctypes.c_int64 * m)(*[t.shape[1] * t.element_size() for t in srcs])
+    dp = (ctypes.c_int64 * m)(*[int(s[1]) for s in segments])
+    do = (ctypes.c_int64 * m)(*[int(s[2]) for s in segments])
+    dev = srcs[0].device if srcs else device
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(_lib.load().loco_peer_exchange(n, vp, sp, rows, rb, dp, do, int(peers_dev), int(n_peers), int(flag_peers_dev) or None, int(rank), int(channel),
+                                              int(mode), _p(ticket), stream), "loco_peer_exchange")
 
 
 def pair_ce(pw: torch.Tensor, cap_mask: torch.Tensor, reg_mask: torch.Tensor, diag_offset: int = 0,

@@ -16,9 +16,9 @@ of the single-device matrix and the four global losses equal the single-device l
 
 Exchange: on GPUs of one NVSwitch box both steps are PEER STORES into CUDA symmetric memory (torch.distributed._symmetric_memory
 buffers mapped into every process): the rank that produces a slice (caption operand rows from ``loco_lsm_prep``, its distance block from
-the pair kernel) stores it straight into every rank's gathered buffer (``loco_peer_scatter``) and a symmetric-memory barrier orders the
-stores against the consumers — two small kernels and two barriers per step on ONE stream, no NCCL launch, no stream hand-off, no
-re-layout copy (the blocks land in place in the [2, B, B] matrices).  The NCCL all-gather implementation below remains as the path for
+the pair kernel) stores it straight into every rank's gathered buffer and the SAME launch ends with a cross-GPU flag barrier
+(``loco_peer_exchange``) — two small kernels per step on ONE stream, no NCCL launch, no stream hand-off, no re-layout copy (the blocks
+land in place in the [2, B, B] matrices).  The NCCL all-gather implementation below remains as the path for
 process groups without symmetric memory (and is what the gloo / CPU test of the exchange logic exercises); LOCOV_B200_SYMM=0 forces it.
 
 Gradient convention: every rank holds the SAME global loss; its autograd path covers only its own
@@ -183,44 +183,75 @@ _symm_disabled = {}
 
 
 class _SymmState:
-    """Symmetric buffers of one (process group, shape) — allocated and exchanged once (collective), reused by every step."""
+    """Symmetric memory of one (process group, shape): ONE allocation per rank holding every gathered tensor, plus the flag words of
+    the in-kernel barriers — allocated and exchanged once (collective), reused by every step.
 
-    def __init__(self, group, dev, bl, t, d, ld, acc):
+    Regions.  "A side" (written by exchange A, read by the pair kernel only): caption operands hi [B*T, ld] (+ lo), caption masks
+    [B, T].  "B side" (written by exchange B, read by the pair-CE kernel only): pair matrices [2, B, B], caption masks [B, T], region
+    masks [B, Rg].  With the two exchanges alternating, a rank can only be overwritten on one side while it is reading the other:
+    single buffering is race-free (a peer cannot start exchange A of step k+1 before this rank signalled in exchange B of step k,
+    i.e. after its pair kernel; it cannot start exchange B of step k+1 before this rank signalled in exchange A of step k+1, i.e.
+    after its pair-CE kernel of step k)."""
+
+    def __init__(self, group, dev, bl, t, d, ld, rg, acc):
         import torch.distributed._symmetric_memory as symm
         self.w, self.rank = dist.get_world_size(group), dist.get_rank(group)
         b = self.w * bl
-        self.hi = symm.empty((b * t, ld), dtype=torch.bfloat16, device=dev)
-        self.h_hi = symm.rendezvous(self.hi, group)
-        self.lo = self.h_lo = None
-        if acc:
-            self.lo = symm.empty((b * t, ld), dtype=torch.bfloat16, device=dev)
-            self.h_lo = symm.rendezvous(self.lo, group)
-        self.mask = symm.empty((b, t), dtype=torch.float32, device=dev)
-        self.h_mask = symm.rendezvous(self.mask, group)
-        self.pw = symm.empty((2, b, b), dtype=torch.float32, device=dev)
-        self.h_pw = symm.rendezvous(self.pw, group)
-        self.nreg = symm.empty((b,), dtype=torch.float32, device=dev)
-        self.h_nreg = symm.rendezvous(self.nreg, group)
-        self.hi.zero_()
-        if acc:
-            self.lo.zero_()           # (the pad columns [d, ld) of the operand rows stay zero: only [0, ld) of each row is re-written)
-        self.bl, self.t, self.d, self.ld, self.b = bl, t, d, ld, b
+        self.bl, self.t, self.d, self.ld, self.b, self.rg, self.acc = bl, t, d, ld, b, rg, acc
+        sizes = [("hi", b * t * ld * 2), ("lo", b * t * ld * 2 if acc else 0), ("maskA", b * t * 4), ("pw", 2 * b * b * 4), ("maskB", b * t * 4),
+                 ("reg", b * rg * 4)]
+        self.off, total = {}, 0
+        for name, n in sizes:
+            self.off[name] = total
+            total += (n + 255) // 256 * 256
+        self.buf = symm.empty((total,), dtype=torch.uint8, device=dev)
+        self.h = symm.rendezvous(self.buf, group)
+        self.flags = symm.empty((16 * self.w,), dtype=torch.int32, device=dev)
+        self.h_flags = symm.rendezvous(self.flags, group)
+        self.buf.zero_()              # (the pad columns [d, ld) of the operand rows stay zero: whole rows are re-written, pads included)
+        self.flags.zero_()
+        self.ticket = torch.zeros(4, dtype=torch.int32, device=dev)
         torch.cuda.synchronize(dev)
-        self.h_hi.barrier(channel=0)
+        self.h.barrier(channel=0)     # one-off: every rank has zeroed its flags before any exchange kernel runs
+
+        def view(name, dtype, shape):
+            n = 1
+            for k in shape:
+                n *= k
+            nbytes = n * torch.empty((), dtype=dtype).element_size()
+            return self.buf[self.off[name]:self.off[name] + nbytes].view(dtype).view(shape)
+        self.hi = view("hi", torch.bfloat16, (b * t, ld))
+        self.lo = view("lo", torch.bfloat16, (b * t, ld)) if acc else None
+        self.maskA = view("maskA", torch.float32, (b, t))
+        self.pw = view("pw", torch.float32, (2, b, b))
+        self.maskB = view("maskB", torch.float32, (b, t))
+        self.reg = view("reg", torch.float32, (b, rg))
+
+    def exchange(self, segments, channel, mode):
+        """segments: [(region name, src tensor 2-D, dst pitch bytes, byte offset inside the region)]; mode: ops.PEER_* bits"""
+        dbg = os.environ.get("LOCOV_B200_SYMM_DEBUG", "0")     # developer timing experiments: 1 = no exchange at all, 2 = stores without signals / waits
+        if dbg == "1":
+            return
+        if dbg == "2":
+            mode &= ops.PEER_STORE
+            if mode == 0:
+                return
+        ops.peer_exchange([(src, pitch, self.off[name] + off) for name, src, pitch, off in segments], self.h.buffer_ptrs_dev, self.w,
+                          self.h_flags.buffer_ptrs_dev, self.rank, channel, mode, self.ticket, device=self.buf.device)
 
 
-def _symm_state(group, dev, bl, t, d, ld, acc):
+def _symm_state(group, dev, bl, t, d, ld, rg, acc):
     """The symmetric buffers for this shape, or None when symmetric memory is unavailable for the group (then NCCL is used)."""
     if os.environ.get("LOCOV_B200_SYMM", "1") == "0" or dist.get_backend(group) != "nccl":
         return None
     gkey = id(group)
     if _symm_disabled.get(gkey):
         return None
-    key = (gkey, dev.index, bl, t, d, ld, acc)
+    key = (gkey, dev.index, bl, t, d, ld, rg, acc)
     st = _symm_states.get(key)
     if st is None:
         try:
-            st = _SymmState(group, dev, bl, t, d, ld, acc)
+            st = _SymmState(group, dev, bl, t, d, ld, rg, acc)
         except Exception as e:      # noqa: BLE001  (no fabric / IPC support in this process group: fall back to NCCL, once, loudly)
             import warnings
             warnings.warn(f"locov_b200: CUDA symmetric memory is unavailable for this process group ({e}); the sharded LSM head uses NCCL all-gathers")
@@ -241,28 +272,29 @@ class _ShardedLsmSymm(Function):
         dev = feats.device
         if cap_op is None or (cap_op.lo is None) == acc or cap_op.rows != bl * t or cap_op.cols != d or cap_op.ld != st.ld:
             cap_op = ops.split_bf16(cap_loc.reshape(bl * t, d), acc)
-        # 1. this rank's caption operand rows and masks -> every rank's gathered buffers
+        # 1. exchange A: this rank's caption operand rows and caption masks -> every rank's gathered buffers, barrier in the same launch
+        cm = cap_mask_loc.to(torch.float32).contiguous().reshape(1, -1)
         row0 = st.rank * bl * t
-        ops.peer_scatter(cap_op.hi, st.h_hi.buffer_ptrs_dev, st.w, st.ld * 2, row0 * st.ld * 2)
+        segs = [("hi", cap_op.hi, st.ld * 2, row0 * st.ld * 2), ("maskA", cm, bl * t * 4, row0 * 4)]
         if acc:
-            ops.peer_scatter(cap_op.lo, st.h_lo.buffer_ptrs_dev, st.w, st.ld * 2, row0 * st.ld * 2)
-        ops.peer_scatter(cap_mask_loc.to(torch.float32).contiguous().reshape(1, -1), st.h_mask.buffer_ptrs_dev, st.w, bl * t * 4, st.rank * bl * t * 4)
-        nreg_loc = reg_mask.to(torch.float32).sum(1)
-        ops.peer_scatter(nreg_loc.reshape(1, -1), st.h_nreg.buffer_ptrs_dev, st.w, bl * 4, st.rank * bl * 4)
-        # 2. projection of the local regions needs no captions: it runs while the peers' stores are in flight
+            segs.append(("lo", cap_op.lo, st.ld * 2, row0 * st.ld * 2))
+        # 2. the projection of the local regions needs no captions: it runs between the signal and the wait of the exchange
+        st.exchange(segs, 0, ops.PEER_STORE)            # stores only: they drain over NVLink while the projection GEMM runs
         emb_op = LF.project_regions(feats.reshape(bi * rg, v), w, b, d, acc)
-        st.h_hi.barrier(channel=0)                      # every rank's slices have landed in this rank's buffers
+        st.exchange([], 0, ops.PEER_SIGNAL | ops.PEER_WAIT)     # every rank's slices have landed here
         cap_all = ops.Bf16Operand(st.hi, st.lo if acc else None, st.b * t, d)
         stack = LF.new_pair_stack(st.b, bi, dev, want_w2r and want_r2w)
-        ops.lsm_pair(cap_all, st.mask, emb_op, reg_mask, inv_temp, alignment, want_w2r, want_r2w, stack[0], stack[1])
-        # 3. this rank's [2, B, B_loc] block -> its columns of every rank's [2, B, B] matrices, in place (no re-layout)
-        ops.peer_scatter(stack.reshape(2 * st.b, bi), st.h_pw.buffer_ptrs_dev, st.w, st.b * 4, st.rank * bi * 4)
-        st.h_hi.barrier(channel=1)
-        full = st.pw.clone()                            # the symmetric buffer is rewritten by the next step
-        mask_all = st.mask.clone()
-        nreg_all = st.nreg.clone()
-        ctx.ops_saved = (emb_op, ops.Bf16Operand(st.hi.clone(), st.lo.clone() if acc else None, st.b * t, d) if any(ctx.needs_input_grad[:3]) else None)
-        ctx.save_for_backward(feats, w, mask_all, reg_mask)
+        ops.lsm_pair(cap_all, st.maskA, emb_op, reg_mask, inv_temp, alignment, want_w2r, want_r2w, stack[0], stack[1])
+        # 3. exchange B: this rank's [2, B, B_loc] block -> its columns of every rank's [2, B, B] matrices, in place (no re-layout), with
+        #    the masks the pair-CE kernel's empty-pair guard reads
+        rm = reg_mask.to(torch.float32).contiguous()
+        st.exchange([("pw", stack.reshape(2 * st.b, bi), st.b * 4, st.rank * bi * 4), ("maskB", cm, bl * t * 4, row0 * 4),
+                     ("reg", rm.reshape(1, -1), bi * rg * 4, st.rank * bi * rg * 4)], 1, ops.PEER_STORE | ops.PEER_SIGNAL | ops.PEER_WAIT)
+        full = st.pw.clone()                            # (the caller keeps the matrices; the symmetric buffer is rewritten by the next step)
+        mask_all, nreg_all = st.maskB, st.reg           # read by the pair-CE kernel of this step only
+        need = any(ctx.needs_input_grad[:3])
+        ctx.ops_saved = (emb_op, ops.Bf16Operand(st.hi.clone(), st.lo.clone() if acc else None, st.b * t, d) if need else None)
+        ctx.save_for_backward(feats, w, st.maskA.clone() if need else mask_all, reg_mask)
         ctx.meta = (inv_temp, alignment, precision, b is not None, want_w2r, want_r2w, st.rank * bi, bi)
         ctx.mark_non_differentiable(mask_all, nreg_all)
         return full, mask_all, nreg_all
@@ -299,13 +331,13 @@ def sharded_grounding_forward(head, region_features, region_mask, caption_emb, c
     st = None
     if region_features.is_cuda and caption_emb.dim() == 3:
         bl, t, d = caption_emb.shape
-        st = _symm_state(group, region_features.device, bl, t, d, (d + 7) // 8 * 8, head.precision == "fp32")
+        st = _symm_state(group, region_features.device, bl, t, d, (d + 7) // 8 * 8, region_features.shape[1], head.precision == "fp32")
     if st is not None:
         full, mask_all, nreg_all = _ShardedLsmSymm.apply(
             region_features.to(torch.float32).contiguous(), head.v2l_projection.weight, head.v2l_projection.bias,
             caption_emb.to(torch.float32).contiguous(), caption_mask, region_mask, 1.0 / float(head.temperature), amode,
             head.precision, bool(head.align_words), bool(head.align_regions), st, cap_op)
-        losses, info, dists = head._pair_outputs(full, mask_all, nreg_all.reshape(-1, 1))      # [B, 1] "mask" whose row sum is the region count
+        losses, info, dists = head._pair_outputs(full, mask_all, nreg_all)
         head.log_dict(losses)
         head.log_dict(info)
         if head.return_dist:
