@@ -163,8 +163,12 @@ def run_reference(args):
 def graph_time(torch, fn, iters=16, reps=5, warm=3):
     """Average device time (ms) of ONE call of fn(i): `iters` calls (rotating operands) captured in a CUDA graph so that host launch
     overhead (longer than most of these kernels) is not in the number; best of `reps` replays."""
-    for i in range(warm):
-        fn(i)
+    side = torch.cuda.Stream()                       # warm up on a side stream (as the capture runs on one): autograd's AccumulateGrad
+    side.wait_stream(torch.cuda.current_stream())    # nodes must not be pinned to the legacy stream, or a captured backward fails
+    with torch.cuda.stream(side):
+        for i in range(warm):
+            fn(i)
+    torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):

@@ -308,7 +308,56 @@ __device__ __forceinline__ float block_reduce_sum(float v, float *red) {
 // fixed-order shuffle tree.  nblk == 1 (B <= 32): the matrix is staged in shared memory once.  nblk > 1: each CTA scans the
 // whole (L2-resident) matrix for the guard's global maximum, applies the guard on the fly, and the last CTA to finish
 // (ticket counter in `scratch`) adds the per-CTA partial sums in CTA order — deterministic, no float atomics.
-template <bool STAGED>
+// monotone float <-> unsigned mapping (larger float = larger unsigned; 0 is below every finite float): atomicMax on floats
+__device__ __forceinline__ unsigned int float_to_ordered(float f) {
+    const unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(unsigned int u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// scratch layout of the multi-CTA pair-CE (floats): [16] tickets, [16] ordered maxima, [Bc] empty-caption flags, [Bi] empty-image flags,
+// then [nmat][nblk][4] partial sums
+__device__ __forceinline__ float *pce_flags(float *scratch) { return scratch + 32; }
+
+// First launch of the multi-CTA pair-CE (B > 32): what EVERY strip CTA needs and none should recompute — the empty-caption / empty-image
+// flags (a warp per row of the masks) and the maximum of each ORIGINAL matrix for the empty-pair guard (grid-stride scan, one atomicMax per
+// block on the ordered encoding).  With these replicated in each of the 64 strip CTAs of a 256 x 256 matrix they were most of its 28 us.
+__global__ void __launch_bounds__(256) pair_ce_prep_kernel(const float *__restrict__ pw_all, int nmat, int64_t mat_stride, int64_t ld, int Bc, int Bi,
+                                                           const float *__restrict__ cap_mask, int T, const float *__restrict__ reg_mask, int Rg,
+                                                           float *__restrict__ scratch) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float red[32];
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    float *cap_empty = pce_flags(scratch), *img_empty = cap_empty + Bc;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < Bc + Bi; row += gridDim.x * wpb) {
+        float sum = 0.f;
+        if (row < Bc) {
+            for (int t = lane; t < T; t += 32) sum += cap_mask[(int64_t)row * T + t];
+        } else {
+            for (int r = lane; r < Rg; r += 32) sum += reg_mask[(int64_t)(row - Bc) * Rg + r];
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) (row < Bc ? cap_empty[row] : img_empty[row - Bc]) = sum > 0.f ? 0.f : 1.f;
+    }
+    unsigned int *maxenc = reinterpret_cast<unsigned int *>(scratch) + 16;
+    for (int m = 0; m < nmat; ++m) {
+        const float *pw = pw_all + (int64_t)m * mat_stride;
+        float mx = -FLT_MAX;
+        for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < Bc; c += gridDim.x * wpb) {      // warp = row, lane = column: coalesced
+            const float *rowp = pw + (int64_t)c * ld;
+            for (int i = lane; i < Bi; i += 32) mx = fmaxf(mx, rowp[i]);
+        }
+        mx = block_reduce_max(mx, red);
+        if (threadIdx.x == 0) atomicMax(maxenc + m, float_to_ordered(mx));
+    }
+}
+
+// STRIP (B > 32 only): image columns / caption rows per CTA — 32, or 8 for the large matrices of the sharded head (256 x 256: 64 CTAs
+// instead of 16; the kernel is a chain of short dependent passes, so its time is per-CTA latency, not throughput).
+template <bool STAGED, int STRIP = 32>
 __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_all, int64_t mat_stride, int64_t ld, int Bc, int Bi,
                                                        int diag_off, const float *__restrict__ cap_mask, int T,
                                                        const float *__restrict__ reg_mask, int Rg, float *__restrict__ out4_all,
@@ -342,23 +391,24 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
             mx = fmaxf(mx, v);
         }
     } else {
-        // every CTA scans the whole (L2-resident) matrix: warp = row, lane = column — coalesced, no index divisions
+        // flags and the matrix maximum come from pair_ce_prep_kernel (previous launch)
+        const float *flags = pce_flags(scratch);
+        for (int k = tid; k < Bc + Bi; k += nt) cap_empty[k] = flags[k];             // (img_empty follows cap_empty in both places)
+        mx = ordered_to_float(reinterpret_cast<const unsigned int *>(scratch)[16 + mat_id]);
+    }
+    if (STAGED) {
         for (int c = warp; c < Bc; c += nwarp) {
-            const float *row = pw + (int64_t)c * ld;
-            for (int i = lane; i < Bi; i += 32) mx = fmaxf(mx, row[i]);
+            float s = 0.f;
+            for (int t = lane; t < T; t += 32) s += cap_mask[(int64_t)c * T + t];
+            s = warp_sum(s);
+            if (lane == 0) cap_empty[c] = s > 0.f ? 0.f : 1.f;
         }
-    }
-    for (int c = warp; c < Bc; c += nwarp) {
-        float s = 0.f;
-        for (int t = lane; t < T; t += 32) s += cap_mask[(int64_t)c * T + t];
-        s = warp_sum(s);
-        if (lane == 0) cap_empty[c] = s > 0.f ? 0.f : 1.f;
-    }
-    for (int i = warp; i < Bi; i += nwarp) {
-        float s = 0.f;
-        for (int r = lane; r < Rg; r += 32) s += reg_mask[(int64_t)i * Rg + r];
-        s = warp_sum(s);
-        if (lane == 0) img_empty[i] = s > 0.f ? 0.f : 1.f;
+        for (int i = warp; i < Bi; i += nwarp) {
+            float s = 0.f;
+            for (int r = lane; r < Rg; r += 32) s += reg_mask[(int64_t)i * Rg + r];
+            s = warp_sum(s);
+            if (lane == 0) img_empty[i] = s > 0.f ? 0.f : 1.f;
+        }
     }
     if (tid < 128) acc[tid] = 0.f;
     // empty-pair guard (grounding_head.py:240-251): max over the whole ORIGINAL matrix; with several CTAs the entries
@@ -382,9 +432,9 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
         __syncthreads();
     }
     const float inv = 1.0f / (float)Bi;
-    const int i_beg = blk * 32, i_end = min(Bi, i_beg + 32);
-    const int c_beg = blk * 32, c_end = min(Bc, c_beg + 32);
-    // with several CTAs the last block also takes the rows beyond nblk * 32 (Bc > Bi never happens for square
+    const int i_beg = blk * STRIP, i_end = min(Bi, i_beg + STRIP);
+    const int c_beg = blk * STRIP, c_end = min(Bc, c_beg + STRIP);
+    // with several CTAs the last block also takes the rows beyond nblk * STRIP (Bc > Bi never happens for square
     // matrices; kept general)
     const int c_end2 = (blk == nblk - 1) ? Bc : c_end;
     const int i_end2 = (blk == nblk - 1) ? Bi : i_end;
@@ -398,46 +448,56 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
         float *py = px + 32 * 33;          // [nwarp][33] partial minima
         int *pz = reinterpret_cast<int *>(py + 32 * 33);   // [nwarp][33] partial argmin
         float *col_m = reinterpret_cast<float *>(pz + 32 * 33), *col_s = col_m + 32;
-        const int i = i_beg + lane;
+        // lane = (row sub-lane, column of the strip): a warp covers SUB consecutive rows x STRIP columns per load
+        constexpr int SUB = 32 / STRIP;
+        const int colj = lane % STRIP, sub = lane / STRIP;
+        const int i = i_beg + colj;
         const bool col_on = i < i_end2;
         const int tgt = i + diag_off;
         float m = -FLT_MAX, best = FLT_MAX;
         int arg = 0x7fffffff;
         if (col_on)
-            for (int c = warp; c < Bc; c += nwarp) {
+            for (int c = warp * SUB + sub; c < Bc; c += nwarp * SUB) {
                 const float v = val(c, i);
                 m = fmaxf(m, -v);
                 if (v < best) { best = v; arg = c; }        // rows visited in increasing order: first minimum
             }
         px[warp * 33 + lane] = m; py[warp * 33 + lane] = best; pz[warp * 33 + lane] = arg;
         __syncthreads();
-        if (warp == 0) {
+        if (warp == 0 && lane < STRIP) {
             float mm = -FLT_MAX, bb = FLT_MAX;
             int aa = 0x7fffffff;
-            for (int w = 0; w < nwarp; ++w) {
-                mm = fmaxf(mm, px[w * 33 + lane]);
-                const float ob = py[w * 33 + lane];
-                const int oa = pz[w * 33 + lane];
-                if (ob < bb || (ob == bb && oa < aa)) { bb = ob; aa = oa; }
-            }
+            for (int w = 0; w < nwarp; ++w)
+#pragma unroll
+                for (int sl = 0; sl < SUB; ++sl) {
+                    mm = fmaxf(mm, px[w * 33 + sl * STRIP + lane]);
+                    const float ob = py[w * 33 + sl * STRIP + lane];
+                    const int oa = pz[w * 33 + sl * STRIP + lane];
+                    if (ob < bb || (ob == bb && oa < aa)) { bb = ob; aa = oa; }
+                }
             col_m[lane] = mm;
-            pz[lane] = aa;                 // (row 0 of pz now holds the column argmin: read below by warp 0 only)
+            reinterpret_cast<int *>(col_s)[32 + lane] = aa;                 // column argmin
         }
         __syncthreads();
-        const float cm = col_m[lane];
+        const float cm = col_m[colj];
         float s = 0.f;
         if (col_on)
-            for (int c = warp; c < Bc; c += nwarp) s += expf(-val(c, i) - cm);
+            for (int c = warp * SUB + sub; c < Bc; c += nwarp * SUB) s += expf(-val(c, i) - cm);
         px[warp * 33 + lane] = s;          // (the partial maxima in px were consumed before the barrier above)
         __syncthreads();
         if (warp == 0) {
-            float ss = 0.f;
-            for (int w = 0; w < nwarp; ++w) ss += px[w * 33 + lane];
-            col_s[lane] = ss;
             float l = 0.f, a = 0.f;
-            if (col_on && tgt < Bc) {
-                l = (cm + logf(ss)) + val(tgt, i);
-                a = (pz[lane] == tgt) ? 1.f : 0.f;
+            if (lane < STRIP) {
+                float ss = 0.f;
+                for (int w = 0; w < nwarp; ++w)
+#pragma unroll
+                    for (int sl = 0; sl < SUB; ++sl) ss += px[w * 33 + sl * STRIP + lane];
+                col_s[lane] = ss;
+                const int i0 = i_beg + lane, tg = i0 + diag_off;
+                if (i0 < i_end2 && tg < Bc) {
+                    l = (col_m[lane] + logf(ss)) + val(tg, i0);
+                    a = (reinterpret_cast<int *>(col_s)[32 + lane] == tg) ? 1.f : 0.f;
+                }
             }
             l = warp_sum(l);
             a = warp_sum(a);
@@ -445,8 +505,8 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
         }
         __syncthreads();
         if (dcap != nullptr && col_on) {
-            const float cs = col_s[lane];
-            for (int c = warp; c < Bc; c += nwarp) {
+            const float cs = col_s[colj];
+            for (int c = warp * SUB + sub; c < Bc; c += nwarp * SUB) {
                 float g = 0.f;
                 if (tgt < Bc && !(cap_empty[c] > 0.f && img_empty[i] > 0.f))
                     g = (((c == tgt) ? 1.f : 0.f) - expf(-val(c, i) - cm) / cs) * inv;
@@ -534,7 +594,7 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
         return;
     }
     // several CTAs: publish the partials, the last CTA adds them in CTA order
-    float *parts = scratch + 16 + ((int64_t)mat_id * nblk) * 4;
+    float *parts = scratch + 32 + Bc + Bi + ((int64_t)mat_id * nblk) * 4;
     unsigned int *ticket = reinterpret_cast<unsigned int *>(scratch) + mat_id;
     if (warp < 4 && lane == 0) parts[blk * 4 + warp] = part;
     __threadfence();
@@ -548,7 +608,10 @@ __global__ void __launch_bounds__(1024) pair_ce_kernel(float *__restrict__ pw_al
             for (int j = 0; j < nblk; ++j) v += __ldcg(parts + j * 4 + tid);
             out4[tid] = v * inv;
         }
-        if (tid == 0) *ticket = 0;   // ready for the next launch
+        if (tid == 0) {              // ready for the next launch
+            *ticket = 0;
+            reinterpret_cast<unsigned int *>(scratch)[16 + mat_id] = 0u;
+        }
         for (int idx = tid; idx < Bc * Bi; idx += nt) {
             const int c = idx / Bi, i = idx - c * Bi;
             if (cap_empty[c] > 0.f && img_empty[i] > 0.f) pw[(int64_t)c * ld + i] = guard;
@@ -997,9 +1060,12 @@ int loco_peer_exchange(int nseg, const void *const *src, const int64_t *src_pitc
     return LOCO_OK;
 }
 
+static int pair_ce_strip(int Bc, int Bi) { return (Bc > Bi ? Bc : Bi) >= 128 ? 8 : 32; }
+
 int64_t loco_pair_ce_workspace_bytes(int nmat, int Bc, int Bi) {
-    const int nblk = ((Bc > Bi ? Bc : Bi) + 31) / 32;
-    return (int64_t)(16 + (int64_t)nmat * nblk * 4) * (int64_t)sizeof(float);
+    const int strip = pair_ce_strip(Bc, Bi);
+    const int nblk = ((Bc > Bi ? Bc : Bi) + strip - 1) / strip;
+    return (int64_t)(32 + Bc + Bi + (int64_t)nmat * nblk * 4) * (int64_t)sizeof(float);
 }
 
 int loco_pair_ce(float *pw, int nmat, int64_t mat_stride, int64_t ld, int Bc, int Bi, int diag_offset, const float *cap_mask,
@@ -1010,7 +1076,8 @@ int loco_pair_ce(float *pw, int nmat, int64_t mat_stride, int64_t ld, int Bc, in
     LOCO_REQUIRE(pw && cap_mask && reg_mask && out4, LOCO_E_BADARG, "pair_ce: null pointer");
     const size_t base = (32 + (size_t)Bc + Bi + 128) * sizeof(float);
     LOCO_REQUIRE(base <= 48 * 1024, LOCO_E_UNSUPPORTED, "pair_ce: batch too large (Bc=%d Bi=%d)", Bc, Bi);
-    const int nblk = ((Bc > Bi ? Bc : Bi) + 31) / 32;
+    const int strip_w = (Bc <= 32 && Bi <= 32) ? 32 : pair_ce_strip(Bc, Bi);
+    const int nblk = ((Bc > Bi ? Bc : Bi) + strip_w - 1) / strip_w;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (nblk == 1) {
         const size_t staged = base + (size_t)Bc * (Bi + 1) * sizeof(float);
@@ -1019,9 +1086,18 @@ int loco_pair_ce(float *pw, int nmat, int64_t mat_stride, int64_t ld, int Bc, in
     } else {
         LOCO_REQUIRE(workspace != nullptr, LOCO_E_BADARG, "pair_ce: B > 32 needs loco_pair_ce_workspace_bytes() of ZERO-INITIALISED workspace "
                      "(the kernel leaves it zeroed again)");
-        const size_t strip = base + (size_t)(3 * 32 * 33 + 64) * sizeof(float);      // per-warp partial statistics of the column pass
-        LOCO_CUDA(launch_kernel(pair_ce_kernel<false>, dim3(nmat, nblk), dim3(1024), strip, st, 1, pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T,
-                                reg_mask, Rg, out4, dpw_caption, dpw_image, static_cast<float *>(workspace)));
+        const size_t strip = base + (size_t)(3 * 32 * 33 + 96) * sizeof(float);      // per-warp partial statistics of the column pass
+        int pblocks = (Bc + Bi + 7) / 8;
+        if (pblocks > 148) pblocks = 148;
+        LOCO_CUDA(launch_kernel(pair_ce_prep_kernel, dim3(pblocks), dim3(256), 0, st, 1, static_cast<const float *>(pw), nmat, mat_stride, ld, Bc, Bi, cap_mask, T,
+                                reg_mask, Rg, static_cast<float *>(workspace)));
+        count_launch();
+        if (strip_w == 8)
+            LOCO_CUDA(launch_kernel(pair_ce_kernel<false, 8>, dim3(nmat, nblk), dim3(1024), strip, st, 1, pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T,
+                                    reg_mask, Rg, out4, dpw_caption, dpw_image, static_cast<float *>(workspace)));
+        else
+            LOCO_CUDA(launch_kernel(pair_ce_kernel<false, 32>, dim3(nmat, nblk), dim3(1024), strip, st, 1, pw, mat_stride, ld, Bc, Bi, diag_offset, cap_mask, T,
+                                    reg_mask, Rg, out4, dpw_caption, dpw_image, static_cast<float *>(workspace)));
     }
     count_launch();
     LOCO_CUDA(cudaGetLastError());
