@@ -294,6 +294,28 @@ int loco_pair_ce(float *pw, int nmat, int64_t mat_stride, int64_t ld, int Bc, in
                  const float *cap_mask, int T, const float *reg_mask, int Rg, float *out4,
                  float *dpw_caption, float *dpw_image, void *workspace, void *stream);
 
+/* ---- distillation losses on the pair matrices ------------------------------------------------------------------------------------
+ * Replaces: distill_mmss_gcnn.py:226-289 MultiDistillLoss.forward (6 softmax / log_softmax over [B,B], 4 nn.KLDivLoss, transposes) and
+ *           :381-433 MultiDistillLossL2.forward (4 nn.MSELoss), called three times per training step at
+ *           distill_prop_mmss_gcnn.py:424-442, plus autograd's backward of each: here one launch for the loss and one for all gradients.
+ * trans (teacher), w2r, r2w: [B,B] fp32 pair matrices (rows = captions, columns = images; row strides ld_*).
+ * kind 0: KD with the teacher as target (DISTILLATION_TEACHER_TRANSFORMER = True); 1: KD with the students as targets (False, the shipped
+ * coco_lsm.yaml:63); 2: MSE.  loss[0] = weighted loss (overwritten).  g_trans / g_w2r / g_r2w: dense [B,B] gradients of the loss, each may
+ * be NULL (a detached side, DISTILLATION_DETACH_TEACHER, or no gradient wanted).  workspace: loco_pair_distill_workspace_bytes(B)
+ * bytes, ZERO-INITIALISED once (left zeroed by every launch).  Deterministic (fixed summation order). */
+int64_t loco_pair_distill_workspace_bytes(int B);
+int loco_pair_distill(const float *trans, int64_t ld_trans, const float *w2r, int64_t ld_w2r, const float *r2w, int64_t ld_r2w, int B,
+                      float temperature, int kind, float loss_weight, float *loss, float *g_trans, float *g_w2r, float *g_r2w,
+                      void *workspace, void *stream);
+
+/* ---- device-side statistics of a logged tensor -----------------------------------------------------------------------------------
+ * Replaces: logged_module.py:8-18 stats() — tensor.cpu() plus four scalar reductions with a host synchronisation each — called by
+ *           LoggedModule.log for every logged tensor (seven per GroundingHead.forward, grounding_head.py:97-114,158,253-255).
+ * x: n fp32 values (contiguous).  out4 (device) = {min, max, mean, std (unbiased, as torch.Tensor.std)}.  workspace:
+ * loco_tensor_stats_workspace_bytes() bytes, 8-byte aligned, ZERO-INITIALISED once (left zeroed).  Nothing is copied to the host. */
+int64_t loco_tensor_stats_workspace_bytes(void);
+int loco_tensor_stats(const float *x, int64_t n, float *out4, void *workspace, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

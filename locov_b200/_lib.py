@@ -51,6 +51,10 @@ SIGNATURES = {
                                 _vp, _vp, _i64, _vp]),
     "loco_peer_exchange": (_i, [_i, _c.POINTER(_vp), _c.POINTER(_i64), _c.POINTER(_i), _c.POINTER(_i64), _c.POINTER(_i64), _c.POINTER(_i64), _vp, _i, _vp, _i, _i,
                                 _i, _vp, _vp]),
+    "loco_pair_distill_workspace_bytes": (_i64, [_i]),
+    "loco_pair_distill": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _f, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "loco_tensor_stats_workspace_bytes": (_i64, []),
+    "loco_tensor_stats": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "loco_pair_ce_workspace_bytes": (_i64, [_i, _i, _i]),
     "loco_pair_ce": (_i, [_vp, _i, _i64, _i64, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
 }

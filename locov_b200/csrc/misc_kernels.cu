@@ -819,6 +819,155 @@ __global__ void __launch_bounds__(256) peer_scatter_kernel(const PeerSegs segs, 
     if (mode & 4) peer_wait_flags(flag_peers, n_peers, rank, channel);
 }
 
+// ---- distillation losses on the pair matrices (distill_mmss_gcnn.py:211-289 KD, :381-433 MSE) -------------------------------------------
+// Three [B, B] matrices: a teacher (`trans`) and the two student matrices of the LSM head.  KD: for both softmax directions (dim 0 =
+// "choose caption", dim 1 = "choose image") and both students, KL(target || input) * temperature^2, batch-mean; the target is the
+// teacher (kind 0: DISTILLATION_TEACHER_TRANSFORMER) or the student (kind 1: the shipped coco_lsm.yaml).  MSE (kind 2): every pair
+// compared as is and transposed (the same value twice).
+// Launch 1 (lines): a warp per (direction, line) computes the three log-sum-exps and the two KL sums of that line — a line of one
+// direction only needs the same line of the other matrices — and its loss share; the last block adds the shares in line order.
+// Launch 2 (gradients, optional): a thread per element combines the statistics of its column and of its row.
+// workspace (floats): [16] ticket, [2][B][5] line statistics {lse_t, lse_w, lse_r, kl_w, kl_r}, [2][B] loss shares.
+__global__ void __launch_bounds__(256) pair_distill_lines_kernel(const float *__restrict__ tm, int64_t ld_t, const float *__restrict__ wm, int64_t ld_w,
+                                                                 const float *__restrict__ rm, int64_t ld_r, int B, float inv_temp, int kind,
+                                                                 float loss_scale, float *__restrict__ loss, float *__restrict__ ws) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float red[32];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    float *stats = ws + 16, *share = stats + 10 * (int64_t)B;
+    for (int line = blockIdx.x * wpb + (threadIdx.x >> 5); line < 2 * B; line += gridDim.x * wpb) {
+        const int dir = line / B, idx = line - dir * B;
+        // element k of the line: dir 0 (softmax over dim 0) walks down column idx, dir 1 along row idx
+        const int64_t st_t = dir == 0 ? ld_t : 1, st_w = dir == 0 ? ld_w : 1, st_r = dir == 0 ? ld_r : 1;
+        const float *pt = tm + (dir == 0 ? idx : idx * ld_t), *pw = wm + (dir == 0 ? idx : idx * ld_w), *pr = rm + (dir == 0 ? idx : idx * ld_r);
+        float out = 0.f;
+        if (kind == 2) {
+            if (dir == 1)                                   // (every element once: the row lines)
+                for (int k = lane; k < B; k += 32) {
+                    const float t = pt[k * st_t], dw = t - pw[k * st_w], dr = t - pr[k * st_r];
+                    out += dw * dw + dr * dr;
+                }
+            out = warp_sum(out);
+        } else {
+            float mt = -FLT_MAX, mw = -FLT_MAX, mr = -FLT_MAX;
+            for (int k = lane; k < B; k += 32) {
+                mt = fmaxf(mt, -pt[k * st_t] * inv_temp); mw = fmaxf(mw, -pw[k * st_w] * inv_temp); mr = fmaxf(mr, -pr[k * st_r] * inv_temp);
+            }
+            mt = warp_max(mt); mw = warp_max(mw); mr = warp_max(mr);
+            float s_t = 0.f, s_w = 0.f, s_r = 0.f;
+            for (int k = lane; k < B; k += 32) {
+                s_t += expf(-pt[k * st_t] * inv_temp - mt); s_w += expf(-pw[k * st_w] * inv_temp - mw); s_r += expf(-pr[k * st_r] * inv_temp - mr);
+            }
+            const float lse_t = mt + logf(warp_sum(s_t)), lse_w = mw + logf(warp_sum(s_w)), lse_r = mr + logf(warp_sum(s_r));
+            float kw = 0.f, kr = 0.f;
+            for (int k = lane; k < B; k += 32) {
+                const float lp = -pt[k * st_t] * inv_temp - lse_t, lw = -pw[k * st_w] * inv_temp - lse_w, lr = -pr[k * st_r] * inv_temp - lse_r;
+                if (kind == 0) { const float p = expf(lp); kw += p * (lp - lw); kr += p * (lp - lr); }
+                else { kw += expf(lw) * (lw - lp); kr += expf(lr) * (lr - lp); }
+            }
+            kw = warp_sum(kw); kr = warp_sum(kr);
+            if (lane == 0) {
+                float *q = stats + 5 * (int64_t)line;
+                q[0] = lse_t; q[1] = lse_w; q[2] = lse_r; q[3] = kw; q[4] = kr;
+            }
+            out = kw + kr;
+        }
+        if (lane == 0) share[line] = out;
+    }
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(ws);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        float v = 0.f;
+        for (int j = threadIdx.x; j < 2 * B; j += blockDim.x) v += __ldcg(share + j);         // fixed order per thread, then the fixed tree
+        v = block_reduce_sum(v, red);
+        if (threadIdx.x == 0) {
+            *loss = v * loss_scale;
+            *ticket = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) pair_distill_grad_kernel(const float *__restrict__ tm, int64_t ld_t, const float *__restrict__ wm, int64_t ld_w,
+                                                                const float *__restrict__ rm, int64_t ld_r, int B, float inv_temp, int kind, float gscale,
+                                                                float *__restrict__ g_t, float *__restrict__ g_w, float *__restrict__ g_r,
+                                                                const float *__restrict__ ws) {
+    pdl_trigger();
+    pdl_wait();
+    const float *stats = ws + 16;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)B * B; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e / B), i = (int)(e - (int64_t)c * B);
+        const float t = tm[(int64_t)c * ld_t + i], w = wm[(int64_t)c * ld_w + i], r = rm[(int64_t)c * ld_r + i];
+        float gt = 0.f, gw = 0.f, gr = 0.f;
+        if (kind == 2) {
+            gw = (w - t) * gscale; gr = (r - t) * gscale; gt = -(gw + gr);
+        } else {
+            const float at = -t * inv_temp, aw = -w * inv_temp, ar = -r * inv_temp;
+#pragma unroll
+            for (int dir = 0; dir < 2; ++dir) {
+                const float *q = stats + 5 * (int64_t)(dir * B + (dir == 0 ? i : c));
+                const float lp = at - q[0], lw = aw - q[1], lr = ar - q[2];
+                const float p = expf(lp), qw = expf(lw), qr = expf(lr);
+                if (kind == 0) { gw += qw - p; gr += qr - p; gt += p * ((lp - lw) - q[3]) + p * ((lp - lr) - q[4]); }
+                else { gt += (p - qw) + (p - qr); gw += qw * ((lw - lp) - q[3]); gr += qr * ((lr - lp) - q[4]); }
+            }
+            gt *= gscale; gw *= gscale; gr *= gscale;
+        }
+        if (g_t != nullptr) g_t[e] = gt;
+        if (g_w != nullptr) g_w[e] = gw;
+        if (g_r != nullptr) g_r[e] = gr;
+    }
+}
+
+// ---- device-side tensor statistics for LoggedModule.log (logged_module.py:8-18: min / max / mean / std of every logged tensor) ----------
+// The reference copies each logged tensor to the host and issues four scalar reductions per call (seven calls per LSM forward); here the
+// four numbers of one tensor come from ONE launch and stay on the device until somebody reads log_info.  Partial (min, max, sum, sum of
+// squares) per block in double precision, combined in block order by the last block; std is the unbiased one of torch.Tensor.std().
+__global__ void __launch_bounds__(256) tensor_stats_kernel(const float *__restrict__ x, int64_t n, float *__restrict__ out4, double *__restrict__ ws) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ double sd[4][8];
+    __shared__ int s_last;
+    float mn = FLT_MAX, mx = -FLT_MAX;
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+        s1 += (double)v; s2 += (double)v * (double)v;
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) { sd[0][w] = mn; sd[1][w] = mx; sd[2][w] = s1; sd[3][w] = s2; }
+    __syncthreads();
+    double *parts = ws + 2;                    // [grid][4]
+    if (threadIdx.x == 0) {
+        double a = sd[0][0], b = sd[1][0], c = 0.0, d = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { a = fmin(a, sd[0][k]); b = fmax(b, sd[1][k]); c += sd[2][k]; d += sd[3][k]; }
+        parts[4 * blockIdx.x] = a; parts[4 * blockIdx.x + 1] = b; parts[4 * blockIdx.x + 2] = c; parts[4 * blockIdx.x + 3] = d;
+        __threadfence();
+        unsigned int *ticket = reinterpret_cast<unsigned int *>(ws);
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+        if (s_last) {
+            __threadfence();
+            double a2 = parts[0], b2 = parts[1], c2 = 0.0, d2 = 0.0;
+            for (int k = 0; k < (int)gridDim.x; ++k) { a2 = fmin(a2, parts[4 * k]); b2 = fmax(b2, parts[4 * k + 1]); c2 += parts[4 * k + 2]; d2 += parts[4 * k + 3]; }
+            const double mean = c2 / (double)n;
+            const double var = n > 1 ? fmax(d2 - (double)n * mean * mean, 0.0) / (double)(n - 1) : 0.0;
+            out4[0] = (float)a2; out4[1] = (float)b2; out4[2] = (float)mean; out4[3] = (float)sqrt(var);
+            *ticket = 0;
+        }
+    }
+}
+
 }  // namespace loco
 
 using namespace loco;
@@ -1061,6 +1210,48 @@ int loco_peer_exchange(int nseg, const void *const *src, const int64_t *src_pitc
 }
 
 static int pair_ce_strip(int Bc, int Bi) { return (Bc > Bi ? Bc : Bi) >= 128 ? 8 : 32; }
+
+int64_t loco_pair_distill_workspace_bytes(int B) { return (int64_t)(16 + 12 * (int64_t)B) * (int64_t)sizeof(float); }
+
+int loco_pair_distill(const float *trans, int64_t ld_trans, const float *w2r, int64_t ld_w2r, const float *r2w, int64_t ld_r2w, int B, float temperature,
+                      int kind, float loss_weight, float *loss, float *g_trans, float *g_w2r, float *g_r2w, void *workspace, void *stream) {
+    LOCO_REQUIRE(B >= 1 && ld_trans >= B && ld_w2r >= B && ld_r2w >= B && kind >= 0 && kind <= 2 && temperature > 0.f, LOCO_E_BADARG,
+                 "pair_distill: bad arguments B=%d kind=%d temperature=%g", B, kind, (double)temperature);
+    LOCO_REQUIRE(trans && w2r && r2w && loss && workspace, LOCO_E_BADARG, "pair_distill: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float inv_temp = 1.0f / temperature;
+    // KD: sum of KL * T^2 / B (kldiv 'batchmean' divides by the first dimension);  MSE: 2 * (mean + mean)
+    const float loss_scale = kind == 2 ? 2.0f * loss_weight / ((float)B * (float)B) : loss_weight * temperature * temperature / (float)B;
+    int blocks = (2 * B + 7) / 8;
+    if (blocks > 148) blocks = 148;
+    LOCO_CUDA(launch_kernel(pair_distill_lines_kernel, dim3(blocks), dim3(256), 0, st, 1, trans, ld_trans, w2r, ld_w2r, r2w, ld_r2w, B, inv_temp, kind,
+                            loss_scale, loss, static_cast<float *>(workspace)));
+    count_launch();
+    if (g_trans || g_w2r || g_r2w) {
+        // d/dx of a = -x / T brings -1 / T:  KD: -weight * T / B;  MSE: 2 * (2 / B^2) * weight
+        const float gscale = kind == 2 ? 4.0f * loss_weight / ((float)B * (float)B) : -loss_weight * temperature / (float)B;
+        int gb = (int)(((int64_t)B * B + 255) / 256);
+        if (gb > 148 * 4) gb = 148 * 4;
+        LOCO_CUDA(launch_kernel(pair_distill_grad_kernel, dim3(gb), dim3(256), 0, st, 1, trans, ld_trans, w2r, ld_w2r, r2w, ld_r2w, B, inv_temp, kind, gscale,
+                                g_trans, g_w2r, g_r2w, static_cast<const float *>(workspace)));
+        count_launch();
+    }
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+int64_t loco_tensor_stats_workspace_bytes(void) { return (int64_t)(2 + 4 * 256) * (int64_t)sizeof(double); }
+
+int loco_tensor_stats(const float *x, int64_t n, float *out4, void *workspace, void *stream) {
+    LOCO_REQUIRE(n >= 1 && x && out4 && workspace, LOCO_E_BADARG, "tensor_stats: bad arguments n=%lld", (long long)n);
+    LOCO_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, LOCO_E_ALIGN, "tensor_stats: workspace must be 8-byte aligned");
+    int blocks = (int)((n + 1023) / 1024 < 256 ? (n + 1023) / 1024 : 256);
+    if (blocks < 1) blocks = 1;
+    LOCO_CUDA(launch_kernel(tensor_stats_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, x, n, out4, static_cast<double *>(workspace)));
+    count_launch();
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
 
 int64_t loco_pair_ce_workspace_bytes(int nmat, int Bc, int Bi) {
     const int strip = pair_ce_strip(Bc, Bi);

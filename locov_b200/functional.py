@@ -477,3 +477,35 @@ def pair_losses(pw, cap_mask, reg_mask, diag_offset=0):
         # no graph: `pw` is the fresh output of the pair kernel, so the guard may write it in place
         return pw, ops.pair_ce(pw, cap_mask, reg_mask, int(diag_offset))
     return _PairCE.apply(pw, cap_mask, reg_mask, int(diag_offset))
+
+
+# ------------------------------------------------------------------------------------------------
+# distillation losses on the pair matrices
+# ------------------------------------------------------------------------------------------------
+class _PairDistill(Function):
+    """MultiDistillLoss / MultiDistillLossL2 (distill_mmss_gcnn.py:211-289, 381-433): loss and all gradients from two launches."""
+
+    @staticmethod
+    def forward(ctx, trans, w2r, r2w, temperature, kind, loss_weight, detach_teacher):
+        need_t, need_w, need_r = ctx.needs_input_grad[:3]
+        # DISTILLATION_DETACH_TEACHER: the teacher side carries no gradient — `trans` when it is the target (kind 0 / MSE with a
+        # transformer teacher), the two student matrices when THEY are the targets (kind 1)
+        if detach_teacher:
+            if kind == ops.DISTILL_KD_STUDENT_TARGET:
+                need_w = need_r = False
+            else:
+                need_t = False
+        loss, gt, gw, gr = ops.pair_distill(trans, w2r, r2w, temperature, kind, loss_weight, grad_trans=need_t, grad_students=need_w or need_r)
+        ctx.save_for_backward(gt, gw if need_w else None, gr if need_r else None)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        gt, gw, gr = ctx.saved_tensors
+        return (gt * g if gt is not None else None), (gw * g if gw is not None else None), (gr * g if gr is not None else None), None, None, None, None
+
+
+def pair_distill(trans, w2r, r2w, temperature, kind, loss_weight=1.0, detach_teacher=False):
+    return _PairDistill.apply(trans.to(torch.float32), w2r.to(torch.float32), r2w.to(torch.float32), float(temperature), int(kind), float(loss_weight),
+                              bool(detach_teacher))

@@ -61,6 +61,8 @@ def get_cfg(stage="stt"):
                        DEFORM_ON_PER_STAGE=[False, False, False, False]),
             MMSS_HEAD=_n(TYPES=("GroundingHead",), DEFAULT_HEAD="GroundingHead", TIE_VL_PROJECTION_WEIGHTS=lsm,
                          IN_FEATURES="res5", SPATIAL_DROPOUT=100 if lsm else -1, DISTILLATION_LOSS=lsm,
+                         DISTILLATION_LOSS_TYPE="KD", DISTILLATION_TEMPERATURE=10.0 if lsm else 1.0, DISTILLATION_LOSS_WEIGHT=1.0,
+                         DISTILLATION_DETACH_TEACHER=False, DISTILLATION_TEACHER_TRANSFORMER=not lsm,
                          GROUNDING=_n(LOCAL_METRIC="dot", GLOBAL_METRIC="aligned_local", ALIGNMENT="softmax",
                                       ALIGNMENT_TEMPERATURE=10.0, LOSS="cross_entropy", NEGATIVE_MINING="random",
                                       TRIPLET_MARGIN=1.0, ALIGN_WORDS_TO_REGIONS=True, ALIGN_REGIONS_TO_WORDS=True,

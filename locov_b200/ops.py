@@ -500,6 +500,51 @@ def lsm_pair_bwd(cap: Bf16Operand, cap_mask: torch.Tensor, emb: Bf16Operand, reg
     return demb, dcap
 
 
+DISTILL_KD_TEACHER_TARGET, DISTILL_KD_STUDENT_TARGET, DISTILL_MSE = 0, 1, 2
+
+
+def pair_distill(trans: torch.Tensor, w2r: torch.Tensor, r2w: torch.Tensor, temperature: float, kind: int, loss_weight: float = 1.0,
+                 grad_trans: bool = False, grad_students: bool = False):
+    """Distillation loss on the [B,B] pair matrices (distill_mmss_gcnn.py:226-289, 381-433): returns (loss scalar tensor,
+    g_trans or None, g_w2r or None, g_r2w or None)."""
+    _need_cuda(trans, w2r, r2w)
+    b = trans.shape[0]
+    mats = []
+    for m in (trans, w2r, r2w):
+        if m.shape != (b, b) or m.dtype != torch.float32:
+            raise LocoError("pair_distill: expects three fp32 [B,B] matrices")
+        mats.append(m if m.stride(1) == 1 else m.contiguous())
+    dev = trans.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    gt = torch.empty((b, b), dtype=torch.float32, device=dev) if grad_trans else None
+    gw = torch.empty((b, b), dtype=torch.float32, device=dev) if grad_students else None
+    gr = torch.empty((b, b), dtype=torch.float32, device=dev) if grad_students else None
+    lib = _lib.load()
+    ws = _zero_workspace(dev, lib.loco_pair_distill_workspace_bytes(b), "pair_distill")
+    rc = lib.loco_pair_distill(_p(mats[0]), mats[0].stride(0), _p(mats[1]), mats[1].stride(0), _p(mats[2]), mats[2].stride(0), b, float(temperature), int(kind),
+                               float(loss_weight), _p(loss), _p(gt), _p(gw), _p(gr), _p(ws), _stream(trans))
+    if rc != 0:
+        _drop_zero_workspace(dev, "pair_distill")
+    _lib.check(rc, "loco_pair_distill")
+    return loss, gt, gw, gr
+
+
+def tensor_stats(x: torch.Tensor) -> torch.Tensor:
+    """[min, max, mean, std] of a CUDA tensor as a 4-element device tensor, one launch, no host synchronisation."""
+    _need_cuda(x)
+    xf = x.detach().to(torch.float32).contiguous().reshape(-1)
+    out = torch.empty(4, dtype=torch.float32, device=x.device)
+    if xf.numel() == 0:
+        return out.fill_(float("nan"))
+    lib = _lib.load()
+    ws = _zero_workspace(x.device, lib.loco_tensor_stats_workspace_bytes(), "tensor_stats")
+    rc = lib.loco_tensor_stats(_p(xf), xf.numel(), _p(out), _p(ws), _stream(xf))
+    if rc != 0:
+        _drop_zero_workspace(x.device, "tensor_stats")
+    _lib.check(rc, "loco_tensor_stats")
+    return out
+
+
 PEER_STORE, PEER_SIGNAL, PEER_WAIT = 1, 2, 4
 
 

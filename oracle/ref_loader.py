@@ -68,7 +68,7 @@ def _stub_modules():
     mod("detectron2.layers", ShapeSpec=S.ShapeSpec, batched_nms=S.batched_nms, cat=S.cat, cross_entropy=S.cross_entropy,
         nonzero_tuple=S.nonzero_tuple)
     mod("detectron2.structures", Boxes=S.Boxes, Instances=S.Instances, ImageList=None, pairwise_iou=None)
-    mod("detectron2.modeling")
+    mod("detectron2.modeling", META_ARCH_REGISTRY=_Registry("META_ARCH"))
     mod("detectron2.modeling.box_regression", Box2BoxTransform=S.Box2BoxTransform)
     mod("detectron2.modeling.roi_heads", ROI_HEADS_REGISTRY=S.ROI_HEADS_REGISTRY, ROIHeads=S.ROIHeads)
     mod("detectron2.modeling.roi_heads.fast_rcnn", fast_rcnn_inference=S.fast_rcnn_inference,
@@ -76,14 +76,17 @@ def _stub_modules():
         _log_classification_stats=S._log_classification_stats)
     mod("detectron2.modeling.poolers", ROIPooler=S.ROIPooler)
     mod("detectron2.modeling.sampling", subsample_labels=None)
-    mod("detectron2.modeling.backbone")
+    mod("detectron2.modeling.backbone", build_backbone=None)
     mod("detectron2.modeling.backbone.resnet", BottleneckBlock=S.BottleneckBlock, ResNet=S.ResNet)
     mod("detectron2.modeling.proposal_generator")
     mod("detectron2.modeling.proposal_generator.proposal_utils", add_ground_truth_to_proposals=None)
     mod("fvcore")
     mod("fvcore.nn", giou_loss=S.giou_loss, smooth_l1_loss=S.smooth_l1_loss)
-    for name in ["ovr", "ovr.modeling", "ovr.modeling.mmss_heads", "ovr.modeling.roi_heads"]:
+    for name in ["ovr", "ovr.modeling", "ovr.modeling.mmss_heads", "ovr.modeling.roi_heads", "ovr.modeling.meta_arch", "ovr.modeling.language"]:
         mod(name)
+    # imported at module level by distill_mmss_gcnn.py:9-14, used only by the meta-architecture class (out of scope)
+    mod("ovr.modeling.language.backbone", build_backbone=None)
+    mod("ovr.modeling.mmss_heads.mmss_heads", build_mmss_heads=None)
     # multi-token class scoring head: imported by box_emb_head.py:21-23, never instantiated on this path
     mod("ovr.modeling.roi_heads.box_emb_grounding_head", EmbeddingGroundingFastRCNNOutputLayers=type("EmbeddingGroundingFastRCNNOutputLayers", (), {}))
     return mods
@@ -94,6 +97,7 @@ _REF_FILES = {
     "ovr.modeling.mmss_heads.grounding_head": "ovr/modeling/mmss_heads/grounding_head.py",
     "ovr.modeling.roi_heads.box_emb_head": "ovr/modeling/roi_heads/box_emb_head.py",
     "ovr.modeling.roi_heads.roi_emb_heads": "ovr/modeling/roi_heads/roi_emb_heads.py",
+    "ovr.modeling.meta_arch.distill_mmss_gcnn": "ovr/modeling/meta_arch/distill_mmss_gcnn.py",
 }
 
 
@@ -177,6 +181,13 @@ def make_grounding_cfg(alignment="softmax", temperature=10.0, loss="cross_entrop
              TRIPLET_MARGIN=margin, ALIGN_WORDS_TO_REGIONS=align_words, ALIGN_REGIONS_TO_WORDS=align_regions,
              TEXT_INPUT=text_input)
     return _Cfg(MODEL=_Cfg(MMSS_HEAD=_Cfg(GROUNDING=g, DISTILLATION_LOSS=distillation)))
+
+
+def load_reference_distill():
+    """Returns the reference's distill_mmss_gcnn module: ``MultiDistillLoss`` / ``MultiDistillLossJS`` / ``MultiDistillLossL2``
+    (distill_mmss_gcnn.py:211-433) are plain torch modules; the meta-architecture class in the same file is never instantiated."""
+    mods = _load_reference_modules(["ovr.modeling.logged_module", "ovr.modeling.meta_arch.distill_mmss_gcnn"])
+    return mods["ovr.modeling.meta_arch.distill_mmss_gcnn"]
 
 
 def make_roi_cfg(stage="stt", **over):
