@@ -484,6 +484,12 @@ def roi_workloads(torch, dist, M, ops, synthetic, dev, pk, world, rank, max_over
         out[tag] = {"shape": f"[2,{C},{feats[0].shape[2]},{feats[0].shape[3]}] x {R} RoIs -> [{R},{C},{ps},{ps}] fp32", "ms": ms, "algorithmic_MB": nbytes / 1e6,
                     "bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]}
         if tag == "roi_align_cfg1_faithful":
+            # the same pooling written channels-last (what cuDNN's res5 wants), fp32 and bf16 — algorithmic bytes follow the output dtype
+            for sub, dt, esz in (("channels_last_fp32", torch.float32, 4), ("channels_last_bf16", torch.bfloat16, 2)):
+                nb = R * C * ps * ps * esz + feats[0].numel() * 4 + rois.numel() * 4
+                m = graph_time(torch, lambda i: ops.roi_align(feats[i % 2], rois, ps, 1.0 / stride, channels_last=True, out_dtype=dt), iters=8)
+                out[f"roi_align_cfg1_{sub}"] = {"ms": m, "algorithmic_MB": nb / 1e6, "bound": "hbm", "achieved": nb / (m * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                                                "unit": "GB/s", "frac": nb / (m * 1e-3) / 1e9 / pk["hbm_gbs"]}
             dout = torch.randn(R, C, ps, ps, device=dev)
             msb = graph_time(torch, lambda i: ops.roi_align_backward(dout, feats[0].shape, rois, 1.0 / stride), iters=4)
             nb = dout.numel() * 4 + 2 * feats[0].numel() * 4
@@ -499,6 +505,19 @@ def roi_workloads(torch, dist, M, ops, synthetic, dev, pk, world, rank, max_over
                                             "sample": "one call of torchvision.ops.roi_align (the compiled CPU op the reference reaches) on the same inputs"}
             del dout
         del feats
+    torch.cuda.empty_cache()
+
+    # ---- spatial mean of the res5 output (+ the projection's bf16 operand), configs[1] and configs[4] row counts ----------------
+    for tag, R, cl, dt in (("spatial_mean_cfg1_nchw_fp32", 1024, False, torch.float32), ("spatial_mean_cfg5_nchw_fp32", 8000, False, torch.float32),
+                           ("spatial_mean_cfg5_channels_last_bf16", 8000, True, torch.bfloat16)):
+        xs_ = [torch.randn(R, 2048, 7, 7, device=dev, dtype=dt) for _ in range(2)]
+        if cl:
+            xs_ = [t.contiguous(memory_format=torch.channels_last) for t in xs_]
+        nb = xs_[0].numel() * xs_[0].element_size() + R * 2048 * (4 + 2 + 2)
+        m = graph_time(torch, lambda i: ops.spatial_mean(xs_[i % 2], True), iters=8)
+        out[tag] = {"shape": f"[{R},2048,7,7] -> [{R},2048] fp32 + bf16 (hi, lo) operand", "ms": m, "algorithmic_MB": nb / 1e6, "bound": "hbm",
+                    "achieved": nb / (m * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": nb / (m * 1e-3) / 1e9 / pk["hbm_gbs"]}
+        del xs_
     torch.cuda.empty_cache()
 
     # ---- RoI x class scoring (forward: scores + probabilities) ----------------------------------------------------

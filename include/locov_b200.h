@@ -66,7 +66,10 @@ int loco_debug_timeline_read(unsigned long long *host, int max_ctas);
  *           -> Detectron2 ROIPooler/ROIAlign -> torchvision.ops.roi_align(aligned=True) CUDA kernel.
  * feat  [N,C,H,W] (LOCO_NCHW) or [N,H,W,C] (LOCO_NHWC), fp32.
  * rois  [R,5] fp32 rows (batch_idx, x1, y1, x2, y2) in image coordinates.
- * out   [R,C,PH,PW] fp32 (NCHW).
+ * out   out_layout LOCO_NCHW: [R,C,PH,PW] fp32 (what the reference's res5 stage receives); LOCO_NHWC: [R,PH,PW,C] channels-last in
+ *       fp32 or bf16 (out_dtype) — what cuDNN's tensor-core convolutions of res5 want (torch.channels_last), half the bytes of the
+ *       dominant write of the path in bf16, and no shared-memory staging (a warp writes 512 / 256 contiguous bytes per bin).
+ *       Channels-last output needs C % 4 == 0 and a 16-byte aligned pointer.
  * Sampling-grid coordinates and integer tap indices are bit-exact with the float32 reference
  * arithmetic (loco_roi_align_grid_dump exposes them); pooled values are toleranced (1e-4 rel).
  * workspace: loco_roi_align_workspace_bytes() bytes (0 for LOCO_NHWC; an NCHW map is transposed to
@@ -75,7 +78,8 @@ int loco_debug_timeline_read(unsigned long long *host, int max_ctas);
 int64_t loco_roi_align_workspace_bytes(int N, int C, int H, int W, int feat_layout);
 int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_layout,
                        const float *rois, int R, int PH, int PW, float spatial_scale,
-                       int sampling_ratio, int aligned, float *out, void *workspace, void *stream);
+                       int sampling_ratio, int aligned, void *out, int out_layout, int out_dtype, void *workspace,
+                       void *stream);
 
 /* Backward of the above (torchvision roi_align_backward semantics): dfeat [N,C,H,W] fp32 = gradient w.r.t. the feature
  * map.  With `workspace` (loco_roi_align_bwd_workspace_bytes() bytes, 16-byte aligned, contents ignored) and C % 4 == 0 the
@@ -86,6 +90,17 @@ int64_t loco_roi_align_bwd_workspace_bytes(int N, int C, int H, int W, int R);
 int loco_roi_align_bwd(const float *dout, int N, int C, int H, int W, const float *rois, int R,
                        int PH, int PW, float spatial_scale, int sampling_ratio, int aligned,
                        float *dfeat, void *workspace, void *stream);
+
+
+/* Spatial mean of the res5 output: replaces ``box_features.mean(dim=[2, 3])`` (reference ovr/modeling/roi_heads/roi_emb_heads.py:262,
+ * :329 and :351) and the fp32 -> bf16 operand split that would follow it.
+ * x      layout LOCO_NCHW: [R, C, HW] fp32; LOCO_NHWC: [R, HW, C] fp32 or bf16 (dtype), C % 4 == 0.
+ * out    [R, ldo] fp32 means (fp32 accumulation, fixed order).
+ * hi/lo  optional bf16 operand of the projection GEMM [R, ldh] (hi = rn(mean), lo = rn(mean - hi); lo may be NULL); NULL to skip.
+ * loco_spatial_mean_bwd writes dx = dy / HW broadcast over the positions, in the layout / dtype of x. */
+int loco_spatial_mean(const void *x, int64_t R, int C, int HW, int layout, int dtype, float *out, int64_t ldo, uint16_t *hi,
+                      uint16_t *lo, int64_t ldh, void *stream);
+int loco_spatial_mean_bwd(const float *dy, int64_t lddy, int64_t R, int C, int HW, int layout, int dtype, void *dx, void *stream);
 
 /* Debug/parity entry: for every roi r, bin (ph,pw) and sample (iy,ix) with iy,ix < max_grid writes
  *   grid_hw [R,2] int32            (gh, gw) — the adaptive sample counts

@@ -26,9 +26,11 @@ SIGNATURES = {
     "loco_launch_count": (_c.c_longlong, []),
     "loco_debug_timeline_read": (_i, [_vp, _i]),
     "loco_roi_align_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
-    "loco_roi_align_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp]),
+    "loco_roi_align_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _i, _i, _vp, _i, _i, _vp, _vp]),
     "loco_roi_align_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
     "loco_roi_align_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp]),
+    "loco_spatial_mean": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "loco_spatial_mean_bwd": (_i, [_vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp]),
     "loco_roi_align_grid_dump": (_i, [_vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "loco_split_bf16": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i, _vp]),
     "loco_transpose_bf16": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),

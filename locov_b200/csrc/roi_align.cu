@@ -391,7 +391,22 @@ __device__ __forceinline__ Quad pooled_column(const char *p, const int (&yo)[4],
 // and overlap in at most two (consecutive) columns, so every column of the row's footprint is loaded exactly once.
 // The slot tags are compared at run time, so a non-monotonic list (fixed sampling ratio on a flipped box) only costs
 // extra loads.  All branches are warp-uniform.
-template <int NY, bool PAIR>
+// Where the pooled 4 channels of bin `pw` go.  OUT = 0: the shared-memory tile of the NCHW write-out (row = channel; trow = this lane's
+// tile row of the bin row, rstep = 32 tile rows).  OUT = 1 / 2: straight to a CHANNELS-LAST output [R, PH, PW, C] in fp32 / bf16 —
+// the lane's 4 channels are 16 / 8 contiguous bytes, a warp writes 512 / 256 contiguous bytes per bin, no staging, no write-out phase
+// (trow = address of the lane's channels in bin 0 of the bin row, NULL for lanes past C; rstep = bytes per bin = C * element size).
+template <int OUT>
+__device__ __forceinline__ void put_bin(float *trow, int rstep, int pw, const Quad &a) {
+    if (OUT == 0) {
+        trow[pw] = a.lo.x; trow[pw + rstep] = a.lo.y; trow[pw + 2 * rstep] = a.hi.x; trow[pw + 3 * rstep] = a.hi.y;
+    } else if (trow != nullptr) {
+        char *p = reinterpret_cast<char *>(trow) + (size_t)pw * rstep;
+        if (OUT == 1) __stcs(reinterpret_cast<float4 *>(p), make_float4(a.lo.x, a.lo.y, a.hi.x, a.hi.y));
+        else __stcs(reinterpret_cast<uint2 *>(p), make_uint2(pack_bf16x2_rn(a.lo.x, a.lo.y), pack_bf16x2_rn(a.hi.x, a.hi.y)));
+    }
+}
+
+template <int NY, bool PAIR, int OUT>
 __device__ __noinline__ void pool_bin_row(const char *fb, const MergedEntry *yt, int ny, const MergedEntry *xtab,
                                              const int *xcnt, int xstride, int PW, float inv_cnt, float *trow, int rstep) {
     int yo[4] = {0, 0, 0, 0};
@@ -443,7 +458,7 @@ __device__ __noinline__ void pool_bin_row(const char *fb, const MergedEntry *yt,
         for (int pw = 0; pw < PW; ++pw) {
             const Quad a = bin(xtab, xcnt[pw]);
             xtab += xstride;
-            trow[pw] = a.lo.x; trow[pw + rstep] = a.lo.y; trow[pw + 2 * rstep] = a.hi.x; trow[pw + 3 * rstep] = a.hi.y;
+            put_bin<OUT>(trow, rstep, pw, a);
         }
     }
 }
@@ -462,7 +477,7 @@ struct WalkBin {
     float w[4];      // dense weights of columns base .. base + 3 (zero beyond GW)
 };
 
-template <int GW, int NY, bool PAIR>
+template <int GW, int NY, bool PAIR, int OUT>
 __device__ __noinline__ void walk_bin_row(const char *fb, const MergedEntry *yt, const WalkBin *xw, const int *xadv, int x0_bytes,
                                            int colstride, int xlast_bytes, int PW, float inv_cnt, float *trow, int rstep) {
     // xlast_bytes = byte offset of the LAST column the walk consumes: the look-ahead load past it is redirected to it
@@ -517,24 +532,24 @@ __device__ __noinline__ void walk_bin_row(const char *fb, const MergedEntry *yt,
 #pragma unroll 1
         for (int pw = 0; pw < PW; ++pw) {
             const Quad a = bin(pw);
-            trow[pw] = a.lo.x; trow[pw + rstep] = a.lo.y; trow[pw + 2 * rstep] = a.hi.x; trow[pw + 3 * rstep] = a.hi.y;
+            put_bin<OUT>(trow, rstep, pw, a);
         }
     }
 }
 
-template <int GW, bool PAIR>
+template <int GW, bool PAIR, int OUT>
 __device__ __forceinline__ bool walk_dispatch(int ny, const char *fb, const MergedEntry *yt, const WalkBin *xw, const int *xadv,
                                               int x0_bytes, int colstride, int xlast_bytes, int PW, float inv_cnt, float *trow, int rstep) {
     switch (ny) {                                      // warp-uniform
-        case 1: walk_bin_row<GW, 1, PAIR>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
-        case 2: walk_bin_row<GW, 2, PAIR>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
-        case 3: walk_bin_row<GW, 3, PAIR>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
-        case 4: walk_bin_row<GW, 4, PAIR>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
+        case 1: walk_bin_row<GW, 1, PAIR, OUT>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
+        case 2: walk_bin_row<GW, 2, PAIR, OUT>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
+        case 3: walk_bin_row<GW, 3, PAIR, OUT>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
+        case 4: walk_bin_row<GW, 4, PAIR, OUT>(fb, yt, xw, xadv, x0_bytes, colstride, xlast_bytes, PW, inv_cnt, trow, rstep); return true;
         default: return false;
     }
 }
 
-template <bool PAIR, bool MULTI>
+template <bool PAIR, bool MULTI, int OUT>
 __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const float *__restrict__ feat,   // [N,H,W,C]
                                                                         const float *__restrict__ rois, int C, int H, int W,
                                                                         int PH, int PW, float scale, int sampling_ratio,
@@ -622,10 +637,19 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
     const size_t tile_floats = (size_t)RV_CC * tstride;
     const int cl = 4 * lane;
     float *t0 = tile + (wgroup < nconc ? wgroup : 0) * tile_floats + (size_t)lane * tstride;   // rows lane, 32 + lane, 64 + lane, 96 + lane
-    const int rstep = 32 * tstride;
+    // OUT = 0: rstep = 32 tile rows; channels-last output: bytes per bin (C * element size), t0 is re-pointed per slab below
+    const int esize = OUT == 2 ? 2 : 4;
+    const int rstep = OUT == 0 ? 32 * tstride : C * esize;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto store_bin = [&](int o, const float4 &a) {
-        t0[o] = a.x; t0[o + rstep] = a.y; t0[o + 2 * rstep] = a.z; t0[o + 3 * rstep] = a.w;
+        if (OUT == 0) {
+            t0[o] = a.x; t0[o + rstep] = a.y; t0[o + 2 * rstep] = a.z; t0[o + 3 * rstep] = a.w;
+        } else {
+            Quad q;
+            q.lo = make_float2(a.x, a.y);
+            q.hi = make_float2(a.z, a.w);
+            put_bin<OUT>(t0, rstep, o, q);
+        }
     };
 
     for (int sl0 = 0; sl0 < slabs; sl0 += nconc) {
@@ -634,7 +658,11 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
         const bool work = wgroup < nconc && sl < slabs && c0 < C;   // warp-uniform
         const bool active = work && (c0 + cl) < C;             // C % 4 == 0: a lane's 4 channels are all in or all out
         const char *fb = reinterpret_cast<const char *>(feat + (size_t)g.batch * H * W * C + (active ? c0 + cl : 0));
-        if (sl0 > 0) __syncthreads();                          // the previous slabs' write-out has drained the tiles
+        if (OUT == 0) {
+            if (sl0 > 0) __syncthreads();                      // the previous slabs' write-out has drained the tiles
+        } else {                                               // channels-last output: this lane's 4 channels of bin 0 of the roi
+            t0 = active ? reinterpret_cast<float *>(reinterpret_cast<char *>(out) + ((size_t)r * PHW * C + c0 + cl) * esize) : nullptr;
+        }
 
         if (!work) {
         } else if (empty) {
@@ -644,20 +672,21 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
             for (int ph = wrow; ph < PH; ph += row_step) {
                 const MergedEntry *yt = ytab + ph * ystride;
                 const int ny = ycnt[ph];
-                float *trow = t0 + ph * PW;
+                float *trow = OUT == 0 ? t0 + ph * PW
+                                       : (t0 != nullptr ? reinterpret_cast<float *>(reinterpret_cast<char *>(t0) + (size_t)ph * PW * rstep) : nullptr);
                 if (walk_ok) {                                 // CTA-uniform: column walk (GW = sampling grid width of this roi)
                     bool done;
-                    if (g.gw == 1) done = walk_dispatch<1, PAIR>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
-                    else if (g.gw == 2) done = walk_dispatch<2, PAIR>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
-                    else done = walk_dispatch<3, PAIR>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
+                    if (g.gw == 1) done = walk_dispatch<1, PAIR, OUT>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
+                    else if (g.gw == 2) done = walk_dispatch<2, PAIR, OUT>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
+                    else done = walk_dispatch<3, PAIR, OUT>(ny, fb, yt, xw, xadv, walk_x0, walk_colstride, walk_xlast, PW, inv_cnt, trow, rstep);
                     if (done) continue;
                 }
                 switch (ny) {                                  // warp-uniform
-                    case 1: pool_bin_row<1, PAIR>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
-                    case 2: pool_bin_row<2, PAIR>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
-                    case 3: pool_bin_row<3, PAIR>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
-                    case 4: pool_bin_row<4, PAIR>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
-                    default: pool_bin_row<0, PAIR>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
+                    case 1: pool_bin_row<1, PAIR, OUT>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
+                    case 2: pool_bin_row<2, PAIR, OUT>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
+                    case 3: pool_bin_row<3, PAIR, OUT>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
+                    case 4: pool_bin_row<4, PAIR, OUT>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
+                    default: pool_bin_row<0, PAIR, OUT>(fb, yt, ny, xtab, xcnt, xstride, PW, inv_cnt, trow, rstep); break;
                 }
             }
         } else {
@@ -682,6 +711,7 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
                     store_bin(ph * PW + pw, acc);
                 }
         }
+        if (OUT != 0) continue;                                // channels-last output went straight to global memory
         if (bulk_out) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // tile writes -> visible to the copy engine
         __syncthreads();
 
@@ -1037,6 +1067,115 @@ __global__ void roi_align_grid_kernel(const float *__restrict__ rois, int R, int
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Spatial mean of the res5 output — the reference's ``box_features.mean(dim=[2, 3])`` (roi_emb_heads.py:262, :329, :351) — which is the
+// largest read between RoIAlign and the predictor: [R, 2048, 7, 7] is 3.2 GB at R = 8000.  One pass, fp32 accumulation in a fixed
+// order, and the bf16 (hi, lo) operand of the projection GEMM written by the same pass (what would otherwise be a separate split
+// kernel re-reading the [R, C] means).
+//   CL = true  : x is channels-last [R, HW, C] (fp32 or bf16): a thread owns 4 channels, walks HW; a warp reads 512 / 256 contiguous
+//                bytes per position.
+//   CL = false : x is [R, C, HW] fp32: a warp owns 32 consecutive (r, c) rows, 4 rows in flight at a time (8 loads per lane), so
+//                the 32 means leave as one 128-byte store.
+template <typename T>
+__device__ __forceinline__ float4 load_ch4(const T *p);
+template <>
+__device__ __forceinline__ float4 load_ch4<float>(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
+template <>
+__device__ __forceinline__ float4 load_ch4<uint16_t>(const uint16_t *p) {
+    const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(p));
+    return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+}
+
+__device__ __forceinline__ void mean_store(float m, int64_t r, int c, float *out, int64_t ldo, uint16_t *hi, uint16_t *lo, int64_t ldh) {
+    out[r * ldo + c] = m;
+    if (hi != nullptr) {
+        uint16_t h, l;
+        split_bf16(m, h, l);
+        hi[r * ldh + c] = h;
+        if (lo != nullptr) lo[r * ldh + c] = l;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) spatial_mean_cl_kernel(const T *__restrict__ x, int64_t R, int C, int HW, float inv, float *__restrict__ out,
+                                                              int64_t ldo, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, int64_t ldh) {
+    pdl_trigger();
+    pdl_wait();
+    const int c4n = C / 4;
+    const int64_t total = R * c4n;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / c4n;
+        const int c = (int)(i - r * c4n) * 4;
+        const T *p = x + (r * HW) * C + c;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        int s = 0;
+        for (; s + 7 <= HW; s += 7) {                    // 7 independent loads in flight (HW = 49 -> 7 rounds)
+            float4 v[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) v[k] = load_ch4<T>(p + (int64_t)(s + k) * C);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) { a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w; }
+        }
+        for (; s < HW; ++s) {
+            const float4 v = load_ch4<T>(p + (int64_t)s * C);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        const float4 m = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+        *reinterpret_cast<float4 *>(out + r * ldo + c) = m;
+        if (hi != nullptr) {
+            uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+            split_bf16(m.x, h0, l0); split_bf16(m.y, h1, l1); split_bf16(m.z, h2, l2); split_bf16(m.w, h3, l3);
+            *reinterpret_cast<uint2 *>(hi + r * ldh + c) = make_uint2(h0 | ((uint32_t)h1 << 16), h2 | ((uint32_t)h3 << 16));
+            if (lo != nullptr) *reinterpret_cast<uint2 *>(lo + r * ldh + c) = make_uint2(l0 | ((uint32_t)l1 << 16), l2 | ((uint32_t)l3 << 16));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) spatial_mean_rows_kernel(const float *__restrict__ x, int64_t rows, int C, int HW, float inv, float *__restrict__ out,
+                                                                int64_t ldo, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, int64_t ldh) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp * 32; base < rows; base += nwarps * 32) {
+        float mine = 0.f;
+        for (int g = 0; g < 32 && base + g < rows; g += 4) {
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int s = lane; s < HW; s += 32) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (base + g + k < rows) a[k] += __ldcs(x + (base + g + k) * HW + s);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float t = warp_sum(a[k]);
+                if (lane == g + k) mine = t;
+            }
+        }
+        const int64_t row = base + lane;
+        if (row < rows) mean_store(mine * inv, row / C, (int)(row % C), out, ldo, hi, lo, ldh);
+    }
+}
+
+// gradient of the mean: dx[r, c, s] = dy[r, c] / HW in the layout / dtype of x (each thread writes 4 channels x one position, or 4 positions)
+template <typename T, bool CL>
+__global__ void __launch_bounds__(256) spatial_mean_bwd_kernel(const float *__restrict__ dy, int64_t lddy, int64_t R, int C, int HW, float inv, T *__restrict__ dx) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t total = R * (int64_t)C * HW;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r;
+        int c;
+        if (CL) { c = (int)(i % C); r = i / ((int64_t)C * HW); }
+        else    { const int64_t rc = i / HW; r = rc / C; c = (int)(rc - r * C); }
+        const float g = dy[r * lddy + c] * inv;
+        if (sizeof(T) == 4) reinterpret_cast<float *>(dx)[i] = g;
+        else reinterpret_cast<uint16_t *>(dx)[i] = f32_to_bf16_rn(g);
+    }
+}
+
 }  // namespace loco
 
 using namespace loco;
@@ -1049,8 +1188,11 @@ int64_t loco_roi_align_workspace_bytes(int N, int C, int H, int W, int feat_layo
 }
 
 int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_layout, const float *rois, int R,
-                       int PH, int PW, float spatial_scale, int sampling_ratio, int aligned, float *out,
+                       int PH, int PW, float spatial_scale, int sampling_ratio, int aligned, void *out_v, int out_layout, int out_dtype,
                        void *workspace, void *stream) {
+    float *out = static_cast<float *>(out_v);
+    LOCO_REQUIRE((out_layout == LOCO_NCHW && out_dtype == LOCO_F32) || (out_layout == LOCO_NHWC && (out_dtype == LOCO_F32 || out_dtype == LOCO_BF16)),
+                 LOCO_E_UNSUPPORTED, "roi_align_fwd: output layout %d / dtype %d (NCHW fp32, or channels-last fp32 / bf16)", out_layout, out_dtype);
     LOCO_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0 && R >= 0, LOCO_E_BADARG,
                  "roi_align_fwd: bad shape N=%d C=%d H=%d W=%d PH=%d PW=%d R=%d", N, C, H, W, PH, PW, R);
     LOCO_REQUIRE(feat_layout == LOCO_NCHW || feat_layout == LOCO_NHWC, LOCO_E_BADARG, "roi_align_fwd: bad layout %d", feat_layout);
@@ -1073,8 +1215,11 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
     // vectorised kernel: 4 channels per lane (128-bit taps), byte offsets inside one image kept in 32 bits
     const bool v4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(nhwc) & 15) == 0) && ((long long)H * W * C * 4 < (1ll << 31)) &&
                     PHW <= RV_THREADS;
+    const int out_mode = out_layout == LOCO_NCHW ? 0 : (out_dtype == LOCO_F32 ? 1 : 2);
+    LOCO_REQUIRE(out_mode == 0 || (v4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0), LOCO_E_UNSUPPORTED,
+                 "roi_align_fwd: channels-last output needs C %% 4 == 0 and 16-byte aligned feature / output pointers");
     if (v4) {
-        const bool pair = (PW % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+        const bool pair = out_mode == 0 && (PW % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
         // copy-engine write-out needs dense 16-byte aligned channel rows (PH*PW % 4 == 0: 14x14 yes, 7x7 no); its tile
         // stride PH*PW = 0 (mod 4) makes the paired 8-byte tile stores 2-way bank conflicted, which costs less than the
         // LDS + STG write-out loop it removes (LOCOV_B200_ROI_BULK=0 restores the loop for A/B measurements)
@@ -1091,7 +1236,7 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
         const int nconc = RV_WARPS / PH > 1 ? RV_WARPS / PH : 1;            // slabs pooled at the same time (see the kernel)
         while (slabs < nconc && nslab % (slabs * 2) == 0) slabs *= 2;       // keep every warp group busy
         const int nchunks = nslab / slabs;
-        const size_t smem = (size_t)RV_TILE_OFFSET + (size_t)nconc * RV_CC * tstride * sizeof(float);
+        const size_t smem = (size_t)RV_TILE_OFFSET + (out_mode == 0 ? (size_t)nconc * RV_CC * tstride * sizeof(float) : 0);   // no tile for channels-last
         CUtensorMap omap;
         memset(&omap, 0, sizeof(omap));
         if (bulk_out) {
@@ -1102,10 +1247,13 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
         LOCO_REQUIRE((long long)R * nchunks < (1ll << 31), LOCO_E_UNSUPPORTED, "roi_align_fwd: too many (roi, channel-slab) tiles");
         typedef void (*v4_fn)(const float *, const float *, int, int, int, int, int, float, int, int, int, int, int, int, float *, const CUtensorMap);
         const bool multi = nconc > 1;
-        const v4_fn fn = pair ? (multi ? roi_align_fwd_v4_kernel<true, true> : roi_align_fwd_v4_kernel<true, false>)
-                              : (multi ? roi_align_fwd_v4_kernel<false, true> : roi_align_fwd_v4_kernel<false, false>);
-        static thread_local size_t smem_set[4] = {0, 0, 0, 0};
-        const int vi = (pair ? 2 : 0) + (multi ? 1 : 0);
+        v4_fn fn;
+        if (out_mode == 1) fn = multi ? roi_align_fwd_v4_kernel<false, true, 1> : roi_align_fwd_v4_kernel<false, false, 1>;
+        else if (out_mode == 2) fn = multi ? roi_align_fwd_v4_kernel<false, true, 2> : roi_align_fwd_v4_kernel<false, false, 2>;
+        else fn = pair ? (multi ? roi_align_fwd_v4_kernel<true, true, 0> : roi_align_fwd_v4_kernel<true, false, 0>)
+                       : (multi ? roi_align_fwd_v4_kernel<false, true, 0> : roi_align_fwd_v4_kernel<false, false, 0>);
+        static thread_local size_t smem_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int vi = out_mode == 0 ? (pair ? 2 : 0) + (multi ? 1 : 0) : 4 + 2 * (out_mode - 1) + (multi ? 1 : 0);
         if (smem > 48 * 1024 && smem > smem_set[vi]) {
             LOCO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             smem_set[vi] = smem;
@@ -1206,4 +1354,62 @@ int loco_roi_align_grid_dump(const float *rois, int R, int H, int W, int PH, int
     return LOCO_OK;
 }
 
+int loco_spatial_mean(const void *x, int64_t R, int C, int HW, int layout, int dtype, float *out, int64_t ldo, uint16_t *hi, uint16_t *lo, int64_t ldh,
+                      void *stream) {
+    LOCO_REQUIRE(R >= 0 && C >= 1 && HW >= 1 && ldo >= C, LOCO_E_BADARG, "spatial_mean: bad shape R=%lld C=%d HW=%d", (long long)R, C, HW);
+    LOCO_REQUIRE((layout == LOCO_NCHW && dtype == LOCO_F32) || (layout == LOCO_NHWC && (dtype == LOCO_F32 || dtype == LOCO_BF16)), LOCO_E_UNSUPPORTED,
+                 "spatial_mean: layout %d / dtype %d (NCHW fp32, or channels-last fp32 / bf16)", layout, dtype);
+    LOCO_REQUIRE(lo == nullptr || hi != nullptr, LOCO_E_BADARG, "spatial_mean: lo without hi");
+    LOCO_REQUIRE(hi == nullptr || ldh >= C, LOCO_E_BADARG, "spatial_mean: operand row stride %lld < C", (long long)ldh);
+    if (R == 0) return LOCO_OK;
+    LOCO_REQUIRE(x && out, LOCO_E_BADARG, "spatial_mean: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float inv = 1.0f / (float)HW;
+    const int sms = current_device_sm_count();
+    if (layout == LOCO_NHWC) {
+        const int esz = dtype == LOCO_F32 ? 4 : 2;
+        LOCO_REQUIRE(C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && ldo % 4 == 0 &&
+                         (hi == nullptr || (((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 7) == 0 && ldh % 4 == 0)),
+                     LOCO_E_ALIGN, "spatial_mean: channels-last input needs C %% 4 == 0 and 16-byte aligned rows");
+        const int64_t total = R * (C / 4);
+        const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sms * 16);
+        if (dtype == LOCO_F32)
+            LOCO_CUDA(launch_kernel(spatial_mean_cl_kernel<float>, dim3(blocks), dim3(256), 0, st, 1, static_cast<const float *>(x), R, C, HW, inv, out, ldo,
+                                    hi, lo, ldh));
+        else
+            LOCO_CUDA(launch_kernel(spatial_mean_cl_kernel<uint16_t>, dim3(blocks), dim3(256), 0, st, 1, static_cast<const uint16_t *>(x), R, C, HW, inv, out,
+                                    ldo, hi, lo, ldh));
+    } else {
+        const int64_t rows = R * C;
+        const int blocks = (int)std::min<int64_t>((rows + 255) / 256, (int64_t)sms * 8);
+        LOCO_CUDA(launch_kernel(spatial_mean_rows_kernel, dim3(blocks), dim3(256), 0, st, 1, static_cast<const float *>(x), rows, C, HW, inv, out, ldo, hi, lo,
+                                ldh));
+    }
+    count_launch();
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+int loco_spatial_mean_bwd(const float *dy, int64_t lddy, int64_t R, int C, int HW, int layout, int dtype, void *dx, void *stream) {
+    LOCO_REQUIRE(R >= 0 && C >= 1 && HW >= 1 && lddy >= C, LOCO_E_BADARG, "spatial_mean_bwd: bad shape R=%lld C=%d HW=%d", (long long)R, C, HW);
+    LOCO_REQUIRE((layout == LOCO_NCHW && dtype == LOCO_F32) || (layout == LOCO_NHWC && (dtype == LOCO_F32 || dtype == LOCO_BF16)), LOCO_E_UNSUPPORTED,
+                 "spatial_mean_bwd: layout %d / dtype %d", layout, dtype);
+    if (R == 0) return LOCO_OK;
+    LOCO_REQUIRE(dy && dx, LOCO_E_BADARG, "spatial_mean_bwd: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float inv = 1.0f / (float)HW;
+    const int64_t total = R * (int64_t)C * HW;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)current_device_sm_count() * 32);
+    if (layout == LOCO_NCHW)
+        LOCO_CUDA(launch_kernel(spatial_mean_bwd_kernel<float, false>, dim3(blocks), dim3(256), 0, st, 1, dy, lddy, R, C, HW, inv, static_cast<float *>(dx)));
+    else if (dtype == LOCO_F32)
+        LOCO_CUDA(launch_kernel(spatial_mean_bwd_kernel<float, true>, dim3(blocks), dim3(256), 0, st, 1, dy, lddy, R, C, HW, inv, static_cast<float *>(dx)));
+    else
+        LOCO_CUDA(launch_kernel(spatial_mean_bwd_kernel<uint16_t, true>, dim3(blocks), dim3(256), 0, st, 1, dy, lddy, R, C, HW, inv, static_cast<uint16_t *>(dx)));
+    count_launch();
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
 }  // extern "C"
+

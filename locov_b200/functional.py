@@ -80,10 +80,10 @@ def clear_weight_cache():
 # ------------------------------------------------------------------------------------------------
 class _RoIAlign(Function):
     @staticmethod
-    def forward(ctx, feat, rois, ph, pw, scale, sampling_ratio, aligned):
+    def forward(ctx, feat, rois, ph, pw, scale, sampling_ratio, aligned, channels_last, out_dtype):
         ctx.save_for_backward(rois)
         ctx.cfg = (tuple(feat.shape), scale, sampling_ratio, aligned)
-        return ops.roi_align(feat, rois, (ph, pw), scale, sampling_ratio, aligned)
+        return ops.roi_align(feat, rois, (ph, pw), scale, sampling_ratio, aligned, channels_last, out_dtype)
 
     @staticmethod
     @once_differentiable
@@ -91,13 +91,50 @@ class _RoIAlign(Function):
         (rois,) = ctx.saved_tensors
         shape, scale, sampling_ratio, aligned = ctx.cfg
         dfeat = ops.roi_align_backward(dout, shape, rois, scale, sampling_ratio, aligned)
-        return dfeat, None, None, None, None, None, None
+        return dfeat, None, None, None, None, None, None, None, None
 
 
-def roi_align(feat, rois, output_size, spatial_scale, sampling_ratio=0, aligned=True):
-    """Differentiable RoIAlign (torchvision.ops.roi_align semantics; reference roi_emb_heads.py:243-245)."""
+def roi_align(feat, rois, output_size, spatial_scale, sampling_ratio=0, aligned=True, channels_last=False, out_dtype=torch.float32):
+    """Differentiable RoIAlign (torchvision.ops.roi_align semantics; reference roi_emb_heads.py:243-245).
+
+    ``channels_last`` / ``out_dtype``: the pooled [R,C,PH,PW] tensor in ``torch.channels_last`` memory format, fp32 or bf16 —
+    the layout cuDNN's tensor-core convolutions of the res5 stage take without a transpose."""
     ph, pw = (output_size, output_size) if isinstance(output_size, int) else output_size
-    return _RoIAlign.apply(feat, rois, int(ph), int(pw), float(spatial_scale), int(sampling_ratio), bool(aligned))
+    return _RoIAlign.apply(feat, rois, int(ph), int(pw), float(spatial_scale), int(sampling_ratio), bool(aligned),
+                           bool(channels_last), out_dtype)
+
+
+class _SpatialMean(Function):
+    last_operand = None          # forward's bf16 operand, handed to spatial_mean() below (a Function returns tensors only)
+
+    @staticmethod
+    def forward(ctx, x, operand):
+        ctx.meta = (tuple(x.shape), x.dtype, (not x.is_contiguous()) and x.is_contiguous(memory_format=torch.channels_last))
+        out, _SpatialMean.last_operand = ops.spatial_mean(x, operand)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        shape, dtype, cl = ctx.meta
+        return ops.spatial_mean_backward(dy, shape, dtype, cl), None
+
+
+def spatial_mean(x, operand_precision: Optional[str] = None):
+    """``x.mean(dim=[2, 3])`` of the res5 output (reference roi_emb_heads.py:262, :329, :351) as one pass over x.
+
+    With ``operand_precision`` ("fp32" / "bf16" — the precision of the box predictor that consumes the result) the same pass also
+    writes the bf16 operand of the predictor's projection GEMM; it rides on the returned tensor as ``_loco_operand`` and
+    ``box_predict`` picks it up instead of re-reading the means in a split kernel."""
+    operand = None if operand_precision is None else _acc(operand_precision)
+    if operand is not None and _use_tf32(operand, x.shape[1]):
+        operand = None                       # the TF32 projection reads the fp32 means directly
+    out = _SpatialMean.apply(x, operand)
+    op = _SpatialMean.last_operand
+    _SpatialMean.last_operand = None
+    if op is not None:
+        out._loco_operand = (op, operand, out._version)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -158,14 +195,15 @@ class _BoxPredict(Function):
     reference box_emb_head.py:179-212 (bbox_pred, emb_pred, cls_score as three cuBLAS GEMMs)."""
 
     @staticmethod
-    def forward(ctx, x, w_emb, b_emb, w_box, b_box, w_cls, b_cls, precision, want_probs, aux_box):
+    def forward(ctx, x, w_emb, b_emb, w_box, b_box, w_cls, b_cls, precision, want_probs, aux_box, x_op=None):
         acc = _acc(precision)
         d = w_emb.shape[0]
         nbox = w_box.shape[0]
         w_cat = _cat_weight(w_emb, w_box)
         b_cat = torch.cat([b_emb.detach(), b_box.detach()]).to(torch.float32)
         if not _use_tf32(acc, x.shape[1]):
-            a_op = ops.split_bf16(x, acc)
+            # the producer of x (spatial_mean) may already have written its bf16 operand in the same pass
+            a_op = x_op if x_op is not None else ops.split_bf16(x, acc)
             wcat_op = weight_operand(w_cat, acc, tag="cat")
             out, e_op = ops.linear_fwd(a_op, wcat_op, b_cat, want_f32=True, n_bf16=d, accurate_out=acc)
         else:       # reduced-precision mode: TF32 projection straight from the fp32 activations (no split pass)
@@ -231,7 +269,7 @@ class _BoxPredict(Function):
             dwb = None
         if not need_bb:
             dbb = None
-        return dx, dwe, dbe, dwb, dbb, None, None, None, None, None
+        return dx, dwe, dbe, dwb, dbb, None, None, None, None, None, None
 
 
 _cat_cache = {}
@@ -263,7 +301,11 @@ def _cat_weight(w_emb, w_box):
 def box_predict(x, w_emb, b_emb, w_box, b_box, w_cls, b_cls=None, precision="fp32", want_probs=True):
     """Returns (scores, deltas, BoxScoreAux)."""
     aux = []
-    scores, deltas = _BoxPredict.apply(x, w_emb, b_emb, w_box, b_box, w_cls, b_cls, precision, want_probs, aux)
+    x_op = None
+    carried = getattr(x, "_loco_operand", None)          # written by spatial_mean() in the pass that produced x
+    if carried is not None and carried[1] == _acc(precision) and carried[2] == x._version and carried[0].rows == x.shape[0] and carried[0].cols == x.shape[1]:
+        x_op = carried[0]
+    scores, deltas = _BoxPredict.apply(x, w_emb, b_emb, w_box, b_box, w_cls, b_cls, precision, want_probs, aux, x_op)
     return scores, deltas, aux[0]
 
 

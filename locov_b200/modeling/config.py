@@ -4,8 +4,10 @@ Reference: ovr/config/config.py:4-174 (add_ovr_config) + the Detectron2 defaults
 SURVEY.md Appendix C + the two shipped YAMLs (configs/coco_stt.yaml, configs/coco_lsm.yaml).
 ``get_cfg()`` returns a yacs-like attribute node so the drop-in modules can be built without
 Detectron2; a real Detectron2 ``CfgNode`` works the same way (attribute access only).
-``MODEL.B200.PRECISION`` is the one new, optional key: "fp32" (three-pass fp32-accurate tensor-core
-mode, the reference's numerics) or "bf16".
+``MODEL.B200`` holds this library's optional keys (absent = the reference's behaviour):
+  PRECISION              "fp32" (three-pass fp32-accurate tensor-core mode, the reference's numerics) or "bf16";
+  POOLER_CHANNELS_LAST   RoIAlign writes the pooled tensor in torch.channels_last memory format (same logical shape/values);
+  POOLER_BF16            ... and in bf16 (reduced precision: for a res5 stage run in bf16 by the caller).
 """
 import copy
 
@@ -46,7 +48,7 @@ def get_cfg(stage="stt"):
         MODEL=_n(
             MASK_ON=False, KEYPOINT_ON=False,
             LOAD_EMB_PRED_FROM_MMSS_HEAD=True,
-            B200=_n(PRECISION="fp32"),
+            B200=_n(PRECISION="fp32", POOLER_CHANNELS_LAST=False, POOLER_BF16=False),
             ROI_HEADS=_n(NAME="EmbeddingProposalsRes5ROIHeads" if lsm else "EmbeddingRes5ROIHeads",
                          IN_FEATURES=["res4"], NUM_CLASSES=80 if lsm else 48,
                          BATCH_SIZE_PER_IMAGE=200 if lsm else 512, POSITIVE_FRACTION=1.0, IOU_THRESHOLDS=[0.5],

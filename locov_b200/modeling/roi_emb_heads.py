@@ -62,6 +62,7 @@ class EmbeddingRes5ROIHeads(nn.Module):
         if getattr(cfg.MODEL, "MASK_ON", False):
             raise NotImplementedError("MODEL.MASK_ON: the reference's mask path calls un-imported helpers (roi_emb_heads.py:206)")
         stride = input_shape[in_features[0]].stride
+        b200 = getattr(cfg.MODEL, "B200", None)                 # this library's optional keys; absent in the reference's cfg
         ret = {
             "in_features": in_features,
             "num_classes": roi.NUM_CLASSES,
@@ -71,7 +72,9 @@ class EmbeddingRes5ROIHeads(nn.Module):
             "proposal_sampler": proposal_sampler,
             "pooler": ROIPooler(output_size=cfg.MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION, scales=(1.0 / stride,),
                                 sampling_ratio=cfg.MODEL.ROI_BOX_HEAD.POOLER_SAMPLING_RATIO,
-                                pooler_type=cfg.MODEL.ROI_BOX_HEAD.POOLER_TYPE),
+                                pooler_type=cfg.MODEL.ROI_BOX_HEAD.POOLER_TYPE,
+                                channels_last=bool(getattr(b200, "POOLER_CHANNELS_LAST", False)),
+                                out_dtype=torch.bfloat16 if getattr(b200, "POOLER_BF16", False) else torch.float32),
         }
         if res5 is None:
             res5, out_channels = cls._build_res5_block(cfg)
@@ -102,6 +105,13 @@ class EmbeddingRes5ROIHeads(nn.Module):
         x = self.pooler(features, boxes)
         return self.res5(x)
 
+    def _pooled_mean(self, box_features):
+        """``box_features.mean(dim=[2, 3])`` (roi_emb_heads.py:262, :329, :351) as one pass that also writes the bf16 operand of
+        the predictor's projection GEMM.  On the CPU (the CPU unit tests of the host logic) it is the torch expression."""
+        if not box_features.is_cuda:
+            return box_features.mean(dim=[2, 3])
+        return LF.spatial_mean(box_features, getattr(self.box_predictor, "precision", None)).to(box_features.dtype)
+
     def forward(self, images, features, proposals, targets=None):
         del images
         if self.training:
@@ -110,7 +120,7 @@ class EmbeddingRes5ROIHeads(nn.Module):
         del targets
         proposal_boxes = [x.proposal_boxes for x in proposals]
         box_features = self._shared_roi_transform([features[f] for f in self.in_features], proposal_boxes)
-        predictions = self.box_predictor(box_features.mean(dim=[2, 3]))
+        predictions = self.box_predictor(self._pooled_mean(box_features))
         if self.training:
             del features
             return [], self.box_predictor.losses(predictions, proposals)
@@ -138,7 +148,7 @@ class EmbeddingProposalsRes5ROIHeads(EmbeddingRes5ROIHeads):
         box_features = self._shared_roi_transform([features[f] for f in self.in_features], proposal_boxes)
         del features
         losses = {}
-        box_features = box_features.mean(dim=[2, 3])
+        box_features = self._pooled_mean(box_features)
         predictions = self.box_predictor(box_features)
         box_features = list(box_features.split(boxes_per_image, dim=0))
         losses.update(self.box_predictor.losses(predictions, proposals))
@@ -147,6 +157,6 @@ class EmbeddingProposalsRes5ROIHeads(EmbeddingRes5ROIHeads):
     def inference_detection(self, features, proposals):
         proposal_boxes = [x.proposal_boxes for x in proposals]
         box_features = self._shared_roi_transform([features[f] for f in self.in_features], proposal_boxes)
-        predictions = self.box_predictor(box_features.mean(dim=[2, 3]))
+        predictions = self.box_predictor(self._pooled_mean(box_features))
         pred_instances, _ = self.box_predictor.inference(predictions, proposals)
         return self.forward_with_given_boxes(features, pred_instances), {}

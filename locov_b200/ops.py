@@ -16,6 +16,7 @@ from ._lib import LocoError
 
 ALIGN_SOFTMAX, ALIGN_HARDMAX = 0, 1
 NCHW, NHWC = 0, 1
+F32, BF16 = 0, 1          # LOCO_F32 / LOCO_BF16 (include/locov_b200.h)
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -72,9 +73,14 @@ def _drop_zero_workspace(device, tag):
 
 
 def roi_align(feat: torch.Tensor, rois: torch.Tensor, output_size, spatial_scale: float, sampling_ratio: int = 0,
-              aligned: bool = True) -> torch.Tensor:
-    """feat [N,C,H,W] fp32 (contiguous NCHW, or channels_last memory format), rois [R,5] -> [R,C,PH,PW]."""
+              aligned: bool = True, channels_last: bool = False, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """feat [N,C,H,W] fp32 (contiguous NCHW, or channels_last memory format), rois [R,5] -> [R,C,PH,PW].
+
+    ``channels_last=True`` returns the same logical [R,C,PH,PW] tensor in ``torch.channels_last`` memory format (what cuDNN's
+    tensor-core convolutions of res5 consume without a transpose), in fp32 or bf16 (``out_dtype``)."""
     _need_cuda(feat, rois)
+    if out_dtype not in (torch.float32, torch.bfloat16) or (out_dtype == torch.bfloat16 and not channels_last):
+        raise LocoError("roi_align: output is NCHW fp32, or channels-last fp32 / bf16")
     if feat.dtype != torch.float32:
         raise LocoError("roi_align: fp32 features only")
     ph, pw = (output_size, output_size) if isinstance(output_size, int) else output_size
@@ -87,13 +93,70 @@ def roi_align(feat: torch.Tensor, rois: torch.Tensor, output_size, spatial_scale
         feat, layout = feat.contiguous(), NCHW
     rois = rois.to(torch.float32).contiguous()
     r = rois.shape[0]
-    out = torch.empty((r, c, ph, pw), dtype=torch.float32, device=feat.device)
+    if channels_last:
+        out = torch.empty((r, ph, pw, c), dtype=out_dtype, device=feat.device).permute(0, 3, 1, 2)
+    else:
+        out = torch.empty((r, c, ph, pw), dtype=torch.float32, device=feat.device)
     lib = _lib.load()
     ws = _workspace(feat.device, lib.loco_roi_align_workspace_bytes(n, c, h, w, layout), "roi_align")
     _lib.check(lib.loco_roi_align_fwd(_p(feat), n, c, h, w, layout, _p(rois), r, ph, pw, float(spatial_scale),
-                                      int(sampling_ratio), int(bool(aligned)), _p(out), _p(ws), _stream(feat)),
+                                      int(sampling_ratio), int(bool(aligned)), _p(out), NHWC if channels_last else NCHW,
+                                      BF16 if out_dtype == torch.bfloat16 else F32, _p(ws), _stream(feat)),
                "loco_roi_align_fwd")
     return out
+
+
+def _mean_layout(x: torch.Tensor):
+    """(tensor, layout, dtype code) of a [R,C,PH,PW] tensor as the spatial-mean kernels take it."""
+    if x.dim() != 4:
+        raise LocoError("spatial_mean: expects [R, C, PH, PW]")
+    if x.dtype == torch.float32 and x.is_contiguous():
+        return x, NCHW, F32
+    if x.dtype in (torch.float32, torch.bfloat16) and x.shape[1] % 4 == 0:
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        return x, NHWC, F32 if x.dtype == torch.float32 else BF16
+    return x.to(torch.float32).contiguous(), NCHW, F32
+
+
+def spatial_mean(x: torch.Tensor, operand: Optional[bool] = None):
+    """x [R,C,PH,PW] (NCHW fp32, or channels-last fp32 / bf16) -> (mean [R,C] fp32, Bf16Operand of it or None).
+
+    ``operand``: None = no bf16 operand, False = hi only, True = hi + lo (the fp32-accurate three-pass operand)."""
+    _need_cuda(x)
+    x, layout, dt = _mean_layout(x)
+    r, c, ph, pw = x.shape
+    out = torch.empty((r, c), dtype=torch.float32, device=x.device)
+    op = None
+    if operand is not None:
+        ld = _round_up(c, 8)
+        mk = torch.empty if ld == c else torch.zeros
+        hi = mk((r, ld), dtype=torch.bfloat16, device=x.device)
+        lo = mk((r, ld), dtype=torch.bfloat16, device=x.device) if operand else None
+        op = Bf16Operand(hi, lo, r, c)
+    lib = _lib.load()
+    _lib.check(lib.loco_spatial_mean(_p(x), r, c, ph * pw, layout, dt, _p(out), c, _p(op.hi) if op else None,
+                                     _p(op.lo) if op is not None and op.lo is not None else None, op.ld if op else 0, _stream(x)),
+               "loco_spatial_mean")
+    return out, op
+
+
+def spatial_mean_backward(dy: torch.Tensor, shape, dtype: torch.dtype = torch.float32, channels_last: bool = False) -> torch.Tensor:
+    """dx [R,C,PH,PW] = dy [R,C] / (PH*PW) broadcast over the positions; NCHW fp32, or channels-last fp32 / bf16."""
+    _need_cuda(dy)
+    dy = dy.to(torch.float32)
+    if dy.dim() != 2 or dy.stride(1) != 1:
+        dy = dy.reshape(shape[0], shape[1]).contiguous()
+    r, c, ph, pw = shape
+    if channels_last and dtype in (torch.float32, torch.bfloat16):
+        dx = torch.empty((r, ph, pw, c), dtype=dtype, device=dy.device).permute(0, 3, 1, 2)
+        layout, dt = NHWC, F32 if dtype == torch.float32 else BF16
+    else:
+        dx, layout, dt = torch.empty((r, c, ph, pw), dtype=torch.float32, device=dy.device), NCHW, F32
+    lib = _lib.load()
+    _lib.check(lib.loco_spatial_mean_bwd(_p(dy), dy.stride(0) if r > 0 else c, r, c, ph * pw, layout, dt, _p(dx), _stream(dy)),
+               "loco_spatial_mean_bwd")
+    return dx if dx.dtype == dtype else dx.to(dtype)
 
 
 def roi_align_backward(dout: torch.Tensor, feat_shape, rois: torch.Tensor, spatial_scale: float,

@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_version_and_error_plumbing():
     lib = _lib.load()
     assert lib.loco_version() >= 100
-    rc = lib.loco_roi_align_fwd(None, 0, 0, 0, 0, 0, None, 0, 7, 7, 0.0625, 0, 1, None, None, None)
+    rc = lib.loco_roi_align_fwd(None, 0, 0, 0, 0, 0, None, 0, 7, 7, 0.0625, 0, 1, None, 0, 0, None, None)
     assert rc == -1                                    # LOCO_E_BADARG
     assert b"roi_align_fwd" in lib.loco_last_error()
     rc = lib.loco_lsm_pair_fwd(None, None, 0, None, None, None, 0, None, 4, 200, 4, 10, 64, 0.1, 0, None, None, 4, None, None)

@@ -146,3 +146,50 @@ def test_full_size_properties(cuda_device):
     sub = [0, 1, 127, 128, 511, 512, 1023]
     ref = torch.from_numpy(ora.roi_align_fwd(feat[:, sub].numpy(), rois.numpy(), 14, 1 / 16, 0, True))
     assert relerr(a[:, sub].cpu(), ref) < 1e-4
+
+
+@pytest.mark.parametrize("feat_layout", ["nchw", "nhwc"])
+@pytest.mark.parametrize("c,ps,scale,hw,sr", [(96, 14, 1 / 16, (50, 76), 0), (1024, 7, 1 / 16, (25, 38), 0), (36, 7, 1 / 32, (25, 38), 2),
+                                              (256, 14, 1 / 16, (50, 76), 0)])
+def test_channels_last_output(cuda_device, feat_layout, c, ps, scale, hw, sr):
+    """the pooled tensor in torch.channels_last memory format (fp32 / bf16) holds the numbers of the NCHW output."""
+    torch.manual_seed(c + ps)
+    feat = torch.randn(2, c, *hw)
+    rois = torch.cat([_rois(2, 96, 800, 1216, seed=c), EDGE]).to(cuda_device)
+    f = feat.to(cuda_device)
+    if feat_layout == "nhwc":
+        f = f.contiguous(memory_format=torch.channels_last)
+    nchw = ops.roi_align(f, rois, ps, scale, sr, True)
+    cl = ops.roi_align(f, rois, ps, scale, sr, True, channels_last=True)
+    assert cl.shape == nchw.shape and cl.dtype == torch.float32
+    assert cl.is_contiguous(memory_format=torch.channels_last)
+    assert float((cl - nchw).abs().max()) <= 1e-6
+    ref = torch.from_numpy(ora.roi_align_fwd(feat.numpy(), rois.cpu().numpy(), ps, scale, sr, True))
+    assert relerr(cl.cpu(), ref) < 1e-4 and float((cl.cpu() - ref).abs().max()) < 1e-5
+    b = ops.roi_align(f, rois, ps, scale, sr, True, channels_last=True, out_dtype=torch.bfloat16)
+    assert b.dtype == torch.bfloat16 and b.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(b, cl.to(torch.bfloat16))              # round-to-nearest-even of the same fp32 value
+
+
+def test_channels_last_output_edge_cases(cuda_device):
+    from locov_b200._lib import LocoError
+    feat = torch.randn(2, 16, 20, 30, device=cuda_device)
+    empty = ops.roi_align(feat, torch.zeros(0, 5, device=cuda_device), 7, 1 / 16, 0, True, channels_last=True, out_dtype=torch.bfloat16)
+    assert empty.shape == (0, 16, 7, 7) and empty.dtype == torch.bfloat16
+    with pytest.raises(LocoError):                            # 4-channel lanes: C % 4 == 0
+        ops.roi_align(torch.randn(1, 6, 20, 30, device=cuda_device), torch.tensor([[0, 1., 1., 90., 80.]], device=cuda_device), 7, 1 / 16, 0, True,
+                      channels_last=True)
+    with pytest.raises(LocoError):                            # bf16 only in the channels-last layout
+        ops.roi_align(feat, torch.tensor([[0, 1., 1., 90., 80.]], device=cuda_device), 7, 1 / 16, 0, True, out_dtype=torch.bfloat16)
+    # module interface + gradient through the channels-last output
+    pooler = M.ROIPooler(7, (1 / 16,), 0, "ROIAlignV2", channels_last=True)
+    f = feat.clone().requires_grad_(True)
+    boxes = [torch.tensor([[10., 20., 200., 220.], [5., 5., 400., 300.]], device=cuda_device), torch.tensor([[50., 60., 300., 310.]], device=cuda_device)]
+    y = pooler([f], boxes)
+    assert y.shape == (3, 16, 7, 7) and y.is_contiguous(memory_format=torch.channels_last)
+    f2 = feat.clone().requires_grad_(True)
+    y2 = M.ROIPooler(7, (1 / 16,), 0, "ROIAlignV2")([f2], boxes)
+    w = torch.randn_like(y2)
+    (y * w).sum().backward()
+    (y2 * w).sum().backward()
+    assert float((f.grad - f2.grad).abs().max()) <= 1e-5
