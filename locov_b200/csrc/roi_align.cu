@@ -1132,30 +1132,68 @@ __global__ void __launch_bounds__(256) spatial_mean_cl_kernel(const T *__restric
     }
 }
 
-__global__ void __launch_bounds__(256) spatial_mean_rows_kernel(const float *__restrict__ x, int64_t rows, int C, int HW, float inv, float *__restrict__ out,
-                                                                int64_t ldo, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, int64_t ldh) {
+// One warp owns 32 consecutive (r, c) rows = one contiguous span of 32 * HW floats: the span is copied to shared memory with 16-byte
+// cp.async (no registers, everything in flight at once — 6.3 KB per warp at HW = 49), then lane j adds up row j from shared memory
+// in a fixed order (row stride HW | 1 floats: odd, so the 32 lanes hit 32 different banks) and the 32 means leave as one 128-byte store.
+constexpr int SM_WARPS = 4;
+__global__ void __launch_bounds__(SM_WARPS * 32) spatial_mean_rows_kernel(const float *__restrict__ x, int64_t rows, int C, int HW, float inv,
+                                                                          float *__restrict__ out, int64_t ldo, uint16_t *__restrict__ hi,
+                                                                          uint16_t *__restrict__ lo, int64_t ldh) {
+    extern __shared__ __align__(16) float sm_rows[];
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int stride = HW | 1;
+    float *buf = sm_rows + (size_t)wib * 32 * stride;
+    const uint32_t sbuf = smem_u32(buf);
+    const int64_t warp = (int64_t)blockIdx.x * SM_WARPS + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * SM_WARPS;
+    const bool linear = (HW & 1) != 0;                  // stride == HW: the span is copied as it lies
+    for (int64_t base = warp * 32; base < rows; base += nwarps * 32) {
+        const int nrow = (int)min((int64_t)32, rows - base);
+        const int n = nrow * HW;
+        const float *src = x + base * HW;
+        if (linear && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            const int n4 = n >> 2;
+            for (int i = lane; i < n4; i += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbuf + i * 16), "l"(src + i * 4) : "memory");
+            for (int i = (n4 << 2) + lane; i < n; i += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbuf + i * 4), "l"(src + i) : "memory");
+        } else {
+            for (int i = lane; i < n; i += 32) {
+                const int row = i / HW;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbuf + (row * stride + (i - row * HW)) * 4), "l"(src + i) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (lane < nrow) {
+            const float *p = buf + lane * stride;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;           // four chains, combined in a fixed order
+            int t = 0;
+            for (; t + 4 <= HW; t += 4) { a0 += p[t]; a1 += p[t + 1]; a2 += p[t + 2]; a3 += p[t + 3]; }
+            for (; t < HW; ++t) a0 += p[t];
+            const int64_t row = base + lane;
+            mean_store(((a0 + a1) + (a2 + a3)) * inv, row / C, (int)(row % C), out, ldo, hi, lo, ldh);
+        }
+        __syncwarp();                                        // the buffer is refilled by the next round
+    }
+}
+
+// fall-back for very large maps (the span of 32 rows does not fit shared memory): lanes stride over the row, warp reduction
+__global__ void __launch_bounds__(256) spatial_mean_rows_big_kernel(const float *__restrict__ x, int64_t rows, int C, int HW, float inv, float *__restrict__ out,
+                                                                    int64_t ldo, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, int64_t ldh) {
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t base = warp * 32; base < rows; base += nwarps * 32) {
-        float mine = 0.f;
-        for (int g = 0; g < 32 && base + g < rows; g += 4) {
-            float a[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int s = lane; s < HW; s += 32) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (base + g + k < rows) a[k] += __ldcs(x + (base + g + k) * HW + s);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float t = warp_sum(a[k]);
-                if (lane == g + k) mine = t;
-            }
-        }
-        const int64_t row = base + lane;
-        if (row < rows) mean_store(mine * inv, row / C, (int)(row % C), out, ldo, hi, lo, ldh);
+    for (int64_t row = warp; row < rows; row += nwarps) {
+        float a = 0.f;
+        for (int s = lane; s < HW; s += 32) a += __ldcs(x + row * HW + s);
+        a = warp_sum(a);
+        if (lane == 0) mean_store(a * inv, row / C, (int)(row % C), out, ldo, hi, lo, ldh);
     }
 }
 
@@ -1381,9 +1419,22 @@ int loco_spatial_mean(const void *x, int64_t R, int C, int HW, int layout, int d
                                     ldo, hi, lo, ldh));
     } else {
         const int64_t rows = R * C;
-        const int blocks = (int)std::min<int64_t>((rows + 255) / 256, (int64_t)sms * 8);
-        LOCO_CUDA(launch_kernel(spatial_mean_rows_kernel, dim3(blocks), dim3(256), 0, st, 1, static_cast<const float *>(x), rows, C, HW, inv, out, ldo, hi, lo,
-                                ldh));
+        const size_t smem = (size_t)SM_WARPS * 32 * (HW | 1) * sizeof(float);
+        if (smem <= 96 * 1024) {
+            static thread_local size_t smem_set = 0;
+            if (smem > 48 * 1024 && smem > smem_set) {
+                LOCO_CUDA(cudaFuncSetAttribute(spatial_mean_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                smem_set = smem;
+            }
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / smem));
+            const int blocks = (int)std::min<int64_t>((rows + 32 * SM_WARPS - 1) / (32 * SM_WARPS), (int64_t)sms * per_sm);
+            LOCO_CUDA(launch_kernel(spatial_mean_rows_kernel, dim3(blocks), dim3(SM_WARPS * 32), smem, st, 1, static_cast<const float *>(x), rows, C, HW, inv,
+                                    out, ldo, hi, lo, ldh));
+        } else {
+            const int blocks = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)sms * 8);
+            LOCO_CUDA(launch_kernel(spatial_mean_rows_big_kernel, dim3(blocks), dim3(256), 0, st, 1, static_cast<const float *>(x), rows, C, HW, inv, out, ldo,
+                                    hi, lo, ldh));
+        }
     }
     count_launch();
     LOCO_CUDA(cudaGetLastError());

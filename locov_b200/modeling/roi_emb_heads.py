@@ -13,6 +13,7 @@ from typing import Callable, List, Optional
 import torch
 from torch import nn
 
+from .. import functional as LF
 from .box_emb_head import build_box_predictor
 from .configurable import configurable
 from .poolers import ROIPooler

@@ -41,7 +41,8 @@ def test_on_the_grounding_head_outputs_and_config_builder(cuda_device):
     with torch.no_grad():
         head.v2l_projection.weight.copy_(w); head.v2l_projection.bias.copy_(b)
     _, _, d = head({k: v.to(cuda_device) for k, v in ii.items()}, {k: v.to(cuda_device) for k, v in ic.items()})
-    teacher = (d["w2r"].detach() * 0.7 + 0.1).requires_grad_(True)
+    g = torch.Generator(device=cuda_device).manual_seed(5)          # a teacher of the same scale but unrelated: KL well away from 0 (no cancellation)
+    teacher = (torch.randn(d["w2r"].shape, generator=g, device=cuda_device) * d["w2r"].detach().std() + d["w2r"].detach().mean()).requires_grad_(True)
     loss = loss_mod(teacher, d["w2r"], d["r2w"])
     loss.backward()
     ref = distill.kd_loss(teacher.detach().cpu().double(), d["w2r"].detach().cpu().double(), d["r2w"].detach().cpu().double(), 10.0, 1.0, False, False)

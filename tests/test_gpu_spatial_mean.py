@@ -21,13 +21,14 @@ def _x(r, c, hw, layout, dtype, dev, seed=0):
 
 
 @pytest.mark.parametrize("layout,dtype", [("nchw", torch.float32), ("cl", torch.float32), ("cl", torch.bfloat16)])
-@pytest.mark.parametrize("r,c,hw", [(37, 64, (7, 7)), (5, 2048, (7, 7)), (300, 20, (4, 5)), (2, 8, (14, 14)), (1, 4, (1, 1))])
+@pytest.mark.parametrize("r,c,hw", [(37, 64, (7, 7)), (5, 2048, (7, 7)), (300, 20, (4, 5)), (2, 8, (14, 14)), (1, 4, (1, 1)), (3, 5, (3, 3)),
+                                    (2, 8, (50, 76))])
 def test_mean_matches_torch_in_double(cuda_device, layout, dtype, r, c, hw):
     x = _x(r, c, hw, layout, dtype, cuda_device, seed=r + c)
     out, op = ops.spatial_mean(x, operand=True)
     ref = x.double().mean(dim=[2, 3])
     assert out.shape == (r, c) and out.dtype == torch.float32
-    assert relerr(out.cpu(), ref.cpu()) < 1e-6
+    assert relerr(out.cpu(), ref.cpu()) < (1e-6 if hw[0] * hw[1] <= 196 else 5e-6)       # (3800 sequential fp32 additions at 50 x 76)
     # the operand written by the same pass is exactly the split of the fp32 mean
     want = ops.split_bf16(out, True)
     assert torch.equal(op.hi[:, :c], want.hi[:, :c]) and torch.equal(op.lo[:, :c], want.lo[:, :c])
@@ -79,6 +80,7 @@ def test_operand_is_picked_up_by_the_box_predictor(cuda_device, precision):
         x = LF.spatial_mean(feats, precision)
         assert hasattr(x, "_loco_operand")
         lib = _lib.load()
+        LF.box_predict(x.clone(), we, be, wb, bb, wc, bc, precision)      # (fills the weight-operand caches)
         n0 = lib.loco_launch_count()
         s1, d1, _ = LF.box_predict(x, we, be, wb, bb, wc, bc, precision)
         n1 = lib.loco_launch_count()
