@@ -102,6 +102,26 @@ int loco_spatial_mean(const void *x, int64_t R, int C, int HW, int layout, int d
                       uint16_t *lo, int64_t ldh, void *stream);
 int loco_spatial_mean_bwd(const float *dy, int64_t lddy, int64_t R, int C, int HW, int layout, int dtype, void *dx, void *stream);
 
+
+/* Inference tail of the box predictor: Detectron2 `fast_rcnn_inference` as reached from `EmbeddingFastRCNNOutputLayers.inference`
+ * (reference ovr/modeling/roi_heads/roi_emb_heads.py:280 and :357 -> FastRCNNOutputLayers.inference): Box2BoxTransform.apply_deltas +
+ * clip to the image, rows with a non-finite box or score dropped, `score > score_thresh` over the K foreground columns, per-class NMS
+ * (torchvision IoU expression, class-agnostic boxes: box_emb_head.py:137), the `topk` best per image.  All images in 4 launches.
+ * probs        [R, ld_probs] fp32 probabilities, K + 1 columns used (column K = background, never a candidate).
+ * deltas       [R, ld_deltas] fp32 (first 4 columns), proposals [R, 4] fp32 (x1, y1, x2, y2).
+ * img_offsets  device int32 [n_img + 1]: rows of image i are [img_offsets[i], img_offsets[i+1]); img_hw device fp32 [n_img, 2] = (h, w).
+ * max_rows_per_image  largest image row count (<= 2048).   reg_weights4_host: HOST pointer to (wx, wy, ww, wh).
+ * outputs      out_boxes [n_img, topk, 4], out_scores [n_img, topk], out_classes / out_rows int64 [n_img, topk] (out_rows = index of
+ *              the RoI among the VALID rows of its image, as the reference returns it), out_count int32 [n_img]; entries beyond
+ *              out_count[i] are not written.  Order: score descending, ties by (RoI, class) ascending.
+ * workspace    loco_box_inference_workspace_bytes() bytes, 16-byte aligned. */
+int64_t loco_box_inference_workspace_bytes(int R, int K, int n_img, int max_rows_per_image, int topk);
+int loco_box_inference(const float *probs, int64_t ld_probs, const float *deltas, int64_t ld_deltas, const float *proposals,
+                       const int32_t *img_offsets, const float *img_hw, int n_img, int max_rows_per_image, int R, int K,
+                       const float *reg_weights4_host, float scale_clamp, float score_thresh, float nms_thresh, int topk,
+                       float *out_boxes, float *out_scores, int64_t *out_classes, int64_t *out_rows, int32_t *out_count,
+                       void *workspace, void *stream);
+
 /* Debug/parity entry: for every roi r, bin (ph,pw) and sample (iy,ix) with iy,ix < max_grid writes
  *   grid_hw [R,2] int32            (gh, gw) — the adaptive sample counts
  *   yx      [R,PH,PW,max_grid,max_grid,2] fp32   unclamped sample coordinate (y, x)

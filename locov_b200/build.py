@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 # LOCOV_B200_NVCC_EXTRA adds compiler flags (e.g. -DLOCOV_EXP=3) to it
 LIBDIR = os.path.join(HERE, os.environ.get("LOCOV_B200_LIBDIR", "lib"))
 LIBNAME = "liblocov_b200.so"
-SOURCES = ["api.cu", "roi_align.cu", "misc_kernels.cu", "tc_ops.cu"]
+SOURCES = ["api.cu", "roi_align.cu", "misc_kernels.cu", "tc_ops.cu", "box_infer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",

@@ -73,8 +73,8 @@ def _box_tensor(b):
 
 
 def fast_rcnn_inference_single_image(boxes, scores, image_shape, score_thresh, nms_thresh, topk_per_image):
-    """Detectron2 fast_rcnn_inference_single_image (kept in PyTorch/torchvision: NMS is outside the
-    named hot path)."""
+    """Detectron2 fast_rcnn_inference_single_image with torch / torchvision operators: the path for CPU tensors (host-logic
+    tests) and for settings outside loco_box_inference's range; CUDA inference goes through the kernel (see ``inference``)."""
     from torchvision.ops import batched_nms
     valid = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)
     if not bool(valid.all()):
@@ -321,6 +321,28 @@ class EmbeddingFastRCNNOutputLayers(nn.Module):
         return boxes.split([len(p) for p in proposals])
 
     def inference(self, predictions, proposals):
+        """Detectron2 FastRCNNOutputLayers.inference -> fast_rcnn_inference.  On the device the whole tail (box decoding, score
+        threshold, per-class NMS, top-k; all images) is four launches of loco_box_inference and ONE device->host copy of the per-image
+        detection counts; the per-image torchvision path below remains for CPU tensors and for settings outside the kernel's range
+        (no top-k limit, more than 2048 proposals in an image)."""
+        scores_all, deltas_all = predictions
+        rows = [len(p) for p in proposals]
+        if (scores_all.is_cuda and len(proposals) and 1 <= self.test_topk_per_image <= 1024 and max(rows) <= 2048
+                and scores_all.shape[0] > 0 and max(rows) * self.num_classes < 2 ** 32):
+            probs = self._fused_aux(scores_all, want_probs=True).probs
+            proposal_boxes = _cat([_box_tensor(p.proposal_boxes) for p in proposals], 0)
+            b, s, c, r, n = ops.box_inference(probs, deltas_all.detach(), proposal_boxes, rows, [x.image_size for x in proposals],
+                                              self.box2box_transform.weights, self.box2box_transform.scale_clamp, self.test_score_thresh,
+                                              self.test_nms_thresh, self.test_topk_per_image)
+            results, kept = [], []
+            for i, (cnt, p) in enumerate(zip(n.tolist(), proposals)):
+                inst = Instances(p.image_size)
+                inst.pred_boxes = Boxes(b[i, :cnt])
+                inst.scores = s[i, :cnt]
+                inst.pred_classes = c[i, :cnt]
+                results.append(inst)
+                kept.append(r[i, :cnt])
+            return results, kept
         boxes = self.predict_boxes(predictions, proposals)
         scores = self.predict_probs(predictions, proposals)
         image_shapes = [x.image_size for x in proposals]

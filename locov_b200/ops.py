@@ -592,6 +592,56 @@ def pair_distill(trans: torch.Tensor, w2r: torch.Tensor, r2w: torch.Tensor, temp
     return loss, gt, gw, gr
 
 
+_small_dev = {}      # small host-built index tensors (image row offsets, image sizes) by (device, kind, values)
+
+
+def _small_device_tensor(dev, kind, values, dtype):
+    key = (dev, kind, values)
+    t = _small_dev.get(key)
+    if t is None:
+        if len(_small_dev) > 256:
+            _small_dev.clear()
+        t = torch.tensor(values, dtype=dtype).reshape(-1).to(dev)
+        _small_dev[key] = t
+    return t
+
+
+def box_inference(probs: torch.Tensor, deltas: torch.Tensor, proposals: torch.Tensor, rows_per_image, image_sizes, reg_weights,
+                  scale_clamp: float, score_thresh: float, nms_thresh: float, topk: int):
+    """Detectron2 ``fast_rcnn_inference`` for all images of a batch (reference roi_emb_heads.py:280 / :357) in four launches.
+
+    probs [R, K+1] fp32 probabilities, deltas [R, 4], proposals [R, 4]; ``rows_per_image`` python ints, ``image_sizes`` (h, w) pairs.
+    Returns (boxes [n,topk,4], scores [n,topk], classes [n,topk] int64, rows [n,topk] int64, counts [n] int32) on the device;
+    entries past counts[i] are unspecified."""
+    _need_cuda(probs, deltas, proposals)
+    n_img = len(rows_per_image)
+    r, k1 = probs.shape
+    if sum(rows_per_image) != r or deltas.shape[0] != r or proposals.shape != (r, 4) or len(image_sizes) != n_img:
+        raise LocoError("box_inference: inconsistent row counts")
+    probs = probs if probs.dtype == torch.float32 and probs.stride(1) == 1 else probs.to(torch.float32).contiguous()
+    deltas = deltas if deltas.dtype == torch.float32 and deltas.stride(1) == 1 else deltas.to(torch.float32).contiguous()
+    proposals = proposals.to(torch.float32).contiguous()
+    dev = probs.device
+    offs = [0]
+    for n in rows_per_image:
+        offs.append(offs[-1] + int(n))
+    img_off = _small_device_tensor(dev, "off", tuple(offs), torch.int32)
+    img_hw = _small_device_tensor(dev, "hw", tuple(float(v) for hw in image_sizes for v in hw), torch.float32)
+    max_rows = max([int(n) for n in rows_per_image] + [0])
+    boxes = torch.empty((n_img, topk, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((n_img, topk), dtype=torch.float32, device=dev)
+    classes = torch.empty((n_img, topk), dtype=torch.int64, device=dev)
+    rows = torch.empty((n_img, topk), dtype=torch.int64, device=dev)
+    counts = torch.empty((n_img,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    ws = _workspace(dev, lib.loco_box_inference_workspace_bytes(r, k1 - 1, n_img, max_rows, topk), "box_inference")
+    w4 = (ctypes.c_float * 4)(*[float(v) for v in reg_weights])
+    _lib.check(lib.loco_box_inference(_p(probs), probs.stride(0), _p(deltas), deltas.stride(0), _p(proposals), _p(img_off), _p(img_hw), n_img, max_rows,
+                                      r, k1 - 1, w4, float(scale_clamp), float(score_thresh), float(nms_thresh), int(topk),
+                                      _p(boxes), _p(scores), _p(classes), _p(rows), _p(counts), _p(ws), _stream(probs)), "loco_box_inference")
+    return boxes, scores, classes, rows, counts
+
+
 def tensor_stats(x: torch.Tensor) -> torch.Tensor:
     """[min, max, mean, std] of a CUDA tensor as a 4-element device tensor, one launch, no host synchronisation."""
     _need_cuda(x)

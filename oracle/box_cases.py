@@ -21,6 +21,12 @@ BOX_CASES = {
     "standardize_train": dict(R=96, K=20, V=256, D=64, n_img=2, seed=111, stage="stt",
                               over={"MODEL.ROI_BOX_HEAD.STANDARDIZE_EMB_PRED": True, "MODEL.ROI_BOX_HEAD.FREEZE_EMB_PRED": False}, mode="train", cls_gain=4.0),
     "detach_train": dict(R=128, K=30, V=256, D=64, n_img=2, seed=108, stage="lsm", over={}, mode="train"),
+    # the inference tail at LVIS settings (coco/lvis evaluation: score threshold 1e-4, 300 detections per image): ~10^5 candidates per
+    # image, every class has many -> torchvision's per-class ("vanilla") batched NMS in the reference
+    "k1203_lvis": dict(R=600, K=1203, V=2048, D=768, n_img=2, seed=112, stage="stt", mode="eval", rows=8, cls_gain=8.0,
+                       over={"MODEL.ROI_HEADS.SCORE_THRESH_TEST": 1e-4, "TEST.DETECTIONS_PER_IMAGE": 300}),
+    "k65_dense": dict(R=900, K=65, V=256, D=64, n_img=3, seed=113, stage="stt", mode="eval", rows=8, cls_gain=2.0,
+                      over={"MODEL.ROI_HEADS.SCORE_THRESH_TEST": 0.001, "MODEL.ROI_HEADS.NMS_THRESH_TEST": 0.3, "TEST.DETECTIONS_PER_IMAGE": 50}),
     "reset": dict(R=64, K=48, V=256, D=64, n_img=2, seed=109, stage="stt", over={}, mode="eval", K2=65),
 }
 

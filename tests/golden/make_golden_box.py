@@ -1,5 +1,5 @@
 """Generates tests/golden/box_*.npz and tests/golden/roiheads_*.npz — run in the BUILD container only
-(needs /root/reference):   python tests/golden/make_golden_box.py
+(needs /root/reference):   python tests/golden/make_golden_box.py [case names ...]
 
 Every vector is the output of the reference's OWN source, imported unmodified through oracle/ref_loader.py:
   box_*.npz      : ``build_box_predictor(cfg, input_shape)`` -> ``EmbeddingFastRCNNOutputLayers`` (box_emb_head.py:60-249):
@@ -161,12 +161,15 @@ def roi_case(mod, name, cls_name, stage, mode):
 
 def main():
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])                      # optional: names of the cases to (re)generate
     bmod = ref_loader.load_reference_box_head()
     for name, c in BOX_CASES.items():
-        box_case(bmod, name, c)
+        if not only or name in only:
+            box_case(bmod, name, c)
     rmod = ref_loader.load_reference_roi_heads()
     for name, (cls_name, stage, mode) in ROI_CASES.items():
-        roi_case(rmod, name, cls_name, stage, mode)
+        if not only or name in only:
+            roi_case(rmod, name, cls_name, stage, mode)
 
 
 if __name__ == "__main__":

@@ -136,3 +136,12 @@ def test_box_predictor_state_keys_match_the_reference_class():
     bp = M.build_box_predictor(M.get_cfg("stt"), 2048)
     bp.set_class_embeddings(torch.zeros(66, 768))
     assert sorted(bp.state_dict().keys()) == sorted(z["state_keys"].tolist())
+
+
+def test_host_feed_refuses_a_cpu_device():
+    import locov_b200
+    from locov_b200._lib import LocoError
+    with pytest.raises(LocoError):
+        locov_b200.HostFeed("cpu")
+    with pytest.raises(LocoError):
+        locov_b200.HostFeed("cuda:0", depth=1)
