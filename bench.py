@@ -537,7 +537,46 @@ def roi_workloads(torch, dist, M, ops, synthetic, dev, pk, world, rank, max_over
                 dt = time.perf_counter() - t0
         out["box_cfg1_fwd"]["cpu_baseline"] = {"ms": dt * 1e3, "kind": "port", "cores": torch.get_num_threads(),
                                                "sample": "one pass of the restated predictor (3 F.linear + softmax, torch CPU fp32) on the same inputs"}
-    box_fwd("box_cfg5_fwd", 8000, 1203, 3)
+    x5, we5, wb5, cls5 = box_fwd("box_cfg5_fwd", 8000, 1203, 3)
+
+    # ---- configs[4] inference tail: box decoding + threshold + per-class NMS + top-k for 8 images x 1000 RoIs x 1203 classes ---------
+    from locov_b200.modeling.box_emb_head import fast_rcnn_inference_single_image
+    bp = predictor(1203, "fp32", cls5 * 8.0, we5, wb5)          # (class matrix scaled so that the softmax is peaked, as trained embeddings are)
+    pb = synthetic.coco_boxes(8, 1000, seed=SEED + 3)[:, 1:]
+    pb[:, 2:] = torch.maximum(pb[:, 2:], pb[:, :2] + 8)
+    props = [M.Instances((800, 1216), proposal_boxes=M.Boxes(pb[i * 1000:(i + 1) * 1000].to(dev))) for i in range(8)]
+    with torch.no_grad():
+        pred = bp(x5.to(dev))
+        probs = bp.predict_probs(pred, props)
+        boxes = bp.predict_boxes(pred, props)
+    tail = {}
+    for name, (thr, topk) in {"coco_settings": (0.05, 100), "lvis_settings": (1e-4, 300)}.items():
+        bp.test_score_thresh, bp.test_topk_per_image = thr, topk
+
+        def ours():
+            with torch.no_grad():
+                return bp.inference(pred, props)
+
+        def stock():
+            return [fast_rcnn_inference_single_image(b, s, (800, 1216), thr, bp.test_nms_thresh, topk) for b, s in zip(boxes, probs)]
+        res = {}
+        for tag, fn, reps in (("ms", ours, 10), ("torchvision_cuda_ms", stock, 2)):
+            fn()
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                out_ = fn()
+            b_.record()
+            torch.cuda.synchronize()
+            res[tag] = a.elapsed_time(b_) / reps
+        res["detections"] = int(sum(len(r) for r in ours()[0]))
+        res["candidates"] = int(sum(int((p[:, :-1] > thr).sum()) for p in probs))
+        tail[name] = res
+    out["box_inference_cfg5"] = {"shape": "8 images x 1000 RoIs x 1203 classes, NMS 0.5", **tail,
+                                 "note": "ms = EmbeddingFastRCNNOutputLayers.inference (4 launches of loco_box_inference + the device->host copy of the 8 detection counts); "
+                                         "torchvision_cuda_ms = the same tail per image with torch.nonzero + torchvision.ops.batched_nms on the same device (what the reference reaches)"}
+    del bp, pred, probs, boxes
 
     # ---- configs[2]: training step of the box head, fwd + bwd, weights frozen as in coco_stt.yaml:36 ---------------------
     R, K = 8192, 48

@@ -60,7 +60,9 @@ __global__ void __launch_bounds__(BI_THREADS) box_decode_kernel(const float *__r
         const float w = __fsub_rn(p.z, p.x), h = __fsub_rn(p.w, p.y);
         const float cx = __fadd_rn(p.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(p.y, __fmul_rn(0.5f, h));
         const float dx = __fdiv_rn(d[0], wx), dy = __fdiv_rn(d[1], wy);
-        const float dw = fminf(__fdiv_rn(d[2], ww), clampv), dh = fminf(__fdiv_rn(d[3], wh), clampv);
+        float dw = __fdiv_rn(d[2], ww), dh = __fdiv_rn(d[3], wh);
+        dw = dw > clampv ? clampv : dw;                                   // torch.clamp(max=): a NaN stays a NaN (fminf would drop it)
+        dh = dh > clampv ? clampv : dh;
         const float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, h), cy);
         const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
         float4 b = make_float4(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), __fsub_rn(pcy, __fmul_rn(0.5f, ph)), __fadd_rn(pcx, __fmul_rn(0.5f, pw)),
