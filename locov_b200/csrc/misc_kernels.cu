@@ -699,23 +699,32 @@ __global__ void __launch_bounds__(128) skinny_grad_partial_kernel(const float *_
 #pragma unroll
     for (int j = 0; j < J; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (v0 < V) {
-        for (int r = r0; r < r1; ++r) {
-            float4 xv;
-            if (v0 + 3 < V) xv = __ldg(reinterpret_cast<const float4 *>(x + (int64_t)r * ld_x + v0));
-            else {
-                xv = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float *xr = x + (int64_t)r * ld_x + v0;
-                xv.x = xr[0];
-                if (v0 + 1 < V) xv.y = xr[1];
-                if (v0 + 2 < V) xv.z = xr[2];
-            }
+        auto load_x = [&](int r) -> float4 {
+            if (v0 + 3 < V) return __ldcs(reinterpret_cast<const float4 *>(x + (int64_t)r * ld_x + v0));
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float *xr = x + (int64_t)r * ld_x + v0;
+            xv.x = xr[0];
+            if (v0 + 1 < V) xv.y = xr[1];
+            if (v0 + 2 < V) xv.z = xr[2];
+            return xv;
+        };
+        auto accumulate = [&](int r, const float4 &xv) {
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const float g = __ldg(dy + (int64_t)r * ld_dy + j);           // warp-uniform address: one broadcast load
                 acc[j].x = fmaf(g, xv.x, acc[j].x); acc[j].y = fmaf(g, xv.y, acc[j].y);
                 acc[j].z = fmaf(g, xv.z, acc[j].z); acc[j].w = fmaf(g, xv.w, acc[j].w);
             }
+        };
+        int r = r0;
+        for (; r + 8 <= r1; r += 8) {                      // 8 independent 128-bit loads in flight per thread, rows added in order
+            float4 xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xv[u] = load_x(r + u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) accumulate(r + u, xv[u]);
         }
+        for (; r < r1; ++r) accumulate(r, load_x(r));
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             float *dst = part + ((int64_t)blockIdx.y * J + j) * V + v0;
@@ -726,23 +735,44 @@ __global__ void __launch_bounds__(128) skinny_grad_partial_kernel(const float *_
         }
     }
 }
+// partials [nchunk][J*V] -> dw: thread = (element, quarter of the chunks); the four quarter sums are combined in a fixed order.
+// Block 0 also forms the bias gradient (column sums of dy): warp = (column j, quarter of the rows), same fixed-order combination.
 __global__ void __launch_bounds__(256) skinny_grad_reduce_kernel(const float *__restrict__ part, int nchunk, int JV, float *__restrict__ dw,
                                                                  const float *__restrict__ dy, int64_t ld_dy, int R, int J, float *__restrict__ db) {
+    __shared__ float sm[4][64];
+    __shared__ float sb[32];
     pdl_trigger();
     pdl_wait();
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int idx = blockIdx.x * 64 + e;
+    float v = 0.f;
     if (idx < JV) {
-        float v = 0.f;
-        for (int c = 0; c < nchunk; ++c) v += part[(int64_t)c * JV + idx];
-        dw[idx] = v;
+        int c = q;
+        for (; c + 12 < nchunk; c += 16) {
+            const float a0 = part[(int64_t)c * JV + idx], a1 = part[(int64_t)(c + 4) * JV + idx], a2 = part[(int64_t)(c + 8) * JV + idx],
+                        a3 = part[(int64_t)(c + 12) * JV + idx];
+            v += a0; v += a1; v += a2; v += a3;
+        }
+        for (; c < nchunk; c += 4) v += part[(int64_t)c * JV + idx];
     }
-    if (db != nullptr && blockIdx.x == 0) {           // bias gradient: column sums of dy, warp j sums column j in a fixed order
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-        if (w < J) {
-            float v = 0.f;
-            for (int r = lane; r < R; r += 32) v += dy[(int64_t)r * ld_dy + w];
-            v = warp_sum(v);
-            if (lane == 0) db[w] = v;
+    sm[q][e] = v;
+    __syncthreads();
+    if (q == 0 && idx < JV) dw[idx] = (sm[0][e] + sm[1][e]) + (sm[2][e] + sm[3][e]);
+    if (db != nullptr && blockIdx.x == 0) {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;           // 8 warps
+        for (int j0 = 0; j0 < J; j0 += 2) {                                // two columns per round, four row quarters each
+            const int j = j0 + (w >> 2), rq = w & 3;
+            float t = 0.f;
+            if (j < J)
+                for (int r = rq * 32 + lane; r < R; r += 128) t += dy[(int64_t)r * ld_dy + j];
+            t = warp_sum(t);
+            if (lane == 0) sb[w] = t;
+            __syncthreads();
+            if (threadIdx.x < 2 && j0 + (int)threadIdx.x < J) {
+                const int b = threadIdx.x * 4;
+                db[j0 + threadIdx.x] = (sb[b] + sb[b + 1]) + (sb[b + 2] + sb[b + 3]);
+            }
+            __syncthreads();
         }
     }
 }
@@ -1121,12 +1151,16 @@ int loco_box_reg_loss(const float *deltas, int64_t ld_deltas, const float *propo
     return LOCO_OK;
 }
 
-static int skinny_chunks(int R) {
-    int c = (R + 255) / 256;
-    if (c > 64) c = 64;
+// row chunks: enough blocks for ~4 per SM (the kernel streams x once and has to keep the HBM pipe full), at least 16 rows each
+static int skinny_chunks(int R, int V) {
+    const int bx = (V + 511) / 512;
+    int c = (4 * 148 + bx - 1) / bx;
+    const int cap = (R + 15) / 16;
+    if (c > cap) c = cap;
+    if (c > 256) c = 256;
     return c < 1 ? 1 : c;
 }
-int64_t loco_skinny_grad_workspace_bytes(int R, int J, int V) { return (int64_t)skinny_chunks(R) * J * V * (int64_t)sizeof(float); }
+int64_t loco_skinny_grad_workspace_bytes(int R, int J, int V) { return (int64_t)skinny_chunks(R, V) * J * V * (int64_t)sizeof(float); }
 
 int loco_skinny_grad(const float *dy, int64_t ld_dy, const float *x, int64_t ld_x, int R, int J, int V, float *dw, float *db, void *workspace,
                      void *stream) {
@@ -1140,7 +1174,7 @@ int loco_skinny_grad(const float *dy, int64_t ld_dy, const float *x, int64_t ld_
     }
     LOCO_REQUIRE(dy && x && workspace, LOCO_E_BADARG, "skinny_grad: null pointer");
     LOCO_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && ld_x % 4 == 0, LOCO_E_ALIGN, "skinny_grad: x must be 16-byte aligned with ld_x %% 4 == 0");
-    const int nchunk = skinny_chunks(R), rpc = (R + nchunk - 1) / nchunk;
+    const int nchunk = skinny_chunks(R, V), rpc = (R + nchunk - 1) / nchunk;
     dim3 grid((unsigned)((V + 511) / 512), (unsigned)nchunk);
     float *part = static_cast<float *>(workspace);
 #define LOCO_SKINNY(JJ) LOCO_CUDA(launch_kernel(skinny_grad_partial_kernel<JJ>, grid, dim3(128), 0, st, 1, dy, ld_dy, x, ld_x, R, V, rpc, part))
@@ -1156,7 +1190,7 @@ int loco_skinny_grad(const float *dy, int64_t ld_dy, const float *x, int64_t ld_
     }
 #undef LOCO_SKINNY
     count_launch();
-    LOCO_CUDA(launch_kernel(skinny_grad_reduce_kernel, dim3((unsigned)((J * V + 255) / 256)), dim3(256), 0, st, 1, static_cast<const float *>(part), nchunk,
+    LOCO_CUDA(launch_kernel(skinny_grad_reduce_kernel, dim3((unsigned)((J * V + 63) / 64)), dim3(256), 0, st, 1, static_cast<const float *>(part), nchunk,
                             J * V, dw, dy, ld_dy, R, J, db));
     count_launch();
     LOCO_CUDA(cudaGetLastError());

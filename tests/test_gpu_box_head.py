@@ -190,9 +190,16 @@ def test_eval_matches_reference_golden(cuda_device, name, precision):
         n_ref = len(z[f"inst{i}_scores"])
         assert abs(len(r) - n_ref) <= (0 if precision == "fp32" else max(2, n_ref // 20))
         if precision == "fp32" and n_ref:
-            assert relerr(r.scores.cpu(), z[f"inst{i}_scores"]) < 10 * ptol
-            assert (r.pred_classes.cpu().numpy() == z[f"inst{i}_classes"]).mean() > 0.97
-            assert relerr(r.pred_boxes.tensor.cpu(), z[f"inst{i}_boxes"]) < 1e-3
+            # detections as a set of (class, kept RoI): near-equal scores may swap places in the list (our scores differ from the
+            # reference's in the 5th digit) and a swap at the top-k boundary exchanges one member
+            assert relerr(r.scores.cpu(), z[f"inst{i}_scores"]) < 10 * ptol                    # (both lists are sorted by score)
+            ours = {(int(a), int(b)): j for j, (a, b) in enumerate(zip(r.pred_classes.cpu(), kept[i].cpu()))}
+            ref = {(int(a), int(b)): j for j, (a, b) in enumerate(zip(z[f"inst{i}_classes"], z[f"inst{i}_kept"]))}
+            both = sorted(set(ours) & set(ref))
+            assert len(both) >= 0.97 * n_ref
+            jo, jr = [ours[k] for k in both], [ref[k] for k in both]
+            assert relerr(r.pred_boxes.tensor.cpu()[jo], z[f"inst{i}_boxes"][jr]) < 1e-3
+            assert relerr(r.scores.cpu()[jo], z[f"inst{i}_scores"][jr]) < 10 * ptol
     if "K2" in c:
         bp.set_class_embeddings(d["cls2"])
         with torch.no_grad():
