@@ -958,6 +958,7 @@ __global__ void __launch_bounds__(256) pair_distill_grad_kernel(const float *__r
 // The reference copies each logged tensor to the host and issues four scalar reductions per call (seven calls per LSM forward); here the
 // four numbers of one tensor come from ONE launch and stay on the device until somebody reads log_info.  Partial (min, max, sum, sum of
 // squares) per block in double precision, combined in block order by the last block; std is the unbiased one of torch.Tensor.std().
+constexpr int TS_MAX_BLOCKS = 1024;
 __global__ void __launch_bounds__(256) tensor_stats_kernel(const float *__restrict__ x, int64_t n, float *__restrict__ out4, double *__restrict__ ws) {
     pdl_trigger();
     pdl_wait();
@@ -965,36 +966,63 @@ __global__ void __launch_bounds__(256) tensor_stats_kernel(const float *__restri
     __shared__ int s_last;
     float mn = FLT_MAX, mx = -FLT_MAX;
     double s1 = 0.0, s2 = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float v = x[i];
-        mn = fminf(mn, v); mx = fmaxf(mx, v);
-        s1 += (double)v; s2 += (double)v * (double)v;
+    auto take = [&](float v) { mn = fminf(mn, v); mx = fmaxf(mx, v); s1 += (double)v; s2 += (double)v * (double)v; };
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {                  // 128-bit loads, two in flight per thread
+        const int64_t n4 = n >> 2;
+        const float4 *x4 = reinterpret_cast<const float4 *>(x);
+        int64_t i = tid;
+        for (; i + nthr < n4; i += 2 * nthr) {
+            const float4 a = __ldcs(x4 + i), b = __ldcs(x4 + i + nthr);
+            take(a.x); take(a.y); take(a.z); take(a.w); take(b.x); take(b.y); take(b.z); take(b.w);
+        }
+        for (; i < n4; i += nthr) {
+            const float4 a = __ldcs(x4 + i);
+            take(a.x); take(a.y); take(a.z); take(a.w);
+        }
+        for (int64_t j = (n4 << 2) + tid; j < n; j += nthr) take(x[j]);
+    } else {
+        for (int64_t i = tid; i < n; i += nthr) take(x[i]);
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    auto warp_combine = [&]() {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (lane == 0) { sd[0][w] = mn; sd[1][w] = mx; sd[2][w] = s1; sd[3][w] = s2; }
-    __syncthreads();
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+    };
+    auto block_combine = [&](double &a, double &b, double &c, double &d) {      // fixed order: shuffle tree, then warps 0..7 in order
+        warp_combine();
+        if (lane == 0) { sd[0][w] = mn; sd[1][w] = mx; sd[2][w] = s1; sd[3][w] = s2; }
+        __syncthreads();
+        a = sd[0][0]; b = sd[1][0]; c = 0.0; d = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { a = fmin(a, sd[0][k]); b = fmax(b, sd[1][k]); c += sd[2][k]; d += sd[3][k]; }
+    };
+    double a, b, c, d;
+    block_combine(a, b, c, d);
     double *parts = ws + 2;                    // [grid][4]
     if (threadIdx.x == 0) {
-        double a = sd[0][0], b = sd[1][0], c = 0.0, d = 0.0;
-        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { a = fmin(a, sd[0][k]); b = fmax(b, sd[1][k]); c += sd[2][k]; d += sd[3][k]; }
         parts[4 * blockIdx.x] = a; parts[4 * blockIdx.x + 1] = b; parts[4 * blockIdx.x + 2] = c; parts[4 * blockIdx.x + 3] = d;
         __threadfence();
         unsigned int *ticket = reinterpret_cast<unsigned int *>(ws);
         s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
-        if (s_last) {
-            __threadfence();
-            double a2 = parts[0], b2 = parts[1], c2 = 0.0, d2 = 0.0;
-            for (int k = 0; k < (int)gridDim.x; ++k) { a2 = fmin(a2, parts[4 * k]); b2 = fmax(b2, parts[4 * k + 1]); c2 += parts[4 * k + 2]; d2 += parts[4 * k + 3]; }
-            const double mean = c2 / (double)n;
-            const double var = n > 1 ? fmax(d2 - (double)n * mean * mean, 0.0) / (double)(n - 1) : 0.0;
-            out4[0] = (float)a2; out4[1] = (float)b2; out4[2] = (float)mean; out4[3] = (float)sqrt(var);
-            *ticket = 0;
-        }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // the last block combines the per-block partials: thread t takes blocks t, t + 256, ... in order, then the same fixed-order tree
+    mn = FLT_MAX; mx = -FLT_MAX; s1 = 0.0; s2 = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) {
+        mn = fminf(mn, (float)parts[4 * k]); mx = fmaxf(mx, (float)parts[4 * k + 1]); s1 += parts[4 * k + 2]; s2 += parts[4 * k + 3];
+    }
+    __syncthreads();                           // (sd is reused)
+    block_combine(a, b, c, d);
+    if (threadIdx.x == 0) {
+        const double mean = c / (double)n;
+        const double var = n > 1 ? fmax(d - (double)n * mean * mean, 0.0) / (double)(n - 1) : 0.0;
+        out4[0] = (float)a; out4[1] = (float)b; out4[2] = (float)mean; out4[3] = (float)sqrt(var);
+        *reinterpret_cast<unsigned int *>(ws) = 0;
     }
 }
 
@@ -1274,12 +1302,13 @@ int loco_pair_distill(const float *trans, int64_t ld_trans, const float *w2r, in
     return LOCO_OK;
 }
 
-int64_t loco_tensor_stats_workspace_bytes(void) { return (int64_t)(2 + 4 * 256) * (int64_t)sizeof(double); }
+int64_t loco_tensor_stats_workspace_bytes(void) { return (int64_t)(2 + 4 * TS_MAX_BLOCKS) * (int64_t)sizeof(double); }
 
 int loco_tensor_stats(const float *x, int64_t n, float *out4, void *workspace, void *stream) {
     LOCO_REQUIRE(n >= 1 && x && out4 && workspace, LOCO_E_BADARG, "tensor_stats: bad arguments n=%lld", (long long)n);
     LOCO_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, LOCO_E_ALIGN, "tensor_stats: workspace must be 8-byte aligned");
-    int blocks = (int)((n + 1023) / 1024 < 256 ? (n + 1023) / 1024 : 256);
+    const int64_t cap = std::min<int64_t>(TS_MAX_BLOCKS, (int64_t)current_device_sm_count() * 4);
+    int blocks = (int)std::min<int64_t>((n + 2047) / 2048, cap);
     if (blocks < 1) blocks = 1;
     LOCO_CUDA(launch_kernel(tensor_stats_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, x, n, out4, static_cast<double *>(workspace)));
     count_launch();
