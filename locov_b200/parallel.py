@@ -211,6 +211,7 @@ class _SymmState:
         self.buf.zero_()              # (the pad columns [d, ld) of the operand rows stay zero: whole rows are re-written, pads included)
         self.flags.zero_()
         self.ticket = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.side = torch.cuda.Stream(dev)       # exchange A runs beside the projection GEMM
         torch.cuda.synchronize(dev)
         self.h.barrier(channel=0)     # one-off: every rank has zeroed its flags before any exchange kernel runs
 
@@ -278,10 +279,28 @@ class _ShardedLsmSymm(Function):
         segs = [("hi", cap_op.hi, st.ld * 2, row0 * st.ld * 2), ("maskA", cm, bl * t * 4, row0 * 4)]
         if acc:
             segs.append(("lo", cap_op.lo, st.ld * 2, row0 * st.ld * 2))
-        # 2. the projection of the local regions needs no captions: it runs between the signal and the wait of the exchange
-        st.exchange(segs, 0, ops.PEER_STORE)            # stores only: they drain over NVLink while the projection GEMM runs
-        emb_op = LF.project_regions(feats.reshape(bi * rg, v), w, b, d, acc)
-        st.exchange([], 0, ops.PEER_SIGNAL | ops.PEER_WAIT)     # every rank's slices have landed here
+        # 2. the projection of the local regions needs no captions.  Exchange A (stores + fence + signal) runs on a side stream BESIDE
+        #    the projection GEMM (130 of the 148 SMs), so the NVLink round trips and the system-scope fence are off the critical path;
+        #    after the GEMM the main stream only polls flags that have long been set.  (LOCOV_B200_SYMM_SIDE=0: stores, GEMM, then
+        #    signal + wait in stream order — the round-2a arrangement, kept for A/B measurements.)
+        if os.environ.get("LOCOV_B200_SYMM_SIDE", "1") != "0":
+            cur = torch.cuda.current_stream(dev)
+            fork, join = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(cur)
+            st.side.wait_event(fork)
+            with torch.cuda.stream(st.side):
+                st.exchange(segs, 0, ops.PEER_STORE | ops.PEER_SIGNAL)
+                join.record(st.side)
+            for t_ in (cap_op.hi, cap_op.lo, cm):
+                if t_ is not None:
+                    t_.record_stream(st.side)
+            emb_op = LF.project_regions(feats.reshape(bi * rg, v), w, b, d, acc)
+            cur.wait_event(join)
+            st.exchange([], 0, ops.PEER_WAIT)           # every rank's slices have landed here
+        else:
+            st.exchange(segs, 0, ops.PEER_STORE)
+            emb_op = LF.project_regions(feats.reshape(bi * rg, v), w, b, d, acc)
+            st.exchange([], 0, ops.PEER_SIGNAL | ops.PEER_WAIT)
         cap_all = ops.Bf16Operand(st.hi, st.lo if acc else None, st.b * t, d)
         stack = LF.new_pair_stack(st.b, bi, dev, want_w2r and want_r2w)
         ops.lsm_pair(cap_all, st.maskA, emb_op, reg_mask, inv_temp, alignment, want_w2r, want_r2w, stack[0], stack[1])
