@@ -261,7 +261,8 @@ int loco_lsm_prep(const float *cap, int64_t rows, int64_t cols, int64_t cap_ld, 
  * Either output may be NULL (ALIGN_WORDS_TO_REGIONS / ALIGN_REGIONS_TO_WORDS off).
  * The [B^2,T,Rg] similarity tensor never leaves the SM (TMEM -> registers -> two scalars per pair).
  * Limits: T <= 128, Rg <= 256 (else LOCO_E_UNSUPPORTED).
- * workspace: loco_lsm_pair_workspace_bytes(Bc,T,Bi,Rg) bytes of scratch, 16-byte aligned. */
+ * workspace: loco_lsm_pair_workspace_bytes(Bc,T,Bi,Rg) bytes, 16-byte aligned.  RESERVED: the query returns 16 today (every reduction
+ *   of the kernel happens on-chip); callers pass a valid pointer so that a later revision may use scratch without an ABI change. */
 int64_t loco_lsm_pair_workspace_bytes(int Bc, int T, int Bi, int Rg);
 int loco_lsm_pair_fwd(const uint16_t *cap_hi, const uint16_t *cap_lo, int64_t ldcap,
                       const float *cap_mask, const uint16_t *emb_hi, const uint16_t *emb_lo,

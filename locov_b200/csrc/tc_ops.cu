@@ -649,12 +649,8 @@ struct LsmFwdParams {
 };
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-#ifndef LOCOV_EXP
-#define LOCOV_EXP 0
-#endif
-// developer experiments (build with LOCOV_B200_NVCC_EXTRA=-DLOCOV_EXP=n): results are garbage, timings show what a piece costs
-__device__ __forceinline__ float exp_col(float x) { return (LOCOV_EXP == 1 || LOCOV_EXP == 3 || LOCOV_EXP == 6) ? x : ex2_ftz(x); }     // no MUFU in the column pass
-__device__ __forceinline__ float exp_row(float x) { return (LOCOV_EXP == 2 || LOCOV_EXP == 3 || LOCOV_EXP == 6) ? x : ex2_ftz(x); }     // no MUFU in the row pass
+__device__ __forceinline__ float exp_col(float x) { return ex2_ftz(x); }
+__device__ __forceinline__ float exp_row(float x) { return ex2_ftz(x); }
 
 // LDT > 0: the parked sub-tile's row stride is this compile-time constant (every transposed store is one STS with an immediate
 // offset); LDT == 0: run-time stride p.ldt (caption groups whose padded word count exceeds the constant).
@@ -821,7 +817,7 @@ struct EpiLsmFwd {
                     if (k + 1 >= valid) v[k + 1] = 0u;
                 }
                 const float2 raw = f2(__uint_as_float(v[k]), __uint_as_float(v[k + 1]));
-                if (store && LOCOV_EXP != 4 && LOCOV_EXP != 6) {
+                if (store) {
                     if (!TAIL || k < valid) pp[(size_t)k * ldt] = raw.x;
                     if (!TAIL || k + 1 < valid) pp[(size_t)(k + 1) * ldt] = raw.y;
                 }
