@@ -75,6 +75,25 @@ int make_tmap_f32_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t
     return make_tmap_2d(map, base, rows, cols, ld_elems, box_rows, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4);
 }
 
+// bf16 row-major OUTPUT of a GEMM epilogue as 32 x 32 element boxes (64-byte rows) with the 64-byte swizzle: the epilogue warp owning
+// 32 accumulator rows stages a 32-column block in shared memory (lane = row, 16-byte chunk c of row r at chunk position
+// c ^ ((r >> 1) & 3): the 32 lanes of a store instruction cover all 32 banks) and one thread hands it to the copy engine.
+int make_tmap_bf16_out(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld_elems) {
+    encode_tiled_fn fn = get_encode_fn();
+    LOCO_REQUIRE(fn != nullptr, LOCO_E_DRIVER, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    LOCO_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld_elems * 2) % 16 == 0 && rows >= 1 && cols >= 1, LOCO_E_ALIGN,
+                 "bf16 GEMM output is not addressable by a TMA store (base %p, ld %llu)", base, (unsigned long long)ld_elems);
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LOCO_REQUIRE(r == CUDA_SUCCESS, LOCO_E_DRIVER, "cuTensorMapEncodeTiled (bf16 output) failed with CUresult %d (rows=%llu cols=%llu ld=%llu)", (int)r,
+                 (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems);
+    return LOCO_OK;
+}
+
 // Developer probe: with LOCOV_B200_TIMELINE=1 every tensor-core kernel writes up to 16 globaltimer stamps per CTA (entry, setup
 // done, first stage landed, last MMA issued, last accumulator complete, epilogue done, exit) into this buffer; the most
 // recent launch overwrites it.  Read back with loco_debug_timeline_read().

@@ -44,6 +44,7 @@ int make_tmap_f32_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t
 // 4-D store map of a pooled [R, C, PH*PW] fp32 output seen as [R][C/4][4][PH*PW]: box = {PH*PW, 1, 32, 1}, i.e. the 32 dense
 // tile rows that hold channels 4*l + j (l = 0..31) of one 128-channel slab (roi_align.cu); stores past C/4 are clipped.
 int make_tmap_roi_out(CUtensorMap *map, const float *out, uint64_t R, uint64_t C, uint64_t PHW);
+int make_tmap_bf16_out(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld_elems);
 int current_device_sm_count();
 void count_launch(int n = 1);   // bumps the library-wide kernel-launch counter (loco_launch_count)
 

@@ -29,6 +29,7 @@ constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
 
 struct TcMaps {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    CUtensorMap o_hi, o_lo;      // output maps of policies that leave through TMA stores (Epi::kWantsMaps), unused otherwise
 };
 
 struct TcCore {
@@ -224,6 +225,7 @@ __device__ __forceinline__ void mma_issue_loop(const TcCore &core, unsigned char
 //   __device__ void finish(const Params&, const TcCore&, int cta, ...same...);
 //   static constexpr bool kHasPrefetch;  true: prefetch(const Params&, const TcCore&, int cta, int chunk, row, lane, q, smem) runs before the
 //                                        wait for the chunk's accumulator (masks / per-tile inputs load under the MMAs)
+//   static constexpr bool kWantsMaps;    true: the policy stores through TMA: members map_hi / map_lo (const CUtensorMap *) are set to TcMaps::o_hi / o_lo
 //   static constexpr bool kSelfRelease;  true: chunk() itself arrives on the accumulator-empty barrier (members release_bar / release_local)
 // PAIR = true is the CTA-pair (cta_group::2) instantiation: a kernel containing cta_group::2 instructions can only be
 // launched as a cluster of two, so it is a separate instantiation from the single-CTA / multicast-cluster one.
@@ -360,6 +362,7 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
         const int q = warp & 3;            // TMEM lane quarter accessible to this warp
         const int row = q * 32 + lane;     // accumulator row owned by this thread
         Epi epi;
+        if constexpr (Epi::kWantsMaps) { epi.map_hi = &maps.o_hi; epi.map_lo = &maps.o_lo; }
         epi.begin(ep, core, cta, row, lane, q, epi_smem);
         for (int ch = 0; ch < nchunks; ++ch) {
             const int acc = ch % core.acc_stages;

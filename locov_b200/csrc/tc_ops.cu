@@ -20,7 +20,9 @@ constexpr float LSM_PAD = -3.0e38f;    // padding columns of a tile: exp2(LSM_PA
 struct EpiLinear {
     static constexpr int kEpiWarps = 4;
     static constexpr int kMinBlocks = 1;
-    static constexpr bool kHasPrefetch = false, kSelfRelease = false;
+    static constexpr bool kHasPrefetch = false, kSelfRelease = false, kWantsMaps = true;
+    static constexpr int kStageBytes = 4 * 2 * 2048 + 512;       // tma_out: per epilogue warp one 32 x 32 bf16 block for hi and one for lo (+ alignment)
+    const CUtensorMap *map_hi, *map_lo;
     struct Params {
         const float *bias;
         float *out_f32;
@@ -31,6 +33,7 @@ struct EpiLinear {
         int M, N, tiles_n;
         int grid;        // CTAs launched: persistent tile striding (tile = cta + chunk * grid)
         int vec_f32;     // out_f32 rows are 16-byte aligned: 128-bit stores
+        int tma_out;     // bf16 outputs leave through shared memory + TMA tensor stores (TcMaps::o_hi / o_lo)
     };
     static __device__ __forceinline__ void coords(const Params &p, const TcCore &core, int cta, int ch, int &row_a, int &row_b) {
         const int tile = cta + ch * p.grid;
@@ -42,8 +45,7 @@ struct EpiLinear {
     // 64 of bf16) in the row-major output, written with 128-bit stores straight from registers — whole 32-byte
     // sectors per thread, no shared-memory transpose, ~12 instructions per 32 outputs.
     __device__ __forceinline__ void chunk(const Params &p, const TcCore &core, int cta, int ch, uint32_t taddr, int row, int lane,
-                                          int q, unsigned char *) {
-        (void)q;
+                                          int q, unsigned char *smem) {
         const int tile = cta + ch * p.grid;
         const int grow = (tile / p.tiles_n) * TC_BLOCK_M + row;
         const int n0 = (tile % p.tiles_n) * core.block_n;
@@ -59,8 +61,7 @@ struct EpiLinear {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
             }
-            if (!row_ok) continue;             // (after the warp-collective loads / shuffles)
-            if (p.out_f32 != nullptr) {
+            if (p.out_f32 != nullptr && row_ok) {
                 float *dst = p.out_f32 + (int64_t)grow * p.ld_f32 + gc0;
                 if (p.vec_f32 && cols_valid == 32) {
 #pragma unroll
@@ -83,6 +84,36 @@ struct EpiLinear {
                     if (want_lo)
                         lp[j] = pack_bf16x2_rn(v[2 * j] - __uint_as_float(hp[j] << 16), v[2 * j + 1] - __uint_as_float(hp[j] & 0xFFFF0000u));
                 }
+                if (p.tma_out && core.block_n - c0 >= 32) {     // (a narrower last block of the tile would spill into the neighbouring tile's columns: direct stores)
+                    // Through the copy engine: the direct stores below touch 32 different 128-byte lines per instruction (lane = row),
+                    // ~32 LSU cycles each; here the warp's 32 x 32 block is staged with conflict-free 16-byte shared stores (64-byte
+                    // swizzle of the output map) and one thread issues a tensor store per matrix.  Rows past M and columns past
+                    // n_bf16 are clipped by the map.  One buffer per warp: the wait for the previous block's read sits behind
+                    // this block's TMEM load and conversion.
+                    unsigned char *stage = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem) + 511) & ~(uintptr_t)511) + q * 4096;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                    const int sw = (lane >> 1) & 3;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int pos = (c ^ sw) * 16 + lane * 64;
+                        *reinterpret_cast<uint4 *>(stage + pos) = make_uint4(hp[4 * c], hp[4 * c + 1], hp[4 * c + 2], hp[4 * c + 3]);
+                        if (want_lo) *reinterpret_cast<uint4 *>(stage + 2048 + pos) = make_uint4(lp[4 * c], lp[4 * c + 1], lp[4 * c + 2], lp[4 * c + 3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int r0 = (tile / p.tiles_n) * TC_BLOCK_M + q * 32;
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(reinterpret_cast<uint64_t>(map_hi)), "r"(smem_u32(stage)), "r"(gc0), "r"(r0) : "memory");
+                        if (want_lo)
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"(reinterpret_cast<uint64_t>(map_lo)), "r"(smem_u32(stage + 2048)), "r"(gc0), "r"(r0) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    continue;
+                }
+                if (!row_ok) continue;
                 uint16_t *dh = p.out_hi + (int64_t)grow * p.ld_bf16 + gc0;     // 64-byte aligned: base 16 B, ld % 8, gc0 % 32
                 uint16_t *dl = p.out_lo ? p.out_lo + (int64_t)grow * p.ld_bf16 + gc0 : nullptr;
                 if (cb == 32) {
@@ -102,7 +133,9 @@ struct EpiLinear {
             }
         }
     }
-    __device__ __forceinline__ void finish(const Params &, const TcCore &, int, int, int, int, unsigned char *) {}
+    __device__ __forceinline__ void finish(const Params &p, const TcCore &, int, int, int lane, int, unsigned char *) {
+        if (p.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the staging buffers die with the CTA
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -111,7 +144,7 @@ struct EpiLinear {
 struct EpiScore {
     static constexpr int kEpiWarps = 4;
     static constexpr int kMinBlocks = 1;
-    static constexpr bool kHasPrefetch = false, kSelfRelease = false;
+    static constexpr bool kHasPrefetch = false, kSelfRelease = false, kWantsMaps = false;
     struct Params {
         const float *bias;
         float *logits;
@@ -337,7 +370,7 @@ template <bool BWD>
 struct EpiLsm {
     static constexpr int kEpiWarps = 8;
     static constexpr int kMinBlocks = 2;      // two CTAs per SM: one tile's epilogue overlaps the other's loads / MMAs
-    static constexpr bool kHasPrefetch = false, kSelfRelease = false;
+    static constexpr bool kHasPrefetch = false, kSelfRelease = false, kWantsMaps = false;
     static constexpr int kThreads = 32 * kEpiWarps;
     typedef LsmParams Params;
     static __device__ __forceinline__ void coords(const Params &p, const TcCore &, int cta, int, int &row_a, int &row_b) {
@@ -665,7 +698,7 @@ template <int LDT>
 struct EpiLsmFwd {
     static constexpr int kEpiWarps = 16;
     static constexpr int kMinBlocks = 1;
-    static constexpr bool kHasPrefetch = true, kSelfRelease = true;
+    static constexpr bool kHasPrefetch = true, kSelfRelease = true, kWantsMaps = false;
     static constexpr int kCbt = 192;       // >= per_tile * Tp (per_tile <= 16, per_tile * T <= 128, Tp <= T + 3)
     typedef LsmFwdParams Params;
     uint32_t release_bar;        // set by the core: shared::cluster address of the leader's accumulator-empty barrier
@@ -1172,11 +1205,20 @@ static int linear_launch(const void *A_hi, const void *A_lo, int64_t lda, const 
     }
     p.grid = grid;
     core.single_wave = grid <= sms ? 1 : 0;
-    const size_t smem = tc_finalize(core, K, A_lo ? 3 : 1, chunks, 0);
+    // bf16 outputs through TMA stores when the grid is a single wave (nothing else on the SM hides the epilogue, and the whole shared
+    // memory is this CTA's); LOCOV_B200_EPI_TMA=0 keeps the direct stores for A/B measurements
+    static const bool tma_allowed = []() { const char *e = getenv("LOCOV_B200_EPI_TMA"); return !(e != nullptr && e[0] == '0'); }();
+    p.tma_out = (out_hi != nullptr && core.single_wave && tma_allowed) ? 1 : 0;
+    const size_t smem = tc_finalize(core, K, A_lo ? 3 : 1, chunks, p.tma_out ? EpiLinear::kStageBytes : 0);
     TcMaps maps;
+    memset(&maps, 0, sizeof(maps));
     int rc = fill_maps(maps, static_cast<const uint16_t *>(A_hi), static_cast<const uint16_t *>(A_lo), M, lda, static_cast<const uint16_t *>(W_hi),
                        static_cast<const uint16_t *>(W_lo), N, ldw, K, core);
     if (rc != LOCO_OK) return rc;
+    if (p.tma_out) {
+        if ((rc = make_tmap_bf16_out(&maps.o_hi, out_hi, (uint64_t)M, (uint64_t)p.n_bf16, (uint64_t)ld_bf16)) != LOCO_OK) return rc;
+        if ((rc = make_tmap_bf16_out(&maps.o_lo, out_lo ? out_lo : out_hi, (uint64_t)M, (uint64_t)p.n_bf16, (uint64_t)ld_bf16)) != LOCO_OK) return rc;
+    }
     if (core.two_cta) return tc_launch<EpiLinear, true>(maps, core, p, grid, smem, static_cast<cudaStream_t>(stream));
     return tc_launch<EpiLinear>(maps, core, p, grid, smem, static_cast<cudaStream_t>(stream));
 }
