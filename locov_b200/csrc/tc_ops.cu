@@ -34,9 +34,19 @@ struct EpiLinear {
         int grid;        // CTAs launched: persistent tile striding (tile = cta + chunk * grid)
         int vec_f32;     // out_f32 rows are 16-byte aligned: 128-bit stores
         int tma_out;     // bf16 outputs leave through shared memory + TMA tensor stores (TcMaps::o_hi / o_lo)
+        int pair_units;  // > 0: persistent CTA pairs — pair u of `pair_units` owns the 256-row tiles u, u + pair_units, ... of the
+                         // (row pair, column) grid; `cta` is the virtual index of this CTA's 128-row tile of the first one
     };
+    // virtual 128-row tile (row tile * tiles_n + column tile) of this CTA's chunk `ch`
+    static __device__ __forceinline__ int tile_of(const Params &p, int cta, int ch) {
+        if (p.pair_units == 0) return cta + ch * p.grid;
+        const int tm0 = cta / p.tiles_n, tn0 = cta - tm0 * p.tiles_n;
+        const int u = (tm0 >> 1) * p.tiles_n + tn0 + ch * p.pair_units;
+        const int um = u / p.tiles_n;
+        return (2 * um + (tm0 & 1)) * p.tiles_n + (u - um * p.tiles_n);
+    }
     static __device__ __forceinline__ void coords(const Params &p, const TcCore &core, int cta, int ch, int &row_a, int &row_b) {
-        const int tile = cta + ch * p.grid;
+        const int tile = tile_of(p, cta, ch);
         row_a = (tile / p.tiles_n) * TC_BLOCK_M;
         row_b = (tile % p.tiles_n) * core.block_n;
     }
@@ -46,7 +56,7 @@ struct EpiLinear {
     // sectors per thread, no shared-memory transpose, ~12 instructions per 32 outputs.
     __device__ __forceinline__ void chunk(const Params &p, const TcCore &core, int cta, int ch, uint32_t taddr, int row, int lane,
                                           int q, unsigned char *smem) {
-        const int tile = cta + ch * p.grid;
+        const int tile = tile_of(p, cta, ch);
         const int grow = (tile / p.tiles_n) * TC_BLOCK_M + row;
         const int n0 = (tile % p.tiles_n) * core.block_n;
         const bool row_ok = grow < p.M;
@@ -1196,7 +1206,17 @@ static int linear_launch(const void *A_hi, const void *A_lo, int64_t lda, const 
     p.tiles_n = core.clusters_n * core.cn;                                      // virtual (padded) tile grid
     const int tiles = tc_round_up((M + TC_BLOCK_M - 1) / TC_BLOCK_M, core.cm) * p.tiles_n;
     int grid = tiles, chunks = 1;
-    if (core.cm * core.cn == 1 && tiles > sms) {
+    p.pair_units = 0;
+    static const bool pair_persist = []() { const char *e = getenv("LOCOV_B200_PAIR_PERSIST"); return !(e != nullptr && e[0] == '0'); }();
+    if (core.two_cta && tiles / 2 > sms / 2 && pair_persist) {
+        // persistent CTA pairs: one pair per two SMs strides over the 256-row tiles; two TMEM accumulator stages let the epilogue of
+        // tile i overlap the MMAs of tile i + 1 (multi-wave pair grids paid set-up + epilogue per tile before)
+        const int pairs_total = tiles / 2, slots = sms / 2;
+        grid = 2 * slots;
+        chunks = (pairs_total + slots - 1) / slots;
+        core.total_tiles = pairs_total;
+        p.pair_units = slots;
+    } else if (core.cm * core.cn == 1 && tiles > sms) {
         // persistent: one CTA per SM strides over the tiles; two TMEM accumulator stages let the epilogue of tile i
         // overlap the MMAs of tile i + 1
         grid = sms;
