@@ -122,6 +122,20 @@ int loco_box_inference(const float *probs, int64_t ld_probs, const float *deltas
                        float *out_boxes, float *out_scores, int64_t *out_classes, int64_t *out_rows, int32_t *out_count,
                        void *workspace, void *stream);
 
+
+/* Multi-token class scoring: the reduction of ``GroundingModule.forward`` (reference ovr/modeling/roi_heads/box_emb_grounding_head.py:
+ * 130-221, reached from EmbeddingGroundingFastRCNNOutputLayers.forward_cls_prediction :419-427) after the token GEMM
+ * (token_score = Linear(D -> total tokens), :93).  Class k owns the token columns [seg_off[k], seg_off[k+1]) of raw [R, ld_raw]:
+ *   s = raw * inv_temp;  a = softmax over the class's tokens (alignment 0) or one-hot of the first maximum (alignment 1);
+ *   scores[r, k] = sum_t a_t * s_t     (= -global_dist of the reference; a class without tokens scores 0).
+ * att (optional, [R, ld_raw]): the attention weight of every token column (the reference's tok_attention, unpadded).
+ * loco_token_pool_bwd: draw[r, t] = dscores[r, k(t)] * d scores / d raw  (softmax Jacobian through the attention; hardmax: the
+ * direct term only, as autograd gives for argmax + one_hot). */
+int loco_token_pool_fwd(const float *raw, int64_t ld_raw, const int32_t *seg_off, int R, int K1, float inv_temp, int alignment,
+                        float *scores, int64_t ld_scores, float *att, void *stream);
+int loco_token_pool_bwd(const float *raw, int64_t ld_raw, const int32_t *seg_off, int R, int K1, float inv_temp, int alignment,
+                        const float *dscores, int64_t ld_dscores, float *draw, int64_t ld_draw, void *stream);
+
 /* Debug/parity entry: for every roi r, bin (ph,pw) and sample (iy,ix) with iy,ix < max_grid writes
  *   grid_hw [R,2] int32            (gh, gw) — the adaptive sample counts
  *   yx      [R,PH,PW,max_grid,max_grid,2] fp32   unclamped sample coordinate (y, x)

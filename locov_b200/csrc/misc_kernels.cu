@@ -954,6 +954,57 @@ __global__ void __launch_bounds__(256) pair_distill_grad_kernel(const float *__r
     }
 }
 
+// ---- multi-token class scoring: GroundingModule of box_emb_grounding_head.py:60-237 -------------------------------------
+// Every class k owns the token columns [seg[k], seg[k+1]) of the token-logit matrix raw = e . tokens^T (one GEMM on the tensor-core
+// core).  score[r, k] = sum_t a_t * s_t with s = raw / temperature and a = softmax over the class's tokens (hardmax: the first
+// maximum).  Thread = (RoI, class); a class has a handful of tokens, neighbouring threads read neighbouring segments.
+// The reference pads every class to max_tok and fills the padding with min(s) - 100 before the softmax: weight exp(-100 - ...) = 0.
+template <bool BWD>
+__global__ void __launch_bounds__(256) token_pool_kernel(const float *__restrict__ raw, int64_t ld_raw, const int32_t *__restrict__ seg, int R, int K1,
+                                                         float inv_temp, int hardmax, float *__restrict__ scores, int64_t ld_s,
+                                                         float *__restrict__ att, const float *__restrict__ dscores, int64_t ld_ds,
+                                                         float *__restrict__ draw, int64_t ld_draw) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t total = (int64_t)R * K1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / K1), k = (int)(i - (int64_t)r * K1);
+        const int t0 = seg[k], t1 = seg[k + 1];
+        const float *p = raw + (int64_t)r * ld_raw;
+        float m = -FLT_MAX;
+        int am = t0;
+        for (int t = t0; t < t1; ++t) {
+            const float v = p[t] * inv_temp;
+            if (v > m) { m = v; am = t; }
+        }
+        float sum = 0.f, acc = 0.f;
+        if (!hardmax)
+            for (int t = t0; t < t1; ++t) {
+                const float v = p[t] * inv_temp, e = expf(v - m);
+                sum += e;
+                acc = fmaf(e, v, acc);
+            }
+        const float score = t1 > t0 ? (hardmax ? m : acc / sum) : 0.f;
+        if (!BWD) {
+            scores[(int64_t)r * ld_s + k] = score;
+            if (att != nullptr)
+                for (int t = t0; t < t1; ++t) att[(int64_t)r * ld_raw + t] = hardmax ? (t == am ? 1.f : 0.f) : expf(p[t] * inv_temp - m) / sum;
+        } else {
+            // d score / d raw_t = a_t (1 + s_t - score) / temperature  (softmax);  1 / temperature at the maximum (hardmax)
+            const float g = dscores[(int64_t)r * ld_ds + k] * inv_temp;
+            for (int t = t0; t < t1; ++t) {
+                float d;
+                if (hardmax) d = t == am ? g : 0.f;
+                else {
+                    const float v = p[t] * inv_temp;
+                    d = g * (expf(v - m) / sum) * (1.f + v - score);
+                }
+                draw[(int64_t)r * ld_draw + t] = d;
+            }
+        }
+    }
+}
+
 // ---- device-side tensor statistics for LoggedModule.log (logged_module.py:8-18: min / max / mean / std of every logged tensor) ----------
 // The reference copies each logged tensor to the host and issues four scalar reductions per call (seven calls per LSM forward); here the
 // four numbers of one tensor come from ONE launch and stay on the device until somebody reads log_info.  Partial (min, max, sum, sum of
@@ -1298,6 +1349,34 @@ int loco_pair_distill(const float *trans, int64_t ld_trans, const float *w2r, in
                                 g_trans, g_w2r, g_r2w, static_cast<const float *>(workspace)));
         count_launch();
     }
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+int loco_token_pool_fwd(const float *raw, int64_t ld_raw, const int32_t *seg_off, int R, int K1, float inv_temp, int alignment, float *scores,
+                        int64_t ld_scores, float *att, void *stream) {
+    LOCO_REQUIRE(R >= 0 && K1 >= 1 && ld_scores >= K1 && inv_temp > 0.f && (alignment == 0 || alignment == 1), LOCO_E_BADARG,
+                 "token_pool_fwd: bad arguments R=%d K1=%d alignment=%d", R, K1, alignment);
+    if (R == 0) return LOCO_OK;
+    LOCO_REQUIRE(raw && seg_off && scores, LOCO_E_BADARG, "token_pool_fwd: null pointer");
+    const int blocks = (int)std::min<int64_t>(((int64_t)R * K1 + 255) / 256, (int64_t)current_device_sm_count() * 16);
+    LOCO_CUDA(launch_kernel(token_pool_kernel<false>, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, raw, ld_raw, seg_off, R, K1, inv_temp,
+                            alignment, scores, ld_scores, att, (const float *)nullptr, (int64_t)0, (float *)nullptr, (int64_t)0));
+    count_launch();
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+int loco_token_pool_bwd(const float *raw, int64_t ld_raw, const int32_t *seg_off, int R, int K1, float inv_temp, int alignment, const float *dscores,
+                        int64_t ld_dscores, float *draw, int64_t ld_draw, void *stream) {
+    LOCO_REQUIRE(R >= 0 && K1 >= 1 && ld_dscores >= K1 && inv_temp > 0.f && (alignment == 0 || alignment == 1), LOCO_E_BADARG,
+                 "token_pool_bwd: bad arguments R=%d K1=%d alignment=%d", R, K1, alignment);
+    if (R == 0) return LOCO_OK;
+    LOCO_REQUIRE(raw && seg_off && dscores && draw, LOCO_E_BADARG, "token_pool_bwd: null pointer");
+    const int blocks = (int)std::min<int64_t>(((int64_t)R * K1 + 255) / 256, (int64_t)current_device_sm_count() * 16);
+    LOCO_CUDA(launch_kernel(token_pool_kernel<true>, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, raw, ld_raw, seg_off, R, K1, inv_temp,
+                            alignment, (float *)nullptr, (int64_t)0, (float *)nullptr, dscores, ld_dscores, draw, ld_draw));
+    count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;
 }

@@ -104,6 +104,31 @@ def roi_align(feat, rois, output_size, spatial_scale, sampling_ratio=0, aligned=
                            bool(channels_last), out_dtype)
 
 
+class _TokenPool(Function):
+    @staticmethod
+    def forward(ctx, raw, seg_off, inv_temp, hardmax):
+        scores, _ = ops.token_pool(raw, seg_off, inv_temp, hardmax)
+        ctx.save_for_backward(raw, seg_off)
+        ctx.meta = (inv_temp, hardmax)
+        return scores
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dscores):
+        raw, seg_off = ctx.saved_tensors
+        inv_temp, hardmax = ctx.meta
+        return ops.token_pool_backward(raw, seg_off, inv_temp, hardmax, dscores), None, None, None
+
+
+def grounding_scores(e, w_tok, seg_off, temperature: float, alignment: str = "softmax", precision: str = "fp32"):
+    """Multi-token class scores (reference box_emb_grounding_head.py:89-221): token logits e . w_tok^T on the tensor-core GEMM core,
+    then the per-class attention pooling; differentiable w.r.t. e."""
+    if alignment not in ("softmax", "hardmax"):
+        raise LocoError(f"grounding_scores: alignment {alignment!r}")
+    raw = linear(e, w_tok, None, precision)
+    return _TokenPool.apply(raw.contiguous(), seg_off, 1.0 / float(temperature), alignment == "hardmax")
+
+
 class _SpatialMean(Function):
     last_operand = None          # forward's bf16 operand, handed to spatial_mean() below (a Function returns tensors only)
 

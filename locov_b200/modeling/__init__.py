@@ -1,5 +1,6 @@
 """Host-side mirror of the reference's ovr/modeling interfaces for the region-text path."""
 from .box_emb_head import Box2BoxTransform, EmbeddingFastRCNNOutputLayers, build_box_predictor  # noqa: F401
+from .box_emb_grounding_head import EmbeddingGroundingFastRCNNOutputLayers, GroundingModule  # noqa: F401
 from .config import CfgNode, get_cfg  # noqa: F401
 from .distill import MultiDistillLoss, MultiDistillLossJS, MultiDistillLossL2, build_distill_loss  # noqa: F401
 from .grounding_head import GroundingHead, build_grounding_head  # noqa: F401

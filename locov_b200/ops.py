@@ -592,6 +592,33 @@ def pair_distill(trans: torch.Tensor, w2r: torch.Tensor, r2w: torch.Tensor, temp
     return loss, gt, gw, gr
 
 
+def token_pool(raw: torch.Tensor, seg_off: torch.Tensor, inv_temp: float, hardmax: bool, want_attention: bool = False):
+    """Multi-token class scoring reduction (box_emb_grounding_head.py:130-221): raw [R, Ttot] token logits, seg_off int32 [K1+1]
+    (device) -> (scores [R, K1], attention [R, Ttot] or None)."""
+    _need_cuda(raw, seg_off)
+    if raw.dtype != torch.float32 or raw.dim() != 2 or raw.stride(1) != 1 or seg_off.dtype != torch.int32:
+        raise LocoError("token_pool: expects fp32 [R, Ttot] logits with unit column stride and int32 segment offsets")
+    r, k1 = raw.shape[0], seg_off.numel() - 1
+    scores = torch.empty((r, k1), dtype=torch.float32, device=raw.device)
+    att = torch.zeros((r, raw.stride(0) if r else raw.shape[1]), dtype=torch.float32, device=raw.device)[:, :raw.shape[1]] if want_attention else None
+    _lib.check(_lib.load().loco_token_pool_fwd(_p(raw), raw.stride(0) if r else raw.shape[1], _p(seg_off), r, k1, float(inv_temp), int(bool(hardmax)),
+                                               _p(scores), k1, _p(att), _stream(raw)), "loco_token_pool_fwd")
+    return scores, att
+
+
+def token_pool_backward(raw: torch.Tensor, seg_off: torch.Tensor, inv_temp: float, hardmax: bool, dscores: torch.Tensor) -> torch.Tensor:
+    _need_cuda(raw, dscores)
+    r, k1 = raw.shape[0], seg_off.numel() - 1
+    dscores = dscores.to(torch.float32)
+    if dscores.stride(1) != 1:
+        dscores = dscores.contiguous()
+    draw = torch.zeros_like(raw)          # (token columns outside every segment — there are none — would keep 0)
+    _lib.check(_lib.load().loco_token_pool_bwd(_p(raw), raw.stride(0) if r else raw.shape[1], _p(seg_off), r, k1, float(inv_temp), int(bool(hardmax)),
+                                               _p(dscores), dscores.stride(0) if r else k1, _p(draw), draw.stride(0) if r else raw.shape[1], _stream(raw)),
+               "loco_token_pool_bwd")
+    return draw
+
+
 _small_dev = {}      # small host-built index tensors (image row offsets, image sizes) by (device, kind, values)
 
 

@@ -98,6 +98,7 @@ _REF_FILES = {
     "ovr.modeling.roi_heads.box_emb_head": "ovr/modeling/roi_heads/box_emb_head.py",
     "ovr.modeling.roi_heads.roi_emb_heads": "ovr/modeling/roi_heads/roi_emb_heads.py",
     "ovr.modeling.meta_arch.distill_mmss_gcnn": "ovr/modeling/meta_arch/distill_mmss_gcnn.py",
+    "ovr.modeling.roi_heads.box_emb_grounding_head": "ovr/modeling/roi_heads/box_emb_grounding_head.py",
 }
 
 
@@ -138,6 +139,13 @@ def load_reference_box_head():
     class (oracle/d2_stubs.FastRCNNOutputLayers: losses / inference), and ``build_box_predictor`` (:239-249)."""
     mods = _load_reference_modules(["ovr.modeling.logged_module", "ovr.modeling.roi_heads.box_emb_head"])
     return mods["ovr.modeling.roi_heads.box_emb_head"]
+
+
+def load_reference_grounding_box_head():
+    """Returns the reference's box_emb_grounding_head module: ``GroundingModule`` (box_emb_grounding_head.py:60-277, multi-token
+    class scoring) and ``EmbeddingGroundingFastRCNNOutputLayers`` (:280-434) on the restated Detectron2 base class."""
+    mods = _load_reference_modules(["ovr.modeling.logged_module", "ovr.modeling.roi_heads.box_emb_grounding_head"])
+    return mods["ovr.modeling.roi_heads.box_emb_grounding_head"]
 
 
 def load_reference_roi_heads():
@@ -209,6 +217,9 @@ def make_roi_cfg(stage="stt", **over):
                               BBOX_REG_LOSS_WEIGHT=1.0),
             RESNETS=_Cfg(NUM_GROUPS=1, WIDTH_PER_GROUP=64, RES2_OUT_CHANNELS=256, STRIDE_IN_1X1=True, NORM="FrozenBN",
                          DEFORM_ON_PER_STAGE=[False, False, False, False]),
+            # read by EmbeddingGroundingFastRCNNOutputLayers.from_config (box_emb_grounding_head.py:349-361); MAX_TOKENS is the key
+            # the reference's config.py never defines — it is set through ``over`` by the cases that need it
+            MMSS_HEAD=_Cfg(GROUNDING=_Cfg(LOCAL_METRIC="dot", GLOBAL_METRIC="aligned_local", ALIGNMENT="softmax", ALIGNMENT_TEMPERATURE=10.0)),
         ),
         TEST=_Cfg(DETECTIONS_PER_IMAGE=100),
     )
@@ -217,6 +228,6 @@ def make_roi_cfg(stage="stt", **over):
         parts = k.split(".")
         for p in parts[:-1]:
             node = node[p]
-        assert parts[-1] in node, k
+        assert parts[-1] in node or parts[-1] == "MAX_TOKENS", k
         node[parts[-1]] = v
     return cfg

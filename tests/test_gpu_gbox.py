@@ -1,0 +1,128 @@
+"""Multi-token class scoring on the B200: the drop-in EmbeddingGroundingFastRCNNOutputLayers / GroundingModule against
+vectors produced by the reference's own classes (tests/golden/gbox_*.npz, box_emb_grounding_head.py:60-434)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import locov_b200.modeling as M
+from locov_b200 import _lib, ops
+from oracle import box_cases, box_head, grounding_module as gm
+from util import relerr
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def _predictor(c, d, dev, precision):
+    cfg = M.get_cfg("stt")
+    cfg.MODEL.ROI_BOX_HEAD.NAME = "EmbeddingGroundingFastRCNNOutputLayers"
+    cfg.MODEL.ROI_BOX_HEAD.EMB_DIM = c["D"]
+    cfg.MODEL.ROI_HEADS.NUM_CLASSES = c["K"]
+    cfg.MODEL.ROI_HEADS.MAX_TOKENS = c["max_tok"]
+    cfg.MODEL.MMSS_HEAD.GROUNDING.ALIGNMENT = c["alignment"]
+    cfg.MODEL.MMSS_HEAD.GROUNDING.ALIGNMENT_TEMPERATURE = c["temperature"]
+    cfg.MODEL.ROI_BOX_HEAD.NORMALIZE_EMB_PRED = bool(c.get("normalize", False))
+    cfg.MODEL.B200.PRECISION = precision
+    bp = M.build_box_predictor(cfg, c["V"]).to(dev)
+    with torch.no_grad():
+        bp.emb_pred.weight.copy_(d["w_emb"]); bp.emb_pred.bias.copy_(d["b_emb"])
+        bp.bbox_pred.weight.copy_(d["w_box"]); bp.bbox_pred.bias.copy_(d["b_box"])
+    bp.set_class_embeddings(d["embs"])
+    return bp
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", sorted(n for n, c in gm.GBOX_CASES.items() if c["mode"] == "eval"))
+def test_eval_matches_the_reference_class(cuda_device, name, precision):
+    c = gm.GBOX_CASES[name]
+    d = gm.gbox_inputs(c)
+    z = np.load(os.path.join(GOLDEN, f"gbox_{name}.npz"))
+    if precision == "bf16" and c["alignment"] == "hardmax":
+        pytest.skip("hardmax picks a token: near-ties flip under bf16 rounding (same rule as the LSM head tests)")
+    bp = _predictor(c, d, cuda_device, precision).eval()
+    n0 = _lib.load().loco_launch_count()
+    with torch.no_grad():
+        scores, deltas = bp(d["x"].to(cuda_device))
+    assert _lib.load().loco_launch_count() - n0 >= 3
+    assert scores.shape == z["scores"].shape
+    tol = TOL[precision] * max(1.0, float(np.abs(z["scores"]).max()) / 10.0)
+    assert relerr(scores.cpu(), z["scores"]) < tol
+    assert relerr(deltas.cpu(), z["deltas"]) < TOL[precision]
+    assert float(scores[:, -1].abs().max()) == 0.0                                   # background logit exactly 0
+    if precision == "fp32":
+        bp.cls_score.return_attention = True
+        with torch.no_grad():
+            e = torch.nn.functional.linear(d["x"].to(cuda_device), bp.emb_pred.weight, bp.emb_pred.bias)
+            if c.get("normalize"):
+                e = e / e.norm(dim=1, keepdim=True)
+            _, att = bp.cls_score(e)
+        assert att.shape == z["tok_attention"].shape
+        assert relerr(att.cpu(), z["tok_attention"]) < 2e-3
+        inst = box_head.instances_from(box_head.make_proposals(2, c["R"] // 2, c["K"], seed=c["seed"] + 1, image_size=box_cases.IMAGE), box_cases.IMAGE,
+                                       M.Instances, M.Boxes, device=cuda_device)
+        bp.cls_score.return_attention = False
+        with torch.no_grad():
+            pred = bp(d["x"].to(cuda_device))
+            results, kept = bp.inference(pred, inst)
+        for i, r in enumerate(results):
+            n_ref = len(z[f"inst{i}_scores"])
+            assert abs(len(r) - n_ref) <= max(1, n_ref // 50)
+            if n_ref and len(r):
+                m = min(n_ref, len(r))
+                assert relerr(r.scores.cpu()[:m], z[f"inst{i}_scores"][:m]) < 1e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", sorted(n for n, c in gm.GBOX_CASES.items() if c["mode"] == "train"))
+def test_train_matches_the_reference_class(cuda_device, name, precision):
+    c = gm.GBOX_CASES[name]
+    d = gm.gbox_inputs(c)
+    z = np.load(os.path.join(GOLDEN, f"gbox_{name}.npz"))
+    if precision == "bf16" and c["alignment"] == "hardmax":
+        pytest.skip("hardmax picks a token: near-ties flip under bf16 rounding")
+    bp = _predictor(c, d, cuda_device, precision).train()
+    inst = box_head.instances_from(box_head.make_proposals(2, c["R"] // 2, c["K"], seed=c["seed"] + 1, image_size=box_cases.IMAGE), box_cases.IMAGE,
+                                   M.Instances, M.Boxes, device=cuda_device)
+    xg = d["x"].to(cuda_device).requires_grad_(True)
+    scores, deltas = bp(xg)
+    losses = bp.losses((scores, deltas), inst)
+    sum(losses.values()).backward()
+    tol = TOL[precision]
+    stol = tol * max(1.0, float(np.abs(z["scores"]).max()) / 10.0)
+    assert relerr(scores.detach().cpu(), z["scores"]) < stol
+    assert relerr(losses["loss_cls"].detach().cpu(), z["loss_cls"]) < 10 * stol
+    assert relerr(losses["loss_box_reg"].detach().cpu(), z["loss_box_reg"]) < tol
+    assert relerr(xg.grad.cpu(), z["grad_x"]) < 20 * stol
+    for pname, p in bp.named_parameters():
+        assert bool(z["requires_grad::" + pname]) == p.requires_grad, pname
+        if p.requires_grad:
+            assert p.grad is not None, pname
+            assert relerr(p.grad.cpu(), z["grad::" + pname]) < 20 * stol, pname
+
+
+def test_token_pool_kernel_against_the_oracle_in_double(cuda_device):
+    g = torch.Generator().manual_seed(8)
+    r, d = 300, 48
+    embs = {k: torch.randn(1 + (k * 7) % 6, d, generator=g) for k in range(40)}
+    tok, off = gm.class_token_matrix(embs, d)
+    e = torch.randn(r, d, generator=g)
+    raw = (e.double() @ tok.double().t()).float().to(cuda_device)
+    seg = off.to(torch.int32).to(cuda_device)
+    for alignment in ("softmax", "hardmax"):
+        want, att = gm.grounding_scores(e, tok, off, 5.0, alignment)
+        got, flat = ops.token_pool(raw, seg, 1 / 5.0, alignment == "hardmax", want_attention=True)
+        assert relerr(got.cpu(), want) < 1e-5
+        assert relerr(flat.cpu(), torch.cat(att, 1)) < 1e-5
+        gsc = torch.randn(r, 41, generator=g)
+        rawd = (e.double() @ tok.double().t()).requires_grad_(True)
+        s, out = rawd / 5.0, []
+        for k in range(41):
+            sk = s[:, int(off[k]):int(off[k + 1])]
+            a = torch.softmax(sk, 1) if alignment == "softmax" else torch.nn.functional.one_hot(sk.argmax(1), sk.shape[1]).double()
+            out.append((a * sk).sum(1))
+        (torch.stack(out, 1) * gsc.double()).sum().backward()
+        draw = ops.token_pool_backward(raw, seg, 1 / 5.0, alignment == "hardmax", gsc.to(cuda_device))
+        assert relerr(draw.cpu(), rawd.grad) < 1e-5

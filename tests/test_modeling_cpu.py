@@ -145,3 +145,25 @@ def test_host_feed_refuses_a_cpu_device():
         locov_b200.HostFeed("cpu")
     with pytest.raises(LocoError):
         locov_b200.HostFeed("cuda:0", depth=1)
+
+
+def test_multi_token_box_predictor_is_built_from_a_cfg_like_the_reference():
+    """box_emb_head.py:239-249 resolves "EmbeddingGroundingFastRCNNOutputLayers" too; its from_config (box_emb_grounding_head.py:349-381)
+    builds the GroundingModule from the MMSS_HEAD.GROUNDING keys.  State-dict keys as in the reference (tests/golden/gbox_*.npz)."""
+    import numpy as np
+    cfg = M.get_cfg("stt")
+    cfg.MODEL.ROI_BOX_HEAD.NAME = "EmbeddingGroundingFastRCNNOutputLayers"
+    cfg.MODEL.ROI_BOX_HEAD.EMB_DIM = 16
+    cfg.MODEL.MMSS_HEAD.GROUNDING.ALIGNMENT = "hardmax"
+    bp = M.build_box_predictor(cfg, M.ShapeSpec(channels=24))
+    assert isinstance(bp, M.EmbeddingGroundingFastRCNNOutputLayers) and isinstance(bp.cls_score, M.GroundingModule)
+    assert bp.cls_score.alignment == "hardmax" and bp.cls_score.temperature == 10.0 and bp.num_classes is None
+    assert bp.emb_pred.weight.requires_grad                      # (the reference never applies FREEZE_EMB_PRED in this class)
+    bp.set_class_embeddings({0: torch.randn(2, 16), 1: torch.randn(1, 16), 2: np.random.randn(3, 16).astype("float32")})
+    assert bp.num_classes == 3 and bp.cls_score.token_score.weight.shape == (7, 16)
+    assert bp.cls_score.seg_off.tolist() == [0, 2, 3, 6, 7] and bp.cls_score.num_tok.tolist() == [2, 1, 3, 1]
+    assert float(bp.cls_score.token_score.weight[-1].abs().sum()) == 0.0          # the background token
+    z = np.load("tests/golden/gbox_soft_t10.npz")
+    assert sorted(bp.state_dict().keys()) == list(z["state_keys"])
+    with pytest.raises(NotImplementedError):
+        M.GroundingModule(16, 3, 4, local_metric="cosine", normalize_emb=True)
