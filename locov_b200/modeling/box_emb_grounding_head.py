@@ -91,6 +91,8 @@ class GroundingModule(LoggedModule):
                 tok_class = torch.repeat_interleave(torch.arange(k1, device=raw.device), self.num_tok.long())
                 tok_pos = torch.arange(raw.shape[1], device=raw.device) - self.seg_off[:-1].long()[tok_class]
                 att[:, tok_class, tok_pos] = flat
+                if self.background_class:
+                    att[:, -1, :] = 0.0      # the reference's mask_emb row of the background class is all zero (:232-236)
         self.log("global_dist", scores)
         return scores, att
 
