@@ -61,6 +61,9 @@ struct TcCore {
     int prefetch;       // > 0: the producer prefetches the A panel into L2 in bursts of `prefetch` consecutive k blocks, one burst
                         // ahead of the loads: a 128-byte-wide k block touches every row's DRAM page for 128 bytes only; a burst
                         // turns that into `prefetch` x 128 contiguous bytes per row while the page is open
+    int fuse3;          // set by tc_finalize for passes == 3 when the ring allows it: ONE stage holds the k block of A_hi, A_lo, B_hi and B_lo and
+                        // feeds the three products hi*hi + hi*lo + lo*hi — each operand slice is loaded once per k block instead of once
+                        // per pass (78 -> 52 KB of TMA fill per k block at N = 160: the 3-pass main loop is fill bound, not tensor bound)
     int single_wave;    // 1: the grid is at most one CTA per SM, so a second resident CTA would never exist — give the whole
                         // shared memory to the operand ring (bytes in flight per SM bound the TMA ingest rate: Little's law)
 };
@@ -86,15 +89,23 @@ inline size_t tc_finalize(TcCore &core, int K, int passes, int chunks, int epi_s
     core.epi_smem = epi_smem;
     if (core.cm < 1) core.cm = 1;
     if (core.cn < 1) core.cn = 1;
-    const size_t stage_bytes = TC_A_BYTES + (size_t)(core.two_cta ? core.block_n / 2 : core.block_n) * 128;
+    size_t stage_bytes = TC_A_BYTES + (size_t)(core.two_cta ? core.block_n / 2 : core.block_n) * 128;
     if (chunks != 1) core.epi_overlay = 0;
     const long long fixed = 1024 /*alignment slack*/ + 512 /*barriers*/ + core.epi_tail + (core.epi_overlay ? 0 : (long long)epi_smem);
     long long budget = core.single_wave ? 225 : 110;                                // two CTAs per SM unless the grid is one wave
     if (const char *e = getenv("LOCOV_B200_SMEMKB")) { const int v = atoi(e); if (v >= 32 && v <= 225) budget = v; }   // developer sweep knob
+    // fused three-pass stages (see TcCore::fuse3): only without multicast clusters, and only when at least 3 double-width stages fit
+    core.fuse3 = 0;
+    static const bool fuse3_allowed = []() { const char *e = getenv("LOCOV_B200_FUSE3"); return !(e != nullptr && e[0] == '0'); }();
+    if (passes == 3 && fuse3_allowed && !core.tf32 && (core.two_cta || core.cm * core.cn == 1) && !core.epi_overlay &&
+        (budget * 1024 - fixed) / (long long)(2 * stage_bytes) >= 3) {
+        core.fuse3 = 1;
+        stage_bytes *= 2;
+    }
     int stages = (int)((budget * 1024 - fixed) / (long long)stage_bytes);
     if (core.epi_overlay && (long long)epi_smem + fixed > 110 * 1024) stages = 0;    // the overlay itself needs a whole SM
     if (stages < 3) stages = (int)(((long long)225 * 1024 - fixed) / (long long)stage_bytes);
-    const int total_iters = core.num_k_blocks * passes * chunks;
+    const int total_iters = core.num_k_blocks * (core.fuse3 ? 1 : passes) * chunks;
     if (stages > (core.single_wave ? TC_MAX_STAGES : 6)) stages = core.single_wave ? TC_MAX_STAGES : 6;
     if (const char *e = getenv("LOCOV_B200_STAGES")) { const int v = atoi(e); if (v >= 1 && v < stages) stages = v; }   // developer sweep knob
     if (stages > total_iters) stages = total_iters;
@@ -195,6 +206,20 @@ __device__ __forceinline__ void mma_issue_loop(const TcCore &core, unsigned char
             tc_fence_after();
             if (tl != nullptr && it == 0 && ch == 0) tl[2] = global_timer_ns();     // first operand stage landed
             const uint32_t a_addr = smem_base + stage * stage_bytes;
+            if (core.fuse3) {
+                // stage = [A_hi][A_lo][B_hi][B_lo] of one k block: hi*hi + hi*lo + lo*hi per 16-wide K step
+                const uint32_t bb = (stage_bytes - 2u * TC_A_BYTES) / 2u;
+                const uint64_t da_h = umma_desc_k128(a_addr), da_l = umma_desc_k128(a_addr + TC_A_BYTES);
+                const uint64_t db_h = umma_desc_k128(a_addr + 2u * TC_A_BYTES), db_l = umma_desc_k128(a_addr + 2u * TC_A_BYTES + bb);
+                if (!skip_mma) {
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 8u; ks += 2u) {
+                        umma_step<TF32, PAIR>(tmem_d, da_h + ks, db_h + ks, idesc, ks == 0u ? accumulate : 1u);
+                        umma_step<TF32, PAIR>(tmem_d, da_h + ks, db_l + ks, idesc, 1u);
+                        umma_step<TF32, PAIR>(tmem_d, da_l + ks, db_h + ks, idesc, 1u);
+                    }
+                }
+            } else {
             const uint64_t da = umma_desc_k128(a_addr);
             const uint64_t db = umma_desc_k128(a_addr + TC_A_BYTES);
             if (!skip_mma) {
@@ -202,6 +227,7 @@ __device__ __forceinline__ void mma_issue_loop(const TcCore &core, unsigned char
                 umma_step<TF32, PAIR>(tmem_d, da + 2u, db + 2u, idesc, 1u);
                 umma_step<TF32, PAIR>(tmem_d, da + 4u, db + 4u, idesc, 1u);
                 umma_step<TF32, PAIR>(tmem_d, da + 6u, db + 6u, idesc, 1u);
+            }
             }
             accumulate = 1;
             if constexpr (PAIR) {
@@ -238,7 +264,7 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
 
     constexpr bool pair = PAIR;                               // CTA pair: this CTA stages half of the B tile
     const uint32_t b_bytes = (uint32_t)(pair ? core.block_n / 2 : core.block_n) * 128u;
-    const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
+    const uint32_t stage_bytes = (TC_A_BYTES + b_bytes) * (core.fuse3 ? 2u : 1u);
     unsigned char *bar_base = smem + (size_t)core.ring_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(bar_base);
     uint64_t *empty = full + TC_MAX_STAGES;
@@ -302,7 +328,7 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
     pdl_wait();                                                                   // operands / masks of the previous kernel are complete
     if (tl && threadIdx.x == 0) tl[1] = global_timer_ns();                       // setup done (barriers, TMEM, cluster sync)
     const uint32_t tmem_base = *tmem_slot;
-    const int iters_per_chunk = core.num_k_blocks * core.passes;
+    const int iters_per_chunk = core.num_k_blocks * (core.fuse3 ? 1 : core.passes);
     // persistent mode: unit u (a CTA, or a CTA pair) of U launched units processes tiles u, u + U, ...
     const int unit = pair ? (int)blockIdx.x / 2 : (int)blockIdx.x, units = pair ? (int)gridDim.x / 2 : (int)gridDim.x;
     const int nchunks = core.total_tiles > 0 ? max(0, (core.total_tiles - unit + units - 1) / units) : core.chunks;
@@ -313,7 +339,7 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
             for (int ch = 0; ch < nchunks; ++ch) {
                 int row_a, row_b;
                 Epi::coords(ep, core, cta, ch, row_a, row_b);
-                for (int pass = 0; pass < core.passes; ++pass) {
+                for (int pass = 0; pass < (core.fuse3 ? 1 : core.passes); ++pass) {
                     const CUtensorMap *ma = (pass == 2) ? &maps.a_lo : &maps.a_hi;
                     const CUtensorMap *mb = (pass == 1) ? &maps.b_lo : &maps.b_hi;
                     for (int kb = 0; kb < core.num_k_blocks; ++kb) {
@@ -322,6 +348,29 @@ __global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, Epi::kMinBlocks)
                             const int row_pf = pair ? row_a : row_a + rn * a_rows_pf;
                             const int kb0 = kb + core.prefetch;
                             for (int j = kb0; j < kb0 + core.prefetch && j < core.num_k_blocks; ++j) tma_prefetch_2d(ma, j * k_elems, row_pf);
+                        }
+                        if (core.fuse3) {          // one stage = the k block of all four operand matrices (csize == 1 or CTA pair)
+                            mbar_wait(&empty[stage], phase ^ 1u);
+                            unsigned char *s4 = smem + (size_t)stage * stage_bytes;
+                            if (core.debug_mode == 2) {
+                                mbar_arrive(&full[stage]);
+                            } else if constexpr (pair) {
+                                if (rm == 0) mbar_arrive_expect_tx(&full[stage], 2u * stage_bytes);
+                                const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+                                const int rb = row_b + rm * (core.block_n / 2);
+                                tma_load_2d_2sm(s4, &maps.a_hi, lead_full, kb * k_elems, row_a);
+                                tma_load_2d_2sm(s4 + TC_A_BYTES, &maps.a_lo, lead_full, kb * k_elems, row_a);
+                                tma_load_2d_2sm(s4 + 2 * TC_A_BYTES, &maps.b_hi, lead_full, kb * k_elems, rb);
+                                tma_load_2d_2sm(s4 + 2 * TC_A_BYTES + b_bytes, &maps.b_lo, lead_full, kb * k_elems, rb);
+                            } else {
+                                mbar_arrive_expect_tx(&full[stage], stage_bytes);
+                                tma_load_2d(s4, &maps.a_hi, &full[stage], kb * k_elems, row_a);
+                                tma_load_2d(s4 + TC_A_BYTES, &maps.a_lo, &full[stage], kb * k_elems, row_a);
+                                tma_load_2d(s4 + 2 * TC_A_BYTES, &maps.b_hi, &full[stage], kb * k_elems, row_b);
+                                tma_load_2d(s4 + 2 * TC_A_BYTES + b_bytes, &maps.b_lo, &full[stage], kb * k_elems, row_b);
+                            }
+                            if (++stage == (uint32_t)core.stages) { stage = 0; phase ^= 1u; }
+                            continue;
                         }
                         mbar_wait(&empty[stage], phase ^ 1u);
                         unsigned char *sa = smem + (size_t)stage * stage_bytes;
