@@ -64,6 +64,8 @@ def main():
     xa, wa = ops.split_bf16(x, False), ops.split_bf16(w, False)
     report("projection bf16 3200x768x2048 (bf16 out), cold", lambda: ops.linear_fwd(xa, wa, None, want_f32=False, n_bf16=N))
     report("projection bf16 3200x768x2048 (bf16 out), L2-resident", lambda: ops.linear_fwd(xa, wa, None, want_f32=False, n_bf16=N), cold=False)
+    xh, wh = ops.split_bf16(x, True), ops.split_bf16(w, True)
+    report("projection fp32-accurate (3 bf16 passes) 3200x768x2048 (bf16 hi+lo out), cold", lambda: ops.linear_fwd(xh, wh, None, want_f32=False, n_bf16=N, accurate_out=True))
     if "--proj-only" in sys.argv:
         return
     x8 = torch.randn(8192, K, device=dev)
