@@ -4,9 +4,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 LOCOV_B200_SYMM=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 scripts/check_sharded_nccl.py bench 2>&1 | grep -E "parity|Error|error|warn" | tail -4
 if [ "$N" = "2" ]; then timeout 600 python -m pytest tests/test_gpu_sharded_nccl.py -m gpu -q 2>&1 | tail -3; fi
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 500 --warmup 20 > gpurun_out/r2_bench_n${N}.json 2> gpurun_out/r2_bench_n${N}.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus $N --steps 2 --warmup 1 > gpurun_out/r2_bench_ref_n${N}.json 2> gpurun_out/r2_bench_ref_n${N}.err
-tail -c 600 gpurun_out/r2_bench_ref_n${N}.json
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 500 --warmup 20 --no-cpu-baseline --e2e-steps 10 > gpurun_out/r2_bench_n${N}.json 2> gpurun_out/r2_bench_n${N}.err
 python - <<PY
 import json
 try:
