@@ -340,16 +340,18 @@ def run_b200(args):
     precisions[other]["kernels_ms"] = {k: v["ms"] for k, v in kern_other.items()}
     precisions[other]["pair_kernel_frac_of_bf16_peak"] = kern_other["tc_gemm<EpiLsmFwd> (pair)"]["frac"]
     dom = max((k for k in kern if "peak" in kern[k]), key=lambda k: kern[k]["ms"])
-    traffic = None          # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    traffic = tensor_pct = None     # DRAM bytes per launch / tensor-pipe activity of the dominant kernel, from the committed ncu --set full capture
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             ent = json.load(fh).get(f"{dom} [{args.precision}]")
         if ent is not None:
             traffic = float(ent["bytes"])
+            tensor_pct = ent.get("tensor_pipe_active_pct")
     except (OSError, ValueError, KeyError):
         traffic = None
     roofline = {"kernel": dom, "bound": kern[dom]["bound"], "achieved": kern[dom]["achieved"], "peak": kern[dom]["peak"],
                 "unit": kern[dom]["unit"], "frac": kern[dom]["frac"], "traffic": traffic,
+                "tensor_pipe_active_pct_ncu": tensor_pct,      # sm__pipe_tensor_cycles_active of the same kernel in the committed capture (executed, not algorithmic, work)
                 "peak_source": f"{pk['source']} (MEASURED_PEAKS.json burst figure: kernel timed alone)",
                 "algorithmic": "2*M*N*K of the un-collapsed GEMM (tensor) / bytes read+written once (hbm); the fp32-accurate mode runs 3 bf16 passes for the same algorithmic flops",
                 "kernels": kern}
