@@ -104,3 +104,41 @@ def test_rows_with_non_finite_values_are_dropped_and_renumbered(cuda_device):
     deltas[100, 0] = float("inf")
     probs[150, 0] = float("nan")
     _check(probs, deltas, props, rows, 0.01, 0.5, 100, cuda_device)
+
+
+def test_module_routes_by_range_and_the_torchvision_path_agrees(cuda_device):
+    """EmbeddingFastRCNNOutputLayers.inference uses the kernel inside its range (1 <= top-k <= 1024, <= 2048 RoIs per image) and the
+    per-image torchvision path outside it (no top-k limit); on the same predictions both give the same detections."""
+    import locov_b200.modeling as M
+    from locov_b200._lib import LocoError
+    cfg = M.get_cfg("stt")
+    cfg.MODEL.ROI_BOX_HEAD.EMB_DIM = 32
+    bp = M.build_box_predictor(cfg, 64).to(cuda_device).eval()
+    g = torch.Generator().manual_seed(2)
+    bp.set_class_embeddings(torch.cat([torch.randn(9, 32, generator=g) * 3, torch.zeros(1, 32)]))
+    with torch.no_grad():
+        bp.emb_pred.weight.mul_(30.0)
+    props = box_head.make_proposals(2, 120, 9, seed=4, image_size=IMAGE)
+    inst = box_head.instances_from(props, IMAGE, M.Instances, M.Boxes, device=cuda_device)
+    x = torch.randn(240, 64, generator=g).to(cuda_device)
+    lib = _lib.load()
+    with torch.no_grad():
+        pred = bp(x)
+        bp.test_score_thresh, bp.test_topk_per_image = 0.02, 100
+        n0 = lib.loco_launch_count()
+        res_k, kept_k = bp.inference(pred, inst)
+        n_kernel = lib.loco_launch_count() - n0
+        bp.test_topk_per_image = -1                               # Detectron2: no limit -> outside the kernel's range
+        n0 = lib.loco_launch_count()
+        res_t, kept_t = bp.inference(pred, inst)
+        n_torch = lib.loco_launch_count() - n0
+    assert n_kernel >= 4 and n_torch == 0
+    for a, b, ka, kb in zip(res_k, res_t, kept_k, kept_t):
+        m = len(a)
+        assert 0 < m <= 100 and len(b) >= m
+        assert torch.equal(a.pred_classes, b.pred_classes[:m]) and torch.equal(ka, kb[:m])
+        assert torch.equal(a.scores, b.scores[:m])
+        assert float((a.pred_boxes.tensor - b.pred_boxes.tensor[:m]).abs().max()) < 1e-3
+    with pytest.raises(LocoError):                                # the raw entry refuses what it cannot do
+        ops.box_inference(torch.rand(2100, 4, device=cuda_device), torch.zeros(2100, 4, device=cuda_device), torch.rand(2100, 4, device=cuda_device) * 50,
+                          [2100], [IMAGE], WEIGHTS, 4.0, 0.1, 0.5, 100)
