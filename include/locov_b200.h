@@ -72,10 +72,11 @@ int loco_debug_timeline_read(unsigned long long *host, int max_ctas);
  *       Channels-last output needs C % 4 == 0 and a 16-byte aligned pointer.
  * Sampling-grid coordinates and integer tap indices are bit-exact with the float32 reference
  * arithmetic (loco_roi_align_grid_dump exposes them); pooled values are toleranced (1e-4 rel).
- * workspace: loco_roi_align_workspace_bytes() bytes (0 for LOCO_NHWC; an NCHW map is transposed to
- * channels-last into it once per call).
+ * workspace: loco_roi_align_workspace_bytes() bytes: an NCHW map is transposed to channels-last into it once per call, and the
+ * launch order of the rois (heaviest first: a small bucket-sort launch that removes the tail of late, large rois) lives behind it.
+ * NULL is accepted for LOCO_NHWC features (rois are then taken in the given order).
  */
-int64_t loco_roi_align_workspace_bytes(int N, int C, int H, int W, int feat_layout);
+int64_t loco_roi_align_workspace_bytes(int N, int C, int H, int W, int feat_layout, int R);
 int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_layout,
                        const float *rois, int R, int PH, int PW, float spatial_scale,
                        int sampling_ratio, int aligned, void *out, int out_layout, int out_dtype, void *workspace,

@@ -25,7 +25,7 @@ SIGNATURES = {
     "loco_sm_count": (_i, [_i]),
     "loco_launch_count": (_c.c_longlong, []),
     "loco_debug_timeline_read": (_i, [_vp, _i]),
-    "loco_roi_align_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
+    "loco_roi_align_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i]),
     "loco_roi_align_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _i, _i, _vp, _i, _i, _vp, _vp]),
     "loco_roi_align_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
     "loco_roi_align_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp]),

@@ -320,6 +320,36 @@ __global__ void __launch_bounds__(RA_THREADS, 3) roi_align_fwd_generic_kernel(co
 
 
 // ------------------------------------------------------------------------------------------------
+// Launch order of the rois: heaviest first.  The kernels below run one CTA per (roi, channel chunk) in block-index order; a roi's cost
+// grows with its area (more feature columns per bin row, more row taps, the bin-driven fall-backs for the widest sampling grids), the
+// 9 % of the benchmark's boxes above 448 px cost twice the average — and when such a roi is scheduled late, its CTAs are the tail
+// the whole grid waits for (measured: the same boxes sorted largest-first run 10-12 % faster).  One small block buckets the rois
+// by log2(area in feature pixels) and emits the roi indices bucket by bucket, heaviest bucket first (order inside a bucket is
+// whatever the atomics give: it only affects scheduling, never results).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) roi_order_kernel(const float *__restrict__ rois, int R, float scale, int *__restrict__ order) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ int cnt[16], base[16];
+    if (threadIdx.x < 16) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    auto bucket = [&](int r) -> int {
+        const float *q = rois + (size_t)r * 5;
+        const float a = fmaxf((q[3] - q[1]) * scale, 1.f) * fmaxf((q[4] - q[2]) * scale, 1.f);
+        const int b = a == a ? (int)floorf(log2f(a) * 1.5f) : 0;       // (NaN boxes: lightest bucket)
+        return min(max(b, 0), 15);
+    };
+    for (int r = threadIdx.x; r < R; r += blockDim.x) atomicAdd(&cnt[bucket(r)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 15; b >= 0; --b) { base[b] = run; run += cnt[b]; }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) order[atomicAdd(&base[bucket(r)], 1)] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward, vectorised: one CTA = (roi, 128-channel slab), lane = 4 consecutive channels (one LDG.128 per tap
 // serves 4 channels, so the per-tap table lookups / address arithmetic are amortised 4x and a warp request is a
 // full 512-byte run of the NHWC pixel), warp = one bin row.
@@ -555,7 +585,7 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
                                                                         int PH, int PW, float scale, int sampling_ratio,
                                                                         int aligned, int nchunks, int slabs, int tstride,
                                                                         int bulk_out, float *__restrict__ out,
-                                                                        const __grid_constant__ CUtensorMap omap) {
+                                                                        const __grid_constant__ CUtensorMap omap, const int *__restrict__ order) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MergedEntry *ytab = reinterpret_cast<MergedEntry *>(smem_raw);
     MergedEntry *xtab = ytab + RA_TAB;
@@ -567,8 +597,9 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
     WalkBin *xw = reinterpret_cast<WalkBin *>(walk_hdr + 4);  // [32] dense per-bin column weights (16-byte aligned)
     float *tile = reinterpret_cast<float *>(smem_raw + RV_TILE_OFFSET);   // [RV_CC][tstride], 128-byte aligned (TMA store source)
 
-    const int r = blockIdx.x / nchunks;
-    const int chunk = blockIdx.x - r * nchunks;               // this CTA pools `slabs` consecutive 128-channel slabs
+    const int slot = blockIdx.x / nchunks;
+    const int chunk = blockIdx.x - slot * nchunks;            // this CTA pools `slabs` consecutive 128-channel slabs
+    const int r = order != nullptr ? order[slot] : slot;      // launch order: heaviest rois first (roi_order_kernel)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int PHW = PH * PW;
 
@@ -834,7 +865,7 @@ __device__ __noinline__ void walk_bin_row_bwd(char *gb, const MergedEntry *yt, i
 __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_bwd_v4_kernel(const float *__restrict__ dout, const float *__restrict__ rois, int C,
                                                                         int H, int W, int PH, int PW, float scale, int sampling_ratio,
                                                                         int aligned, int nchunks, int slabs, float *__restrict__ dfeat_nhwc,
-                                                                        unsigned char *__restrict__ handled) {
+                                                                        unsigned char *__restrict__ handled, const int *__restrict__ order) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MergedEntry *ytab = reinterpret_cast<MergedEntry *>(smem_raw);
     MergedEntry *xtab = ytab + RA_TAB;
@@ -846,8 +877,9 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_bwd_v4_kernel(const f
     WalkBin8 *xw = reinterpret_cast<WalkBin8 *>(walk_hdr + 4);
     float *tile = reinterpret_cast<float *>(xw + 32);         // [RV_CC][PH*PW | 1]: odd pitch, conflict-free lane-per-row reads
 
-    const int r = blockIdx.x / nchunks;
-    const int chunk = blockIdx.x - r * nchunks;
+    const int slot = blockIdx.x / nchunks;
+    const int chunk = blockIdx.x - slot * nchunks;
+    const int r = order != nullptr ? order[slot] : slot;      // launch order: heaviest rois first (roi_order_kernel)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int PHW = PH * PW, pitch = PHW | 1;
 
@@ -1220,9 +1252,12 @@ using namespace loco;
 
 extern "C" {
 
-int64_t loco_roi_align_workspace_bytes(int N, int C, int H, int W, int feat_layout) {
-    if (feat_layout == LOCO_NHWC) return 0;
-    return (int64_t)N * C * H * W * (int64_t)sizeof(float);
+static int64_t roi_order_bytes(int R) { return R > 0 ? (((int64_t)R * 4 + 255) / 256) * 256 : 0; }
+
+// [transposed map (NCHW input only)] [launch order: R ints]
+int64_t loco_roi_align_workspace_bytes(int N, int C, int H, int W, int feat_layout, int R) {
+    const int64_t map = feat_layout == LOCO_NHWC ? 0 : (((int64_t)N * C * H * W * (int64_t)sizeof(float) + 255) / 256) * 256;
+    return map + roi_order_bytes(R);
 }
 
 int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_layout, const float *rois, int R,
@@ -1268,9 +1303,16 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
         else if (pair) { tstride = PHW; while (tstride % 4 != 2) ++tstride; }     // S = 2 (mod 4): conflict-free STS.64 columns
         else tstride = PHW | 1;
         const int nslab = (C + RV_CC - 1) / RV_CC;
-        // each CTA pools `slabs` consecutive slabs with one set of tap tables, as long as the grid keeps >= 8 waves
+        // each CTA pools `slabs` consecutive slabs with one set of tap tables (the per-CTA prologue — geometry, tap tables, walk program —
+        // is ~30 % of the samples at 2 slabs), as long as the grid keeps >= 8 waves; with the launch order below (no tail of late heavy
+        // rois) the channels-last modes afford 6 waves: 4 slabs per CTA at the benchmark shape (225 -> 217 us)
         int slabs = 1;
-        while (slabs < 4 && nslab % (slabs * 2) == 0 && (long long)R * (nslab / (slabs * 2)) >= 8ll * 2 * 148) slabs *= 2;
+        static const bool order_allowed = []() { const char *e = getenv("LOCOV_B200_ROI_ORDER"); return !(e != nullptr && e[0] == '0'); }();
+        const bool will_order = order_allowed && workspace != nullptr;
+        const long long min_ctas = (will_order && out_mode != 0 ? 6ll : 8ll) * 2 * 148;
+        while (slabs < 4 && nslab % (slabs * 2) == 0 && (long long)R * (nslab / (slabs * 2)) >= min_ctas) slabs *= 2;
+        static const int slabs_env = []() { const char *e = getenv("LOCOV_B200_ROI_SLABS"); return e != nullptr ? atoi(e) : 0; }();   // developer sweep knob
+        if (slabs_env > 0 && nslab % slabs_env == 0) slabs = slabs_env;
         const int nconc = RV_WARPS / PH > 1 ? RV_WARPS / PH : 1;            // slabs pooled at the same time (see the kernel)
         while (slabs < nconc && nslab % (slabs * 2) == 0) slabs *= 2;       // keep every warp group busy
         const int nchunks = nslab / slabs;
@@ -1283,7 +1325,7 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
         }
         LOCO_REQUIRE(smem <= 200 * 1024, LOCO_E_UNSUPPORTED, "roi_align_fwd: output size %dx%d needs %zu B of shared memory", PH, PW, smem);
         LOCO_REQUIRE((long long)R * nchunks < (1ll << 31), LOCO_E_UNSUPPORTED, "roi_align_fwd: too many (roi, channel-slab) tiles");
-        typedef void (*v4_fn)(const float *, const float *, int, int, int, int, int, float, int, int, int, int, int, int, float *, const CUtensorMap);
+        typedef void (*v4_fn)(const float *, const float *, int, int, int, int, int, float, int, int, int, int, int, int, float *, const CUtensorMap, const int *);
         const bool multi = nconc > 1;
         v4_fn fn;
         if (out_mode == 1) fn = multi ? roi_align_fwd_v4_kernel<false, true, 1> : roi_align_fwd_v4_kernel<false, false, 1>;
@@ -1296,8 +1338,17 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
             LOCO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             smem_set[vi] = smem;
         }
+        // launch order (heaviest rois first) when the grid is more than a few waves and the caller gave workspace
+        const int *order = nullptr;
+        if (will_order && (long long)R * nchunks > 4ll * current_device_sm_count()) {
+            const int64_t map_bytes = feat_layout == LOCO_NHWC ? 0 : (((int64_t)N * C * H * W * (int64_t)sizeof(float) + 255) / 256) * 256;
+            int *ord = reinterpret_cast<int *>(static_cast<unsigned char *>(workspace) + map_bytes);
+            LOCO_CUDA(launch_kernel(roi_order_kernel, dim3(1), dim3(1024), 0, st, 1, rois, R, spatial_scale, ord));
+            count_launch();
+            order = ord;
+        }
         fn<<<R * nchunks, RV_THREADS, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, aligned, nchunks, slabs, tstride,
-                                                  bulk_out, out, omap);
+                                                  bulk_out, out, omap, order);
         count_launch();
         LOCO_CUDA(cudaGetLastError());
         return LOCO_OK;
@@ -1322,7 +1373,8 @@ int loco_roi_align_fwd(const float *feat, int N, int C, int H, int W, int feat_l
 
 int64_t loco_roi_align_bwd_workspace_bytes(int N, int C, int H, int W, int R) {
     if (C % 4 != 0) return 0;                                 // the vectorised path needs 4-channel lanes
-    return (int64_t)N * C * H * W * (int64_t)sizeof(float) + (((int64_t)R + 255) / 256) * 256;
+    // [channels-last accumulation map] [handled flags: R bytes] [launch order: R ints]
+    return (((int64_t)N * C * H * W * (int64_t)sizeof(float) + 255) / 256) * 256 + (((int64_t)R + 255) / 256) * 256 + roi_order_bytes(R);
 }
 
 int loco_roi_align_bwd(const float *dout, int N, int C, int H, int W, const float *rois, int R, int PH, int PW,
@@ -1347,7 +1399,7 @@ int loco_roi_align_bwd(const float *dout, int N, int C, int H, int W, const floa
     }
     // channels-last accumulation map + per-roi "handled" flags live in the workspace
     float *ws = static_cast<float *>(workspace);
-    const size_t map_bytes = (size_t)N * C * H * W * sizeof(float);
+    const size_t map_bytes = (((size_t)N * C * H * W * sizeof(float) + 255) / 256) * 256;
     unsigned char *handled = static_cast<unsigned char *>(workspace) + map_bytes;
     LOCO_CUDA(cudaMemsetAsync(workspace, 0, map_bytes + (size_t)R, st));
     const int nslab = (C + RV_CC - 1) / RV_CC;
@@ -1359,8 +1411,16 @@ int loco_roi_align_bwd(const float *dout, int N, int C, int H, int W, const floa
         LOCO_CUDA(cudaFuncSetAttribute(roi_align_bwd_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
+    const int *order = nullptr;
+    static const bool order_allowed = []() { const char *e = getenv("LOCOV_B200_ROI_ORDER"); return !(e != nullptr && e[0] == '0'); }();
+    if (order_allowed && (long long)R * nchunks > 4ll * current_device_sm_count()) {
+        int *ord = reinterpret_cast<int *>(handled + (((size_t)R + 255) / 256) * 256);
+        LOCO_CUDA(launch_kernel(roi_order_kernel, dim3(1), dim3(1024), 0, st, 1, rois, R, spatial_scale, ord));
+        count_launch();
+        order = ord;
+    }
     roi_align_bwd_v4_kernel<<<R * nchunks, RV_THREADS, smem, st>>>(dout, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, aligned, nchunks, slabs,
-                                                                   ws, handled);
+                                                                   ws, handled, order);
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     // [N][HW][C] -> [N][C][HW]: the forward's transpose with the roles of the two axes swapped (this ASSIGNS dfeat)

@@ -98,7 +98,7 @@ def roi_align(feat: torch.Tensor, rois: torch.Tensor, output_size, spatial_scale
     else:
         out = torch.empty((r, c, ph, pw), dtype=torch.float32, device=feat.device)
     lib = _lib.load()
-    ws = _workspace(feat.device, lib.loco_roi_align_workspace_bytes(n, c, h, w, layout), "roi_align")
+    ws = _workspace(feat.device, lib.loco_roi_align_workspace_bytes(n, c, h, w, layout, r), "roi_align")
     _lib.check(lib.loco_roi_align_fwd(_p(feat), n, c, h, w, layout, _p(rois), r, ph, pw, float(spatial_scale),
                                       int(sampling_ratio), int(bool(aligned)), _p(out), NHWC if channels_last else NCHW,
                                       BF16 if out_dtype == torch.bfloat16 else F32, _p(ws), _stream(feat)),

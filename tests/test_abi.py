@@ -33,8 +33,9 @@ def test_version_and_error_plumbing():
     assert b"roi_align_fwd" in lib.loco_last_error()
     rc = lib.loco_lsm_pair_fwd(None, None, 0, None, None, None, 0, None, 4, 200, 4, 10, 64, 0.1, 0, None, None, 4, None, None)
     assert rc == -2                                    # LOCO_E_UNSUPPORTED: T > 128
-    assert lib.loco_roi_align_workspace_bytes(2, 8, 5, 6, 0) == 2 * 8 * 5 * 6 * 4
-    assert lib.loco_roi_align_workspace_bytes(2, 8, 5, 6, 1) == 0
+    assert lib.loco_roi_align_workspace_bytes(2, 8, 5, 6, 0, 0) == 2048            # the transposed map (1920 B), rounded to 256
+    assert lib.loco_roi_align_workspace_bytes(2, 8, 5, 6, 1, 0) == 0
+    assert lib.loco_roi_align_workspace_bytes(2, 8, 5, 6, 1, 100) == 512           # + the launch order of 100 rois
 
 
 def test_sass_uses_blackwell_tensor_core_and_tma_instructions():
