@@ -657,6 +657,9 @@ __global__ void __launch_bounds__(RV_THREADS, 2) roi_align_fwd_v4_kernel(const f
         xadv[pw] = adv;
     }
     const bool walk_ok = __syncthreads_and(walk_bad ? 0 : 1) != 0;
+#ifdef LOCOV_ROI_PROLOGUE_ONLY          // developer timing probe: what the per-CTA prologue costs on its own (results are garbage)
+    if (walk_ok || !walk_ok) return;
+#endif
     const int walk_x0 = walk_hdr[1] * C * 4, walk_colstride = C * 4, walk_xlast = min(W - 1, walk_hdr[2]) * C * 4;
 
     // Warp roles: a group of PH warps pools one 128-channel slab (warp = bin row); with PH <= RV_WARPS / 2 (7 x 7 pooling)
