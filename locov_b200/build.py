@@ -52,11 +52,26 @@ def is_current():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a and link the C-ABI shared library.  Returns its path."""
+    """Compile every CUDA source for sm_100a and link the C-ABI shared library.  Returns its path.
+
+    Safe to call from several processes at once (one rank per GPU under torchrun): the build runs under an exclusive file lock with
+    per-process object / temporary names, and a process that waited for the lock re-checks the stamp instead of building again."""
     if not force and is_current():
         return lib_path()
     nvcc = _nvcc()
     os.makedirs(LIBDIR, exist_ok=True)
+    import fcntl
+    with open(os.path.join(LIBDIR, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():             # another process built it while this one waited
+                return lib_path()
+            return _build_locked(nvcc, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(nvcc, verbose):
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
 
@@ -72,7 +87,7 @@ def build(force=False, verbose=False):
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = lib_path() + ".tmp"
+    tmp = lib_path() + f".tmp{os.getpid()}"
     r = subprocess.run([nvcc, "-shared", "-o", tmp] + objs + ["-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
