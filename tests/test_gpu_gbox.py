@@ -40,9 +40,7 @@ def test_eval_matches_the_reference_class(cuda_device, name, precision):
     c = gm.GBOX_CASES[name]
     d = gm.gbox_inputs(c)
     z = np.load(os.path.join(GOLDEN, f"gbox_{name}.npz"))
-    if precision == "bf16" and c["alignment"] == "hardmax":
-        pytest.skip("hardmax picks a token: near-ties flip under bf16 rounding (same rule as the LSM head tests)")
-    bp = _predictor(c, d, cuda_device, precision).eval()
+    bp = _predictor(c, d, cuda_device, precision).eval()      # (hardmax in bf16 included: the score is the maximum token similarity, continuous)
     n0 = _lib.load().loco_launch_count()
     with torch.no_grad():
         scores, deltas = bp(d["x"].to(cuda_device))

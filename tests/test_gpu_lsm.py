@@ -35,8 +35,8 @@ def _to(d, dev):
 @pytest.mark.parametrize("name", golden_cases("lsm_"))
 def test_module_matches_reference_golden(cuda_device, name, precision, tol):
     ii, ic, w, b, cfg_kw, exp = golden_lsm(name)
-    if cfg_kw.get("alignment") == "hardmax" and precision == "bf16":
-        pytest.skip("hardmax is an argmax: bf16 rounding may legitimately flip near-ties")
+    # (hardmax in bf16 is tested too: a flipped near-tie changes WHICH region / word is attended, not the attended value beyond the
+    #  rounding error — the pair distances are max-type functions of the similarities, continuous in them)
     head = _head(cuda_device, w.shape[1], w.shape[0], w, b, precision, **cfg_kw)
     with torch.no_grad():
         out = head(_to(ii, cuda_device), _to(ic, cuda_device))
