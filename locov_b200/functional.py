@@ -6,6 +6,7 @@ streams and the autograd graph only.  ``precision`` selects the tensor-core oper
   "bf16" : single bf16 pass (≈4e-3 relative; the north-star tolerance for bf16 is 2e-2)
 """
 import os
+import threading
 import weakref
 from typing import Optional
 
@@ -129,13 +130,14 @@ def grounding_scores(e, w_tok, seg_off, temperature: float, alignment: str = "so
     return _TokenPool.apply(raw.contiguous(), seg_off, 1.0 / float(temperature), alignment == "hardmax")
 
 
-class _SpatialMean(Function):
-    last_operand = None          # forward's bf16 operand, handed to spatial_mean() below (a Function returns tensors only)
+_mean_tls = threading.local()     # forward's bf16 operand, handed to spatial_mean() below (a Function returns tensors only)
 
+
+class _SpatialMean(Function):
     @staticmethod
     def forward(ctx, x, operand):
         ctx.meta = (tuple(x.shape), x.dtype, (not x.is_contiguous()) and x.is_contiguous(memory_format=torch.channels_last))
-        out, _SpatialMean.last_operand = ops.spatial_mean(x, operand)
+        out, _mean_tls.operand = ops.spatial_mean(x, operand)
         return out
 
     @staticmethod
@@ -155,8 +157,8 @@ def spatial_mean(x, operand_precision: Optional[str] = None):
     if operand is not None and _use_tf32(operand, x.shape[1]):
         operand = None                       # the TF32 projection reads the fp32 means directly
     out = _SpatialMean.apply(x, operand)
-    op = _SpatialMean.last_operand
-    _SpatialMean.last_operand = None
+    op = getattr(_mean_tls, "operand", None)
+    _mean_tls.operand = None
     if op is not None:
         out._loco_operand = (op, operand, out._version)
     return out

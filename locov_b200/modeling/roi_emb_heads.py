@@ -111,7 +111,9 @@ class EmbeddingRes5ROIHeads(nn.Module):
         the predictor's projection GEMM.  On the CPU (the CPU unit tests of the host logic) it is the torch expression."""
         if not box_features.is_cuda:
             return box_features.mean(dim=[2, 3])
-        return LF.spatial_mean(box_features, getattr(self.box_predictor, "precision", None)).to(box_features.dtype)
+        # fp32 means whatever the dtype of the res5 output (a bf16 stage included): the predictor computes in fp32 operands anyway, and the
+        # tensor carries the bf16 operand written by the same pass
+        return LF.spatial_mean(box_features, getattr(self.box_predictor, "precision", None))
 
     def forward(self, images, features, proposals, targets=None):
         del images
