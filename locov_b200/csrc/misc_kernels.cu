@@ -1409,7 +1409,9 @@ int loco_pair_ce(float *pw, int nmat, int64_t mat_stride, int64_t ld, int Bc, in
     LOCO_REQUIRE(pw && cap_mask && reg_mask && out4, LOCO_E_BADARG, "pair_ce: null pointer");
     const size_t base = (32 + (size_t)Bc + Bi + 128) * sizeof(float);
     LOCO_REQUIRE(base <= 48 * 1024, LOCO_E_UNSUPPORTED, "pair_ce: batch too large (Bc=%d Bi=%d)", Bc, Bi);
-    const int strip_w = (Bc <= 32 && Bi <= 32) ? 32 : pair_ce_strip(Bc, Bi);
+    // one CTA with the matrix staged in shared memory up to 64 x 64 (N = 2 of the sharded head: one launch instead of prep + strips)
+    static const int staged_max = []() { const char *e = getenv("LOCOV_B200_PCE_STAGED_MAX"); const int v = e ? atoi(e) : 64; return (v >= 32 && v <= 96) ? v : 64; }();
+    const int strip_w = (Bc <= staged_max && Bi <= staged_max) ? staged_max : pair_ce_strip(Bc, Bi);
     const int nblk = ((Bc > Bi ? Bc : Bi) + strip_w - 1) / strip_w;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (nblk == 1) {

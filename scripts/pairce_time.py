@@ -1,8 +1,10 @@
 import sys, torch
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+print("PCE_STAGED_MAX", os.environ.get("LOCOV_B200_PCE_STAGED_MAX", "-"))
 from locov_b200 import ops
 dev = torch.device("cuda:0")
-for B in (64, 128, 256):
+for B in (32, 48, 64, 128, 256):
     pw = torch.randn(2, B, B, device=dev) * 3
     mc = torch.ones(B, 20, device=dev); mr = torch.ones(B, 1, device=dev)
     for _ in range(3): ops.pair_ce(pw.clone(), mc, mr)
