@@ -154,6 +154,16 @@ int loco_roi_align_grid_dump(const float *rois, int R, int H, int W, int PH, int
 int loco_split_bf16(const float *src, int64_t rows, int64_t cols, int64_t src_ld, uint16_t *hi,
                     uint16_t *lo, int64_t dst_ld, int transpose, void *stream);
 
+
+/* loco_lsm_prep with up to three split jobs in the same launch (replaces, for the fp32-accurate LSM step, the separate conversions of
+ * the region features and of the v2l_projection weight — reference grounding_head.py:94-111: the masks, `.to(float)` casts and the
+ * operands of the projection): job j converts src[j] [rows[j], cols[j]] fp32 (row stride src_ld[j]) into hi[j] / lo[j] bf16
+ * [rows[j], dst_ld[j]] (lo[j] may be NULL).  All pointer arrays are HOST arrays of nsplit entries; put the largest job first. */
+int loco_lsm_prep_multi(int nsplit, const float *const *src, const int64_t *rows, const int64_t *cols, const int64_t *src_ld,
+                        uint16_t *const *hi, uint16_t *const *lo, const int64_t *dst_ld, const int64_t *attention_mask,
+                        const int64_t *special_tokens_mask, int64_t n_cap, const void *region_mask, int region_kind, int64_t n_reg,
+                        float *cap_mask, float *reg_mask, void *stream);
+
 /* bf16 [rows, cols] (src_ld) -> bf16 [cols, rows] (dst_ld >= rows; pad columns zero-filled): operand
  * re-layout for the backward GEMMs (dX = dY . W needs W^T K-major, dW = dY^T . X needs both transposed). */
 int loco_transpose_bf16(const uint16_t *src, int64_t rows, int64_t cols, int64_t src_ld, uint16_t *dst,

@@ -35,6 +35,7 @@ SIGNATURES = {
     "loco_box_inference": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "loco_token_pool_fwd": (_i, [_vp, _i64, _vp, _i, _i, _f, _i, _vp, _i64, _vp, _vp]),
     "loco_token_pool_bwd": (_i, [_vp, _i64, _vp, _i, _i, _f, _i, _vp, _i64, _vp, _i64, _vp]),
+    "loco_lsm_prep_multi": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i, _i64, _vp, _vp, _vp]),
     "loco_roi_align_grid_dump": (_i, [_vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "loco_split_bf16": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i, _vp]),
     "loco_transpose_bf16": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),

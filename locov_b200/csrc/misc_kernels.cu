@@ -82,6 +82,40 @@ __global__ void __launch_bounds__(256) lsm_prep_kernel(const float *__restrict__
     }
 }
 
+// ---- LSM input preparation, all of it in ONE launch: up to three fp32 -> bf16 (hi / lo) jobs (region features, projection weight,
+// caption embeddings) and both masks.  The caption / weight / mask jobs are latency-bound on their own (3.5-3.8 us each for a few MB);
+// inside the launch of the HBM-bound feature split (9 us for 26 MB) they cost nothing.  Jobs are laid out largest first.
+struct SplitJobs {
+    const float *src[3];
+    uint16_t *hi[3], *lo[3];
+    long long rows[3], cols[3], src_ld[3], dst_ld[3], nq[3];     // nq = rows * dst_ld / 4 destination quads
+    int n;
+};
+__global__ void __launch_bounds__(256) lsm_prep_multi_kernel(const SplitJobs jobs, const int64_t *__restrict__ att, const int64_t *__restrict__ spe,
+                                                             int64_t n_cap, const void *__restrict__ reg, int reg_kind, int64_t n_reg,
+                                                             float *__restrict__ cap_mask, float *__restrict__ reg_mask) {
+    pdl_trigger();
+    pdl_wait();
+    int64_t total = n_cap + n_reg;
+    for (int j = 0; j < jobs.n; ++j) total += jobs.nq[j];
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t k = idx;
+        bool done = false;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (done || j >= jobs.n) continue;
+            if (k < jobs.nq[j]) {
+                const bool vec_ok = (jobs.src_ld[j] % 4 == 0) && ((reinterpret_cast<uintptr_t>(jobs.src[j]) & 15) == 0);
+                split_quad(jobs.src[j], jobs.cols[j], jobs.src_ld[j], jobs.hi[j], jobs.lo[j], jobs.dst_ld[j], jobs.dst_ld[j] / 4, vec_ok, k);
+                done = true;
+            } else {
+                k -= jobs.nq[j];
+            }
+        }
+        if (!done) mask_item(att, spe, n_cap, reg, reg_kind, cap_mask, reg_mask, k);
+    }
+}
+
 // transposed variant: dst[c, r] = src[r, c]; dst is [cols, dst_ld] with pad [rows, dst_ld) zeroed.
 __global__ void __launch_bounds__(256) split_bf16_t_kernel(const float *__restrict__ src, int rows, int cols, int64_t src_ld,
                                                            uint16_t *__restrict__ hi, uint16_t *__restrict__ lo,
@@ -1139,6 +1173,34 @@ int loco_lsm_prep(const float *cap, int64_t rows, int64_t cols, int64_t cap_ld, 
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     LOCO_CUDA(launch_kernel(lsm_prep_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, cap, rows, cols, cap_ld, cap_hi, cap_lo,
                             dst_ld, attention_mask, special_tokens_mask, n_cap, region_mask, region_kind, n_reg, cap_mask, reg_mask));
+    count_launch();
+    LOCO_CUDA(cudaGetLastError());
+    return LOCO_OK;
+}
+
+int loco_lsm_prep_multi(int nsplit, const float *const *src, const int64_t *rows, const int64_t *cols, const int64_t *src_ld, uint16_t *const *hi,
+                        uint16_t *const *lo, const int64_t *dst_ld, const int64_t *attention_mask, const int64_t *special_tokens_mask, int64_t n_cap,
+                        const void *region_mask, int region_kind, int64_t n_reg, float *cap_mask, float *reg_mask, void *stream) {
+    LOCO_REQUIRE(nsplit >= 1 && nsplit <= 3 && n_cap > 0 && n_reg > 0 && region_kind >= 0 && region_kind <= 2, LOCO_E_BADARG,
+                 "lsm_prep_multi: bad arguments nsplit=%d n_cap=%lld n_reg=%lld", nsplit, (long long)n_cap, (long long)n_reg);
+    LOCO_REQUIRE(src && rows && cols && src_ld && hi && lo && dst_ld && attention_mask && special_tokens_mask && region_mask && cap_mask && reg_mask,
+                 LOCO_E_BADARG, "lsm_prep_multi: null pointer");
+    SplitJobs jobs = {};
+    jobs.n = nsplit;
+    int64_t total = n_cap + n_reg;
+    for (int j = 0; j < nsplit; ++j) {
+        LOCO_REQUIRE(rows[j] > 0 && cols[j] > 0 && src_ld[j] >= cols[j] && src[j] && hi[j], LOCO_E_BADARG, "lsm_prep_multi: bad job %d", j);
+        LOCO_REQUIRE(dst_ld[j] % 8 == 0 && dst_ld[j] >= cols[j], LOCO_E_ALIGN, "lsm_prep_multi: dst_ld of job %d must be a multiple of 8 and >= cols", j);
+        LOCO_REQUIRE((reinterpret_cast<uintptr_t>(hi[j]) & 15) == 0 && (!lo[j] || (reinterpret_cast<uintptr_t>(lo[j]) & 15) == 0), LOCO_E_ALIGN,
+                     "lsm_prep_multi: destination of job %d must be 16-byte aligned", j);
+        jobs.src[j] = src[j]; jobs.hi[j] = hi[j]; jobs.lo[j] = lo[j];
+        jobs.rows[j] = rows[j]; jobs.cols[j] = cols[j]; jobs.src_ld[j] = src_ld[j]; jobs.dst_ld[j] = dst_ld[j];
+        jobs.nq[j] = rows[j] * (dst_ld[j] / 4);
+        total += jobs.nq[j];
+    }
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    LOCO_CUDA(launch_kernel(lsm_prep_multi_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, jobs, attention_mask, special_tokens_mask,
+                            n_cap, region_mask, region_kind, n_reg, cap_mask, reg_mask));
     count_launch();
     LOCO_CUDA(cudaGetLastError());
     return LOCO_OK;

@@ -70,6 +70,19 @@ def weight_operand(w: torch.Tensor, accurate: bool, transpose: bool = False, tag
     return op
 
 
+def weight_operand_if_cached(w: torch.Tensor, accurate: bool, transpose: bool = False, tag: str = ""):
+    """The cached operand of ``w`` when ``weight_operand`` would serve it without a conversion launch, else None."""
+    ent = _wcache.get((w.data_ptr(), tuple(w.shape), tuple(w.stride()), accurate, transpose, tag, w.device.index))
+    if WEIGHT_CACHE and not w.requires_grad and ent is not None and ent[0] == w._version and ent[2]() is w:
+        return ent[1]
+    return None
+
+
+def adopt_weight_operand(w: torch.Tensor, accurate: bool, op: ops.Bf16Operand, transpose: bool = False, tag: str = ""):
+    """Register an operand of ``w`` that another launch produced (ops.lsm_prep with ``extra``) under weight_operand's rules."""
+    _wcache[(w.data_ptr(), tuple(w.shape), tuple(w.stride()), accurate, transpose, tag, w.device.index)] = (w._version, op, weakref.ref(w))
+
+
 def clear_weight_cache():
     """Drop every cached bf16 weight shadow (call after modifying a FROZEN weight through ``.data``)."""
     _wcache.clear()
@@ -439,11 +452,13 @@ def box_reg_loss(deltas, proposal_boxes, gt_boxes, labels, num_classes, reg_weig
 # ------------------------------------------------------------------------------------------------
 # LSM grounding head: projection + pair distances in one autograd node
 # ------------------------------------------------------------------------------------------------
-def project_regions(x2d, w, b, d, acc):
+def project_regions(x2d, w, b, d, acc, x_op=None, w_op=None):
     """v2l_projection (grounding_head.py:111) -> bf16 tensor-core operand of the region embeddings.
-    fp32 mode: hi/lo split + three bf16 passes; reduced-precision mode: TF32 straight from the fp32 features."""
+    fp32 mode: hi/lo split + three bf16 passes; reduced-precision mode: TF32 straight from the fp32 features.
+    ``x_op`` / ``w_op``: operands of x2d / w that the preparation launch already produced (ops.lsm_prep with ``extra``)."""
     if not _use_tf32(acc, x2d.shape[1]):
-        _, emb_op = ops.linear_fwd(ops.split_bf16(x2d, acc), weight_operand(w, acc), b, want_f32=False, n_bf16=d, accurate_out=acc)
+        _, emb_op = ops.linear_fwd(x_op if x_op is not None else ops.split_bf16(x2d, acc), w_op if w_op is not None else weight_operand(w, acc), b,
+                                   want_f32=False, n_bf16=d, accurate_out=acc)
     else:
         _, emb_op = ops.linear_tf32_fwd(x2d, w.detach(), b, want_f32=False, n_bf16=d)
     return emb_op
@@ -459,11 +474,11 @@ class _LsmHead(Function):
     A slice whose alignment is switched off is zero and carries no gradient."""
 
     @staticmethod
-    def forward(ctx, feats, w, b, cap, cap_mask, reg_mask, inv_temp, alignment, precision, want_w2r, want_r2w, cap_op):
+    def forward(ctx, feats, w, b, cap, cap_mask, reg_mask, inv_temp, alignment, precision, want_w2r, want_r2w, cap_op, x_op=None, w_op=None):
         acc = _acc(precision)
         bi, rg, v = feats.shape
         bc, t, d = cap.shape
-        emb_op = project_regions(feats.reshape(bi * rg, v), w, b, d, acc)
+        emb_op = project_regions(feats.reshape(bi * rg, v), w, b, d, acc, x_op, w_op)
         if cap_op is None or (cap_op.lo is None) == acc or cap_op.rows != bc * t or cap_op.cols != d:
             cap_op = ops.split_bf16(cap.reshape(bc * t, d), acc)    # (not prepared by ops.lsm_prep, or for another mode)
         stack = new_pair_stack(bc, bi, feats.device, want_w2r and want_r2w)
@@ -499,11 +514,11 @@ class _LsmHead(Function):
             db = demb.sum(0)
         if need_cap:
             dcap = dcap.reshape(cap_shape)
-        return dx, dw, db, (dcap if need_cap else None), None, None, None, None, None, None, None, None
+        return dx, dw, db, (dcap if need_cap else None), None, None, None, None, None, None, None, None, None, None
 
 
 def lsm_head(feats, w, b, cap, cap_mask, reg_mask, temperature, alignment="softmax", precision="fp32",
-             want_w2r=True, want_r2w=True, cap_op=None):
+             want_w2r=True, want_r2w=True, cap_op=None, x_op=None, w_op=None):
     """Stacked pair distance matrices [2, Bc, Bi] = (w2r, r2w) (rows = captions, cols = images) before the
     empty-pair guard; the slice of a switched-off alignment is zero.  ``cap_op`` = the caption operand when
     ``ops.lsm_prep`` already produced it together with the masks (same values as ``cap``)."""
@@ -511,7 +526,7 @@ def lsm_head(feats, w, b, cap, cap_mask, reg_mask, temperature, alignment="softm
     if amode is None:
         raise NotImplementedError(f"alignment {alignment!r} is not implemented on the B200 path")
     return _LsmHead.apply(feats, w, b, cap, cap_mask, reg_mask, 1.0 / float(temperature), amode, precision,
-                          bool(want_w2r), bool(want_r2w), cap_op)
+                          bool(want_w2r), bool(want_r2w), cap_op, x_op, w_op)
 
 
 class _PairCE(Function):

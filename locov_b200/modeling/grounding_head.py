@@ -69,12 +69,30 @@ class GroundingHead(LoggedModule):
         region_features = input_image["region_features"]
         region_mask = input_image["region_mask"]
         sharded = self.shard_captions and self.process_group is not None
-        cap_op = None
+        cap_op = x_op = w_op = None
+        acc = self.precision == "fp32"
         masks_on_device = att.is_cuda and att.dtype == torch.int64 and spe.dtype == torch.int64 and region_mask.dtype in ops._REG_KIND
         if masks_on_device and caption_emb.is_cuda and caption_emb.dim() == 3:
-            # grounding_head.py:94-106 and the caption operand of the pair GEMM in one launch
+            # grounding_head.py:94-106 and the caption operand of the pair GEMM in one launch; in the fp32-accurate mode the same launch
+            # also converts the region features and (unless its operand is cached) the projection weight: the small jobs are
+            # latency-bound on their own and free inside the HBM-bound feature split
             cap32 = caption_emb.to(torch.float32).contiguous()
-            cap_op, caption_mask, region_mask = ops.lsm_prep(cap32.reshape(-1, cap32.shape[-1]), self.precision == "fp32", att, spe, region_mask)
+            extra = []
+            fuse = acc and not sharded and region_features.is_cuda and region_features.dim() == 3 and not LF._use_tf32(acc, region_features.shape[-1])
+            if fuse:
+                feats32 = region_features.to(torch.float32).contiguous()
+                extra.append(feats32.reshape(-1, feats32.shape[-1]))
+                wgt = self.v2l_projection.weight
+                w_op = LF.weight_operand_if_cached(wgt, acc)
+                if w_op is None:
+                    extra.append(wgt.detach())
+            got = ops.lsm_prep(cap32.reshape(-1, cap32.shape[-1]), acc, att, spe, region_mask, extra=extra)
+            cap_op, caption_mask, region_mask = got[:3]
+            if fuse:
+                x_op = got[3][0]
+                if w_op is None:
+                    w_op = got[3][1]
+                    LF.adopt_weight_operand(wgt, acc, w_op)
         elif masks_on_device:
             caption_mask, region_mask = ops.lsm_masks(att, spe, region_mask)       # grounding_head.py:94-106, one launch
         else:
@@ -95,7 +113,7 @@ class GroundingHead(LoggedModule):
         pw = LF.lsm_head(region_features.to(torch.float32).contiguous(), self.v2l_projection.weight,
                          self.v2l_projection.bias, caption_emb.to(torch.float32).contiguous(), caption_mask,
                          region_mask, self.temperature, self.alignment, self.precision,
-                         want_w2r=self.align_words, want_r2w=self.align_regions, cap_op=cap_op)
+                         want_w2r=self.align_words, want_r2w=self.align_regions, cap_op=cap_op, x_op=x_op, w_op=w_op)
         assert pw.shape == (2, batch_size, batch_size)
         losses, other_info, dists = self._pair_outputs(pw, caption_mask, region_mask)
         self.log_dict(losses)

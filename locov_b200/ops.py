@@ -460,8 +460,11 @@ def lsm_masks(attention_mask: torch.Tensor, special_tokens_mask: torch.Tensor, r
 
 
 def lsm_prep(cap2d: torch.Tensor, accurate: bool, attention_mask: torch.Tensor, special_tokens_mask: torch.Tensor,
-             region_mask: torch.Tensor):
-    """Caption embeddings [B*T, D] fp32 -> Bf16Operand, plus (caption_mask, region_mask) as in ``lsm_masks`` — one launch."""
+             region_mask: torch.Tensor, extra=()):
+    """Caption embeddings [B*T, D] fp32 -> Bf16Operand, plus (caption_mask, region_mask) as in ``lsm_masks`` — one launch.
+
+    ``extra``: up to two more 2-D fp32 matrices (the region features, the projection weight) converted to operands of the same
+    precision IN THE SAME LAUNCH; their operands are returned as a fourth element (list)."""
     _need_cuda(cap2d, attention_mask, special_tokens_mask, region_mask)
     if cap2d.dim() != 2 or cap2d.dtype != torch.float32:
         raise LocoError("lsm_prep: expects 2-D fp32 caption embeddings")
@@ -470,17 +473,41 @@ def lsm_prep(cap2d: torch.Tensor, accurate: bool, attention_mask: torch.Tensor, 
     if cap2d.stride(1) != 1:
         cap2d = cap2d.contiguous()
     att, spe, reg = attention_mask.contiguous(), special_tokens_mask.contiguous(), region_mask.contiguous()
-    rows, cols = cap2d.shape
-    ld = _round_up(max(cols, 1), 8)
-    hi = torch.empty((rows, ld), dtype=torch.bfloat16, device=cap2d.device)
-    lo = torch.empty((rows, ld), dtype=torch.bfloat16, device=cap2d.device) if accurate else None
     cap_mask = torch.empty(att.shape, dtype=torch.float32, device=att.device)
     reg_mask = torch.empty(reg.shape, dtype=torch.float32, device=att.device)
+
+    def operand(x):
+        rows, cols = x.shape
+        ld = _round_up(max(cols, 1), 8)
+        hi = torch.empty((rows, ld), dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty((rows, ld), dtype=torch.bfloat16, device=x.device) if accurate else None
+        return Bf16Operand(hi, lo, rows, cols)
     lib = _lib.load()
-    _lib.check(lib.loco_lsm_prep(_p(cap2d), rows, cols, cap2d.stride(0), _p(hi), _p(lo) if accurate else None, ld, _p(att), _p(spe),
-                                 att.numel(), _p(reg), _REG_KIND[reg.dtype], reg.numel(), _p(cap_mask), _p(reg_mask), _stream(cap2d)),
-               "loco_lsm_prep")
-    return Bf16Operand(hi, lo, rows, cols), cap_mask, reg_mask
+    cap_op = operand(cap2d)
+    if not extra:
+        _lib.check(lib.loco_lsm_prep(_p(cap2d), cap_op.rows, cap_op.cols, cap2d.stride(0), _p(cap_op.hi), _p(cap_op.lo) if accurate else None, cap_op.ld,
+                                     _p(att), _p(spe), att.numel(), _p(reg), _REG_KIND[reg.dtype], reg.numel(), _p(cap_mask), _p(reg_mask),
+                                     _stream(cap2d)), "loco_lsm_prep")
+        return cap_op, cap_mask, reg_mask
+    if len(extra) > 2:
+        raise LocoError("lsm_prep: at most two extra matrices")
+    srcs, outs = [], []
+    for x in extra:
+        _need_cuda(x)
+        if x.dim() != 2 or x.dtype != torch.float32:
+            raise LocoError("lsm_prep: extra matrices must be 2-D fp32")
+        x = x if x.stride(1) == 1 else x.contiguous()
+        srcs.append(x)
+        outs.append(operand(x))
+    jobs = sorted(zip(srcs + [cap2d], outs + [cap_op]), key=lambda so: -so[0].numel())         # largest job first
+    n = len(jobs)
+    vp, i64 = ctypes.c_void_p * n, ctypes.c_int64 * n
+    _lib.check(lib.loco_lsm_prep_multi(
+        n, vp(*[x.data_ptr() for x, _ in jobs]), i64(*[x.shape[0] for x, _ in jobs]), i64(*[x.shape[1] for x, _ in jobs]),
+        i64(*[x.stride(0) for x, _ in jobs]), vp(*[o.hi.data_ptr() for _, o in jobs]), vp(*[(o.lo.data_ptr() if o.lo is not None else None) for _, o in jobs]),
+        i64(*[o.ld for _, o in jobs]), _p(att), _p(spe), att.numel(), _p(reg), _REG_KIND[reg.dtype], reg.numel(), _p(cap_mask), _p(reg_mask),
+        _stream(cap2d)), "loco_lsm_prep_multi")
+    return cap_op, cap_mask, reg_mask, outs
 
 
 def lsm_pair(cap: Bf16Operand, cap_mask: torch.Tensor, emb: Bf16Operand, reg_mask: torch.Tensor, inv_temperature: float,
