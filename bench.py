@@ -302,7 +302,14 @@ def run_b200(args):
         emb_ops = [ops.linear_fwd(x_ops[i], w_op, bias, want_f32=False, n_bf16=D, accurate_out=acc)[1] for i in range(4)]
         pw = torch.randn(2, b_glob, b_glob, device=dev)
         hi_buf = x_ops[0]
+        # the step's preparation launch: token / region masks + caption operand, and in the fp32-accurate mode the operands of the region
+        # features and of the projection weight as well (ops.lsm_prep with `extra`)
+        ic0, ii0 = dev_sets[0][1], dev_sets[0][0]
+        cap2d = ic0["input_embeddings"].reshape(-1, D).to(torch.float32)
+        prep_extra = (lambda i: [feats[i % nrot], wgt]) if (acc and world == 1) else (lambda i: [])
         k_ms = {
+            "lsm_prep (masks + operands, one launch)": graph_time(torch, lambda i: ops.lsm_prep(cap2d, acc, ic0["attention_mask"], ic0["special_tokens_mask"],
+                                                                                              ii0["region_mask"], extra=prep_extra(i))),
             "split_bf16(features)": graph_time(torch, lambda i: ops.split_bf16(feats[i % nrot], acc, out=hi_buf)) if acc else 0.0,
             "tc_gemm<EpiLinear> (projection)": graph_time(
                 torch, (lambda i: ops.linear_fwd(x_ops[i % nrot], w_op, None, want_f32=False, n_bf16=D, accurate_out=acc)) if acc else
@@ -314,10 +321,17 @@ def run_b200(args):
         gemm_flops = 2.0 * m_rows * V * D
         pair_flops = 2.0 * (b_glob * T) * (B_LOC * RG) * D               # one similarity GEMM serves both alignments
         split_bytes = m_rows * V * (4 + 2 * (2 if acc else 1))
+        prep_bytes = (cap2d.numel() * (4 + 2 * (2 if acc else 1)) + ((m_rows * V + V * D) * (4 + 2 * 2) if (acc and world == 1) else 0))
         kern = {
+            "lsm_prep (masks + operands, one launch)": {"bound": "hbm", "ms": k_ms["lsm_prep (masks + operands, one launch)"],
+                                                        "achieved": prep_bytes / (k_ms["lsm_prep (masks + operands, one launch)"] * 1e-3) / 1e9,
+                                                        "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                                        "note": "fp32-accurate mode, one GPU: region features + projection weight + captions -> bf16 (hi, lo) and both masks; "
+                                                                "otherwise captions + masks only (then latency, not bandwidth, bound)"},
             "split_bf16(features)": {"bound": "hbm", "ms": k_ms["split_bf16(features)"],
                                      "achieved": split_bytes / (max(k_ms["split_bf16(features)"], 1e-9) * 1e-3) / 1e9 if acc else 0.0,
-                                     "peak": pk["hbm_gbs"], "unit": "GB/s", "note": "fp32-accurate mode only; the bf16 mode multiplies the fp32 features in place as TF32"},
+                                     "peak": pk["hbm_gbs"], "unit": "GB/s", "note": "the feature split timed ALONE for reference: in the step it is part of the preparation launch above (sharded head: a launch of its own); "
+                                             "the bf16 mode multiplies the fp32 features in place as TF32"},
             "tc_gemm<EpiLinear> (projection)": {"bound": "tensor", "ms": k_ms["tc_gemm<EpiLinear> (projection)"],
                                                 "achieved": gemm_flops / (k_ms["tc_gemm<EpiLinear> (projection)"] * 1e-3) / 1e12,
                                                 "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
